@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules from /root/reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+Inputs and weights are produced by the RNG-free closed forms in oracle/mmd_oracle.py (`synth*`), so
+the fixtures store only the reference's OUTPUTS (forward values, gradients, BN buffers).  Tests
+regenerate the inputs with the same closed forms and compare the oracle (CPU tests) and the CUDA
+path (GPU tests) against these stored reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import mmd_oracle as O  # noqa: E402
+from src.YetAnotherEfficientDet import BiFPN  # noqa: E402  (reference)
+from src.loss.MTALoss import MTALoss  # noqa: E402  (reference)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+LEVEL_NAMES = ("p3", "p4", "p5", "p6", "p7")
+
+
+def load_cell(cell, params, prefix):
+    sd = {k[len(prefix):]: v.clone() for k, v in params.items() if k.startswith(prefix)}
+    missing, unexpected = cell.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return cell
+
+
+def pyramid_inputs(B, C, s3, seed, dtype=torch.float32):
+    sizes = [s3, s3 // 2, s3 // 4, s3 // 8, max(s3 // 16, 1)]
+    return [O.synth((B, C, s, s), seed + i, 1.0, 0.1 * i, dtype) for i, s in enumerate(sizes)]
+
+
+def backbone_inputs(B, conv_channels, s3, seed, dtype=torch.float32):
+    return [O.synth((B, c, s3 >> i, s3 >> i), seed + i, 1.0, 0.0, dtype) for i, c in enumerate(conv_channels)]
+
+
+def run_stack_case(name, C, conv_channels, n_cells, first, B, s3, seed, save_param_grads):
+    """Reference nn.Sequential of BiFPN cells: eval forward, train forward + backward."""
+    params = O.synth_stack_params(C, conv_channels, n_cells, seed, first_cell_first_time=first)
+    cells = [load_cell(BiFPN(C, conv_channels, first_time=(i == 0 and first)), params, "%d." % i)
+             for i in range(n_cells)]
+    stack = torch.nn.Sequential(*cells)
+    out = {}
+    mk = (lambda: backbone_inputs(B, conv_channels, s3, seed + 50)) if first else \
+        (lambda: pyramid_inputs(B, C, s3, seed + 50))
+
+    stack.eval()
+    with torch.no_grad():
+        ev = stack(tuple(mk()))
+    for n, t in zip(LEVEL_NAMES, ev):
+        out["eval_" + n] = t.numpy()
+
+    stack.train()
+    xs = [x.requires_grad_(True) for x in mk()]
+    tr = stack(tuple(xs))
+    gouts = [O.synth(tuple(t.shape), seed + 70 + i, 1.0, 0.0) for i, t in enumerate(tr)]
+    loss = sum((t * g).sum() for t, g in zip(tr, gouts))
+    loss.backward()
+    for n, t in zip(LEVEL_NAMES, tr):
+        out["train_" + n] = t.detach().numpy()
+    for i, x in enumerate(xs):
+        out["grad_in%d" % i] = x.grad.numpy()
+    sd = stack.state_dict()
+    for k, v in sd.items():
+        if "running_" in k or "num_batches" in k:
+            out["buf_" + k] = v.numpy()
+    for k, v in stack.named_parameters():
+        if save_param_grads:
+            out["pgrad_" + k] = v.grad.numpy()
+        else:  # two numbers per parameter keep the fixture small at C=112
+            out["pgsum_" + k] = np.array([v.grad.double().sum().item(), v.grad.double().norm().item()])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "->", len(out), "arrays")
+
+
+def structured_features(B, C, sizes, seed):
+    """Features whose channel-pooled attention is far from uniform (SURVEY.md 8d 'structured' set)."""
+    fs = []
+    for i, s in enumerate(sizes):
+        base = O.synth((B, C, s, s), seed + i, 1.0, 0.0)
+        mod = torch.exp(1.5 * O.synth((B, 1, s, s), seed + 100 + i, 1.0, 0.0))
+        fs.append(base * mod)
+    return fs
+
+
+def run_mta_case(name, B, C, sizes, seed):
+    out = {}
+    crit = MTALoss(T="9", p="2")   # strings, as extract_criterions_from_config passes them
+    g_s = [f.requires_grad_(True) for f in structured_features(B, C, sizes, seed)]
+    teachers = [structured_features(B, C, sizes, seed + 10 * (k + 1)) for k in range(3)]
+    go = torch.tensor([0.005 * (i + 1) for i in range(len(sizes))])
+
+    loss1 = crit(g_s, teachers[0])                      # shipped-cfg branch (MTALoss.py:17-19)
+    (loss1 * go).sum().backward()
+    out["loss_single"] = loss1.detach().numpy()
+    for i, f in enumerate(g_s):
+        out["grad_single_%d" % i] = f.grad.numpy().copy()
+        f.grad = None
+
+    loss3 = crit(g_s, teachers)                         # multi-teacher product branch (:20-34)
+    (loss3 * go).sum().backward()
+    out["loss_multi"] = loss3.detach().numpy()
+    for i, f in enumerate(g_s):
+        out["grad_multi_%d" % i] = f.grad.numpy().copy()
+        f.grad = None
+
+    crit_d = MTALoss()                                  # fp64 landmark for the loss values
+    l64 = crit_d([f.detach().double() for f in g_s], [f.double() for f in teachers[0]])
+    out["loss_single_fp64"] = l64.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "->", len(out), "arrays")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    # small-channel cases pin every term of the oracle, including all parameter gradients
+    run_stack_case("cell_c16", 16, [8, 12, 20], 1, False, B=2, s3=16, seed=1, save_param_grads=True)
+    run_stack_case("first_c16", 16, [8, 12, 20], 1, True, B=2, s3=16, seed=2, save_param_grads=True)
+    run_stack_case("stack3_c16", 16, [8, 12, 20], 3, True, B=2, s3=32, seed=3, save_param_grads=True)
+    # odd top level (P7 = 3x3) : P3=48 .. P6=6
+    run_stack_case("stack2_c16_odd", 16, [8, 12, 20], 2, True, B=1, s3=48, seed=4, save_param_grads=True)
+    # D2 channel counts (what the CUDA kernels are built for), tiny spatial size
+    run_stack_case("stack2_c112", 112, [48, 120, 352], 2, True, B=2, s3=16, seed=5, save_param_grads=False)
+    run_stack_case("cell_c112", 112, [48, 120, 352], 1, False, B=2, s3=16, seed=6, save_param_grads=False)
+    run_mta_case("mta_c112", B=2, C=112, sizes=[12, 6, 3], seed=7)
+    run_mta_case("mta_c16", B=3, C=16, sizes=[16, 8, 4, 2, 1], seed=8)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,295 @@
+"""CPU oracle for the MM-DistillNet distillation hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain-PyTorch (CPU, fp32 or fp64) restatement of the reference's algorithm for the
+path named by BASELINE.json: the EfficientDet BiFPN cell / stack and the MTA loss.  It is the
+checker the CUDA path is compared against; it is NOT part of the product.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` leg may import it.
+The product package (`mm_distillnet_b200`) never imports anything from `oracle/`.
+
+Pinning: the reference ships no tests or golden vectors, so this restatement is
+pinned against OUTPUTS OF THE REFERENCE ITSELF, run in the build container from /root/reference by
+`oracle/make_golden.py`; the vectors live in `tests/golden/*.npz` and `tests/test_oracle_golden.py`
+checks this file against them (forward values, input gradients, parameter gradients, BN running
+statistics, MTA losses and MTA gradients).
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+Parameters are passed as a flat dict keyed by the reference's own state_dict names, so a reference
+`state_dict()` can be used directly.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BN_MOMENTUM = 0.01   # src/YetAnotherEfficientDet.py:176, :239-265
+BN_EPS = 1e-3        # same lines
+FUSION_EPS = 1e-4    # src/YetAnotherEfficientDet.py:200 (epsilon=1e-4)
+
+UP_NODES = ("conv6_up", "conv5_up", "conv4_up", "conv3_up")
+DOWN_NODES = ("conv4_down", "conv5_down", "conv6_down", "conv7_down")
+PROJ_NAMES = ("p5_down_channel", "p4_down_channel", "p3_down_channel", "p5_to_p6",
+              "p4_down_channel_2", "p5_down_channel_2")
+
+
+# ----------------------------------------------------------------------------------------------
+# primitives
+# ----------------------------------------------------------------------------------------------
+def same_pad(size, kernel, stride):
+    """TF-"SAME" padding split.  src/YetAnotherEfficientNet.py:54-60 (conv) and :93-99 (pool):
+    extra = (ceil(size/stride)-1)*stride - size + kernel; before = extra//2; after = extra-before."""
+    extra = (math.ceil(size / stride) - 1) * stride - size + kernel
+    before = extra // 2
+    return before, extra - before
+
+
+def maxpool_same(x):
+    """MaxPool2dStaticSamePadding(3, 2): zero-pad (NOT -inf) then 3x3/s2 max.
+    src/YetAnotherEfficientNet.py:90-104, instantiated at src/YetAnotherEfficientDet.py:228-231."""
+    h, w = x.shape[-2:]
+    top, bottom = same_pad(h, 3, 2)
+    left, right = same_pad(w, 3, 2)
+    x = F.pad(x, [left, right, top, bottom])
+    return F.max_pool2d(x, 3, 2)
+
+
+def upsample2(x):
+    """nn.Upsample(scale_factor=2, mode='nearest'): out[y,x] = in[y//2, x//2].
+    src/YetAnotherEfficientDet.py:223-226."""
+    return x.repeat_interleave(2, dim=-2).repeat_interleave(2, dim=-1)
+
+
+def swish(x):
+    """MemoryEfficientSwish forward x*sigmoid(x); autograd of this expression equals the
+    hand-written backward at src/YetAnotherEfficientNet.py:126-137."""
+    return x * torch.sigmoid(x)
+
+
+def batch_norm(x, p, prefix, training, stats_out=None):
+    """nn.BatchNorm2d(momentum=0.01, eps=1e-3).  Train: batch mean / biased variance normalise,
+    running <- 0.99*running + 0.01*(mean, unbiased var), num_batches_tracked += 1.
+    Eval: running statistics.  src/YetAnotherEfficientDet.py:176,187 and :239-265.
+    The running-stat update is returned through `stats_out` (dict) instead of mutating `p`."""
+    w, b = p[prefix + ".weight"], p[prefix + ".bias"]
+    rm, rv = p[prefix + ".running_mean"], p[prefix + ".running_var"]
+    if training:
+        mean = x.mean(dim=(0, 2, 3))
+        var = x.var(dim=(0, 2, 3), unbiased=False)
+        if stats_out is not None:
+            n = x.numel() // x.shape[1]
+            with torch.no_grad():
+                stats_out[prefix + ".running_mean"] = (1 - BN_MOMENTUM) * rm + BN_MOMENTUM * mean
+                stats_out[prefix + ".running_var"] = (1 - BN_MOMENTUM) * rv + BN_MOMENTUM * var * (n / max(n - 1, 1))
+                nbt = p.get(prefix + ".num_batches_tracked")
+                if nbt is not None:
+                    stats_out[prefix + ".num_batches_tracked"] = nbt + 1
+    else:
+        mean, var = rm, rv
+    inv = torch.rsqrt(var + BN_EPS)
+    return (x - mean[None, :, None, None]) * (inv * w)[None, :, None, None] + b[None, :, None, None]
+
+
+def separable_block(x, p, prefix, training, stats_out=None):
+    """SeparableConvBlock.forward: depthwise 3x3 (no bias, SAME pad = 1,1,1,1) -> pointwise 1x1
+    (+bias) -> BatchNorm; no activation inside BiFPN.  src/YetAnotherEfficientDet.py:154-192,
+    padding src/YetAnotherEfficientNet.py:51-65."""
+    c = x.shape[1]
+    h, w = x.shape[-2:]
+    top, bottom = same_pad(h, 3, 1)
+    left, right = same_pad(w, 3, 1)
+    x = F.pad(x, [left, right, top, bottom])
+    x = F.conv2d(x, p[prefix + ".depthwise_conv.conv.weight"], None, groups=c)
+    x = F.conv2d(x, p[prefix + ".pointwise_conv.conv.weight"], p[prefix + ".pointwise_conv.conv.bias"])
+    return batch_norm(x, p, prefix + ".bn", training, stats_out)
+
+
+def projection(x, p, prefix, training, stats_out=None):
+    """First-cell `pX_down_channel` = 1x1 conv (+bias) -> BatchNorm.
+    src/YetAnotherEfficientDet.py:237-266."""
+    x = F.conv2d(x, p[prefix + ".0.conv.weight"], p[prefix + ".0.conv.bias"])
+    return batch_norm(x, p, prefix + ".1", training, stats_out)
+
+
+def fusion_weights(w, eps=FUSION_EPS):
+    """Fast normalised fusion: relu(w) / (sum(relu(w)) + eps).
+    src/YetAnotherEfficientDet.py:338-339 (and the 7 sibling sites)."""
+    w = F.relu(w)
+    return w / (torch.sum(w, dim=0) + eps)
+
+
+# ----------------------------------------------------------------------------------------------
+# BiFPN cell / stack
+# ----------------------------------------------------------------------------------------------
+def bifpn_cell(inputs, p, prefix="", first_time=False, training=False, attention=True,
+               eps=FUSION_EPS, stats_out=None):
+    """One BiFPN cell.  src/YetAnotherEfficientDet.py:320-392 (attention=True) and :394-442
+    (attention=False: plain sums).  `p` holds the cell's tensors under `prefix`."""
+    q = prefix
+
+    def fw(name, n):
+        if attention:
+            return fusion_weights(p[q + name], eps)
+        return [1.0] * n
+
+    if first_time:
+        p3, p4, p5 = inputs
+        p6_in = maxpool_same(projection(p5, p, q + "p5_to_p6", training, stats_out))     # :324
+        p7_in = maxpool_same(p6_in)                                                       # :325
+        p3_in = projection(p3, p, q + "p3_down_channel", training, stats_out)            # :327
+        p4_in = projection(p4, p, q + "p4_down_channel", training, stats_out)            # :328
+        p5_in = projection(p5, p, q + "p5_down_channel", training, stats_out)            # :329
+    else:
+        p3_in, p4_in, p5_in, p6_in, p7_in = inputs
+
+    sep = lambda x, name: separable_block(x, p, q + name, training, stats_out)
+
+    w = fw("p6_w1", 2)
+    p6_up = sep(swish(w[0] * p6_in + w[1] * upsample2(p7_in)), "conv6_up")               # :338-341
+    w = fw("p5_w1", 2)
+    p5_up = sep(swish(w[0] * p5_in + w[1] * upsample2(p6_up)), "conv5_up")               # :344-347
+    w = fw("p4_w1", 2)
+    p4_up = sep(swish(w[0] * p4_in + w[1] * upsample2(p5_up)), "conv4_up")               # :350-353
+    w = fw("p3_w1", 2)
+    p3_out = sep(swish(w[0] * p3_in + w[1] * upsample2(p4_up)), "conv3_up")              # :356-359
+
+    if first_time:
+        p4_in = projection(p4, p, q + "p4_down_channel_2", training, stats_out)          # :362
+        p5_in = projection(p5, p, q + "p5_down_channel_2", training, stats_out)          # :363
+
+    w = fw("p4_w2", 3)
+    p4_out = sep(swish(w[0] * p4_in + w[1] * p4_up + w[2] * maxpool_same(p3_out)), "conv4_down")  # :366-370
+    w = fw("p5_w2", 3)
+    p5_out = sep(swish(w[0] * p5_in + w[1] * p5_up + w[2] * maxpool_same(p4_out)), "conv5_down")  # :373-377
+    w = fw("p6_w2", 3)
+    p6_out = sep(swish(w[0] * p6_in + w[1] * p6_up + w[2] * maxpool_same(p5_out)), "conv6_down")  # :380-384
+    w = fw("p7_w2", 2)
+    p7_out = sep(swish(w[0] * p7_in + w[1] * maxpool_same(p6_out)), "conv7_down")        # :387-390
+    return p3_out, p4_out, p5_out, p6_out, p7_out
+
+
+def bifpn_stack(inputs, p, n_cells, prefix="", first_cell_first_time=True, training=False,
+                attention=True, stats_out=None):
+    """nn.Sequential(*[BiFPN(..., first_time=(i == 0), attention=...)]) as built at
+    src/YetAnotherEfficientDet.py:639-644 and called at :668.  Keys are `<prefix><i>.<name>`."""
+    feats = inputs
+    for i in range(n_cells):
+        feats = bifpn_cell(feats, p, prefix + "%d." % i, first_time=(i == 0 and first_cell_first_time),
+                           training=training, attention=attention, stats_out=stats_out)
+    return feats
+
+
+# ----------------------------------------------------------------------------------------------
+# MTA loss
+# ----------------------------------------------------------------------------------------------
+def mta_at(f, p=2.0):
+    """MTALoss.at: F.normalize(f.pow(p).mean(1).view(B, -1)) (L2, dim=1, eps 1e-12).
+    src/loss/MTALoss.py:76-77."""
+    a = f.pow(p).mean(1).reshape(f.size(0), -1)
+    return a / a.norm(p=2, dim=1, keepdim=True).clamp_min(1e-12)
+
+
+def mta_level(f_s, f_t, T=9.0, p=2.0):
+    """MTALoss.mtaloss for one pyramid level.  `f_t` is a tensor or a list of teacher tensors
+    (product of attentions + L1 renormalisation when more than one).  The reference feeds
+    PROBABILITIES (not log-probabilities) as kl_div's input; that quirk is kept:
+    loss = sum_b sum_i t*(log t - s) / B.  src/loss/MTALoss.py:36-74."""
+    a_s = mta_at(f_s, p)
+    if torch.is_tensor(f_t):
+        a_t = mta_at(f_t, p)
+    elif len(f_t) == 1:
+        a_t = mta_at(f_t[0], p)
+    else:
+        m = mta_at(f_t[0], p)
+        for k in range(1, len(f_t)):
+            m = m * mta_at(f_t[k], p)
+        a_t = m / m.abs().sum(dim=1, keepdim=True).clamp_min(1e-12)
+    s = torch.softmax(a_s / T, dim=1)
+    t = torch.softmax(a_t / T, dim=1)
+    return (torch.xlogy(t, t) - t * s).sum() / f_s.size(0)
+
+
+def mta_loss(g_s, g_t, T=9.0, p=2.0):
+    """MTALoss.forward: stack of per-level losses; `g_t` is a list of tensors (one teacher) or a
+    list of per-teacher lists.  src/loss/MTALoss.py:15-34."""
+    T, p = float(T), float(p)
+    if torch.is_tensor(g_t[0]):
+        return torch.stack([mta_level(fs, ft, T, p) for fs, ft in zip(g_s, g_t)], dim=0)
+    return torch.stack([mta_level(g_s[i], [ft[i] for ft in g_t], T, p) for i in range(len(g_s))], dim=0)
+
+
+def mta_grad_closed_form(f_s, a_t_normalised, grad_out, T=9.0):
+    """Closed-form d(loss)/d(f_s) for p=2, used to cross-check autograd:
+    g=-t/B; dz=s*(g-<g,s>); da_hat=dz/T; da=(da_hat - a_hat<a_hat,da_hat>)/||a||; df=(2/C) f da."""
+    B, C = f_s.shape[:2]
+    a = f_s.pow(2).mean(1).reshape(B, -1)
+    nrm = a.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    ah = a / nrm
+    s = torch.softmax(ah / T, dim=1)
+    t = torch.softmax(a_t_normalised / T, dim=1)
+    g = -t / B
+    dz = s * (g - (g * s).sum(1, keepdim=True))
+    dah = dz / T
+    da = (dah - ah * (ah * dah).sum(1, keepdim=True)) / nrm
+    return grad_out * (2.0 / C) * f_s * da.reshape(B, 1, *f_s.shape[2:])
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic, RNG-free data so fixtures never depend on a torch/numpy RNG stream
+# ----------------------------------------------------------------------------------------------
+def synth(shape, seed, scale=1.0, offset=0.0, dtype=torch.float32):
+    """Deterministic pseudo-random tensor from a closed form (no RNG): values in about [-1, 1]."""
+    n = 1
+    for s in shape:
+        n *= s
+    i = torch.arange(n, dtype=torch.float64)
+    v = torch.sin(i * (0.618033988749895 + 0.0137 * seed) + 1.7 * seed) * 0.7 \
+        + torch.sin(i * (2.39996322972865 + 0.0071 * seed) + 0.3 * seed) * 0.3
+    return (v * scale + offset).reshape(shape).to(dtype)
+
+
+def synth_cell_params(num_channels, conv_channels, first_time, seed, prefix="", dtype=torch.float32):
+    """A full parameter/buffer dict for one cell with the reference's state_dict names and shapes
+    (SURVEY.md A.4), filled from `synth` with values that exercise every term (non-trivial BN
+    affine and running stats, fusion weights with a negative entry so the ReLU clamps)."""
+    C = num_channels
+    p = {}
+    k = [seed * 1000]
+
+    def nxt():
+        k[0] += 1
+        return k[0]
+
+    def bn(pre):
+        p[pre + ".weight"] = synth((C,), nxt(), 0.5, 1.0, dtype)
+        p[pre + ".bias"] = synth((C,), nxt(), 0.2, 0.0, dtype)
+        p[pre + ".running_mean"] = synth((C,), nxt(), 0.3, 0.0, dtype)
+        p[pre + ".running_var"] = synth((C,), nxt(), 0.5, 1.2, dtype)
+        p[pre + ".num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
+
+    for name in UP_NODES + DOWN_NODES:
+        pre = prefix + name
+        p[pre + ".depthwise_conv.conv.weight"] = synth((C, 1, 3, 3), nxt(), 0.4, 0.0, dtype)
+        p[pre + ".pointwise_conv.conv.weight"] = synth((C, C, 1, 1), nxt(), 1.5 / math.sqrt(C), 0.0, dtype)
+        p[pre + ".pointwise_conv.conv.bias"] = synth((C,), nxt(), 0.1, 0.0, dtype)
+        bn(pre + ".bn")
+    if first_time:
+        cin = {"p5_down_channel": conv_channels[2], "p4_down_channel": conv_channels[1],
+               "p3_down_channel": conv_channels[0], "p5_to_p6": conv_channels[2],
+               "p4_down_channel_2": conv_channels[1], "p5_down_channel_2": conv_channels[2]}
+        for name in PROJ_NAMES:
+            pre = prefix + name
+            p[pre + ".0.conv.weight"] = synth((C, cin[name], 1, 1), nxt(), 1.5 / math.sqrt(cin[name]), 0.0, dtype)
+            p[pre + ".0.conv.bias"] = synth((C,), nxt(), 0.1, 0.0, dtype)
+            bn(pre + ".1")
+    for name, n in (("p6_w1", 2), ("p5_w1", 2), ("p4_w1", 2), ("p3_w1", 2),
+                    ("p4_w2", 3), ("p5_w2", 3), ("p6_w2", 3), ("p7_w2", 2)):
+        p[prefix + name] = synth((n,), nxt(), 0.9, 0.8, dtype)   # in about [-0.1, 1.7]: some clamp at 0
+    return p
+
+
+def synth_stack_params(num_channels, conv_channels, n_cells, seed, prefix="", first_cell_first_time=True,
+                       dtype=torch.float32):
+    p = {}
+    for i in range(n_cells):
+        p.update(synth_cell_params(num_channels, conv_channels, i == 0 and first_cell_first_time,
+                                   seed + i, prefix + "%d." % i, dtype))
+    return p

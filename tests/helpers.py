@@ -1,0 +1,72 @@
+"""Shared helpers for the parity tests (the oracle is the checker, never the product)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import mmd_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LEVELS = ("p3", "p4", "p5", "p6", "p7")
+
+# name -> (C, conv_channels, n_cells, first, B, s3, seed)   (must mirror oracle/make_golden.py main())
+STACK_CASES = {
+    "cell_c16": (16, [8, 12, 20], 1, False, 2, 16, 1),
+    "first_c16": (16, [8, 12, 20], 1, True, 2, 16, 2),
+    "stack3_c16": (16, [8, 12, 20], 3, True, 2, 32, 3),
+    "stack2_c16_odd": (16, [8, 12, 20], 2, True, 1, 48, 4),
+    "stack2_c112": (112, [48, 120, 352], 2, True, 2, 16, 5),
+    "cell_c112": (112, [48, 120, 352], 1, False, 2, 16, 6),
+}
+MTA_CASES = {"mta_c112": (2, 112, [12, 6, 3], 7), "mta_c16": (3, 16, [16, 8, 4, 2, 1], 8)}
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def pyramid_inputs(B, C, s3, seed, dtype=torch.float32):
+    sizes = [s3, s3 // 2, s3 // 4, s3 // 8, max(s3 // 16, 1)]
+    return [O.synth((B, C, s, s), seed + i, 1.0, 0.1 * i, dtype) for i, s in enumerate(sizes)]
+
+
+def backbone_inputs(B, conv_channels, s3, seed, dtype=torch.float32):
+    return [O.synth((B, c, s3 >> i, s3 >> i), seed + i, 1.0, 0.0, dtype) for i, c in enumerate(conv_channels)]
+
+
+def stack_case_inputs(name, dtype=torch.float32):
+    C, cc, n_cells, first, B, s3, seed = STACK_CASES[name]
+    params = O.synth_stack_params(C, cc, n_cells, seed, first_cell_first_time=first, dtype=dtype)
+    xs = backbone_inputs(B, cc, s3, seed + 50, dtype) if first else pyramid_inputs(B, C, s3, seed + 50, dtype)
+    return params, xs
+
+
+def stack_case_gouts(name, outs):
+    seed = STACK_CASES[name][6]
+    return [O.synth(tuple(t.shape), seed + 70 + i, 1.0, 0.0).to(t.dtype) for i, t in enumerate(outs)]
+
+
+def structured_features(B, C, sizes, seed, dtype=torch.float32):
+    fs = []
+    for i, s in enumerate(sizes):
+        base = O.synth((B, C, s, s), seed + i, 1.0, 0.0)
+        mod = torch.exp(1.5 * O.synth((B, 1, s, s), seed + 100 + i, 1.0, 0.0))
+        fs.append((base * mod).to(dtype))
+    return fs
+
+
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    d = (a - b).norm().item()
+    n = b.norm().item()
+    return d / n if n > 0 else d
+
+
+def max_rel(a, b):
+    """max |a-b| / max|b| : the 'relative' error used for the 1e-4 bar on dense tensors."""
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    m = b.abs().max().item()
+    d = (a - b).abs().max().item()
+    return d / m if m > 0 else d

@@ -1,0 +1,102 @@
+"""Pin the oracle (oracle/mmd_oracle.py) against outputs of the real reference (tests/golden/)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmd_oracle as O
+from tests import helpers as H
+
+TOL = 2e-5   # oracle and reference are both fp32 torch-CPU; differences are summation-order only
+
+
+@pytest.mark.parametrize("name", sorted(H.STACK_CASES))
+def test_stack_matches_reference(name):
+    C, cc, n_cells, first, B, s3, seed = H.STACK_CASES[name]
+    g = H.golden(name)
+    params, xs = H.stack_case_inputs(name)
+
+    with torch.no_grad():
+        ev = O.bifpn_stack(tuple(xs), params, n_cells, first_cell_first_time=first, training=False)
+    for n, t in zip(H.LEVELS, ev):
+        assert tuple(t.shape) == g["eval_" + n].shape
+        assert H.max_rel(t, g["eval_" + n]) < TOL, (name, n)
+
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in params.items()}
+    xs = [x.requires_grad_(True) for x in xs]
+    stats = {}
+    tr = O.bifpn_stack(tuple(xs), leaf, n_cells, first_cell_first_time=first, training=True, stats_out=stats)
+    gouts = H.stack_case_gouts(name, tr)
+    sum((t * go).sum() for t, go in zip(tr, gouts)).backward()
+    for n, t in zip(H.LEVELS, tr):
+        # train-mode BN over a handful of values (P7 is 1x1, B=2) amplifies rounding: 1e-4 bar
+        assert H.max_rel(t.detach(), g["train_" + n]) < 1e-4, (name, n)
+    for i, x in enumerate(xs):
+        assert H.rel_l2(x.grad, g["grad_in%d" % i]) < 2e-4, (name, i)
+    for k, v in stats.items():
+        ref = g["buf_" + k]
+        if "num_batches" in k:
+            assert int(v) == int(ref)
+        else:
+            assert H.max_rel(v, ref) < TOL, k
+    for k, v in leaf.items():
+        if not (torch.is_tensor(v) and v.requires_grad):
+            continue
+        if k.endswith("conv.bias"):
+            # a bias feeding a train-mode BatchNorm has a mathematically zero gradient: rounding noise only
+            continue
+        if "pgrad_" + k in g:
+            ref = g["pgrad_" + k]
+            # fusion-weight gradients are differences of large sums: looser bar
+            tol = 1e-2 if k[-3:-1] == "_w" else 5e-4
+            assert H.rel_l2(v.grad, ref) < tol or np.abs(ref).max() < 1e-6, k
+        else:
+            s, nrm = g["pgsum_" + k]
+            assert abs(v.grad.double().norm().item() - nrm) <= 5e-4 * max(nrm, 1e-6), k
+
+
+@pytest.mark.parametrize("name", sorted(H.MTA_CASES))
+def test_mta_matches_reference(name):
+    B, C, sizes, seed = H.MTA_CASES[name]
+    g = H.golden(name)
+    go = torch.tensor([0.005 * (i + 1) for i in range(len(sizes))])
+    teachers = [H.structured_features(B, C, sizes, seed + 10 * (k + 1)) for k in range(3)]
+    for branch, g_t in (("single", teachers[0]), ("multi", teachers)):
+        g_s = [f.requires_grad_(True) for f in H.structured_features(B, C, sizes, seed)]
+        loss = O.mta_loss(g_s, g_t, T="9", p="2")
+        (loss * go).sum().backward()
+        assert np.allclose(loss.detach().numpy(), g["loss_" + branch], rtol=0, atol=2e-6)
+        for i, f in enumerate(g_s):
+            assert H.rel_l2(f.grad, g["grad_%s_%d" % (branch, i)]) < 1e-4, (branch, i)
+    # fp64 oracle agrees with the fp64 reference run to rounding
+    l64 = O.mta_loss([f.double() for f in H.structured_features(B, C, sizes, seed)],
+                     [f.double() for f in teachers[0]])
+    assert np.allclose(l64.numpy(), g["loss_single_fp64"], rtol=0, atol=1e-12)
+
+
+def test_mta_closed_form_gradient():
+    """SURVEY.md A.3 closed form (what the CUDA backward implements) == autograd, in fp64."""
+    B, C, sizes, seed = H.MTA_CASES["mta_c16"]
+    fs = [f.double().requires_grad_(True) for f in H.structured_features(B, C, sizes, seed)]
+    ft = [f.double() for f in H.structured_features(B, C, sizes, seed + 10)]
+    loss = O.mta_loss(fs, ft)
+    loss.sum().backward()
+    for f, t in zip(fs, ft):
+        cf = O.mta_grad_closed_form(f.detach(), O.mta_at(t), 1.0)
+        assert H.rel_l2(cf, f.grad) < 1e-10
+
+
+def test_landmarks():
+    """SURVEY.md 8c numeric landmarks: near-uniform attention -> loss = -ln(HW) - 1/HW."""
+    torch.manual_seed(0)
+    for s in (6, 12, 24):
+        fs, ft = torch.randn(2, 112, s, s), torch.randn(2, 112, s, s)
+        l = O.mta_level(fs, ft).item()
+        n = s * s
+        assert abs(l - (-np.log(n) - 1.0 / n)) < 2e-3
+    w = O.fusion_weights(torch.ones(2))
+    assert abs(w[0].item() - 0.499975) < 1e-6
+    w = O.fusion_weights(torch.ones(3))
+    assert abs(w[0].item() - 0.333322) < 1e-6
+    x = -torch.ones(1, 1, 4, 4)
+    assert O.maxpool_same(x).flatten().tolist() == [-1.0, 0.0, 0.0, 0.0]   # zero pad wins at the border
