@@ -1,0 +1,161 @@
+/*
+ * mmd.h — C ABI of libmmd_b200.so: the sm_100a kernels behind the MM-DistillNet distillation hot path.
+ *
+ * The reference (robot-learning-freiburg/MM-DistillNet) is pure PyTorch and has no FFI for this path; the
+ * "interface each entry point replaces" is therefore the reference's Python call site:
+ *
+ *   mmd_mta_fwd / mmd_mta_bwd      replace  MTALoss.forward / .mtaloss / .at and their autograd
+ *                                           (src/loss/MTALoss.py:15-34, :36-74, :76-77)
+ *   mmd_bifpn_run                  replaces nn.Sequential(*[BiFPN(...)]) forward and its autograd
+ *                                           (src/YetAnotherEfficientDet.py:639-644, :668; one cell :320-392;
+ *                                            SeparableConvBlock.forward :182-192; same-pad conv / pool
+ *                                            src/YetAnotherEfficientNet.py:51-65, :90-104; swish :126-137)
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer borrowed for
+ * the duration of the call; nothing is allocated or freed inside; all work is enqueued asynchronously on the
+ * caller's stream (a cudaStream_t passed as void*) and never synchronises the host, so calls are CUDA-graph
+ * capture safe.  Return value 0 = OK, otherwise a cudaError_t (or a negative MMD_E* argument error); the message
+ * is available from the thread-local mmd_last_error().  No exceptions cross the ABI.
+ *
+ * Layout: activations are NHWC ([B][H][W][C], i.e. torch channels_last of a logical [B,C,H,W] tensor) unless a
+ * call says otherwise; parameters are the reference's own fp32 tensors in their native PyTorch layouts
+ * (depthwise [C,1,3,3], pointwise [Cout,Cin,1,1], BatchNorm vectors [C]) — the kernels fold / transpose on load,
+ * so no packed copies can go stale.
+ */
+#ifndef MMD_H
+#define MMD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMD_VERSION 100
+
+typedef void* mmd_stream_t; /* cudaStream_t */
+
+enum { MMD_F32 = 0, MMD_BF16 = 1 };               /* storage type of activations (arithmetic is fp32) */
+enum { MMD_NHWC = 0, MMD_NCHW = 1 };              /* MTA accepts both; BiFPN is NHWC only */
+enum { MMD_E_ARG = -1, MMD_E_UNSUPPORTED = -2 };
+
+int mmd_version(void);
+const char* mmd_last_error(void);
+/* number of kernels this library has launched in the calling process (all threads); for bench accounting */
+unsigned long long mmd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MTA loss (src/loss/MTALoss.py).  One call handles every pyramid level and every teacher.
+ *   a = mean_c f^p ; a^ = a / max(||a||_2, 1e-12) ; teachers: product of a^_k, L1-renormalised when n_teachers>1
+ *   loss[l] = sum_b sum_i t (log t - s) / B  with s = softmax(a^_s/T), t = softmax(a^_t/T)   (reference quirk:
+ *   probabilities, not log-probabilities, are the kl_div input — reproduced as is).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define MMD_MTA_MAX_LEVELS 8
+#define MMD_MTA_MAX_TEACHERS 4
+
+typedef struct {
+  int32_t n_levels, n_teachers, B, C;
+  int32_t dtype;  /* MMD_F32 / MMD_BF16 : element type of fs / ft / grad_fs */
+  int32_t layout; /* MMD_NHWC / MMD_NCHW */
+  float T, p;
+  int32_t H[MMD_MTA_MAX_LEVELS], W[MMD_MTA_MAX_LEVELS];
+  const void* fs[MMD_MTA_MAX_LEVELS];                       /* student features, one per level            */
+  const void* ft[MMD_MTA_MAX_TEACHERS][MMD_MTA_MAX_LEVELS]; /* teacher features [teacher][level]          */
+  float* att_ws;  /* workspace, (1+n_teachers) * B * sum_l(H*W) floats: channel-pooled maps a              */
+  float* ga_ws;   /* workspace, B * sum_l(H*W) floats: d loss[l] / d a_s (per unit upstream grad); may be  */
+                  /* NULL for a forward that will never be differentiated                                  */
+  float* loss_b;  /* workspace, n_levels * B floats: per-sample loss terms                                 */
+  float* loss;    /* out, n_levels floats                                                                  */
+} MmdMtaArgs;
+
+int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream);
+/* grad_fs[l] = grad_loss[l] * (p/C) * fs[l]^(p-1) * ga_ws  (same dtype/layout as fs); needs ga_ws from the fwd */
+int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* const* grad_fs, mmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BiFPN stack.  The host describes the whole multi-cell forward (or backward) as a flat list of ops over
+ * tensors addressed as base[i] + offset, so one op list is built once per shape and replayed with fresh arenas.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct { int32_t base; int32_t pad_; int64_t off; } MmdRef; /* address = bases[base] + off ; base < 0 : NULL */
+
+typedef struct {
+  MmdRef data;      /* NHWC [B][H][W][C], storage dtype                                                        */
+  MmdRef bn;        /* NULL: values are final.  Otherwise float[4*C] = scale, shift, mean, invstd of a          */
+                    /* train-mode BatchNorm that consumers apply ON LOAD (y = scale*x + shift)                  */
+  int32_t H, W, C, pad_;
+} MmdTensor;
+
+enum { MMD_IN_SAME = 0, MMD_IN_UP2 = 1, MMD_IN_POOL = 2 };  /* how a node resamples an input (nearest x2 / 3x3 s2 same-pad max) */
+enum { MMD_CONS_SAME = 0, MMD_CONS_UP2 = 1, MMD_CONS_POOL = 2 }; /* how a consumer used the tensor whose gradient is gathered */
+
+typedef struct {    /* one gradient source of a tensor (backward is a gather: no atomics on activations) */
+  MmdTensor du;     /* the consumer's dL/du (pre-swish fused sum) at the consumer's resolution                  */
+  int32_t mode;     /* MMD_CONS_*                                                                               */
+  int32_t fw_k, fw_n; /* edge weight = relu(fw[k]) / (sum_j relu(fw[j]) + fw_eps); fw == NULL -> 1             */
+  float fw_eps;
+  const float* fw;
+  MmdRef slot;      /* double[2*C]: sum(G), sum(G*xhat) pushed through this edge by the consumer               */
+  MmdRef pidx;      /* uint8 arg-max index per pooled output element (mode POOL)                               */
+} MmdCons;
+
+enum {
+  MMD_OP_NODE_FWD = 1,  /* fused: resample + BN-on-load + weighted add + swish -> depthwise 3x3 -> pointwise 1x1 (+bias) [-> BN stats] */
+  MMD_OP_PROJ_FWD = 2,  /* first-cell 1x1 projection Cin -> C (+bias) [-> BN stats]                                                  */
+  MMD_OP_BNAPPLY = 3,   /* out = [pool3x3s2](scale*x + shift): materialise a deferred tensor (P6/P7 synthesis, stack outputs)        */
+  MMD_OP_NODE_BWD = 4,  /* backward of NODE_FWD (two kernels: pointwise/BN part, depthwise/fusion part)                              */
+  MMD_OP_PROJ_BWD = 5,  /* backward of PROJ_FWD                                                                                      */
+  MMD_OP_PULL = 6,      /* dx = gathered gradient of `out` from its consumers (stack inputs, P6/P7 synthesis)                        */
+  MMD_OP_SLOT = 7       /* slot = (sum G, sum G*xhat) for a deferred tensor consumed by a BNAPPLY op                                 */
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t train;          /* 1: batch statistics, deferred-BN output, running-stat update; 0: running stats folded into the 1x1 conv */
+  int32_t n_in;
+  int32_t swish;          /* NODE: apply x*sigmoid(x) to the fused sum (BiFPN nodes: 1; bare SeparableConvBlock: 0) */
+  MmdTensor in[3];
+  int32_t mode[3];        /* MMD_IN_* */
+  float fw_eps;
+  const float* fw;        /* raw fusion weights [n_in] (fp32 parameter) or NULL for an unweighted sum */
+  /* parameters: absolute device pointers to the reference's fp32 tensors */
+  const float* dw_w;      /* [C,1,3,3]   (NODE)        */
+  const float* pw_w;      /* [C,Cin,1,1]               */
+  const float* pw_b;      /* [C]                       */
+  const float* bn_w;      /* gamma [C]                 */
+  const float* bn_b;      /* beta  [C]                 */
+  float* bn_rm;           /* running_mean [C]          */
+  float* bn_rv;           /* running_var  [C]          */
+  int64_t* bn_nbt;        /* num_batches_tracked       */
+  const float* in_bn_w[3];/* gamma / beta of each deferred input's producer (for the fusion-weight gradient) */
+  const float* in_bn_b[3];
+  int32_t Cin;            /* PROJ: input channels */
+  int32_t accumulate_dx;  /* PROJ_BWD / PULL: add into dx instead of overwriting */
+  float bn_eps, bn_momentum;
+  MmdTensor out;          /* fwd: produced tensor; bwd: the same tensor (its raw values are read again) */
+  MmdRef save_d;          /* NODE train: depthwise output kept for the pointwise weight gradient */
+  MmdRef pidx[3];         /* NODE / BNAPPLY train: arg-max indices written for pooled inputs */
+  MmdRef stats;           /* double[2*C] accumulators, zero on entry, re-zeroed by the kernel */
+  MmdRef counter;         /* uint32, zero on entry, re-zeroed by the kernel */
+  /* backward only */
+  int32_t n_cons, pad_;
+  MmdCons cons[3];        /* who consumed `out` */
+  MmdRef du;              /* NODE_BWD: dL/du written [B][H][W][C] */
+  MmdRef dd;              /* NODE_BWD: scratch for dL/d(depthwise output) [B][H][W][C] */
+  MmdRef in_slot[3];      /* NODE_BWD: double[2*C] per input edge (zero on entry) */
+  MmdRef dx;              /* PROJ_BWD: dL/d(input) [B][H][W][Cin]; PULL: gathered dL/d(out) */
+  MmdRef g_dw, g_pw, g_pb, g_bn_w, g_bn_b, g_fw; /* fp32 parameter gradients (zero on entry; accumulated) */
+} MmdOp;
+
+/* Run `n_ops` ops in order on `stream`.  `C` is the pyramid channel count (112 for EfficientDet-D2). */
+int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases,
+                  int32_t B, int32_t C, int32_t dtype, mmd_stream_t stream);
+
+/* sizeof(MmdOp) / sizeof(MmdMtaArgs) as compiled, so a binding can verify its struct mirror */
+size_t mmd_sizeof_op(void);
+size_t mmd_sizeof_mta_args(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMD_H */

@@ -1,0 +1,16 @@
+"""mm_distillnet_b200 — B200-native (sm_100a) implementation of MM-DistillNet's distillation hot path:
+the EfficientDet-D2 BiFPN stack (forward + backward) and the MTA multi-teacher alignment loss.
+
+Public API mirrors the reference (robot-learning-freiburg/MM-DistillNet):
+    BiFPN, SeparableConvBlock      src/YetAnotherEfficientDet.py:154-442
+    BiFPNStack                     the nn.Sequential of cells built at src/YetAnotherEfficientDet.py:639-644
+    MTALoss                        src/loss/MTALoss.py:9-77
+    patch_reference()              rebinds the reference's module globals to these classes (drop-in seam)
+"""
+from .bifpn import BiFPN, BiFPNStack, SeparableConvBlock  # noqa: F401
+from .mta import MTALoss  # noqa: F401
+from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
+from ._lib import build, launch_count  # noqa: F401
+
+__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "build",
+           "launch_count"]

@@ -1,0 +1,132 @@
+"""ctypes binding of libmmd_b200.so (the C ABI declared in include/mmd.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
+SOURCES = ("api.cu", "mta.cu", "bifpn_fwd.cu", "bifpn_bwd.cu", "bifpn_run.cu")
+
+MMD_F32, MMD_BF16 = 0, 1
+MMD_NHWC, MMD_NCHW = 0, 1
+MTA_MAX_LEVELS, MTA_MAX_TEACHERS = 8, 4
+
+IN_SAME, IN_UP2, IN_POOL = 0, 1, 2
+CONS_SAME, CONS_UP2, CONS_POOL = 0, 1, 2
+OP_NODE_FWD, OP_PROJ_FWD, OP_BNAPPLY, OP_NODE_BWD, OP_PROJ_BWD, OP_PULL, OP_SLOT = 1, 2, 3, 4, 5, 6, 7
+
+
+class MtaArgs(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int32), ("n_teachers", C.c_int32), ("B", C.c_int32), ("C", C.c_int32),
+        ("dtype", C.c_int32), ("layout", C.c_int32), ("T", C.c_float), ("p", C.c_float),
+        ("H", C.c_int32 * MTA_MAX_LEVELS), ("W", C.c_int32 * MTA_MAX_LEVELS),
+        ("fs", C.c_void_p * MTA_MAX_LEVELS),
+        ("ft", (C.c_void_p * MTA_MAX_LEVELS) * MTA_MAX_TEACHERS),
+        ("att_ws", C.c_void_p), ("ga_ws", C.c_void_p), ("loss_b", C.c_void_p), ("loss", C.c_void_p),
+    ]
+
+
+class Ref(C.Structure):
+    _fields_ = [("base", C.c_int32), ("pad_", C.c_int32), ("off", C.c_int64)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("data", Ref), ("bn", Ref), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Cons(C.Structure):
+    _fields_ = [("du", Tensor), ("mode", C.c_int32), ("fw_k", C.c_int32), ("fw_n", C.c_int32), ("fw_eps", C.c_float),
+                ("fw", C.c_void_p), ("slot", Ref), ("pidx", Ref)]
+
+
+class Op(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("train", C.c_int32), ("n_in", C.c_int32), ("swish", C.c_int32),
+        ("inp", Tensor * 3), ("mode", C.c_int32 * 3), ("fw_eps", C.c_float),
+        ("fw", C.c_void_p),
+        ("dw_w", C.c_void_p), ("pw_w", C.c_void_p), ("pw_b", C.c_void_p), ("bn_w", C.c_void_p), ("bn_b", C.c_void_p),
+        ("bn_rm", C.c_void_p), ("bn_rv", C.c_void_p), ("bn_nbt", C.c_void_p),
+        ("in_bn_w", C.c_void_p * 3), ("in_bn_b", C.c_void_p * 3),
+        ("Cin", C.c_int32), ("accumulate_dx", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("out", Tensor),
+        ("save_d", Ref), ("pidx", Ref * 3), ("stats", Ref), ("counter", Ref),
+        ("n_cons", C.c_int32), ("pad_", C.c_int32),
+        ("cons", Cons * 3),
+        ("du", Ref), ("dd", Ref), ("in_slot", Ref * 3), ("dx", Ref),
+        ("g_dw", Ref), ("g_pw", Ref), ("g_pb", Ref), ("g_bn_w", Ref), ("g_bn_b", Ref), ("g_fw", Ref),
+    ]
+
+
+NULL_REF = (-1, 0, 0)
+
+
+def nvcc_command(out_path=LIB_PATH, extra=()):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out_path, *extra, *srcs]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA sources into mm_distillnet_b200/libmmd_b200.so (in-tree, sm_100a only)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "mmd.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library (building it first if the sources are newer).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    L.mmd_version.restype = C.c_int
+    L.mmd_last_error.restype = C.c_char_p
+    L.mmd_launch_count.restype = C.c_ulonglong
+    L.mmd_sizeof_op.restype = C.c_size_t
+    L.mmd_sizeof_mta_args.restype = C.c_size_t
+    L.mmd_mta_fwd.restype = C.c_int
+    L.mmd_mta_fwd.argtypes = [C.POINTER(MtaArgs), C.c_void_p]
+    L.mmd_mta_bwd.restype = C.c_int
+    L.mmd_mta_bwd.argtypes = [C.POINTER(MtaArgs), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.mmd_bifpn_run.restype = C.c_int
+    L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
+                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    if L.mmd_sizeof_op() != C.sizeof(Op) or L.mmd_sizeof_mta_args() != C.sizeof(MtaArgs):
+        raise RuntimeError("libmmd_b200.so struct layout mismatch: Op %d vs %d, MtaArgs %d vs %d" % (
+            L.mmd_sizeof_op(), C.sizeof(Op), L.mmd_sizeof_mta_args(), C.sizeof(MtaArgs)))
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mmd_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib().mmd_launch_count())
+
+
+EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run",
+           "mmd_sizeof_op", "mmd_sizeof_mta_args")

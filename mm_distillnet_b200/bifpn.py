@@ -1,0 +1,671 @@
+"""Drop-in for the reference's BiFPN (src/YetAnotherEfficientDet.py:154-442) on hand-written sm_100a kernels.
+
+`BiFPN`, `SeparableConvBlock` keep the reference constructor / forward signatures and the exact `state_dict`
+names and shapes, so reference checkpoints load with strict `load_state_dict`.  `BiFPNStack` is an
+`nn.Sequential` of cells (what `YetAnotherEfficientDet.__init__` builds at :639-644) whose forward runs ALL cells
+as one op list through `mmd_bifpn_run`: intermediate tensors stay pre-BatchNorm in HBM and are normalised,
+resampled, fused and swish-ed while the consuming kernel loads them.
+
+CUDA only; parameters stay fp32 (master copies owned by PyTorch), activations are float32 or bfloat16 NHWC
+(`channels_last`).  There is no CPU fallback and no PyTorch-op fallback.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+BN_MOMENTUM = 0.01   # src/YetAnotherEfficientDet.py:176
+BN_EPS = 1e-3
+_ALIGN = 256
+KERNEL_CHANNELS = 112  # EfficientDet-D2 (the kernels' compile-time channel count)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (names matter: they are the state_dict contract)
+# ------------------------------------------------------------------------------------------------------------
+class _ParamOnly(nn.Module):
+    def forward(self, *a, **k):
+        raise NotImplementedError(
+            "%s only holds parameters for the fused sm_100a kernels; call the enclosing BiFPN / SeparableConvBlock"
+            % type(self).__name__)
+
+
+class Conv2dStaticSamePadding(_ParamOnly):
+    """Parameter holder mirroring src/YetAnotherEfficientNet.py:27-65 (`.conv` is a plain nn.Conv2d, same init)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, bias=True, groups=1, dilation=1, **kwargs):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, bias=bias, groups=groups)
+
+
+class MaxPool2dStaticSamePadding(_ParamOnly):
+    """Stateless placeholder for src/YetAnotherEfficientNet.py:68-104 (the pooling is fused into the node kernels)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+
+class _Stateless(_ParamOnly):
+    pass
+
+
+class SeparableConvBlock(nn.Module):
+    """depthwise 3x3 (no bias) -> pointwise 1x1 (+bias) -> BatchNorm(momentum .01, eps 1e-3).
+    Signature of src/YetAnotherEfficientDet.py:154-192.  Only the configuration BiFPN uses is supported by the
+    kernels (out_channels == in_channels, norm=True, activation=False)."""
+
+    def __init__(self, in_channels, out_channels=None, norm=True, activation=False, onnx_export=False):
+        super(SeparableConvBlock, self).__init__()
+        if out_channels is None:
+            out_channels = in_channels
+        if out_channels != in_channels or not norm or activation:
+            raise NotImplementedError("mm_distillnet_b200.SeparableConvBlock implements the BiFPN configuration only "
+                                      "(out_channels == in_channels, norm=True, activation=False)")
+        self.depthwise_conv = Conv2dStaticSamePadding(in_channels, in_channels, kernel_size=3, stride=1,
+                                                      groups=in_channels, bias=False)
+        self.pointwise_conv = Conv2dStaticSamePadding(in_channels, out_channels, kernel_size=1, stride=1)
+        self.norm = norm
+        self.bn = nn.BatchNorm2d(num_features=out_channels, momentum=BN_MOMENTUM, eps=BN_EPS)
+        self.activation = activation
+        self._runner = None
+
+    def forward(self, x):
+        if self._runner is None:
+            self._runner = _Runner()
+        return self._runner.run([self], (x,), self.training, kind="sep")[0]
+
+
+class BiFPN(nn.Module):
+    """One BiFPN cell; signature, attribute names and semantics of src/YetAnotherEfficientDet.py:195-442."""
+
+    def __init__(self, num_channels, conv_channels, first_time=False, epsilon=1e-4, onnx_export=False, attention=True):
+        super(BiFPN, self).__init__()
+        self.epsilon = epsilon
+        self.num_channels = num_channels
+        self.conv_channels = list(conv_channels) if conv_channels is not None else None
+        # construction order mirrors the reference so the same torch seed gives the same initial weights
+        self.conv6_up = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv5_up = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv4_up = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv3_up = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv4_down = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv5_down = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv6_down = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+        self.conv7_down = SeparableConvBlock(num_channels, onnx_export=onnx_export)
+
+        for lvl in (6, 5, 4, 3):
+            setattr(self, "p%d_upsample" % lvl, _Stateless())
+        for lvl in (4, 5, 6, 7):
+            setattr(self, "p%d_downsample" % lvl, MaxPool2dStaticSamePadding(3, 2))
+        self.swish = _Stateless()
+
+        self.first_time = first_time
+        if self.first_time:
+            def proj(cin):
+                return nn.Sequential(Conv2dStaticSamePadding(cin, num_channels, 1),
+                                     nn.BatchNorm2d(num_channels, momentum=BN_MOMENTUM, eps=BN_EPS))
+            self.p5_down_channel = proj(conv_channels[2])
+            self.p4_down_channel = proj(conv_channels[1])
+            self.p3_down_channel = proj(conv_channels[0])
+            self.p5_to_p6 = nn.Sequential(Conv2dStaticSamePadding(conv_channels[2], num_channels, 1),
+                                          nn.BatchNorm2d(num_channels, momentum=BN_MOMENTUM, eps=BN_EPS),
+                                          MaxPool2dStaticSamePadding(3, 2))
+            self.p6_to_p7 = nn.Sequential(MaxPool2dStaticSamePadding(3, 2))
+            self.p4_down_channel_2 = proj(conv_channels[1])
+            self.p5_down_channel_2 = proj(conv_channels[2])
+
+        for name, n in (("p6_w1", 2), ("p5_w1", 2), ("p4_w1", 2), ("p3_w1", 2),
+                        ("p4_w2", 3), ("p5_w2", 3), ("p6_w2", 3), ("p7_w2", 2)):
+            setattr(self, name, nn.Parameter(torch.ones(n, dtype=torch.float32), requires_grad=True))
+            setattr(self, name + "_relu", _Stateless())
+        self.attention = attention
+        self._runner = None
+
+    def forward(self, inputs):
+        """(p3, p4, p5) for a first cell, (p3..p7) otherwise -> (p3_out, ..., p7_out), as :289-318."""
+        if self._runner is None:
+            self._runner = _Runner()
+        return self._runner.run([self], tuple(inputs), self.training, kind="cells")
+
+
+class BiFPNStack(nn.Sequential):
+    """nn.Sequential(*[BiFPN(...)]) (src/YetAnotherEfficientDet.py:639-644) executed as ONE fused op list."""
+
+    def __init__(self, *cells):
+        super().__init__(*cells)
+        self._runner = None
+
+    def forward(self, inputs):
+        cells = list(self)
+        fusable = all(isinstance(c, BiFPN) for c in cells) and len({c.training for c in cells}) == 1 and \
+            all(not c.first_time for c in cells[1:])
+        if not fusable:
+            for c in cells:
+                inputs = c(inputs)
+            return inputs
+        if self._runner is None:
+            self._runner = _Runner()
+        return self._runner.run(cells, tuple(inputs), cells[0].training, kind="cells")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# graph -> op list
+# ------------------------------------------------------------------------------------------------------------
+class _Arena:
+    def __init__(self):
+        self.size = 0
+
+    def alloc(self, nbytes):
+        off = self.size
+        self.size = (off + nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        return off
+
+
+class _Tn:
+    """A tensor of the plan.  `bn` is the (base, off) of its deferred-BatchNorm vector or None when final."""
+    __slots__ = ("H", "W", "C", "base", "off", "bn", "consumers", "producer", "bn_mod")
+
+    def __init__(self, H, W, Cc, base, off, bn=None, producer=None, bn_mod=None):
+        self.H, self.W, self.C, self.base, self.off, self.bn = H, W, Cc, base, off, bn
+        self.consumers = []
+        self.producer = producer
+        self.bn_mod = bn_mod      # nn.BatchNorm2d whose affine applies to this deferred tensor
+
+
+class _OpN:
+    __slots__ = ("kind", "ins", "modes", "conv", "bn", "dw", "fw", "fw_eps", "swish", "out", "save_d", "pidx",
+                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref")
+
+    def __init__(self, kind):
+        self.kind = kind
+        self.ins, self.modes = [], []
+        self.conv = self.bn = self.dw = self.fw = None
+        self.fw_eps = 0.0
+        self.swish = 0
+        self.out = None
+        self.save_d = None
+        self.pidx = [None, None, None]
+        self.stats = self.counter = self.du = self.bwd_counter = None
+        self.slots = [None, None, None]
+        self.glike = None      # BNAPPLY: (base, off) of the gradient of its output
+        self.cin = 0
+        self.gref = {}
+
+
+# fixed base indices
+B_FWD, B_PERSIST, B_BWD, B_ZERO, B_EXT = 0, 1, 2, 3, 4
+
+
+def _ref(pair):
+    if pair is None:
+        return _lib.Ref(-1, 0, 0)
+    return _lib.Ref(int(pair[0]), 0, int(pair[1]))
+
+
+def _tensor(t, with_bn=True):
+    return _lib.Tensor(_ref((t.base, t.off)), _ref(t.bn if with_bn else None), t.H, t.W, t.C, 0)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _Plan:
+    """Op lists + arena layout for one (cells, shapes, dtype, mode) combination."""
+
+    def __init__(self, mods, kind, in_shapes, dtype, train, need_grad, in_need_grad):
+        self.train, self.need_grad = train, need_grad and train
+        self.dtype = dtype
+        self.esize = 4 if dtype == torch.float32 else 2
+        self.B = in_shapes[0][0]
+        self.n_in = len(in_shapes)
+        self.in_need_grad = list(in_need_grad)
+        self.fwd_arena, self.persist, self.bwd_arena, self.zero_arena = _Arena(), _Arena(), _Arena(), _Arena()
+        self.ops = []
+        self.Cc = None
+        ext = [_Tn(s[2], s[3], s[1], B_EXT + i, 0) for i, s in enumerate(in_shapes)]
+        self.ext = ext
+        self.n_out = 5 if kind == "cells" else 1
+        self.B_OUT = B_EXT + self.n_in
+        self.B_GOUT = self.B_OUT + self.n_out
+        self.B_GIN = self.B_GOUT + self.n_out
+        self.n_bases = self.B_GIN + self.n_in
+        if kind == "sep":
+            self.Cc = in_shapes[0][1]
+            outs = [self._node(mods[0], [(ext[0], _lib.IN_SAME)], None, 0.0, swish=0)]
+        else:
+            outs = self._cells(mods, ext)
+        self.out_shapes = [(self.B, self.Cc, t.H, t.W) for t in outs]
+        self._finish_outputs(outs)
+        self.params = self._collect_params(mods)
+        self.fwd_ops = self._emit_fwd()
+        self.bwd_ops = self._emit_bwd() if self.need_grad else None
+
+    # ---- graph construction --------------------------------------------------------------------------------
+    def _new_raw(self, H, W, bn_mod):
+        n = self.B * H * W * self.Cc * self.esize
+        t = _Tn(H, W, self.Cc, B_FWD, self.fwd_arena.alloc(n), producer=None, bn_mod=bn_mod)
+        if self.train:
+            t.bn = (B_FWD, self.fwd_arena.alloc(4 * self.Cc * 4))
+        return t
+
+    def _train_storage(self, op):
+        if self.train:
+            op.stats = (B_PERSIST, self.persist.alloc(2 * self.Cc * 8))
+            op.counter = (B_PERSIST, self.persist.alloc(4))
+            op.bwd_counter = (B_PERSIST, self.persist.alloc(4))
+
+    def _node(self, sep, ins, fw, fw_eps, swish=1):
+        op = _OpN(_lib.OP_NODE_FWD)
+        op.ins = [t for t, _ in ins]
+        op.modes = [m for _, m in ins]
+        op.conv, op.bn, op.dw = sep.pointwise_conv.conv, sep.bn, sep.depthwise_conv.conv
+        op.fw, op.fw_eps, op.swish = fw, fw_eps, swish
+        H = ins[0][0].H if ins[0][1] == _lib.IN_SAME else None
+        W = ins[0][0].W if ins[0][1] == _lib.IN_SAME else None
+        if H is None:   # first input is always SAME in BiFPN; keep the general rule explicit
+            raise ValueError("the first input of a fusion node must be at the node's resolution")
+        for t, m in ins:
+            if m == _lib.IN_UP2 and (2 * t.H != H or 2 * t.W != W):
+                raise ValueError("BiFPN: upsampled input %dx%d does not match level %dx%d (sizes must halve exactly)"
+                                 % (t.H, t.W, H, W))
+            if m == _lib.IN_POOL and ((t.H + 1) // 2 != H or (t.W + 1) // 2 != W):
+                raise ValueError("BiFPN: pooled input %dx%d does not match level %dx%d" % (t.H, t.W, H, W))
+            if m == _lib.IN_SAME and (t.H != H or t.W != W):
+                raise ValueError("BiFPN: input %dx%d does not match level %dx%d" % (t.H, t.W, H, W))
+        op.out = self._new_raw(H, W, sep.bn)
+        op.out.producer = op
+        self._train_storage(op)
+        if self.need_grad:
+            n = self.B * H * W * self.Cc
+            op.save_d = (B_FWD, self.fwd_arena.alloc(n * self.esize))
+            op.du = _Tn(H, W, self.Cc, B_BWD, self.bwd_arena.alloc(n * self.esize))
+            for i, m in enumerate(op.modes):
+                if m == _lib.IN_POOL:
+                    op.pidx[i] = (B_FWD, self.fwd_arena.alloc(n))
+                op.slots[i] = (B_ZERO, self.zero_arena.alloc(2 * self.Cc * 8))
+        for i, t in enumerate(op.ins):
+            t.consumers.append((op, i))
+        self.ops.append(op)
+        return op.out
+
+    def _proj(self, seq, x):
+        op = _OpN(_lib.OP_PROJ_FWD)
+        op.ins, op.modes = [x], [_lib.IN_SAME]
+        op.conv, op.bn = seq[0].conv, seq[1]
+        op.cin = x.C
+        op.out = self._new_raw(x.H, x.W, seq[1])
+        op.out.producer = op
+        self._train_storage(op)
+        x.consumers.append((op, 0))
+        self.ops.append(op)
+        return op.out
+
+    def _bnapply(self, src, mode, dst=None):
+        """dst = [pool](bn(src)); `dst` None allocates an arena tensor (P6/P7 synthesis)."""
+        op = _OpN(_lib.OP_BNAPPLY)
+        op.ins, op.modes = [src], [mode]
+        H, W = (src.H, src.W) if mode == _lib.IN_SAME else ((src.H + 1) // 2, (src.W + 1) // 2)
+        n = self.B * H * W * self.Cc
+        if dst is None:
+            dst = _Tn(H, W, self.Cc, B_FWD, self.fwd_arena.alloc(n * self.esize))
+        op.out = dst
+        dst.producer = op
+        if self.need_grad:
+            if mode == _lib.IN_POOL:
+                op.pidx[0] = (B_FWD, self.fwd_arena.alloc(n))
+            if src.bn is not None:
+                op.slots[0] = (B_ZERO, self.zero_arena.alloc(2 * self.Cc * 8))
+        src.consumers.append((op, 0))
+        self.ops.append(op)
+        return dst
+
+    def _cells(self, cells, ext):
+        first = cells[0]
+        self.Cc = first.num_channels
+        S, U, P = _lib.IN_SAME, _lib.IN_UP2, _lib.IN_POOL
+        if first.first_time:
+            if len(ext) != 3:
+                raise ValueError("a first_time BiFPN cell takes (p3, p4, p5), got %d inputs" % len(ext))
+            c3, c4, c5 = ext
+            for t, cin in zip(ext, first.conv_channels):
+                if t.C != cin:
+                    raise ValueError("BiFPN first cell: input has %d channels, expected %d" % (t.C, cin))
+            p6_in = self._bnapply(self._proj(first.p5_to_p6, c5), P)          # :324
+            p7_in = self._bnapply(p6_in, P)                                   # :325
+            p3_in = self._proj(first.p3_down_channel, c3)                     # :327-329
+            p4_in = self._proj(first.p4_down_channel, c4)
+            p5_in = self._proj(first.p5_down_channel, c5)
+            p4_in2 = self._proj(first.p4_down_channel_2, c4)                  # :361-363
+            p5_in2 = self._proj(first.p5_down_channel_2, c5)
+        else:
+            if len(ext) != 5:
+                raise ValueError("a BiFPN cell takes (p3, p4, p5, p6, p7), got %d inputs" % len(ext))
+            for t in ext:
+                if t.C != self.Cc:
+                    raise ValueError("BiFPN: input has %d channels, expected %d" % (t.C, self.Cc))
+            p3_in, p4_in, p5_in, p6_in, p7_in = ext
+            p4_in2, p5_in2 = p4_in, p5_in
+        for ci, cell in enumerate(cells):
+            if cell.num_channels != self.Cc:
+                raise ValueError("all cells of a stack must share num_channels")
+            e = cell.epsilon
+            fw = (lambda name: getattr(cell, name)) if cell.attention else (lambda name: None)
+            p6_up = self._node(cell.conv6_up, [(p6_in, S), (p7_in, U)], fw("p6_w1"), e)            # :338-341
+            p5_up = self._node(cell.conv5_up, [(p5_in, S), (p6_up, U)], fw("p5_w1"), e)            # :344-347
+            p4_up = self._node(cell.conv4_up, [(p4_in, S), (p5_up, U)], fw("p4_w1"), e)            # :350-353
+            p3_out = self._node(cell.conv3_up, [(p3_in, S), (p4_up, U)], fw("p3_w1"), e)           # :356-359
+            p4_out = self._node(cell.conv4_down, [(p4_in2, S), (p4_up, S), (p3_out, P)], fw("p4_w2"), e)  # :366-370
+            p5_out = self._node(cell.conv5_down, [(p5_in2, S), (p5_up, S), (p4_out, P)], fw("p5_w2"), e)  # :373-377
+            p6_out = self._node(cell.conv6_down, [(p6_in, S), (p6_up, S), (p5_out, P)], fw("p6_w2"), e)   # :380-384
+            p7_out = self._node(cell.conv7_down, [(p7_in, S), (p6_out, P)], fw("p7_w2"), e)               # :387-390
+            p3_in, p4_in, p5_in, p6_in, p7_in = p3_out, p4_out, p5_out, p6_out, p7_out
+            p4_in2, p5_in2 = p4_in, p5_in
+        return [p3_in, p4_in, p5_in, p6_in, p7_in]
+
+    def _finish_outputs(self, outs):
+        """Train: the raw outputs are normalised into the user-visible tensors.  Eval: the producing kernels write
+        the user-visible tensors directly (BatchNorm is folded into the 1x1 conv)."""
+        self.out_ops = []
+        for k, t in enumerate(outs):
+            dst_base = self.B_OUT + k
+            if self.train:
+                dst = _Tn(t.H, t.W, self.Cc, dst_base, 0)
+                self._bnapply(t, _lib.IN_SAME, dst)
+                op = self.ops[-1]
+                op.glike = (self.B_GOUT + k, 0)
+                self.out_ops.append(op)
+            else:
+                t.base, t.off = dst_base, 0
+
+    def _collect_params(self, mods):
+        ps = []
+        for m in mods:
+            ps.extend(p for p in m.parameters())
+        return ps
+
+    # ---- emission ------------------------------------------------------------------------------------------
+    def _fill_common(self, o, op):
+        o.n_in = len(op.ins)
+        for i, t in enumerate(op.ins):
+            o.inp[i] = _tensor(t)
+            o.mode[i] = op.modes[i]
+            if t.bn is not None and t.bn_mod is not None:
+                o.in_bn_w[i] = _ptr(t.bn_mod.weight)
+                o.in_bn_b[i] = _ptr(t.bn_mod.bias)
+        o.swish = op.swish
+        o.fw = _ptr(op.fw)
+        o.fw_eps = op.fw_eps
+        if op.conv is not None:
+            o.pw_w, o.pw_b = _ptr(op.conv.weight), _ptr(op.conv.bias)
+            o.bn_w, o.bn_b = _ptr(op.bn.weight), _ptr(op.bn.bias)
+            o.bn_rm, o.bn_rv = _ptr(op.bn.running_mean), _ptr(op.bn.running_var)
+            o.bn_nbt = _ptr(op.bn.num_batches_tracked)
+            o.bn_eps, o.bn_momentum = op.bn.eps, (op.bn.momentum if op.bn.momentum is not None else 0.1)
+        if op.dw is not None:
+            o.dw_w = _ptr(op.dw.weight)
+        o.Cin = op.cin
+        o.out = _tensor(op.out)
+        o.save_d = _ref(op.save_d)
+        for i in range(3):
+            o.pidx[i] = _ref(op.pidx[i])
+            o.in_slot[i] = _ref(op.slots[i])
+
+    def _emit_fwd(self):
+        arr = (_lib.Op * len(self.ops))()
+        for o, op in zip(arr, self.ops):
+            o.kind = op.kind
+            o.train = 1 if self.train else 0
+            self._fill_common(o, op)
+            o.stats, o.counter = _ref(op.stats), _ref(op.counter)
+        return arr
+
+    def _cons_of(self, t):
+        """MmdCons entries for every consumer edge of tensor `t`."""
+        res = []
+        for cop, idx in t.consumers:
+            c = _lib.Cons()
+            mode = cop.modes[idx]
+            if cop.kind == _lib.OP_NODE_FWD:
+                c.du = _tensor(cop.du, with_bn=False)
+                c.fw, c.fw_k, c.fw_n, c.fw_eps = _ptr(cop.fw), idx, len(cop.ins), cop.fw_eps
+            elif cop.kind == _lib.OP_BNAPPLY:
+                if cop.glike is None:
+                    raise RuntimeError("internal: BNAPPLY consumer without a gradient tensor")
+                c.du = _lib.Tensor(_ref(cop.glike), _ref(None), cop.out.H, cop.out.W, self.Cc, 0)
+                c.fw = None
+            else:
+                raise RuntimeError("internal: unexpected consumer kind")
+            c.mode = {_lib.IN_SAME: _lib.CONS_SAME, _lib.IN_UP2: _lib.CONS_UP2, _lib.IN_POOL: _lib.CONS_POOL}[mode]
+            c.slot = _ref(cop.slots[idx])
+            c.pidx = _ref(cop.pidx[idx])
+            res.append(c)
+        if len(res) > 3:
+            raise RuntimeError("internal: a tensor has %d consumers (max 3)" % len(res))
+        return res
+
+    def _galloc(self, param):
+        off = self.zero_arena.alloc(param.numel() * 4)
+        self.grad_off[id(param)] = (off, param.numel(), tuple(param.shape))
+        return (B_ZERO, off)
+
+    def _emit_bwd(self):
+        self.grad_off = {}
+        max_n = max(self.B * op.out.H * op.out.W * self.Cc for op in self.ops if op.kind == _lib.OP_NODE_FWD)
+        dd = (B_BWD, self.bwd_arena.alloc(max_n * self.esize))
+        out = []
+        ext_written = set()
+
+        def new(kind, op):
+            o = _lib.Op()
+            o.kind = kind
+            o.train = 1
+            self._fill_common(o, op)
+            o.counter = _ref(op.bwd_counter)
+            return o
+
+        def set_cons(o, t):
+            cons = self._cons_of(t)
+            o.n_cons = len(cons)
+            for i, c in enumerate(cons):
+                o.cons[i] = c
+
+        for op in reversed(self.ops):
+            if op.kind == _lib.OP_BNAPPLY:
+                src = op.ins[0]
+                if op.glike is None:   # internal materialisation (P6 / P7 synthesis): gather its gradient first
+                    n = self.B * op.out.H * op.out.W * self.Cc
+                    op.glike = (B_BWD, self.bwd_arena.alloc(n * self.esize))
+                    o = new(_lib.OP_PULL, op)
+                    set_cons(o, op.out)
+                    o.dx = _ref(op.glike)
+                    out.append(o)
+                if src.bn is not None:
+                    o = new(_lib.OP_SLOT, op)
+                    o.n_cons = 1
+                    c = _lib.Cons()
+                    c.du = _lib.Tensor(_ref(op.glike), _ref(None), op.out.H, op.out.W, self.Cc, 0)
+                    o.cons[0] = c
+                    out.append(o)
+            elif op.kind == _lib.OP_NODE_FWD:
+                o = new(_lib.OP_NODE_BWD, op)
+                set_cons(o, op.out)
+                o.du = _ref((op.du.base, op.du.off))
+                o.dd = _ref(dd)
+                o.g_dw = _ref(self._galloc(op.dw.weight))
+                o.g_pw = _ref(self._galloc(op.conv.weight))
+                o.g_pb = _ref(self._galloc(op.conv.bias))
+                o.g_bn_w = _ref(self._galloc(op.bn.weight))
+                o.g_bn_b = _ref(self._galloc(op.bn.bias))
+                if op.fw is not None:
+                    o.g_fw = _ref(self._galloc(op.fw))
+                out.append(o)
+            elif op.kind == _lib.OP_PROJ_FWD:
+                o = new(_lib.OP_PROJ_BWD, op)
+                set_cons(o, op.out)
+                x = op.ins[0]
+                xi = x.base - B_EXT
+                if self.in_need_grad[xi]:
+                    o.dx = _ref((self.B_GIN + xi, 0))
+                    o.accumulate_dx = 1 if xi in ext_written else 0
+                    ext_written.add(xi)
+                o.g_pw = _ref(self._galloc(op.conv.weight))
+                o.g_pb = _ref(self._galloc(op.conv.bias))
+                o.g_bn_w = _ref(self._galloc(op.bn.weight))
+                o.g_bn_b = _ref(self._galloc(op.bn.bias))
+                out.append(o)
+        # gradients of external pyramid inputs consumed directly by nodes (non-first cells, bare SeparableConvBlock)
+        for xi, x in enumerate(self.ext):
+            if not self.in_need_grad[xi] or xi in ext_written:
+                continue
+            if not x.consumers or any(cop.kind == _lib.OP_PROJ_FWD for cop, _ in x.consumers):
+                continue
+            o = _lib.Op()
+            o.kind = _lib.OP_PULL
+            o.train = 1
+            o.out = _tensor(x)
+            set_cons(o, x)
+            o.dx = _ref((self.B_GIN + xi, 0))
+            out.append(o)
+        arr = (_lib.Op * len(out))()
+        for i, o in enumerate(out):
+            arr[i] = o
+        self._bwd_keep = out
+        return arr
+
+
+class _StackFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, plan, n_in, *tensors):
+        inputs, params = tensors[:n_in], tensors[n_in:]
+        outs, saved = runner._forward(plan, inputs)
+        ctx.runner, ctx.plan, ctx.saved, ctx.n_in = runner, plan, saved, n_in
+        ctx.param_list = params
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan = ctx.plan
+        if not plan.need_grad:
+            raise RuntimeError("mm_distillnet_b200.BiFPN: backward through an eval-mode (folded BatchNorm) forward is "
+                               "not supported; call .train() on the student")
+        gin, gflat = ctx.runner._backward(plan, ctx.saved, gouts)
+        grads = [None, None, None]
+        for i in range(ctx.n_in):
+            grads.append(gin[i] if ctx.needs_input_grad[3 + i] else None)
+        for j, p in enumerate(ctx.param_list):
+            ent = plan.grad_off.get(id(plan.params[j]))
+            if ent is None or not ctx.needs_input_grad[3 + ctx.n_in + j]:
+                grads.append(None)
+            else:
+                off, n, shape = ent
+                grads.append(gflat[off // 4: off // 4 + n].view(shape))
+        return tuple(grads)
+
+
+class _Runner:
+    """Builds / caches plans and runs them through the C ABI."""
+
+    def __init__(self):
+        self.plans = {}
+        self.persist = {}
+
+    def run(self, mods, inputs, training, kind):
+        if len(inputs) == 0:
+            raise ValueError("BiFPN: empty input tuple")
+        x0 = inputs[0]
+        if not x0.is_cuda:
+            raise RuntimeError("mm_distillnet_b200.BiFPN needs CUDA tensors (there is no CPU fallback)")
+        if x0.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("BiFPN activations must be float32 or bfloat16, got %s" % x0.dtype)
+        for x in inputs:
+            if x.dim() != 4 or x.shape[0] != x0.shape[0] or x.dtype != x0.dtype or x.device != x0.device:
+                raise ValueError("BiFPN: inputs must be [B,C,H,W] tensors sharing batch, dtype and device")
+        params = [p for m in mods for p in m.parameters()]
+        if any(p.dtype != torch.float32 for p in params):
+            raise TypeError("BiFPN parameters must stay float32 (master weights); cast activations, not the module")
+        if any(p.device != x0.device for p in params):
+            raise RuntimeError("BiFPN: parameters and inputs live on different devices")
+        grad_on = torch.is_grad_enabled()
+        in_need = [grad_on and x.requires_grad for x in inputs]
+        need_grad = training and grad_on and (any(in_need) or any(p.requires_grad for p in params))
+        Cc = mods[0].num_channels if kind == "cells" else inputs[0].shape[1]
+        if Cc != KERNEL_CHANNELS:
+            raise NotImplementedError("the sm_100a BiFPN kernels are built for %d channels (EfficientDet-D2), got %d"
+                                      % (KERNEL_CHANNELS, Cc))
+        if training and x0.shape[0] * min(x.shape[2] * x.shape[3] for x in inputs) < 1:
+            raise ValueError("empty batch")
+        key = (kind, tuple(tuple(x.shape) for x in inputs), x0.dtype, bool(training), need_grad, tuple(in_need),
+               x0.device.index, len(params), params[0].data_ptr(), params[-1].data_ptr())
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = _Plan(mods, kind, [tuple(x.shape) for x in inputs], x0.dtype, bool(training), need_grad, in_need)
+            plan.device = x0.device
+            self.plans[key] = plan
+            if len(self.plans) > 16:
+                self.plans.pop(next(iter(self.plans)))
+        if need_grad:
+            outs = _StackFunction.apply(self, plan, len(inputs), *inputs, *params)
+        else:
+            with torch.no_grad():
+                outs, _ = self._forward(plan, inputs)
+            outs = tuple(outs)
+        return outs
+
+    def _persist_ws(self, plan):
+        ws = getattr(plan, "_persist_buf", None)
+        if ws is None:
+            ws = torch.zeros(max(plan.persist.size, _ALIGN), dtype=torch.uint8, device=plan.device)
+            plan._persist_buf = ws
+        return ws
+
+    def _call(self, plan, ops, bases):
+        arr = (C.c_void_p * len(bases))(*bases)
+        with torch.cuda.device(plan.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.lib().mmd_bifpn_run(ops, len(ops), arr, len(bases), plan.B, plan.Cc,
+                                          _lib.MMD_F32 if plan.dtype == torch.float32 else _lib.MMD_BF16, stream)
+        _lib.check(rc, "mmd_bifpn_run")
+
+    def _forward(self, plan, inputs):
+        dev = plan.device
+        xs = [x.detach().contiguous(memory_format=torch.channels_last) for x in inputs]
+        arena = torch.empty(max(plan.fwd_arena.size, _ALIGN), dtype=torch.uint8, device=dev)
+        outs = [torch.empty(s, dtype=plan.dtype, device=dev, memory_format=torch.channels_last) for s in plan.out_shapes]
+        bases = [0] * plan.n_bases
+        bases[B_FWD] = arena.data_ptr()
+        bases[B_PERSIST] = self._persist_ws(plan).data_ptr()
+        for i, x in enumerate(xs):
+            bases[B_EXT + i] = x.data_ptr()
+        for k, o in enumerate(outs):
+            bases[plan.B_OUT + k] = o.data_ptr()
+        self._call(plan, plan.fwd_ops, bases)
+        return outs, (xs, arena, outs)
+
+    def _backward(self, plan, saved, gouts):
+        xs, arena, outs = saved
+        dev = plan.device
+        gs = []
+        for g, o in zip(gouts, outs):
+            if g is None:
+                g = torch.zeros_like(o)
+            gs.append(g.detach().to(plan.dtype).contiguous(memory_format=torch.channels_last))
+        bwd = torch.empty(max(plan.bwd_arena.size, _ALIGN), dtype=torch.uint8, device=dev)
+        zero = torch.zeros(max(plan.zero_arena.size, _ALIGN) // 4, dtype=torch.float32, device=dev)
+        gin = [torch.empty_like(x) if need else None for x, need in zip(xs, plan.in_need_grad)]
+        bases = [0] * plan.n_bases
+        bases[B_FWD] = arena.data_ptr()
+        bases[B_PERSIST] = self._persist_ws(plan).data_ptr()
+        bases[B_BWD] = bwd.data_ptr()
+        bases[B_ZERO] = zero.data_ptr()
+        for i, x in enumerate(xs):
+            bases[B_EXT + i] = x.data_ptr()
+            if gin[i] is not None:
+                bases[plan.B_GIN + i] = gin[i].data_ptr()
+        for k, (o, g) in enumerate(zip(outs, gs)):
+            bases[plan.B_OUT + k] = o.data_ptr()
+            bases[plan.B_GOUT + k] = g.data_ptr()
+        self._call(plan, plan.bwd_ops, bases)
+        return gin, zero

@@ -1,0 +1,157 @@
+// BiFPN kernels: resolved (pointer-level) argument structs, tile geometry and the shared fused input loader.
+//
+// Data flow:  every tensor between nodes is stored ONCE, pre-BatchNorm ("raw"), together with a
+// 4*C float vector (scale, shift, mean, invstd).  Consumers apply y = scale*x + shift while loading, resample on
+// the fly (nearest x2 / 3x3-s2 zero-padded max) and fuse the weighted sum + swish, so the reference's padded
+// copies, upsampled / pooled tensors, fused sums and normalised outputs never exist in HBM.
+#pragma once
+#include "common.cuh"
+
+namespace mmd {
+
+constexpr int kThreads = 256;
+constexpr int kTileP = 128;    // output positions per tile == rows of the pointwise GEMM
+constexpr int kHaloMax = 180;  // (TH+2)*(TW+2) upper bound, e.g. (8+2)*(16+2)
+
+struct TensorP {
+  const void* data;
+  const float* bn;  // nullptr: final values
+  int H, W;
+};
+
+struct TileGeom {
+  int H, W, B;
+  int TH, TW, tiles_x, tiles_y, ntiles;
+};
+
+inline TileGeom make_geom(int B, int H, int W) {
+  TileGeom g;
+  g.H = H; g.W = W; g.B = B;
+  // widest divisor of W that is <= 16 (falls back to min(W,16) with masked partial tiles)
+  int tw = W < 16 ? W : 16;
+  for (int t = tw; t >= 8 && t * 2 > tw; --t)
+    if (W % t == 0) { tw = t; break; }
+  int th = kTileP / tw;
+  if (th > H) th = H;
+  while ((th + 2) * (tw + 2) > kHaloMax) --th;
+  for (int t = th; t * 2 > th && t >= 1; --t)
+    if (H % t == 0) { th = t; break; }
+  g.TH = th; g.TW = tw;
+  g.tiles_x = (W + tw - 1) / tw;
+  g.tiles_y = (H + th - 1) / th;
+  g.ntiles = B * g.tiles_x * g.tiles_y;
+  return g;
+}
+
+struct NodeFwdP {
+  TensorP in[3];
+  int mode[3];
+  int n_in, swish, train, Cin;
+  const float* fw;
+  float fw_eps;
+  const float *dw_w, *pw_w, *pw_b, *bn_w, *bn_b;
+  float *bn_rm, *bn_rv;
+  long long* bn_nbt;
+  void* out;
+  float* out_bn;
+  void* save_d;
+  unsigned char* pidx[3];
+  double* stats;
+  unsigned* counter;
+  float bn_eps, bn_mom;
+  TileGeom g;
+};
+
+struct ConsP {
+  const void* du;
+  int H, W;  // consumer resolution
+  int mode;
+  int fw_k, fw_n;
+  float fw_eps;
+  const float* fw;
+  const double* slot;
+  const unsigned char* pidx;
+};
+
+struct NodeBwdP {
+  // forward description (inputs are re-read to rebuild the fused sum)
+  TensorP in[3];
+  int mode[3];
+  int n_in, swish, Cin, accumulate_dx;
+  const float* fw;
+  float fw_eps;
+  const float *dw_w, *pw_w, *bn_w;
+  const float* in_bn_w[3];
+  const float* in_bn_b[3];
+  const void* out;      // raw forward output of this op
+  const float* out_bn;  // its scale/shift/mean/invstd
+  const void* save_d;
+  const unsigned char* pidx[3];  // arg-max indices written by the forward for pooled inputs
+  int n_cons;
+  ConsP cons[3];
+  void* du;
+  void* dd;
+  double* in_slot[3];
+  void* dx;
+  float *g_dw, *g_pw, *g_pb, *g_bn_w, *g_bn_b, *g_fw;
+  unsigned* counter;
+  TileGeom g;
+};
+
+// ---- fused input loader -------------------------------------------------------------------------------------
+// Loads 4 channels of input `t` as seen by an output position (y, x) of a node:
+//   SAME : t[b, y, x]            UP2 : t[b, y>>1, x>>1]   (nn.Upsample nearest x2, YetAnotherEfficientDet.py:223-226)
+//   POOL : max over the 3x3 stride-2 window of the zero-padded, ALREADY NORMALISED tensor
+//          (MaxPool2dStaticSamePadding, YetAnotherEfficientNet.py:90-104; first maximum in row-major order wins).
+// `val` = normalised value (scale*raw+shift), `raw` = the stored element it came from, `arg` = 4 packed
+// window indices (0..8, 9 = padding) for POOL.
+template <typename T, int C>
+__device__ __forceinline__ void load_input(const TensorP& t, int mode, int b, int y, int x, int q, float4 sc, float4 sh,
+                                           float4& val, float4& raw, unsigned& arg) {
+  const T* base = reinterpret_cast<const T*>(t.data);
+  arg = 0u;
+  if (mode != MMD_IN_POOL) {
+    const int sy = (mode == MMD_IN_UP2) ? (y >> 1) : y;
+    const int sx = (mode == MMD_IN_UP2) ? (x >> 1) : x;
+    raw = ld4<T>(base + (((long long)b * t.H + sy) * t.W + sx) * C + 4 * q);
+    val = f4_fma(raw, sc, sh);
+    return;
+  }
+  const int top = pool_pad_before(t.H), left = pool_pad_before(t.W);
+  float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned a[4] = {9u, 9u, 9u, 9u};
+#pragma unroll
+  for (int wy = 0; wy < 3; ++wy) {
+    const int fy = 2 * y - top + wy;
+#pragma unroll
+    for (int wx = 0; wx < 3; ++wx) {
+      const int fx = 2 * x - left + wx;
+      const bool inside = (fy >= 0) && (fy < t.H) && (fx >= 0) && (fx < t.W);
+      float4 rv = f4_zero(), vv = f4_zero();
+      if (inside) {
+        rv = ld4<T>(base + (((long long)b * t.H + fy) * t.W + fx) * C + 4 * q);
+        vv = f4_fma(rv, sc, sh);
+      }
+      const unsigned id = inside ? (unsigned)(wy * 3 + wx) : 9u;
+      if (vv.x > m[0]) { m[0] = vv.x; r[0] = rv.x; a[0] = id; }
+      if (vv.y > m[1]) { m[1] = vv.y; r[1] = rv.y; a[1] = id; }
+      if (vv.z > m[2]) { m[2] = vv.z; r[2] = rv.z; a[2] = id; }
+      if (vv.w > m[3]) { m[3] = vv.w; r[3] = rv.w; a[3] = id; }
+    }
+  }
+  val = make_float4(m[0], m[1], m[2], m[3]);
+  raw = make_float4(r[0], r[1], r[2], r[3]);
+  arg = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
+}
+
+// kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)
+int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
+int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
+int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
+int launch_node_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
+int launch_proj_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
+int launch_pull(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
+int launch_slot(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
+
+}  // namespace mmd

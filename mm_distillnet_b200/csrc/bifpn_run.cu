@@ -1,0 +1,156 @@
+// mmd_bifpn_run: resolve an op list (include/mmd.h) into kernel arguments and enqueue it on the caller's stream.
+#include "bifpn.cuh"
+
+namespace mmd {
+
+static TensorP resolve(const MmdTensor& t, const Bases& B) {
+  TensorP r;
+  r.data = B.get<void>(t.data);
+  r.bn = B.get<float>(t.bn);
+  r.H = t.H;
+  r.W = t.W;
+  return r;
+}
+
+static int fill_fwd(const MmdOp& op, const Bases& B, int batch, NodeFwdP& p) {
+  MMD_CHECK_ARG(op.n_in >= 1 && op.n_in <= 3, "op: n_in=%d", op.n_in);
+  for (int i = 0; i < 3; ++i) {
+    p.in[i] = (i < op.n_in) ? resolve(op.in[i], B) : TensorP{nullptr, nullptr, 0, 0};
+    p.mode[i] = op.mode[i];
+    p.pidx[i] = B.get<unsigned char>(op.pidx[i]);
+    if (i < op.n_in) MMD_CHECK_ARG(p.in[i].data != nullptr, "op: input %d has no data", i);
+  }
+  p.n_in = op.n_in;
+  p.swish = op.swish;
+  p.train = op.train;
+  p.Cin = op.Cin;
+  p.fw = op.fw;
+  p.fw_eps = op.fw_eps;
+  p.dw_w = op.dw_w; p.pw_w = op.pw_w; p.pw_b = op.pw_b; p.bn_w = op.bn_w; p.bn_b = op.bn_b;
+  p.bn_rm = op.bn_rm; p.bn_rv = op.bn_rv; p.bn_nbt = (long long*)op.bn_nbt;
+  p.out = B.get<void>(op.out.data);
+  p.out_bn = B.get<float>(op.out.bn);
+  p.save_d = B.get<void>(op.save_d);
+  p.stats = B.get<double>(op.stats);
+  p.counter = B.get<unsigned>(op.counter);
+  p.bn_eps = op.bn_eps;
+  p.bn_mom = op.bn_momentum;
+  p.g = make_geom(batch, op.out.H, op.out.W);
+  MMD_CHECK_ARG(p.out != nullptr, "op: no output");
+  if (op.kind != MMD_OP_BNAPPLY) {
+    MMD_CHECK_ARG(p.pw_w && p.pw_b && p.bn_w && p.bn_b && p.bn_rm && p.bn_rv, "op: missing conv/bn parameters");
+    if (op.train) MMD_CHECK_ARG(p.out_bn && p.stats && p.counter, "train op: missing bn/stats/counter storage");
+  }
+  return 0;
+}
+
+static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
+  for (int i = 0; i < 3; ++i) {
+    p.in[i] = (i < op.n_in) ? resolve(op.in[i], B) : TensorP{nullptr, nullptr, 0, 0};
+    p.mode[i] = op.mode[i];
+    p.in_bn_w[i] = op.in_bn_w[i];
+    p.in_bn_b[i] = op.in_bn_b[i];
+    p.pidx[i] = B.get<unsigned char>(op.pidx[i]);
+    p.in_slot[i] = B.get<double>(op.in_slot[i]);
+  }
+  p.n_in = op.n_in;
+  p.swish = op.swish;
+  p.Cin = op.Cin;
+  p.accumulate_dx = op.accumulate_dx;
+  p.fw = op.fw;
+  p.fw_eps = op.fw_eps;
+  p.dw_w = op.dw_w; p.pw_w = op.pw_w; p.bn_w = op.bn_w;
+  p.out = B.get<void>(op.out.data);
+  p.out_bn = B.get<float>(op.out.bn);
+  p.save_d = B.get<void>(op.save_d);
+  p.n_cons = op.n_cons;
+  MMD_CHECK_ARG(op.n_cons >= 0 && op.n_cons <= 3, "op: n_cons=%d", op.n_cons);
+  for (int c = 0; c < 3; ++c) {
+    ConsP& cs = p.cons[c];
+    if (c < op.n_cons) {
+      const MmdCons& m = op.cons[c];
+      cs.du = B.get<void>(m.du.data);
+      cs.H = m.du.H; cs.W = m.du.W;
+      cs.mode = m.mode;
+      cs.fw_k = m.fw_k; cs.fw_n = m.fw_n; cs.fw_eps = m.fw_eps; cs.fw = m.fw;
+      cs.slot = B.get<double>(m.slot);
+      cs.pidx = B.get<unsigned char>(m.pidx);
+      MMD_CHECK_ARG(cs.du != nullptr, "op: consumer %d has no gradient tensor", c);
+      if (cs.mode == MMD_CONS_POOL) MMD_CHECK_ARG(cs.pidx != nullptr, "op: pooled consumer %d has no arg-max indices", c);
+    } else {
+      cs = ConsP{nullptr, 0, 0, 0, 0, 0, 0.f, nullptr, nullptr, nullptr};
+    }
+  }
+  p.du = B.get<void>(op.du);
+  p.dd = B.get<void>(op.dd);
+  p.dx = B.get<void>(op.dx);
+  p.g_dw = B.get<float>(op.g_dw); p.g_pw = B.get<float>(op.g_pw); p.g_pb = B.get<float>(op.g_pb);
+  p.g_bn_w = B.get<float>(op.g_bn_w); p.g_bn_b = B.get<float>(op.g_bn_b); p.g_fw = B.get<float>(op.g_fw);
+  p.counter = B.get<unsigned>(op.counter);
+  p.g = make_geom(batch, op.out.H, op.out.W);
+  return 0;
+}
+
+}  // namespace mmd
+
+using namespace mmd;
+
+extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases, int32_t batch,
+                             int32_t C, int32_t dtype, mmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMD_CHECK_ARG(ops != nullptr && n_ops >= 0 && bases != nullptr, "mmd_bifpn_run: null arguments");
+  MMD_CHECK_ARG(batch >= 1, "mmd_bifpn_run: batch=%d", batch);
+  MMD_CHECK_ARG(C == 112, "mmd_bifpn_run: kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
+  Bases B{bases, n_bases};
+  for (int i = 0; i < n_ops; ++i) {
+    const MmdOp& op = ops[i];
+    int rc = 0;
+    switch (op.kind) {
+      case MMD_OP_NODE_FWD:
+      case MMD_OP_PROJ_FWD:
+      case MMD_OP_BNAPPLY: {
+        NodeFwdP p;
+        if ((rc = fill_fwd(op, B, batch, p))) return rc;
+        if (op.kind == MMD_OP_NODE_FWD) {
+          MMD_CHECK_ARG(p.dw_w != nullptr, "node op %d: no depthwise weight", i);
+          for (int k = 0; k < op.n_in; ++k) MMD_CHECK_ARG(op.in[k].C == C, "node op %d: input %d has C=%d", i, k, op.in[k].C);
+          rc = launch_node_fwd(p, C, dtype, stream);
+        } else if (op.kind == MMD_OP_PROJ_FWD) {
+          MMD_CHECK_ARG(op.Cin >= 4 && op.Cin % 4 == 0, "proj op %d: Cin=%d must be a positive multiple of 4", i, op.Cin);
+          rc = launch_proj_fwd(p, C, dtype, stream);
+        } else {
+          rc = launch_bnapply(p, C, dtype, stream);
+        }
+        break;
+      }
+      case MMD_OP_NODE_BWD:
+      case MMD_OP_PROJ_BWD:
+      case MMD_OP_PULL:
+      case MMD_OP_SLOT: {
+        NodeBwdP p;
+        if ((rc = fill_bwd(op, B, batch, p))) return rc;
+        if (op.kind == MMD_OP_NODE_BWD) {
+          MMD_CHECK_ARG(p.out && p.out_bn && p.save_d && p.du && p.dd && p.g_pw && p.counter, "node bwd op %d: missing storage", i);
+          rc = launch_node_bwd(p, C, dtype, stream);
+        } else if (op.kind == MMD_OP_PROJ_BWD) {
+          MMD_CHECK_ARG(p.out && p.out_bn && p.g_pw && p.in[0].data, "proj bwd op %d: missing storage", i);
+          rc = launch_proj_bwd(p, C, dtype, stream);
+        } else if (op.kind == MMD_OP_PULL) {
+          MMD_CHECK_ARG(p.dx != nullptr, "pull op %d: no destination", i);
+          rc = launch_pull(p, C, dtype, stream);
+        } else {
+          MMD_CHECK_ARG(p.in[0].data && p.in[0].bn && p.in_slot[0] && op.n_cons == 1, "slot op %d: missing storage", i);
+          if (op.mode[0] == MMD_IN_POOL) MMD_CHECK_ARG(p.pidx[0] != nullptr, "slot op %d: no arg-max indices", i);
+          rc = launch_slot(p, C, dtype, stream);
+        }
+        break;
+      }
+      default:
+        set_error("mmd_bifpn_run: op %d has unknown kind %d", i, op.kind);
+        return MMD_E_ARG;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -1,0 +1,383 @@
+// MTA multi-teacher alignment loss — forward and backward kernels (sm_100a).
+// Reference semantics: src/loss/MTALoss.py:15-77 (see include/mmd.h).  All of this is HBM-bound streaming work:
+//   mta_pool   reads every feature map once (coalesced 16-byte / 8-byte channel-vector loads, shuffle reduce
+//              over the channel dimension) and writes one float per pixel;
+//   mta_level  one CTA per (level, sample): norms, teacher product, two softmaxes, the KL-style sum and
+//              d loss / d a in a handful of block reductions over data that sits in L2;
+//   mta_bwd    re-reads f_s once and writes grad = go * (p/C) * f^(p-1) * (d loss / d a).
+#include "common.cuh"
+
+namespace mmd {
+
+constexpr int kMaxSeg = (1 + MMD_MTA_MAX_TEACHERS) * MMD_MTA_MAX_LEVELS;
+
+struct MtaSeg {
+  const void* f;  // feature map
+  float* a;       // pooled map [B*HW]
+  int npix;       // B*HW
+  int HW;
+};
+struct MtaPoolP {
+  MtaSeg seg[kMaxSeg];
+  int C;
+  int group;  // lanes cooperating on one pixel (power of two <= 32)
+  float p;
+};
+
+__device__ __forceinline__ float powp(float v, float p, bool p_is_2) { return p_is_2 ? v * v : powf(v, p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) mta_pool_nhwc(const __grid_constant__ MtaPoolP P) {
+  const MtaSeg s = P.seg[blockIdx.y];
+  const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
+  const int C = P.C, NQ = C >> 2, G = P.group, PPW = 32 / G;
+  const bool p2 = (P.p == 2.0f);
+  const int lane = threadIdx.x & 31, gl = lane % G, sub = lane / G;
+  const int wpb = blockDim.x >> 5;
+  const long long nw = (long long)gridDim.x * wpb;
+  const float invC = 1.0f / (float)C;
+  constexpr int U = 4;  // pixel-chunks in flight per warp
+  for (long long chunk = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * U; chunk * PPW < s.npix; chunk += nw * U) {
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      acc[u] = 0.f;
+      long long pix = (chunk + u) * PPW + sub;
+      if (pix < s.npix) {
+        const T* row = f + pix * C;
+        for (int q = gl; q < NQ; q += G) {
+          float4 v = ld4<T>(row + 4 * q);
+          acc[u] += powp(v.x, P.p, p2) + powp(v.y, P.p, p2) + powp(v.z, P.p, p2) + powp(v.w, P.p, p2);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float a = acc[u];
+      for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      long long pix = (chunk + u) * PPW + sub;
+      if (gl == 0 && pix < s.npix) s.a[pix] = a * invC;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mta_pool_nchw(const __grid_constant__ MtaPoolP P) {
+  const MtaSeg s = P.seg[blockIdx.y];
+  const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
+  const int C = P.C;
+  const bool p2 = (P.p == 2.0f);
+  const float invC = 1.0f / (float)C;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < s.npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(pix / s.HW), i = (int)(pix % s.HW);
+    const T* p0 = f + (long long)b * C * s.HW + i;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) acc += powp(ld1<T>(p0 + (long long)c * s.HW), P.p, p2);
+    s.a[pix] = acc * invC;
+  }
+}
+
+// ---- per (level, sample) loss ------------------------------------------------------------------------------
+struct MtaLevelP {
+  const float* att;   // [(1+nt)][Btot]
+  float* ga;          // [Btot] or null
+  float* loss_b;      // [n_levels][B]
+  long long Btot;     // B * sum HW
+  int cum[MMD_MTA_MAX_LEVELS];  // prefix sum of HW
+  int HW[MMD_MTA_MAX_LEVELS];
+  int B, nt;
+  float T;
+};
+
+constexpr int kLvlThreads = 1024;
+
+template <int K>
+__device__ __forceinline__ void block_reduce(float (&v)[K], unsigned max_mask, float* s_red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = ((max_mask >> k) & 1u) ? warp_max(v[k]) : warp_sum(v[k]);
+  __syncthreads();  // s_red may still be read from a previous call
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) s_red[warp * K + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float r = s_red[k];
+    for (int w = 1; w < nw; ++w) {
+      float x = s_red[w * K + k];
+      r = ((max_mask >> k) & 1u) ? fmaxf(r, x) : r + x;
+    }
+    v[k] = r;
+  }
+}
+
+__global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_constant__ MtaLevelP P) {
+  __shared__ float s_red[32 * 5];
+  const int b = blockIdx.x, l = blockIdx.y, n = P.HW[l], nt = P.nt;
+  const long long off = (long long)P.B * P.cum[l] + (long long)b * n;
+  const float* __restrict__ as = P.att + off;
+  const float* __restrict__ at[MMD_MTA_MAX_TEACHERS];
+#pragma unroll
+  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) at[k] = P.att + (long long)(1 + (k < nt ? k : 0)) * P.Btot + off;
+  const float invT = 1.0f / P.T;
+
+  // pass 1: squared L2 norms of the student map and of every teacher map (F.normalize, eps 1e-12)
+  float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float x = as[i];
+    ss[0] += x * x;
+#pragma unroll
+    for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k)
+      if (k < nt) {
+        float y = at[k][i];
+        ss[1 + k] += y * y;
+      }
+  }
+  block_reduce<5>(ss, 0u, s_red);
+  const float nrm_s_raw = sqrtf(ss[0]);
+  const float nrm_s = fmaxf(nrm_s_raw, 1e-12f);
+  float inv_t[MMD_MTA_MAX_TEACHERS];
+#pragma unroll
+  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) inv_t[k] = 1.0f / fmaxf(sqrtf(ss[1 + k]), 1e-12f);
+  const float inv_s = 1.0f / nrm_s;
+
+  auto teacher_m = [&](int i) -> float {  // product of the normalised teacher attentions (MTALoss.py:51-55)
+    float m = at[0][i] * inv_t[0];
+#pragma unroll
+    for (int k = 1; k < MMD_MTA_MAX_TEACHERS; ++k)
+      if (k < nt) m *= at[k][i] * inv_t[k];
+    return m;
+  };
+
+  // pass 2: L1 norm of the teacher product (only used when nt > 1), maxima for the two softmaxes
+  float r2[3] = {0.f, -INFINITY, -INFINITY};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float m = teacher_m(i);
+    r2[0] += fabsf(m);
+    r2[1] = fmaxf(r2[1], as[i] * inv_s);
+    r2[2] = fmaxf(r2[2], m);
+  }
+  block_reduce<3>(r2, 0x6u, s_red);
+  const float inv_l1 = (nt > 1) ? 1.0f / fmaxf(r2[0], 1e-12f) : 1.0f;  // F.normalize(p=1) (MTALoss.py:57)
+  const float max_zs = r2[1] * invT, max_zt = r2[2] * inv_l1 * invT;
+
+  // pass 3: softmax denominators
+  float z[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    z[0] += __expf(as[i] * inv_s * invT - max_zs);
+    z[1] += __expf(teacher_m(i) * inv_l1 * invT - max_zt);
+  }
+  block_reduce<2>(z, 0u, s_red);
+  const float inv_zs = 1.0f / z[0], inv_zt = 1.0f / z[1], log_zt = logf(z[1]);
+
+  // pass 4: loss_b = sum t (log t - s)   (kl_div with a PROBABILITY input: MTALoss.py:62-72), and <g, s>
+  const float invB = 1.0f / (float)P.B;
+  float r4[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float s = __expf(as[i] * inv_s * invT - max_zs) * inv_zs;
+    float zt = teacher_m(i) * inv_l1 * invT - max_zt;
+    float t = __expf(zt) * inv_zt;
+    r4[0] += t * ((zt - log_zt) - s);
+    r4[1] += -t * invB * s;
+  }
+  block_reduce<2>(r4, 0u, s_red);
+  if (threadIdx.x == 0) P.loss_b[l * P.B + b] = r4[0];
+  if (P.ga == nullptr) return;
+
+  // pass 5: <a^, d a^> with d z = s (g - <g,s>), d a^ = d z / T
+  const float gs = r4[1];
+  float r5[1] = {0.f};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float ah = as[i] * inv_s;
+    float s = __expf(ah * invT - max_zs) * inv_zs;
+    float t = __expf(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
+    float dah = s * (-t * invB - gs) * invT;
+    r5[0] += ah * dah;
+  }
+  block_reduce<1>(r5, 0u, s_red);
+  const bool clamped = !(nrm_s_raw > 1e-12f);
+  // pass 6: d a = (d a^ - a^ <a^, d a^>) / ||a||  (or d a^ / eps when the norm was clamped)
+  float* __restrict__ ga = P.ga + off;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float ah = as[i] * inv_s;
+    float s = __expf(ah * invT - max_zs) * inv_zs;
+    float t = __expf(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
+    float dah = s * (-t * invB - gs) * invT;
+    ga[i] = clamped ? dah * inv_s : (dah - ah * r5[0]) * inv_s;
+  }
+}
+
+__global__ void mta_finish_kernel(const float* __restrict__ loss_b, float* __restrict__ loss, int B) {
+  const int l = blockIdx.x;
+  float acc = 0.f;  // fixed order -> deterministic
+  for (int b = threadIdx.x; b < B; b += 32) acc += loss_b[l * B + b];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) loss[l] = acc / (float)B;
+}
+
+// ---- backward ----------------------------------------------------------------------------------------------
+struct MtaBwdSeg {
+  const void* f;
+  void* g;
+  const float* ga;
+  int npix, HW;
+  int level, pad;
+};
+struct MtaBwdP {
+  MtaBwdSeg seg[MMD_MTA_MAX_LEVELS];
+  const float* grad_loss;
+  int C;
+  float p;
+};
+
+template <typename T, bool NCHW>
+__global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ MtaBwdP P) {
+  const MtaBwdSeg s = P.seg[blockIdx.y];
+  const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
+  T* __restrict__ g = reinterpret_cast<T*>(s.g);
+  const int C = P.C;
+  const bool p2 = (P.p == 2.0f);
+  const float coef = P.grad_loss[s.level] * P.p / (float)C;
+  const long long nvec = (long long)s.npix * C / 4;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    long long e = v * 4;
+    if (!NCHW) {
+      float k = coef * s.ga[e / C];
+      float4 x = ld4<T>(f + e);
+      float4 r;
+      if (p2) r = f4_scale(x, k);
+      else r = make_float4(k * powf(x.x, P.p - 1.f), k * powf(x.y, P.p - 1.f), k * powf(x.z, P.p - 1.f), k * powf(x.w, P.p - 1.f));
+      st4<T>(g + e, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        long long ee = e + j;
+        int hw = (int)(ee % s.HW);
+        int b = (int)(ee / ((long long)C * s.HW));
+        float k = coef * s.ga[(long long)b * s.HW + hw];
+        float x = ld1<T>(f + ee);
+        st1<T>(g + ee, p2 ? k * x : k * powf(x, P.p - 1.f));
+      }
+    }
+  }
+}
+
+static int group_lanes(int C) {
+  int nq = C / 4, g = 1;
+  while (g < nq && g < 32) g <<= 1;
+  return g;
+}
+
+}  // namespace mmd
+
+using namespace mmd;
+
+extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMD_CHECK_ARG(a != nullptr, "mmd_mta_fwd: null args");
+  MMD_CHECK_ARG(a->n_levels >= 1 && a->n_levels <= MMD_MTA_MAX_LEVELS, "mmd_mta_fwd: n_levels=%d out of range", a->n_levels);
+  MMD_CHECK_ARG(a->n_teachers >= 1 && a->n_teachers <= MMD_MTA_MAX_TEACHERS, "mmd_mta_fwd: n_teachers=%d out of range", a->n_teachers);
+  MMD_CHECK_ARG(a->B >= 1 && a->C >= 4 && a->C % 4 == 0, "mmd_mta_fwd: B=%d C=%d (C must be a multiple of 4)", a->B, a->C);
+  MMD_CHECK_ARG(a->dtype == MMD_F32 || a->dtype == MMD_BF16, "mmd_mta_fwd: dtype %d", a->dtype);
+  MMD_CHECK_ARG(a->layout == MMD_NHWC || a->layout == MMD_NCHW, "mmd_mta_fwd: layout %d", a->layout);
+  MMD_CHECK_ARG(a->att_ws && a->loss_b && a->loss, "mmd_mta_fwd: null workspace/output");
+  MMD_CHECK_ARG(a->T > 0.f, "mmd_mta_fwd: T must be positive");
+
+  MtaPoolP pp;
+  MtaLevelP lp;
+  int cum = 0, maxpix = 0;
+  for (int l = 0; l < a->n_levels; ++l) {
+    MMD_CHECK_ARG(a->H[l] >= 1 && a->W[l] >= 1, "mmd_mta_fwd: level %d has empty spatial size", l);
+    lp.cum[l] = cum;
+    lp.HW[l] = a->H[l] * a->W[l];
+    cum += lp.HW[l];
+  }
+  const long long Btot = (long long)a->B * cum;
+  int nseg = 0;
+  for (int t = 0; t <= a->n_teachers; ++t)
+    for (int l = 0; l < a->n_levels; ++l) {
+      const void* f = (t == 0) ? a->fs[l] : a->ft[t - 1][l];
+      MMD_CHECK_ARG(f != nullptr, "mmd_mta_fwd: null feature pointer (tensor %d level %d)", t, l);
+      MtaSeg& s = pp.seg[nseg++];
+      s.f = f;
+      s.a = a->att_ws + (long long)t * Btot + (long long)a->B * lp.cum[l];
+      s.npix = a->B * lp.HW[l];
+      s.HW = lp.HW[l];
+      if (s.npix > maxpix) maxpix = s.npix;
+    }
+  pp.C = a->C;
+  pp.group = group_lanes(a->C);
+  pp.p = a->p;
+
+  if (a->layout == MMD_NHWC) {
+    const int ppb = (32 / pp.group) * 8 * 4;  // pixels per block-iteration (8 warps, 4 chunks in flight)
+    int gx = (maxpix + ppb - 1) / ppb;
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, nseg);
+    if (a->dtype == MMD_F32) mta_pool_nhwc<float><<<grid, 256, 0, stream>>>(pp);
+    else mta_pool_nhwc<__nv_bfloat16><<<grid, 256, 0, stream>>>(pp);
+  } else {
+    int gx = (maxpix + 255) / 256;
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 grid(gx, nseg);
+    if (a->dtype == MMD_F32) mta_pool_nchw<float><<<grid, 256, 0, stream>>>(pp);
+    else mta_pool_nchw<__nv_bfloat16><<<grid, 256, 0, stream>>>(pp);
+  }
+  MMD_LAUNCH_CHECK();
+
+  lp.att = a->att_ws;
+  lp.ga = a->ga_ws;
+  lp.loss_b = a->loss_b;
+  lp.Btot = Btot;
+  lp.B = a->B;
+  lp.nt = a->n_teachers;
+  lp.T = a->T;
+  mta_level_kernel<<<dim3(a->B, a->n_levels), kLvlThreads, 0, stream>>>(lp);
+  MMD_LAUNCH_CHECK();
+  mta_finish_kernel<<<a->n_levels, 32, 0, stream>>>(a->loss_b, a->loss, a->B);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* const* grad_fs, mmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMD_CHECK_ARG(a != nullptr && grad_loss != nullptr && grad_fs != nullptr, "mmd_mta_bwd: null args");
+  MMD_CHECK_ARG(a->n_levels >= 1 && a->n_levels <= MMD_MTA_MAX_LEVELS, "mmd_mta_bwd: n_levels=%d out of range", a->n_levels);
+  MMD_CHECK_ARG(a->ga_ws != nullptr, "mmd_mta_bwd: forward was run without ga_ws");
+  MMD_CHECK_ARG(a->C % 4 == 0, "mmd_mta_bwd: C must be a multiple of 4");
+  MtaBwdP bp;
+  int cum = 0;
+  long long maxvec = 0;
+  for (int l = 0; l < a->n_levels; ++l) {
+    MMD_CHECK_ARG(grad_fs[l] != nullptr && a->fs[l] != nullptr, "mmd_mta_bwd: null pointer at level %d", l);
+    MtaBwdSeg& s = bp.seg[l];
+    s.f = a->fs[l];
+    s.g = grad_fs[l];
+    s.HW = a->H[l] * a->W[l];
+    s.npix = a->B * s.HW;
+    s.ga = a->ga_ws + (long long)a->B * cum;
+    s.level = l;
+    cum += s.HW;
+    long long nv = (long long)s.npix * a->C / 4;
+    if (nv > maxvec) maxvec = nv;
+  }
+  bp.grad_loss = grad_loss;
+  bp.C = a->C;
+  bp.p = a->p;
+  long long gx = (maxvec + 255) / 256;
+  if (gx > 148 * 16) gx = 148 * 16;
+  dim3 grid((unsigned)gx, a->n_levels);
+  if (a->layout == MMD_NHWC) {
+    if (a->dtype == MMD_F32) mta_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(bp);
+    else mta_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(bp);
+  } else {
+    if (a->dtype == MMD_F32) mta_bwd_kernel<float, true><<<grid, 256, 0, stream>>>(bp);
+    else mta_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(bp);
+  }
+  MMD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,52 @@
+"""Drop-in seam for the reference code base: there is no plugin registry, classes are resolved by
+module-global name, so `patch_reference()` rebinds those names before any model / criterion is built.
+
+    import mm_distillnet_b200 as mmd
+    mmd.patch_reference()          # then run the reference's train.py / evaluate.py logic unchanged
+
+Rebinds:
+    src.YetAnotherEfficientDet.BiFPN                     -> mm_distillnet_b200.BiFPN   (looked up at :639-644)
+    src.loss.MTALoss.MTALoss, src.utils.utils.MTALoss    -> mm_distillnet_b200.MTALoss (utils.py:50, :1603-1604)
+and wraps YetAnotherEfficientDet.__init__ so `self.bifpn` (an nn.Sequential of cells) becomes a `BiFPNStack` with
+identical children and state_dict keys, which runs all cells as one fused op list.
+"""
+import sys
+
+import torch.nn as nn
+
+from .bifpn import BiFPN, BiFPNStack
+from .mta import MTALoss
+
+
+def fuse_bifpn_stacks(model):
+    """Replace every nn.Sequential made only of our BiFPN cells by a BiFPNStack (same children, same keys)."""
+    for name, child in list(model.named_children()):
+        if isinstance(child, nn.Sequential) and not isinstance(child, BiFPNStack) and len(child) > 0 and \
+                all(isinstance(c, BiFPN) for c in child):
+            setattr(model, name, BiFPNStack(*list(child)))
+        else:
+            fuse_bifpn_stacks(child)
+    return model
+
+
+def patch_reference(det_module=None, loss_module=None, utils_module=None):
+    """Rebind the reference's globals.  Modules default to the already-imported `src.*` modules."""
+    import importlib
+    det = det_module or importlib.import_module("src.YetAnotherEfficientDet")
+    loss = loss_module or importlib.import_module("src.loss.MTALoss")
+    det.BiFPN = BiFPN
+    loss.MTALoss = MTALoss
+    utils = utils_module or sys.modules.get("src.utils.utils")
+    if utils is not None and hasattr(utils, "MTALoss"):
+        utils.MTALoss = MTALoss
+    cls = det.YetAnotherEfficientDet
+    if not getattr(cls, "_mmd_patched", False):
+        orig_init = cls.__init__
+
+        def __init__(self, *args, **kwargs):
+            orig_init(self, *args, **kwargs)
+            fuse_bifpn_stacks(self)
+
+        cls.__init__ = __init__
+        cls._mmd_patched = True
+    return det, loss
