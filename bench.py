@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — distillation hot-path throughput (BASELINE.json metric "distill samples/s"; workload = configs[1]).
+
+One STEP = one pass of the hot path over one synthetic batch per GPU:
+    student 5-cell BiFPN stack forward (train-mode BatchNorm) from C3/C4/C5  [B,48,96,96] [B,120,48,48] [B,352,24,24]
+  + 3 frozen teacher stacks forward (eval, no_grad)
+  + 3 MTA losses (one call per teacher, as the shipped cfg does)  -> loss = 0.005 * sum
+  + backward through MTA and the student stack (all BiFPN parameter gradients + dL/dC3..C5)
+  + (N > 1) one NCCL all-reduce of the flat student gradient buffer.
+
+    python bench.py [--gpus N --steps K --warmup W] [--dtype f32|bf16] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference algorithm (oracle/) on the
+host cores for the same metric; it is the only place besides cpu_baseline where bench.py executes oracle/.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+CC = [48, 120, 352]
+C = 112
+N_CELLS = 5
+N_TEACHERS = 3
+W_KD = 0.005
+S3 = 96           # P3 resolution of a 768x768 input
+POS_PER_SAMPLE = 96 * 96 + 48 * 48 + 24 * 24 + 12 * 12 + 6 * 6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synth_inputs(B, gen, dtype=torch.float32):
+    return [torch.randn(B, c, S3 >> i, S3 >> i, generator=gen).to(dtype) for i, c in enumerate(CC)]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (torch CPU fp32 restatement of the reference path), all host threads
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_state(seed):
+    from oracle import mmd_oracle as O
+    return O.synth_stack_params(C, CC, N_CELLS, seed)
+
+
+def cpu_step(student_p, teacher_ps, xs_s, xs_ts):
+    from oracle import mmd_oracle as O
+    leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in student_p.items()}
+    xs = [x.detach().clone().requires_grad_(True) for x in xs_s]
+    fs = O.bifpn_stack(tuple(xs), leaf, N_CELLS, training=True, stats_out={})
+    kd = []
+    for tp, xt in zip(teacher_ps, xs_ts):
+        with torch.no_grad():
+            ft = O.bifpn_stack(tuple(xt), tp, N_CELLS, training=False)
+        kd.append(O.mta_loss(fs, [f.detach() for f in ft]))
+    kd = torch.stack(kd)
+    (W_KD * kd.sum()).backward()
+    return kd.detach()
+
+
+def time_cpu(B, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    sp = cpu_state(0)
+    tps = [cpu_state(1 + k) for k in range(N_TEACHERS)]
+    xs_s = synth_inputs(B, gen)
+    xs_ts = [synth_inputs(B, gen) for _ in range(N_TEACHERS)]
+    for _ in range(warmup):
+        cpu_step(sp, tps, xs_s, xs_ts)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_step(sp, tps, xs_s, xs_ts)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    B = 4   # bounded sample per step so the whole run ends within minutes; CPU samples/s is ~flat in B
+    ts = time_cpu(B, args.steps, args.warmup)
+    total = sum(ts)
+    v = B * len(ts) / total
+    cores = torch.get_num_threads()
+    sample = "each step = the full hot-path step at batch %d (student+3 teachers+3 MTA+backward), oracle port, torch CPU fp32" % B
+    line = {
+        "impl": "reference", "metric": "distill samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": B},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD = ("cfg2: MTA loss + 5-cell EfficientDet-D2 BiFPN fwd/bwd microbench on synthetic pyramid inputs "
+            "(C3 48@96^2, C4 120@48^2, C5 352@24^2 -> 112 ch P3-P7): student fwd+bwd (train BN) + 3 teacher fwd (eval) "
+            "+ 3 MTA calls")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import mm_distillnet_b200 as mmd
+    from mm_distillnet_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    esize = 4 if dtype == torch.float32 else 2
+    B = args.batch
+
+    torch.manual_seed(0)   # identical student init on every rank (DDP broadcast-at-start semantics)
+    student = mmd.BiFPNStack(*[mmd.BiFPN(C, CC, first_time=(i == 0)) for i in range(N_CELLS)]).to(dev).train()
+    teachers = []
+    for k in range(N_TEACHERS):
+        torch.manual_seed(1 + k)
+        teachers.append(mmd.BiFPNStack(*[mmd.BiFPN(C, CC, first_time=(i == 0)) for i in range(N_CELLS)]).to(dev).eval())
+    step = mmd.DistillStep(student, teachers, mmd.MTALoss(T=9.0, p=2.0), w_kd=W_KD)
+
+    gen = torch.Generator().manual_seed(1000 + rank)
+    def pinned_nhwc(x):   # pinned host staging buffer already in the kernels' NHWC (channels_last) layout
+        h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).contiguous(memory_format=torch.channels_last)
+        if not h.is_pinned():
+            h = h.pin_memory()
+        h.copy_(x)
+        return h
+
+    host_s = [pinned_nhwc(x) for x in synth_inputs(B, gen, dtype)]
+    host_t = [[pinned_nhwc(x) for x in synth_inputs(B, gen, dtype)] for _ in range(N_TEACHERS)]
+    dev_s = [x.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) for x in host_s]
+    dev_t = [[x.to(dev).contiguous(memory_format=torch.channels_last) for x in xs] for xs in host_t]
+    for x in dev_s:
+        x.requires_grad_(True)   # dL/dC3..C5 are part of the path (they feed the student backbone)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def resident_step():
+        for x in dev_s:
+            x.grad = None
+        return step(dev_s, dev_t)
+
+    host_loss = torch.empty(N_TEACHERS, 5, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xs = [x.to(dev, non_blocking=True).requires_grad_(True) for x in host_s]
+        kd = step(xs, host_t)                       # teacher inputs are copied host->device inside the call
+        host_loss.copy_(kd, non_blocking=False)     # device->host read of the step's result
+        return host_loss
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = mmd.launch_count()
+    ms = timed(resident_step, args.steps)
+    launches = mmd.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # per-kernel CUDA-event timing of the same step (separate instrumented pass: event pairs around every launch)
+    roof = None
+    if rank == 0:
+        _lib.prof_enable(True)
+        _lib.prof_collect()
+        nprof = min(args.steps, 5)
+        for _ in range(nprof):
+            resident_step()
+        prof = _lib.prof_collect()
+        _lib.prof_enable(False)
+        peak, peak_src = peaks()
+        total_ms = sum(v["ms"] for v in prof.values())
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        ach = d["algo_bytes"] / (d["ms"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.dtype, {}).get(dom)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_us": 1e3 * d["ms"] / d["launches"], "algo_bytes_per_launch": d["algo_bytes"] / d["launches"],
+                "share_of_kernel_time": d["ms"] / total_ms,
+                "all_kernels": {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] / nprof,
+                                    "GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+                                for k, v in prof.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        Bc = 4
+        ts = time_cpu(Bc, 2, 1)
+        cpu = {"value": Bc * len(ts) / sum(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "2 timed steps (1 warm-up) of the same step at batch %d on the oracle port (torch CPU fp32)" % Bc}
+
+    if rank == 0:
+        h2d = (1 + N_TEACHERS) * B * sum(c * (S3 >> i) ** 2 for i, c in enumerate(CC)) * esize
+        line = {
+            "metric": "distill samples/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": "dp%d (flat-gradient NCCL all-reduce)" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: the step streams ~%.1f GB of activations (L2 = 126 MB); no flush needed"
+                             % (3 * B * 30016512 * esize * 2 / 1e9),
+                       "optimizer": "none (the microbench ends at the averaged gradients)"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": N_TEACHERS * 5 * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (cfg2: 16)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

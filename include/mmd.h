@@ -151,6 +151,14 @@ typedef struct {
 int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases,
                   int32_t B, int32_t C, int32_t dtype, mmd_stream_t stream);
 
+/* Optional profiler: while enabled, every kernel launch of this library is bracketed by a CUDA-event pair on its
+ * stream.  mmd_prof_collect synchronises the device and ADDS, per kernel kind, the elapsed milliseconds, the number
+ * of launches and the algorithmic bytes into the caller's arrays of length mmd_prof_num_kinds(). */
+void mmd_prof_enable(int on);
+int mmd_prof_num_kinds(void);
+const char* mmd_prof_kind_name(int kind);
+int mmd_prof_collect(double* ms, long long* launches, double* algo_bytes);
+
 /* sizeof(MmdOp) / sizeof(MmdMtaArgs) as compiled, so a binding can verify its struct mirror */
 size_t mmd_sizeof_op(void);
 size_t mmd_sizeof_mta_args(void);

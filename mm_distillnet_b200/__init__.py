@@ -10,7 +10,8 @@ Public API mirrors the reference (robot-learning-freiburg/MM-DistillNet):
 from .bifpn import BiFPN, BiFPNStack, SeparableConvBlock  # noqa: F401
 from .mta import MTALoss  # noqa: F401
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
+from .distill import DistillStep  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
-__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "build",
+__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
            "launch_count"]

@@ -111,6 +111,13 @@ def lib():
     L.mmd_bifpn_run.restype = C.c_int
     L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.mmd_prof_enable.argtypes = [C.c_int]
+    L.mmd_prof_enable.restype = None
+    L.mmd_prof_num_kinds.restype = C.c_int
+    L.mmd_prof_kind_name.restype = C.c_char_p
+    L.mmd_prof_kind_name.argtypes = [C.c_int]
+    L.mmd_prof_collect.restype = C.c_int
+    L.mmd_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     if L.mmd_sizeof_op() != C.sizeof(Op) or L.mmd_sizeof_mta_args() != C.sizeof(MtaArgs):
         raise RuntimeError("libmmd_b200.so struct layout mismatch: Op %d vs %d, MtaArgs %d vs %d" % (
             L.mmd_sizeof_op(), C.sizeof(Op), L.mmd_sizeof_mta_args(), C.sizeof(MtaArgs)))
@@ -128,5 +135,20 @@ def launch_count():
     return int(lib().mmd_launch_count())
 
 
+def prof_enable(on):
+    lib().mmd_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """{kernel kind: {"ms": total ms, "launches": n, "algo_bytes": total algorithmic bytes}} since the last collect."""
+    L = lib()
+    n = L.mmd_prof_num_kinds()
+    ms, cnt, by = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)()
+    check(L.mmd_prof_collect(ms, cnt, by), "mmd_prof_collect")
+    return {L.mmd_prof_kind_name(i).decode(): {"ms": ms[i], "launches": int(cnt[i]), "algo_bytes": by[i]}
+            for i in range(n) if cnt[i] > 0}
+
+
 EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run",
-           "mmd_sizeof_op", "mmd_sizeof_mta_args")
+           "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
+           "mmd_prof_collect")

@@ -69,11 +69,9 @@ class SeparableConvBlock(nn.Module):
         self.norm = norm
         self.bn = nn.BatchNorm2d(num_features=out_channels, momentum=BN_MOMENTUM, eps=BN_EPS)
         self.activation = activation
-        self._runner = None
+        self._runner = _Runner()
 
     def forward(self, x):
-        if self._runner is None:
-            self._runner = _Runner()
         return self._runner.run([self], (x,), self.training, kind="sep")[0]
 
 
@@ -121,12 +119,10 @@ class BiFPN(nn.Module):
             setattr(self, name, nn.Parameter(torch.ones(n, dtype=torch.float32), requires_grad=True))
             setattr(self, name + "_relu", _Stateless())
         self.attention = attention
-        self._runner = None
+        self._runner = _Runner()
 
     def forward(self, inputs):
         """(p3, p4, p5) for a first cell, (p3..p7) otherwise -> (p3_out, ..., p7_out), as :289-318."""
-        if self._runner is None:
-            self._runner = _Runner()
         return self._runner.run([self], tuple(inputs), self.training, kind="cells")
 
 
@@ -135,7 +131,7 @@ class BiFPNStack(nn.Sequential):
 
     def __init__(self, *cells):
         super().__init__(*cells)
-        self._runner = None
+        self._runner = _Runner()
 
     def forward(self, inputs):
         cells = list(self)
@@ -145,8 +141,6 @@ class BiFPNStack(nn.Sequential):
             for c in cells:
                 inputs = c(inputs)
             return inputs
-        if self._runner is None:
-            self._runner = _Runner()
         return self._runner.run(cells, tuple(inputs), cells[0].training, kind="cells")
 
 
@@ -225,6 +219,15 @@ class _Plan:
         self.fwd_arena, self.persist, self.bwd_arena, self.zero_arena = _Arena(), _Arena(), _Arena(), _Arena()
         self.ops = []
         self.Cc = None
+        self.params = self._collect_params(mods)
+        self.grad_off = {}
+        if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
+            off = 0
+            for p in self.params:
+                self.grad_off[id(p)] = (off, p.numel(), tuple(p.shape))
+                off += p.numel() * 4
+            self.grad_floats = off // 4
+            self.zero_arena.alloc(off)
         ext = [_Tn(s[2], s[3], s[1], B_EXT + i, 0) for i, s in enumerate(in_shapes)]
         self.ext = ext
         self.n_out = 5 if kind == "cells" else 1
@@ -239,7 +242,6 @@ class _Plan:
             outs = self._cells(mods, ext)
         self.out_shapes = [(self.B, self.Cc, t.H, t.W) for t in outs]
         self._finish_outputs(outs)
-        self.params = self._collect_params(mods)
         self.fwd_ops = self._emit_fwd()
         self.bwd_ops = self._emit_bwd() if self.need_grad else None
 
@@ -447,12 +449,9 @@ class _Plan:
         return res
 
     def _galloc(self, param):
-        off = self.zero_arena.alloc(param.numel() * 4)
-        self.grad_off[id(param)] = (off, param.numel(), tuple(param.shape))
-        return (B_ZERO, off)
+        return (B_ZERO, self.grad_off[id(param)][0])
 
     def _emit_bwd(self):
-        self.grad_off = {}
         max_n = max(self.B * op.out.H * op.out.W * self.Cc for op in self.ops if op.kind == _lib.OP_NODE_FWD)
         dd = (B_BWD, self.bwd_arena.alloc(max_n * self.esize))
         out = []
@@ -555,6 +554,17 @@ class _StackFunction(torch.autograd.Function):
         grads = [None, None, None]
         for i in range(ctx.n_in):
             grads.append(gin[i] if ctx.needs_input_grad[3 + i] else None)
+        if ctx.runner.grad_sink is not None:
+            # flat-gradient mode (DistillStep): hand over the one contiguous fp32 buffer holding every parameter
+            # gradient and make each .grad a view of it, instead of ~360 per-parameter AccumulateGrad kernels
+            flat = gflat[:plan.grad_floats]
+            for j, p in enumerate(ctx.param_list):
+                if ctx.needs_input_grad[3 + ctx.n_in + j]:
+                    off, n, shape = plan.grad_off[id(plan.params[j])]
+                    p.grad = flat[off // 4: off // 4 + n].view(shape)
+            ctx.runner.grad_sink(flat)
+            grads.extend([None] * len(ctx.param_list))
+            return tuple(grads)
         for j, p in enumerate(ctx.param_list):
             ent = plan.grad_off.get(id(plan.params[j]))
             if ent is None or not ctx.needs_input_grad[3 + ctx.n_in + j]:
@@ -570,7 +580,7 @@ class _Runner:
 
     def __init__(self):
         self.plans = {}
-        self.persist = {}
+        self.grad_sink = None   # callable(flat_fp32_grad) -> None; see DistillStep
 
     def run(self, mods, inputs, training, kind):
         if len(inputs) == 0:

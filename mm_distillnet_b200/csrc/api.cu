@@ -2,6 +2,9 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -16,7 +19,64 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
+static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",
+                                           "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot"};
+struct ProfRec { cudaEvent_t a, b; int kind; double bytes; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(int kind, double algo_bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (!g_prof_pool.empty()) {
+    r.a = g_prof_pool.back().first;
+    r.b = g_prof_pool.back().second;
+    g_prof_pool.pop_back();
+  } else {
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+  }
+  r.kind = kind;
+  r.bytes = algo_bytes;
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().b, s);
+}
 }  // namespace mmd
+
+extern "C" void mmd_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(mmd::g_prof_mu);
+  mmd::g_prof_on = on != 0;
+}
+extern "C" int mmd_prof_num_kinds(void) { return mmd::PK_COUNT; }
+extern "C" const char* mmd_prof_kind_name(int k) { return (k >= 0 && k < mmd::PK_COUNT) ? mmd::kProfNames[k] : ""; }
+// Synchronises the device, adds every recorded launch to ms[kind] / launches[kind] / bytes[kind] and clears the log.
+extern "C" int mmd_prof_collect(double* ms, long long* launches, double* bytes) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    mmd::set_error("mmd_prof_collect: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  std::lock_guard<std::mutex> lk(mmd::g_prof_mu);
+  for (auto& r : mmd::g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+      ms[r.kind] += t;
+      launches[r.kind] += 1;
+      bytes[r.kind] += r.bytes;
+    }
+    mmd::g_prof_pool.emplace_back(r.a, r.b);
+  }
+  mmd::g_prof_recs.clear();
+  return 0;
+}
 
 extern "C" int mmd_version(void) { return MMD_VERSION; }
 extern "C" const char* mmd_last_error(void) { return mmd::g_err; }

@@ -43,6 +43,14 @@ inline TileGeom make_geom(int B, int H, int W) {
   return g;
 }
 
+// Algorithmic HBM bytes of one fusion node: every input read once at its own resolution, the output
+// written once.  The backward pair (node_bwd_a + node_bwd_b) is charged twice this (the "fwd+bwd = 3x fwd" convention).
+inline double node_algo_bytes(const TensorP* in, int n_in, const TileGeom& g, int C, size_t esize) {
+  double pos = (double)g.H * g.W;
+  for (int i = 0; i < n_in; ++i) pos += (double)in[i].H * in[i].W;
+  return pos * g.B * C * (double)esize;
+}
+
 struct NodeFwdP {
   TensorP in[3];
   int mode[3];

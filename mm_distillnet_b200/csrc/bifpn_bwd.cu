@@ -696,9 +696,16 @@ static int launch_node_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   MMD_CUDA(cudaFuncSetAttribute(node_bwd_a_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   MMD_CUDA(cudaFuncSetAttribute(node_bwd_b_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   const int grid = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();
-  node_bwd_a_kernel<T, C><<<grid, kThreads, smem_a, s>>>(p);
+  const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, sizeof(T));
+  {
+    ProfScope prof(PK_NODE_BWD_A, bytes, s);
+    node_bwd_a_kernel<T, C><<<grid, kThreads, smem_a, s>>>(p);
+  }
   MMD_LAUNCH_CHECK();
-  node_bwd_b_kernel<T, C><<<grid, kThreads, smem_b, s>>>(p);
+  {
+    ProfScope prof(PK_NODE_BWD_B, bytes, s);
+    node_bwd_b_kernel<T, C><<<grid, kThreads, smem_b, s>>>(p);
+  }
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -710,6 +717,7 @@ static int launch_proj_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   MMD_CUDA(cudaFuncSetAttribute(proj_bwd_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();
   const int gy = (p.Cin + kProjBC - 1) / kProjBC;
+  ProfScope prof(PK_PROJ_BWD, 2.0 * p.g.B * p.g.H * p.g.W * (p.Cin + C) * sizeof(T), s);
   proj_bwd_kernel<T, C><<<dim3(gx, gy), kThreads, smem, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;
@@ -721,6 +729,7 @@ static int launch_pull_t(const NodeBwdP& p, cudaStream_t s) {
   long long total = (long long)p.g.B * p.g.H * p.g.W * (C / 4);
   long long grid = (total + kThreads - 1) / kThreads;
   if (grid > 8LL * sm_count()) grid = 8LL * sm_count();
+  ProfScope prof(PK_PULL, 2.0 * p.g.B * p.g.H * p.g.W * C * sizeof(T), s);
   pull_kernel<T, C><<<(unsigned)grid, kThreads, 0, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;
@@ -733,6 +742,7 @@ static int launch_slot_t(const NodeBwdP& p, cudaStream_t s) {
   long long grid = (npos + 9 * 8 - 1) / (9 * 8);  // ~8 positions per thread-row
   if (grid > 4LL * sm_count()) grid = 4LL * sm_count();
   if (grid < 1) grid = 1;
+  ProfScope prof(PK_SLOT, 2.0 * p.g.B * p.g.H * p.g.W * C * sizeof(T), s);
   slot_kernel<T, C><<<(unsigned)grid, kThreads, 0, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;

@@ -380,6 +380,7 @@ static int launch_node_fwd_t(const NodeFwdP& p, cudaStream_t s) {
     configured = true;
   }
   int grid = p.g.ntiles < num_sms() ? p.g.ntiles : num_sms();
+  ProfScope prof(PK_NODE_FWD, node_algo_bytes(p.in, p.n_in, p.g, C, sizeof(T)), s);
   node_fwd_kernel<T, C><<<grid, kThreads, smem, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;
@@ -396,6 +397,7 @@ static int launch_proj_fwd_t(const NodeFwdP& p, cudaStream_t s) {
     configured = true;
   }
   int grid = p.g.ntiles < 2 * num_sms() ? p.g.ntiles : 2 * num_sms();
+  ProfScope prof(PK_PROJ_FWD, (double)p.g.B * p.g.H * p.g.W * (p.Cin + C) * sizeof(T), s);
   proj_fwd_kernel<T, C><<<grid, kThreads, smem, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;
@@ -407,6 +409,7 @@ static int launch_bnapply_t(const NodeFwdP& p, cudaStream_t s) {
   long long total = (long long)p.g.B * p.g.H * p.g.W * (C / 4);
   long long grid = (total + kThreads - 1) / kThreads;
   if (grid > 8LL * num_sms()) grid = 8LL * num_sms();
+  ProfScope prof(PK_BNAPPLY, node_algo_bytes(p.in, 1, p.g, C, sizeof(T)), s);
   bnapply_kernel<T, C><<<(unsigned)grid, kThreads, 0, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;

@@ -36,6 +36,25 @@ void count_launch();
     MMD_CUDA(cudaGetLastError());                \
   } while (0)
 
+// ---- optional per-kernel CUDA-event timing (mmd_prof_*), used by bench.py for the live roofline number ---------
+enum ProfKind {
+  PK_MTA_POOL = 0, PK_MTA_LEVEL, PK_MTA_FINISH, PK_MTA_BWD, PK_NODE_FWD, PK_PROJ_FWD, PK_BNAPPLY, PK_NODE_BWD_A,
+  PK_NODE_BWD_B, PK_PROJ_BWD, PK_PULL, PK_SLOT, PK_COUNT
+};
+bool prof_enabled();
+void prof_begin(int kind, double algo_bytes, cudaStream_t s);
+void prof_end(cudaStream_t s);
+struct ProfScope {  // brackets exactly one kernel launch on stream `s`
+  cudaStream_t s;
+  bool on;
+  ProfScope(int kind, double algo_bytes, cudaStream_t s_) : s(s_), on(prof_enabled()) {
+    if (on) prof_begin(kind, algo_bytes, s);
+  }
+  ~ProfScope() {
+    if (on) prof_end(s);
+  }
+};
+
 // ---- 4-channel vector access: fp32 = 16 B, bf16 = 8 B ------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float4 ld4(const T* p);

@@ -91,13 +91,20 @@ struct MtaLevelP {
   float T;
 };
 
-constexpr int kLvlThreads = 1024;
+constexpr int kLvlThreads = 512;
 
 template <int K>
-__device__ __forceinline__ void block_reduce(float (&v)[K], unsigned max_mask, float* s_red) {
+__device__ __forceinline__ void block_reduce(double (&v)[K], unsigned max_mask, double* s_red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-  for (int k = 0; k < K; ++k) v[k] = ((max_mask >> k) & 1u) ? warp_max(v[k]) : warp_sum(v[k]);
+  for (int k = 0; k < K; ++k) {
+    const bool mx = (max_mask >> k) & 1u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, v[k], o);
+      v[k] = mx ? fmax(v[k], x) : v[k] + x;
+    }
+  }
   __syncthreads();  // s_red may still be read from a previous call
   if (lane == 0) {
 #pragma unroll
@@ -106,47 +113,48 @@ __device__ __forceinline__ void block_reduce(float (&v)[K], unsigned max_mask, f
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    float r = s_red[k];
+    double r = s_red[k];
     for (int w = 1; w < nw; ++w) {
-      float x = s_red[w * K + k];
-      r = ((max_mask >> k) & 1u) ? fmaxf(r, x) : r + x;
+      const double x = s_red[w * K + k];
+      r = ((max_mask >> k) & 1u) ? fmax(r, x) : r + x;
     }
-    v[k] = r;
+    v[k] = r;   // identical on every thread (fixed summation order -> deterministic)
   }
 }
 
+// All arithmetic after the channel pooling is done in double: the maps are tiny (B * 12 276 floats for D2) and both
+// the loss (= -ln N - 1/N + O(1e-4)) and its gradient (s * (g - <g,s>)) are differences of nearly equal numbers.
 __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_constant__ MtaLevelP P) {
-  __shared__ float s_red[32 * 5];
+  __shared__ double s_red[32 * 5];
   const int b = blockIdx.x, l = blockIdx.y, n = P.HW[l], nt = P.nt;
   const long long off = (long long)P.B * P.cum[l] + (long long)b * n;
   const float* __restrict__ as = P.att + off;
   const float* __restrict__ at[MMD_MTA_MAX_TEACHERS];
 #pragma unroll
   for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) at[k] = P.att + (long long)(1 + (k < nt ? k : 0)) * P.Btot + off;
-  const float invT = 1.0f / P.T;
+  const double invT = 1.0 / (double)P.T;
 
   // pass 1: squared L2 norms of the student map and of every teacher map (F.normalize, eps 1e-12)
-  float ss[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  double ss[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float x = as[i];
+    const double x = as[i];
     ss[0] += x * x;
 #pragma unroll
     for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k)
       if (k < nt) {
-        float y = at[k][i];
+        const double y = at[k][i];
         ss[1 + k] += y * y;
       }
   }
   block_reduce<5>(ss, 0u, s_red);
-  const float nrm_s_raw = sqrtf(ss[0]);
-  const float nrm_s = fmaxf(nrm_s_raw, 1e-12f);
-  float inv_t[MMD_MTA_MAX_TEACHERS];
+  const double nrm_s_raw = sqrt(ss[0]);
+  const double inv_s = 1.0 / fmax(nrm_s_raw, 1e-12);
+  double inv_t[MMD_MTA_MAX_TEACHERS];
 #pragma unroll
-  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) inv_t[k] = 1.0f / fmaxf(sqrtf(ss[1 + k]), 1e-12f);
-  const float inv_s = 1.0f / nrm_s;
+  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) inv_t[k] = 1.0 / fmax(sqrt(ss[1 + k]), 1e-12);
 
-  auto teacher_m = [&](int i) -> float {  // product of the normalised teacher attentions (MTALoss.py:51-55)
-    float m = at[0][i] * inv_t[0];
+  auto teacher_m = [&](int i) -> double {  // product of the normalised teacher attentions (MTALoss.py:51-55)
+    double m = at[0][i] * inv_t[0];
 #pragma unroll
     for (int k = 1; k < MMD_MTA_MAX_TEACHERS; ++k)
       if (k < nt) m *= at[k][i] * inv_t[k];
@@ -154,69 +162,70 @@ __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_con
   };
 
   // pass 2: L1 norm of the teacher product (only used when nt > 1), maxima for the two softmaxes
-  float r2[3] = {0.f, -INFINITY, -INFINITY};
+  double r2[3] = {0.0, -INFINITY, -INFINITY};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float m = teacher_m(i);
-    r2[0] += fabsf(m);
-    r2[1] = fmaxf(r2[1], as[i] * inv_s);
-    r2[2] = fmaxf(r2[2], m);
+    const double m = teacher_m(i);
+    r2[0] += fabs(m);
+    r2[1] = fmax(r2[1], as[i] * inv_s);
+    r2[2] = fmax(r2[2], m);
   }
   block_reduce<3>(r2, 0x6u, s_red);
-  const float inv_l1 = (nt > 1) ? 1.0f / fmaxf(r2[0], 1e-12f) : 1.0f;  // F.normalize(p=1) (MTALoss.py:57)
-  const float max_zs = r2[1] * invT, max_zt = r2[2] * inv_l1 * invT;
+  const double inv_l1 = (nt > 1) ? 1.0 / fmax(r2[0], 1e-12) : 1.0;  // F.normalize(p=1) (MTALoss.py:57)
+  const double max_zs = r2[1] * invT, max_zt = r2[2] * inv_l1 * invT;
 
   // pass 3: softmax denominators
-  float z[2] = {0.f, 0.f};
+  double z[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    z[0] += __expf(as[i] * inv_s * invT - max_zs);
-    z[1] += __expf(teacher_m(i) * inv_l1 * invT - max_zt);
+    z[0] += exp(as[i] * inv_s * invT - max_zs);
+    z[1] += exp(teacher_m(i) * inv_l1 * invT - max_zt);
   }
   block_reduce<2>(z, 0u, s_red);
-  const float inv_zs = 1.0f / z[0], inv_zt = 1.0f / z[1], log_zt = logf(z[1]);
+  const double inv_zs = 1.0 / z[0], inv_zt = 1.0 / z[1], log_zt = log(z[1]);
 
   // pass 4: loss_b = sum t (log t - s)   (kl_div with a PROBABILITY input: MTALoss.py:62-72), and <g, s>
-  const float invB = 1.0f / (float)P.B;
-  float r4[2] = {0.f, 0.f};
+  const double invB = 1.0 / (double)P.B;
+  double r4[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float s = __expf(as[i] * inv_s * invT - max_zs) * inv_zs;
-    float zt = teacher_m(i) * inv_l1 * invT - max_zt;
-    float t = __expf(zt) * inv_zt;
+    const double s = exp(as[i] * inv_s * invT - max_zs) * inv_zs;
+    const double zt = teacher_m(i) * inv_l1 * invT - max_zt;
+    const double t = exp(zt) * inv_zt;
     r4[0] += t * ((zt - log_zt) - s);
     r4[1] += -t * invB * s;
   }
   block_reduce<2>(r4, 0u, s_red);
-  if (threadIdx.x == 0) P.loss_b[l * P.B + b] = r4[0];
+  if (threadIdx.x == 0) P.loss_b[l * P.B + b] = (float)r4[0];
   if (P.ga == nullptr) return;
 
   // pass 5: <a^, d a^> with d z = s (g - <g,s>), d a^ = d z / T
-  const float gs = r4[1];
-  float r5[1] = {0.f};
+  const double gs = r4[1];
+  double r5[1] = {0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float ah = as[i] * inv_s;
-    float s = __expf(ah * invT - max_zs) * inv_zs;
-    float t = __expf(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
-    float dah = s * (-t * invB - gs) * invT;
+    const double ah = as[i] * inv_s;
+    const double s = exp(ah * invT - max_zs) * inv_zs;
+    const double t = exp(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
+    const double dah = s * (-t * invB - gs) * invT;
     r5[0] += ah * dah;
   }
   block_reduce<1>(r5, 0u, s_red);
-  const bool clamped = !(nrm_s_raw > 1e-12f);
+  const bool clamped = !(nrm_s_raw > 1e-12);
   // pass 6: d a = (d a^ - a^ <a^, d a^>) / ||a||  (or d a^ / eps when the norm was clamped)
   float* __restrict__ ga = P.ga + off;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float ah = as[i] * inv_s;
-    float s = __expf(ah * invT - max_zs) * inv_zs;
-    float t = __expf(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
-    float dah = s * (-t * invB - gs) * invT;
-    ga[i] = clamped ? dah * inv_s : (dah - ah * r5[0]) * inv_s;
+    const double ah = as[i] * inv_s;
+    const double s = exp(ah * invT - max_zs) * inv_zs;
+    const double t = exp(teacher_m(i) * inv_l1 * invT - max_zt) * inv_zt;
+    const double dah = s * (-t * invB - gs) * invT;
+    ga[i] = (float)(clamped ? dah * inv_s : (dah - ah * r5[0]) * inv_s);
   }
 }
 
 __global__ void mta_finish_kernel(const float* __restrict__ loss_b, float* __restrict__ loss, int B) {
   const int l = blockIdx.x;
-  float acc = 0.f;  // fixed order -> deterministic
-  for (int b = threadIdx.x; b < B; b += 32) acc += loss_b[l * B + b];
-  acc = warp_sum(acc);
-  if (threadIdx.x == 0) loss[l] = acc / (float)B;
+  double acc = 0.0;  // fixed order -> deterministic
+  for (int b = threadIdx.x; b < B; b += 32) acc += (double)loss_b[l * B + b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) loss[l] = (float)(acc / (double)B);
 }
 
 // ---- backward ----------------------------------------------------------------------------------------------
@@ -313,6 +322,10 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   pp.group = group_lanes(a->C);
   pp.p = a->p;
 
+  double pool_bytes = 0.0;
+  for (int i = 0; i < nseg; ++i) pool_bytes += (double)pp.seg[i].npix * a->C * (a->dtype == MMD_F32 ? 4 : 2);
+  {
+  ProfScope prof(PK_MTA_POOL, pool_bytes, stream);
   if (a->layout == MMD_NHWC) {
     const int ppb = (32 / pp.group) * 8 * 4;  // pixels per block-iteration (8 warps, 4 chunks in flight)
     int gx = (maxpix + ppb - 1) / ppb;
@@ -327,6 +340,7 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
     if (a->dtype == MMD_F32) mta_pool_nchw<float><<<grid, 256, 0, stream>>>(pp);
     else mta_pool_nchw<__nv_bfloat16><<<grid, 256, 0, stream>>>(pp);
   }
+  }
   MMD_LAUNCH_CHECK();
 
   lp.att = a->att_ws;
@@ -336,9 +350,15 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   lp.B = a->B;
   lp.nt = a->n_teachers;
   lp.T = a->T;
-  mta_level_kernel<<<dim3(a->B, a->n_levels), kLvlThreads, 0, stream>>>(lp);
+  {
+    ProfScope prof(PK_MTA_LEVEL, 0.0, stream);
+    mta_level_kernel<<<dim3(a->B, a->n_levels), kLvlThreads, 0, stream>>>(lp);
+  }
   MMD_LAUNCH_CHECK();
-  mta_finish_kernel<<<a->n_levels, 32, 0, stream>>>(a->loss_b, a->loss, a->B);
+  {
+    ProfScope prof(PK_MTA_FINISH, 0.0, stream);
+    mta_finish_kernel<<<a->n_levels, 32, 0, stream>>>(a->loss_b, a->loss, a->B);
+  }
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -371,6 +391,9 @@ extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* co
   long long gx = (maxvec + 255) / 256;
   if (gx > 148 * 16) gx = 148 * 16;
   dim3 grid((unsigned)gx, a->n_levels);
+  double bwd_bytes = 0.0;
+  for (int l = 0; l < a->n_levels; ++l) bwd_bytes += 2.0 * bp.seg[l].npix * a->C * (a->dtype == MMD_F32 ? 4 : 2);
+  ProfScope prof(PK_MTA_BWD, bwd_bytes, stream);
   if (a->layout == MMD_NHWC) {
     if (a->dtype == MMD_F32) mta_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(bp);
     else mta_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(bp);

@@ -1,0 +1,63 @@
+"""Data-parallel distillation step over the hot path (one process per GPU).
+
+Mirrors what the reference's step wrapper + driver do around the BiFPN/MTA path
+(ModelWithNMSLossAugmented.forward, src/optimization/train_methods.py:310-358: student forward with grad, every
+teacher forward under no_grad in eval mode, `criterion_kd(features_s, features_t)` per teacher;
+train_traditional, src/optimization/traditional.py:171-182: loss = w_kd * sum(stack(kd_losses)), backward) and
+replaces the cfg's DataParallel / DDP gradient exchange (train_methods.py:944-961) by ONE NCCL all-reduce of the
+student's flat fp32 gradient buffer (mean over ranks = DDP semantics; BatchNorm statistics stay per rank, MTA's
+'batchmean' is over the local batch, teachers are replicated: no other cross-GPU traffic).
+"""
+import torch
+import torch.distributed as dist
+
+from .bifpn import BiFPN, BiFPNStack
+from .mta import MTALoss
+
+
+class DistillStep:
+    """step(student_inputs, teacher_inputs) -> detached fp32 tensor [n_teachers, n_levels] of MTA losses.
+
+    `student` is a BiFPNStack / BiFPN in train mode, `teachers` a list of BiFPNStack / BiFPN in eval mode.
+    Inputs may live on the host (ideally pinned): they are copied to the device inside the call.  After the call
+    every student parameter's `.grad` is a view into `self.flat_grad` (already averaged over the process group).
+    """
+
+    def __init__(self, student, teachers, criterion=None, w_kd=0.005, process_group=None, device=None):
+        if not isinstance(student, (BiFPN, BiFPNStack)):
+            raise TypeError("DistillStep drives mm_distillnet_b200 BiFPN / BiFPNStack modules")
+        self.student, self.teachers = student, list(teachers)
+        self.criterion = criterion if criterion is not None else MTALoss()
+        self.w_kd = float(w_kd)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.device = device if device is not None else next(student.parameters()).device
+        self.flat_grad = None
+        student._runner.grad_sink = self._on_flat_grad
+        for t in self.teachers:
+            t.eval()
+            for p in t.parameters():
+                p.requires_grad_(False)     # train_methods.py:891-893
+
+    def _on_flat_grad(self, flat):
+        """Called from the student's backward with the single contiguous fp32 gradient buffer."""
+        if self.world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+            flat.mul_(1.0 / self.world)
+        self.flat_grad = flat
+
+    def _to_device(self, xs):
+        return tuple(x if x.device == self.device else x.to(self.device, non_blocking=True) for x in xs)
+
+    def __call__(self, student_inputs, teacher_inputs):
+        xs = self._to_device(student_inputs)
+        feats_s = self.student(xs)                                   # train_methods.py:318
+        kd = []
+        for teacher, tin in zip(self.teachers, teacher_inputs):      # :320-358
+            with torch.no_grad():
+                feats_t = teacher(self._to_device(tin))
+            kd.append(self.criterion(feats_s, [f.detach() for f in feats_t]))
+        kd = torch.stack(kd)
+        loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
+        loss.backward()                                              # :182
+        return kd.detach()

@@ -22,7 +22,7 @@ def build_stack(name, params, dtype=torch.float32):
 def to_dev(xs, dtype=torch.float32, channels_last=False):
     out = []
     for x in xs:
-        x = x.to(DEV).to(dtype)
+        x = x.detach().to(DEV).to(dtype)
         if channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
         out.append(x)
@@ -111,7 +111,7 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         p = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in params.items()}
         leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
                 for k, v in p.items()}
-        xin = [x.to(dt).requires_grad_(training) for x in xs]
+        xin = [x.detach().clone().to(dt).requires_grad_(training) for x in xs]
         if training:
             out = O.bifpn_stack(tuple(xin), leaf, n_cells, first_cell_first_time=first, training=True)
         else:
@@ -128,6 +128,13 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
     if ref64:
         tr32, xin32, leaf32 = oracle_run(torch.float32, True)
         sum((t * go).sum() for t, go in zip(tr32, gouts)).backward()
+    if dtype == torch.bfloat16:   # calibration: the same algorithm executed by PyTorch entirely in bf16
+        trb, xinb, leafb = oracle_run(torch.bfloat16, True)
+        sum((t.float() * go).sum() for t, go in zip(trb, gouts)).backward()
+        for i, n in enumerate(H.LEVELS):
+            m["torchbf16_train_" + n] = H.max_rel(trb[i].detach().float(), tr_ref[i].detach())
+        for i in range(len(xs)):
+            m["torchbf16_grad_in%d" % i] = H.rel_l2(xinb[i].grad.float(), xin_ref[i].grad)
 
     stack.eval()
     with torch.no_grad():

@@ -1,0 +1,155 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/mmd.h declares, the ctypes
+mirrors match the compiled structs, the drop-in modules keep the reference's state_dict contract, the op-list
+builder produces a consistent plan, error behaviour, and the N>1 gradient exchange on gloo (world size 2)."""
+import ctypes
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mm_distillnet_b200 as mmd
+from mm_distillnet_b200 import _lib, bifpn
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mmd.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mmd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared >= {"mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run", "mmd_last_error", "mmd_version"}
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libmmd_b200.so does not export %s" % name
+    assert set(_lib.EXPORTS) == declared
+    assert L.mmd_version() == 100
+
+
+def test_struct_mirrors_match():
+    L = _lib.lib()
+    assert L.mmd_sizeof_op() == ctypes.sizeof(_lib.Op)
+    assert L.mmd_sizeof_mta_args() == ctypes.sizeof(_lib.MtaArgs)
+
+
+@pytest.mark.parametrize("fixture,first", [("cell_c112", False), ("stack2_c112", True)])
+def test_state_dict_contract_matches_reference(fixture, first):
+    """Keys recorded from the real reference (golden fixture) == keys / shapes of our modules; init values too."""
+    g = H.golden(fixture)
+    C, cc, n_cells = H.STACK_CASES[fixture][:3]
+    ref_keys = {k[len("buf_"):] for k in g if k.startswith("buf_")} | {k[len("pgsum_"):] for k in g if k.startswith("pgsum_")}
+    stack = mmd.BiFPNStack(*[mmd.BiFPN(C, cc, first_time=(i == 0 and first)) for i in range(n_cells)])
+    sd = stack.state_dict()
+    assert set(sd.keys()) == ref_keys
+    params, _ = H.stack_case_inputs(fixture)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in params.items()}
+    stack.load_state_dict(params, strict=True)
+    # fusion weights start at one (fast-attention init), BN momentum / eps as the reference
+    cell = mmd.BiFPN(C, cc)
+    assert torch.equal(cell.p4_w2.data, torch.ones(3)) and cell.conv3_up.bn.momentum == 0.01 and cell.conv3_up.bn.eps == 1e-3
+
+
+def test_plan_structure():
+    cells = [mmd.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(5)]
+    shapes = [(16, 48, 96, 96), (16, 120, 48, 48), (16, 352, 24, 24)]
+    plan = bifpn._Plan(cells, "cells", shapes, torch.float32, True, True, [True] * 3)
+    kinds = [o.kind for o in plan.fwd_ops]
+    assert kinds.count(_lib.OP_NODE_FWD) == 40 and kinds.count(_lib.OP_PROJ_FWD) == 6
+    assert kinds.count(_lib.OP_BNAPPLY) == 2 + 5
+    assert plan.out_shapes == [(16, 112, 96 >> i, 96 >> i) for i in range(5)]
+    assert plan.grad_floats == sum(p.numel() for c in cells for p in c.parameters()) == 708159
+    bk = [o.kind for o in plan.bwd_ops]
+    assert bk.count(_lib.OP_NODE_BWD) == 40 and bk.count(_lib.OP_PROJ_BWD) == 6
+    assert all(0 <= o.n_cons <= 3 for o in plan.bwd_ops)
+    # every NODE_BWD gathers from at least one consumer and owns storage
+    for o in plan.bwd_ops:
+        if o.kind == _lib.OP_NODE_BWD:
+            assert o.n_cons >= 1 and o.du.base == bifpn.B_BWD and o.g_pw.base == bifpn.B_ZERO
+    # forward arena allocations do not overlap
+    spans = []
+    for op in plan.ops:
+        if op.out.base == bifpn.B_FWD:
+            spans.append((op.out.off, op.out.off + plan.B * op.out.H * op.out.W * 112 * 4))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    # eval plan: no deferred BatchNorm, outputs written in place by the last cell
+    ev = bifpn._Plan(cells, "cells", shapes, torch.float32, False, False, [False] * 3)
+    assert all(o.out.bn.base < 0 for o in ev.fwd_ops) and ev.bwd_ops is None
+    assert [o.kind for o in ev.fwd_ops].count(_lib.OP_BNAPPLY) == 2
+
+
+def test_shape_validation_and_errors():
+    cells = [mmd.BiFPN(112, [48, 120, 352], first_time=True)]
+    with pytest.raises(ValueError):   # P4 is not exactly half of P3
+        bifpn._Plan(cells, "cells", [(1, 48, 20, 20), (1, 120, 9, 9), (1, 352, 5, 5)], torch.float32, False, False, [False] * 3)
+    with pytest.raises(ValueError):
+        bifpn._Plan(cells, "cells", [(1, 48, 16, 16)] * 5, torch.float32, False, False, [False] * 5)
+    with pytest.raises(RuntimeError):   # CPU tensors: the product path has no CPU fallback
+        cells[0](tuple(torch.randn(1, c, 16 >> i, 16 >> i) for i, c in enumerate([48, 120, 352])))
+    with pytest.raises(RuntimeError):
+        mmd.MTALoss()([torch.randn(1, 112, 4, 4)], [torch.randn(1, 112, 4, 4)])
+    with pytest.raises(NotImplementedError):
+        mmd.SeparableConvBlock(112, 36, norm=False)
+    crit = mmd.MTALoss(T="9", p="2")     # config passes strings (src/utils/utils.py:1603-1604)
+    assert crit.T == 9.0 and crit.p == 2.0
+
+
+def test_patch_reference_rebinds_globals():
+    import types
+    det = types.ModuleType("fake_det")
+
+    class FakeDet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.bifpn = torch.nn.Sequential(*[det.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(2)])
+
+    det.BiFPN = object
+    det.YetAnotherEfficientDet = FakeDet
+    loss = types.ModuleType("fake_loss")
+    loss.MTALoss = object
+    utils = types.ModuleType("fake_utils")
+    utils.MTALoss = object
+    mmd.patch_reference(det, loss, utils)
+    assert det.BiFPN is mmd.BiFPN and loss.MTALoss is mmd.MTALoss and utils.MTALoss is mmd.MTALoss
+    m = det.YetAnotherEfficientDet()
+    assert isinstance(m.bifpn, mmd.BiFPNStack) and list(m.state_dict())[0].startswith("bifpn.0.")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        student = mmd.BiFPNStack(mmd.BiFPN(112, [48, 120, 352], first_time=True))
+        step = mmd.DistillStep(student, [], device=torch.device("cpu"))
+        n = sum(p.numel() for p in student.parameters())
+        flat = torch.full((n,), float(rank + 1))
+        flat[:3] = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1)
+        step._on_flat_grad(flat)                      # the N>1 exchange: one all-reduce (sum) then 1/world
+        out[rank] = (step.flat_grad[:4].tolist(), step.world)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    for r in range(world):
+        vals, w = res[r]
+        assert w == 2
+        assert vals == [1.5, 3.0, 4.5, 1.5]    # mean over ranks (DDP semantics, train_methods.py:957-961)
