@@ -235,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
     launches = mmd.launch_count() - l0
     clocks = sampler.stop() if sampler else None
 
-    for _ in range(2):
+    for _ in range(max(args.warmup, 3)):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
 

@@ -217,6 +217,7 @@ class _Plan:
         self.n_in = len(in_shapes)
         self.in_need_grad = list(in_need_grad)
         self.fwd_arena, self.persist, self.bwd_arena, self.zero_arena = _Arena(), _Arena(), _Arena(), _Arena()
+        self.pool_fwd, self.pool_bwd = [], []
         self.ops = []
         self.Cc = None
         self.params = self._collect_params(mods)
@@ -535,6 +536,26 @@ class _Plan:
         return arr
 
 
+class _Lease:
+    """A pooled device buffer: returned to its plan's pool when the last reference (e.g. the autograd context of the
+    forward that used it) goes away, so steady-state steps never touch the CUDA allocator."""
+    __slots__ = ("buf", "pool")
+
+    def __init__(self, pool, nbytes, device):
+        self.pool = pool
+        self.buf = pool.pop() if pool else torch.empty(max(nbytes, _ALIGN), dtype=torch.uint8, device=device)
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+    def __del__(self):
+        try:
+            if len(self.pool) < 4:
+                self.pool.append(self.buf)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 class _StackFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, plan, n_in, *tensors):
@@ -642,7 +663,7 @@ class _Runner:
     def _forward(self, plan, inputs):
         dev = plan.device
         xs = [x.detach().contiguous(memory_format=torch.channels_last) for x in inputs]
-        arena = torch.empty(max(plan.fwd_arena.size, _ALIGN), dtype=torch.uint8, device=dev)
+        arena = _Lease(plan.pool_fwd, plan.fwd_arena.size, dev)
         outs = [torch.empty(s, dtype=plan.dtype, device=dev, memory_format=torch.channels_last) for s in plan.out_shapes]
         bases = [0] * plan.n_bases
         bases[B_FWD] = arena.data_ptr()
@@ -662,7 +683,7 @@ class _Runner:
             if g is None:
                 g = torch.zeros_like(o)
             gs.append(g.detach().to(plan.dtype).contiguous(memory_format=torch.channels_last))
-        bwd = torch.empty(max(plan.bwd_arena.size, _ALIGN), dtype=torch.uint8, device=dev)
+        bwd = _Lease(plan.pool_bwd, plan.bwd_arena.size, dev)
         zero = torch.zeros(max(plan.zero_arena.size, _ALIGN) // 4, dtype=torch.float32, device=dev)
         gin = [torch.empty_like(x) if need else None for x, need in zip(xs, plan.in_need_grad)]
         bases = [0] * plan.n_bases

@@ -13,6 +13,8 @@
 //   bnapply_kernel    materialises [pool](scale*x+shift): P6/P7 synthesis (:324-325) and the stack outputs.
 //
 // This file is the fp32-exact CUDA-core path (FFMA GEMM from shared memory); see DESIGN.md for the roofline.
+#include <stdlib.h>
+
 #include "bifpn.cuh"
 
 namespace mmd {
@@ -422,7 +424,19 @@ static int launch_bnapply_t(const NodeFwdP& p, cudaStream_t s) {
   set_error("unsupported dtype %d", dtype);                                          \
   return MMD_E_ARG;
 
-int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_node_fwd_t) }
+bool tc_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMD_NO_TC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) {
+  if (dtype == MMD_BF16 && !tc_disabled()) return launch_node_fwd_tc(p, C, s);
+  MMD_DISPATCH(launch_node_fwd_t)
+}
 int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_proj_fwd_t) }
 int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_bnapply_t) }
 

@@ -1,0 +1,279 @@
+// BiFPN fusion node, forward, bf16 storage: the pointwise 1x1 convolution runs on the 5th-generation tensor cores
+// (tcgen05.mma kind::f16, bf16 operands staged in shared memory, fp32 accumulator in TMEM).
+//
+// Per 128-position tile (one CTA, 256 threads, two CTAs per SM):
+//   prologue  : BN-on-load + resample + weighted fusion + swish -> (TH+2)x(TW+2) halo tile v (bf16, smem)
+//   depthwise : 3x3 in fp32 registers -> d (bf16) written straight into the UMMA A-operand layout (smem) and, in
+//               training, to HBM for the backward
+//   pointwise : ONE elected thread issues 7 x tcgen05.mma (M=128, N=112, K=16): D[128x112] = d[128x112] * W^T,
+//               W (bf16, BatchNorm folded in eval mode) resident in smem for the life of the CTA; completion is
+//               signalled through tcgen05.commit -> mbarrier
+//   epilogue  : all 8 warps read the accumulator with tcgen05.ld (32 lanes x 8 columns at a time), add the bias, round
+//               to bf16 into a staging tile; then per-channel sum / sum-of-squares (train) and 16-byte coalesced stores.
+#include "bifpn.cuh"
+#include "tc.cuh"
+
+namespace mmd {
+
+typedef __nv_bfloat16 bf16;
+
+template <int C>
+struct FwdTcSmem {
+  static constexpr int kVBytes = kHaloMax * C * 2;              // halo tile v (bf16); reused as the output staging tile
+  static constexpr int LDS = C + 8;                             // staging row (bf16 elements), 16-byte aligned rows
+  static constexpr int kABytes = kTileP * C * 2;                // A operand: [C/8][128][8] bf16
+  static constexpr int kBBytes = C * C * 2;                     // B operand: [C/8][C][8] bf16
+  static constexpr int kKBytes = 9 * C * 4;
+  static constexpr int kBiasBytes = C * 4;
+  static constexpr int kInScBytes = 3 * 2 * C * 4;
+  static constexpr int offV = 0;
+  static constexpr int offA = offV + ((kVBytes + 127) / 128) * 128;
+  static constexpr int offB = offA + kABytes;
+  static constexpr int offK = offB + ((kBBytes + 127) / 128) * 128;
+  static constexpr int offBias = offK + kKBytes;
+  static constexpr int offInSc = offBias + kBiasBytes;
+  static constexpr int offBar = offInSc + kInScBytes;
+  static constexpr int kBytes = offBar + 16;
+  static_assert(kTileP * LDS * 2 <= kVBytes, "staging tile must fit in the halo tile");
+};
+
+__device__ __forceinline__ float4 ld4_smem_bf16(const bf16* p) { return ld4<bf16>(p); }
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_constant__ NodeFwdP P) {
+  using S = FwdTcSmem<C>;
+  constexpr int NQ = C / 4, NG = C / 8, LDS = S::LDS;
+  constexpr uint32_t kTmemCols = 128;
+  constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* s_v = reinterpret_cast<bf16*>(smem_raw + S::offV);
+  bf16* s_y = s_v;  // staging aliases the halo tile (dead after the depthwise stage)
+  bf16* s_a = reinterpret_cast<bf16*>(smem_raw + S::offA);
+  bf16* s_b = reinterpret_cast<bf16*>(smem_raw + S::offB);
+  float* s_k = reinterpret_cast<float*>(smem_raw + S::offK);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + S::offBias);
+  float* s_insc = reinterpret_cast<float*>(smem_raw + S::offInSc);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + S::offBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + S::offBar + 8);
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TileGeom g = P.g;
+  const bool train = P.train != 0;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+
+  // ---- per-CTA setup ----------------------------------------------------------------------------------------
+  if (warp == 0) tc::tmem_alloc(s_tmem, kTmemCols);
+  if (tid == 32) {
+    tc::mbar_init(s_bar, 1);
+    tc::fence_mbar_init();
+  }
+  float wgt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
+  for (int idx = tid; idx < 9 * C; idx += kThreads) {
+    const int c = idx / 9, tap = idx - c * 9;
+    s_k[tap * C + c] = P.dw_w[idx];
+  }
+  // B operand: W[n][k] (native [out][in]) -> bf16 [k/8][n][k%8]; eval: fold the BatchNorm scale of channel n
+  for (int idx = tid; idx < C * C; idx += kThreads) {
+    const int n = idx / C, k = idx - n * C;
+    float w = P.pw_w[idx];
+    if (!train) w *= P.bn_w[n] * rsqrtf(P.bn_rv[n] + P.bn_eps);
+    s_b[(k >> 3) * (C * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
+  }
+  if (tid < C) {
+    float bia = P.pw_b[tid];
+    if (!train) {
+      const float sc = P.bn_w[tid] * rsqrtf(P.bn_rv[tid] + P.bn_eps);
+      bia = (bia - P.bn_rm[tid]) * sc + P.bn_b[tid];
+    }
+    s_bias[tid] = bia;
+  }
+  for (int idx = tid; idx < 3 * C; idx += kThreads) {
+    const int i = idx / C, c = idx - i * C;
+    const float* bn = (i < P.n_in) ? P.in[i].bn : nullptr;
+    s_insc[(2 * i) * C + c] = bn ? bn[c] : 1.f;
+    s_insc[(2 * i + 1) * C + c] = bn ? bn[C + c] : 0.f;
+  }
+  tc::fence_async_smem();       // s_b is read by the async proxy
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t a_addr = tc::smem_u32(s_a), b_addr = tc::smem_u32(s_b);
+
+  double st_sum = 0.0, st_sq = 0.0;
+  const int HW2 = g.TW + 2;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    const int b = tile / (g.tiles_x * g.tiles_y);
+    const int rem = tile - b * (g.tiles_x * g.tiles_y);
+    const int ty0 = (rem / g.tiles_x) * g.TH, tx0 = (rem % g.tiles_x) * g.TW;
+    const int th = min(g.TH, g.H - ty0), tw = min(g.TW, g.W - tx0);
+
+    // ---- prologue: fused input halo tile (bf16)
+    const int nh = (g.TH + 2) * HW2;
+    for (int idx = tid; idx < nh * NQ; idx += kThreads) {
+      const int hp = idx / NQ, q = idx - hp * NQ;
+      const int hy = hp / HW2, hx = hp - hy * HW2;
+      const int y = ty0 - 1 + hy, x = tx0 - 1 + hx;
+      float4 u = f4_zero();
+      if (y >= 0 && y < g.H && x >= 0 && x < g.W) {
+        const bool center = (hy >= 1 && hy <= th && hx >= 1 && hx <= tw);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < P.n_in) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_insc + (2 * i) * C + 4 * q);
+            const float4 sh = *reinterpret_cast<const float4*>(s_insc + (2 * i + 1) * C + 4 * q);
+            float4 val, raw;
+            unsigned arg;
+            load_input<bf16, C>(P.in[i], P.mode[i], b, y, x, q, sc, sh, val, raw, arg);
+            u = f4_axpy(wgt[i], val, u);
+            if (center && P.mode[i] == MMD_IN_POOL && P.pidx[i] != nullptr)
+              *reinterpret_cast<unsigned*>(P.pidx[i] + (((long long)b * g.H + y) * g.W + x) * C + 4 * q) = arg;
+          }
+        }
+        if (P.swish) {
+          u.x *= sigmoidf_(u.x); u.y *= sigmoidf_(u.y); u.z *= sigmoidf_(u.z); u.w *= sigmoidf_(u.w);
+        }
+      }
+      st4<bf16>(s_v + hp * C + 4 * q, u);
+    }
+    __syncthreads();
+
+    // ---- depthwise 3x3 -> A operand (bf16, [c/8][p][c%8])
+    for (int idx = tid; idx < kTileP * NQ; idx += kThreads) {
+      const int p = idx / NQ, q = idx - p * NQ;
+      const int ty = p / g.TW, tx = p - ty * g.TW;
+      float4 d = f4_zero();
+      if (ty < th && tx < tw) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float4 v = ld4_smem_bf16(s_v + ((ty + dy) * HW2 + tx + dx) * C + 4 * q);
+            const float4 k = *reinterpret_cast<const float4*>(s_k + (dy * 3 + dx) * C + 4 * q);
+            d = f4_fma(v, k, d);
+          }
+        if (P.save_d != nullptr)
+          st4<bf16>(reinterpret_cast<bf16*>(P.save_d) + (((long long)b * g.H + ty0 + ty) * g.W + tx0 + tx) * C + 4 * q, d);
+      }
+      st4<bf16>(s_a + (q >> 1) * (kTileP * 8) + p * 8 + (q & 1) * 4, d);
+    }
+    tc::fence_async_smem();  // the A tile was written through the generic proxy
+    __syncthreads();
+
+    // ---- pointwise 1x1 on the tensor cores: one thread issues, the accumulator lives in TMEM
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) {
+        const uint64_t adesc = tc::make_desc(a_addr + j * 2 * (kTileP * 16), kTileP * 16, 128);
+        const uint64_t bdesc = tc::make_desc(b_addr + j * 2 * (C * 16), C * 16, 128);
+        tc::umma_bf16(tmem_base, adesc, bdesc, kIdesc, j > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(s_bar);
+    }
+    tc::mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+
+    // ---- epilogue: TMEM -> registers -> +bias -> bf16 staging tile
+    {
+      const int row = 32 * (warp & 3) + lane;          // TMEM lane == tile position
+      const int col0 = (warp >> 2) * (C / 2);          // warps 0-3: columns [0,56), warps 4-7: [56,112)
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+      float acc[C / 16][8];
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] += s_bias[col0 + 8 * j + e];
+        *reinterpret_cast<uint4*>(s_y + row * LDS + col0 + 8 * j) = tc::pack8_bf16(acc[j]);
+      }
+    }
+    tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
+    __syncthreads();
+
+    if (train && tid < C) {
+      float s = 0.f, q = 0.f;
+      for (int ty = 0; ty < th; ++ty)
+        for (int tx = 0; tx < tw; ++tx) {
+          const float v = __bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
+          s += v;
+          q = fmaf(v, v, q);
+        }
+      st_sum += (double)s;
+      st_sq += (double)q;
+    }
+    for (int idx = tid; idx < g.TH * g.TW * NG; idx += kThreads) {
+      const int p = idx / NG, gq = idx - p * NG;
+      const int ty = p / g.TW, tx = p - ty * g.TW;
+      if (ty < th && tx < tw)
+        *reinterpret_cast<uint4*>(out + (((long long)b * g.H + ty0 + ty) * g.W + tx0 + tx) * C + 8 * gq) =
+            *reinterpret_cast<const uint4*>(s_y + p * LDS + 8 * gq);
+    }
+    __syncthreads();
+  }
+
+  // ---- teardown + BatchNorm finalisation (last CTA)
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (!train) return;
+  if (tid < C) {
+    atomicAdd(P.stats + tid, st_sum);
+    atomicAdd(P.stats + C + tid, st_sq);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(P.counter, 1u);
+    s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flag == 0) return;
+  __threadfence();
+  if (tid < C) {
+    const double n = (double)g.B * g.H * g.W;
+    const double mean = __ldcg(P.stats + tid) / n;
+    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
+    const float scale = P.bn_w[tid] * invstd;
+    P.out_bn[tid] = scale;
+    P.out_bn[C + tid] = P.bn_b[tid] - (float)mean * scale;
+    P.out_bn[2 * C + tid] = (float)mean;
+    P.out_bn[3 * C + tid] = invstd;
+    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+    P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
+    P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
+    P.stats[tid] = 0.0;
+    P.stats[C + tid] = 0.0;
+  }
+  if (tid == 0) {
+    *P.counter = 0u;
+    if (P.bn_nbt) *P.bn_nbt += 1;
+  }
+}
+
+int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  constexpr int CC = 112;
+  const size_t smem = FwdTcSmem<CC>::kBytes;
+  MMD_CUDA(cudaFuncSetAttribute(node_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.g.ntiles < 2 * sms ? p.g.ntiles : 2 * sms;
+  ProfScope prof(PK_NODE_FWD, node_algo_bytes(p.in, p.n_in, p.g, C, 2), s);
+  node_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmd

@@ -161,7 +161,11 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         cls = "fw" if k[-3:-1] == "_w" else "dw" if "depthwise" in k else "pw" if "pointwise" in k else \
             "proj" if ".0.conv" in k else "bn"
         r = leaf_ref[k].grad
-        worst[cls] = max(worst.get(cls, 0.0), H.rel_l2(p.grad.cpu(), r))
+        e = H.rel_l2(p.grad.cpu(), r)
+        if e > worst.get(cls, 0.0):
+            worst[cls] = e
+            m["worstname_" + cls] = "%s |g|=%.3e" % (k, r.norm().item())
+        worst.setdefault(cls, 0.0)
         if ref64:
             worst32[cls] = max(worst32.get(cls, 0.0), H.rel_l2(leaf32[k].grad, r))
     for k, v in worst.items():
