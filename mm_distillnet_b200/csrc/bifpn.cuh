@@ -156,6 +156,7 @@ __device__ __forceinline__ void load_input(const TensorP& t, int mode, int b, in
 // kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)
 int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, tcgen05 pointwise conv
+int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead
 int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);

@@ -437,7 +437,10 @@ int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) {
   if (dtype == MMD_BF16 && !tc_disabled()) return launch_node_fwd_tc(p, C, s);
   MMD_DISPATCH(launch_node_fwd_t)
 }
-int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_proj_fwd_t) }
+int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) {
+  if (dtype == MMD_BF16 && !tc_disabled() && p.Cin % 8 == 0) return launch_proj_fwd_tc(p, C, s);
+  MMD_DISPATCH(launch_proj_fwd_t)
+}
 int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_bnapply_t) }
 
 }  // namespace mmd

@@ -37,6 +37,92 @@ struct FwdTcSmem {
   static_assert(kTileP * LDS * 2 <= kVBytes, "staging tile must fit in the halo tile");
 };
 
+
+// ---- shared epilogue: TMEM accumulator -> +bias -> bf16 staging tile -> stats + 16-byte coalesced stores -------------
+template <int C>
+__device__ __forceinline__ void tile_epilogue_tc(uint32_t tmem_base, const float* s_bias, bf16* s_y, bf16* out,
+                                                 const TileGeom& g, int b, int ty0, int tx0, int th, int tw, bool train,
+                                                 double& st_sum, double& st_sq) {
+  constexpr int NG = C / 8, LDS = C + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int row = 32 * (warp & 3) + lane;          // TMEM lane == tile position
+    const int col0 = (warp >> 2) * (C / 2);          // warps 0-3: columns [0,56), warps 4-7: [56,112)
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+    float acc[C / 16][8];
+#pragma unroll
+    for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < C / 16; ++j) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[j][e] += s_bias[col0 + 8 * j + e];
+      *reinterpret_cast<uint4*>(s_y + row * LDS + col0 + 8 * j) = tc::pack8_bf16(acc[j]);
+    }
+  }
+  tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
+  __syncthreads();
+  if (train && tid < C) {
+    float s = 0.f, q = 0.f;
+    for (int ty = 0; ty < th; ++ty)
+      for (int tx = 0; tx < tw; ++tx) {
+        const float v = __bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
+        s += v;
+        q = fmaf(v, v, q);
+      }
+    st_sum += (double)s;
+    st_sq += (double)q;
+  }
+  for (int idx = tid; idx < g.TH * g.TW * NG; idx += kThreads) {
+    const int p = idx / NG, gq = idx - p * NG;
+    const int ty = p / g.TW, tx = p - ty * g.TW;
+    if (ty < th && tx < tw)
+      *reinterpret_cast<uint4*>(out + (((long long)b * g.H + ty0 + ty) * g.W + tx0 + tx) * C + 8 * gq) =
+          *reinterpret_cast<const uint4*>(s_y + p * LDS + 8 * gq);
+  }
+  __syncthreads();
+}
+
+template <int C>
+__device__ __forceinline__ void bn_finalize_tc(const NodeFwdP& P, double st_sum, double st_sq, int* s_flag) {
+  const int tid = threadIdx.x;
+  const TileGeom& g = P.g;
+  if (tid < C) {
+    atomicAdd(P.stats + tid, st_sum);
+    atomicAdd(P.stats + C + tid, st_sq);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(P.counter, 1u);
+    *s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (*s_flag == 0) return;
+  __threadfence();
+  if (tid < C) {
+    const double n = (double)g.B * g.H * g.W;
+    const double mean = __ldcg(P.stats + tid) / n;
+    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
+    const float scale = P.bn_w[tid] * invstd;
+    P.out_bn[tid] = scale;
+    P.out_bn[C + tid] = P.bn_b[tid] - (float)mean * scale;
+    P.out_bn[2 * C + tid] = (float)mean;
+    P.out_bn[3 * C + tid] = invstd;
+    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+    P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
+    P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
+    P.stats[tid] = 0.0;
+    P.stats[C + tid] = 0.0;
+  }
+  if (tid == 0) {
+    *P.counter = 0u;
+    if (P.bn_nbt) *P.bn_nbt += 1;
+  }
+}
+
 __device__ __forceinline__ float4 ld4_smem_bf16(const bf16* p) { return ld4<bf16>(p); }
 
 template <int C>
@@ -180,44 +266,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_c
     phase ^= 1u;
     tc::fence_after_sync();
 
-    // ---- epilogue: TMEM -> registers -> +bias -> bf16 staging tile
-    {
-      const int row = 32 * (warp & 3) + lane;          // TMEM lane == tile position
-      const int col0 = (warp >> 2) * (C / 2);          // warps 0-3: columns [0,56), warps 4-7: [56,112)
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
-      float acc[C / 16][8];
-#pragma unroll
-      for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < C / 16; ++j) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j][e] += s_bias[col0 + 8 * j + e];
-        *reinterpret_cast<uint4*>(s_y + row * LDS + col0 + 8 * j) = tc::pack8_bf16(acc[j]);
-      }
-    }
-    tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
-    __syncthreads();
-
-    if (train && tid < C) {
-      float s = 0.f, q = 0.f;
-      for (int ty = 0; ty < th; ++ty)
-        for (int tx = 0; tx < tw; ++tx) {
-          const float v = __bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
-          s += v;
-          q = fmaf(v, v, q);
-        }
-      st_sum += (double)s;
-      st_sq += (double)q;
-    }
-    for (int idx = tid; idx < g.TH * g.TW * NG; idx += kThreads) {
-      const int p = idx / NG, gq = idx - p * NG;
-      const int ty = p / g.TW, tx = p - ty * g.TW;
-      if (ty < th && tx < tw)
-        *reinterpret_cast<uint4*>(out + (((long long)b * g.H + ty0 + ty) * g.W + tx0 + tx) * C + 8 * gq) =
-            *reinterpret_cast<const uint4*>(s_y + p * LDS + 8 * gq);
-    }
-    __syncthreads();
+    tile_epilogue_tc<C>(tmem_base, s_bias, s_y, out, g, b, ty0, tx0, th, tw, train, st_sum, st_sq);
   }
 
   // ---- teardown + BatchNorm finalisation (last CTA)
@@ -225,40 +274,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_c
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
   if (!train) return;
-  if (tid < C) {
-    atomicAdd(P.stats + tid, st_sum);
-    atomicAdd(P.stats + C + tid, st_sq);
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    unsigned ticket = atomicAdd(P.counter, 1u);
-    s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_flag == 0) return;
-  __threadfence();
-  if (tid < C) {
-    const double n = (double)g.B * g.H * g.W;
-    const double mean = __ldcg(P.stats + tid) / n;
-    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
-    const float scale = P.bn_w[tid] * invstd;
-    P.out_bn[tid] = scale;
-    P.out_bn[C + tid] = P.bn_b[tid] - (float)mean * scale;
-    P.out_bn[2 * C + tid] = (float)mean;
-    P.out_bn[3 * C + tid] = invstd;
-    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
-    P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
-    P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
-    P.stats[tid] = 0.0;
-    P.stats[C + tid] = 0.0;
-  }
-  if (tid == 0) {
-    *P.counter = 0u;
-    if (P.bn_nbt) *P.bn_nbt += 1;
-  }
+  bn_finalize_tc<C>(P, st_sum, st_sq, &s_flag);
 }
 
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
@@ -272,6 +288,119 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   const int grid = p.g.ntiles < 2 * sms ? p.g.ntiles : 2 * sms;
   ProfScope prof(PK_NODE_FWD, node_algo_bytes(p.in, p.n_in, p.g, C, 2), s);
   node_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ---- first-cell projection Cin -> C on the tensor cores ------------------------------------------------------------
+// A = the input tile itself: a 16-byte global chunk (position p, channels 8k..8k+7) IS one row of core matrix k, so the
+// NHWC -> UMMA layout change costs nothing.  K is padded to a multiple of 16 with zero chunks (Cin = 120 -> 128).
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_constant__ NodeFwdP P, int Kp) {
+  constexpr int LDS = C + 8;
+  constexpr uint32_t kTmemCols = 128;
+  constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int KG = Kp / 8;
+  bf16* s_a = reinterpret_cast<bf16*>(smem_raw);                                   // [KG][128][8]
+  bf16* s_b = reinterpret_cast<bf16*>(smem_raw + KG * kTileP * 16);                // [KG][C][8]
+  unsigned char* tail = smem_raw + KG * kTileP * 16 + ((KG * C * 16 + 127) / 128) * 128;
+  bf16* s_y = reinterpret_cast<bf16*>(tail);                                       // [128][LDS]
+  float* s_bias = reinterpret_cast<float*>(tail + kTileP * LDS * 2);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(tail + kTileP * LDS * 2 + C * 4);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tail + kTileP * LDS * 2 + C * 4 + 8);
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const TileGeom g = P.g;
+  const bool train = P.train != 0;
+  const int Cin = P.Cin;
+  const bf16* __restrict__ xin = reinterpret_cast<const bf16*>(P.in[0].data);
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+
+  if (warp == 0) tc::tmem_alloc(s_tmem, kTmemCols);
+  if (tid == 32) {
+    tc::mbar_init(s_bar, 1);
+    tc::fence_mbar_init();
+  }
+  for (int idx = tid; idx < C * Kp; idx += kThreads) {
+    const int n = idx / Kp, k = idx - n * Kp;
+    float w = 0.f;
+    if (k < Cin) {
+      w = P.pw_w[(long long)n * Cin + k];
+      if (!train) w *= P.bn_w[n] * rsqrtf(P.bn_rv[n] + P.bn_eps);
+    }
+    s_b[(k >> 3) * (C * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
+  }
+  if (tid < C) {
+    float bia = P.pw_b[tid];
+    if (!train) {
+      const float sc = P.bn_w[tid] * rsqrtf(P.bn_rv[tid] + P.bn_eps);
+      bia = (bia - P.bn_rm[tid]) * sc + P.bn_b[tid];
+    }
+    s_bias[tid] = bia;
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t a_addr = tc::smem_u32(s_a), b_addr = tc::smem_u32(s_b);
+  double st_sum = 0.0, st_sq = 0.0;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    const int b = tile / (g.tiles_x * g.tiles_y);
+    const int rem = tile - b * (g.tiles_x * g.tiles_y);
+    const int ty0 = (rem / g.tiles_x) * g.TH, tx0 = (rem % g.tiles_x) * g.TW;
+    const int th = min(g.TH, g.H - ty0), tw = min(g.TW, g.W - tx0);
+    for (int idx = tid; idx < kTileP * KG; idx += kThreads) {
+      const int p = idx / KG, kg = idx - p * KG;
+      const int ty = p / g.TW, tx = p - ty * g.TW;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ty < th && tx < tw && 8 * kg < Cin)
+        v = *reinterpret_cast<const uint4*>(xin + (((long long)b * g.H + ty0 + ty) * g.W + tx0 + tx) * Cin + 8 * kg);
+      *reinterpret_cast<uint4*>(s_a + kg * (kTileP * 8) + p * 8) = v;
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      for (int j = 0; j < Kp / 16; ++j) {
+        const uint64_t adesc = tc::make_desc(a_addr + j * 2 * (kTileP * 16), kTileP * 16, 128);
+        const uint64_t bdesc = tc::make_desc(b_addr + j * 2 * (C * 16), C * 16, 128);
+        tc::umma_bf16(tmem_base, adesc, bdesc, kIdesc, j > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(s_bar);
+    }
+    tc::mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    tile_epilogue_tc<C>(tmem_base, s_bias, s_y, out, g, b, ty0, tx0, th, tw, train, st_sum, st_sq);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (!train) return;
+  bn_finalize_tc<C>(P, st_sum, st_sq, &s_flag);
+}
+
+int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(p.Cin % 8 == 0, "bf16 projection needs Cin %% 8 == 0, got %d", p.Cin);
+  constexpr int CC = 112;
+  const int Kp = (p.Cin + 15) / 16 * 16, KG = Kp / 8;
+  const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 16;
+  MMD_CHECK_ARG(smem <= 227 * 1024, "projection with Cin=%d does not fit in shared memory", p.Cin);
+  MMD_CUDA(cudaFuncSetAttribute(proj_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int grid = p.g.ntiles < per_sm * sms ? p.g.ntiles : per_sm * sms;
+  ProfScope prof(PK_PROJ_FWD, (double)p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2, s);
+  proj_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p, Kp);
   MMD_LAUNCH_CHECK();
   return 0;
 }

@@ -33,6 +33,9 @@ class DistillStep:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.device = device if device is not None else next(student.parameters()).device
         self.flat_grad = None
+        # the frozen teachers and the student are independent until the MTA loss: each teacher stack runs on its own
+        # CUDA stream so the small pyramid levels (P5-P7: fewer CTAs than SMs) of different networks overlap
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.teachers] if self.device.type == "cuda" else []
         student._runner.grad_sink = self._on_flat_grad
         for t in self.teachers:
             t.eval()
@@ -50,12 +53,20 @@ class DistillStep:
         return tuple(x if x.device == self.device else x.to(self.device, non_blocking=True) for x in xs)
 
     def __call__(self, student_inputs, teacher_inputs):
-        xs = self._to_device(student_inputs)
-        feats_s = self.student(xs)                                   # train_methods.py:318
-        kd = []
-        for teacher, tin in zip(self.teachers, teacher_inputs):      # :320-358
-            with torch.no_grad():
+        main = torch.cuda.current_stream(self.device)
+        feats_t_all = []
+        for teacher, tin, st in zip(self.teachers, teacher_inputs, self.streams):   # train_methods.py:320-336
+            st.wait_stream(main)
+            with torch.cuda.stream(st), torch.no_grad():
                 feats_t = teacher(self._to_device(tin))
+                for f in feats_t:
+                    f.record_stream(main)
+            feats_t_all.append(feats_t)
+        xs = self._to_device(student_inputs)
+        feats_s = self.student(xs)                                   # :318
+        kd = []
+        for feats_t, st in zip(feats_t_all, self.streams):           # :351-358
+            main.wait_stream(st)
             kd.append(self.criterion(feats_s, [f.detach() for f in feats_t]))
         kd = torch.stack(kd)
         loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
