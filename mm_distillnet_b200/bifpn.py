@@ -192,6 +192,31 @@ class _OpN:
 B_FWD, B_PERSIST, B_BWD, B_ZERO, B_EXT = 0, 1, 2, 3, 4
 
 
+def _null_refs(obj):
+    """A zero-initialised ctypes struct has MmdRef.base == 0 (a VALID base); make every reference NULL (base -1)."""
+    for name, typ in obj._fields_:
+        v = getattr(obj, name)
+        if isinstance(v, _lib.Ref):
+            v.base = -1
+        elif isinstance(v, C.Structure):
+            _null_refs(v)
+        elif isinstance(v, C.Array) and len(v) and isinstance(v[0], C.Structure):
+            for e in v:
+                if isinstance(e, _lib.Ref):
+                    e.base = -1
+                else:
+                    _null_refs(e)
+    return obj
+
+
+def _new_op():
+    return _null_refs(_lib.Op())
+
+
+def _new_cons():
+    return _null_refs(_lib.Cons())
+
+
 def _ref(pair):
     if pair is None:
         return _lib.Ref(-1, 0, 0)
@@ -419,6 +444,7 @@ class _Plan:
     def _emit_fwd(self):
         arr = (_lib.Op * len(self.ops))()
         for o, op in zip(arr, self.ops):
+            _null_refs(o)
             o.kind = op.kind
             o.train = 1 if self.train else 0
             self._fill_common(o, op)
@@ -429,7 +455,7 @@ class _Plan:
         """MmdCons entries for every consumer edge of tensor `t`."""
         res = []
         for cop, idx in t.consumers:
-            c = _lib.Cons()
+            c = _new_cons()
             mode = cop.modes[idx]
             if cop.kind == _lib.OP_NODE_FWD:
                 c.du = _tensor(cop.du, with_bn=False)
@@ -459,7 +485,7 @@ class _Plan:
         ext_written = set()
 
         def new(kind, op):
-            o = _lib.Op()
+            o = _new_op()
             o.kind = kind
             o.train = 1
             self._fill_common(o, op)
@@ -485,7 +511,7 @@ class _Plan:
                 if src.bn is not None:
                     o = new(_lib.OP_SLOT, op)
                     o.n_cons = 1
-                    c = _lib.Cons()
+                    c = _new_cons()
                     c.du = _lib.Tensor(_ref(op.glike), _ref(None), op.out.H, op.out.W, self.Cc, 0)
                     o.cons[0] = c
                     out.append(o)
@@ -522,7 +548,7 @@ class _Plan:
                 continue
             if not x.consumers or any(cop.kind == _lib.OP_PROJ_FWD for cop, _ in x.consumers):
                 continue
-            o = _lib.Op()
+            o = _new_op()
             o.kind = _lib.OP_PULL
             o.train = 1
             o.out = _tensor(x)

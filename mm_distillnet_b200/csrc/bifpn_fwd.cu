@@ -44,15 +44,16 @@ __device__ __forceinline__ void tile_epilogue(float (&acc)[8][C / 16], const flo
     for (int j = 0; j < NJ; ++j) s_y[(tm + 16 * r) * C + tn + 16 * j] = acc[r][j] + s_bias[tn + 16 * j];
   __syncthreads();
   if (train && tid < C) {
-    float s = 0.f, q = 0.f;
+    // double accumulation: with eps = 1e-3 and var << eps an fp32 partial sum would show up at the 1e-4 level
+    double s = 0.0, q = 0.0;
     for (int ty = 0; ty < th; ++ty)
       for (int tx = 0; tx < tw; ++tx) {
-        float v = s_y[(ty * g.TW + tx) * C + tid];
+        const double v = (double)s_y[(ty * g.TW + tx) * C + tid];
         s += v;
-        q = fmaf(v, v, q);
+        q = fma(v, v, q);
       }
-    st_sum += (double)s;
-    st_sq += (double)q;
+    st_sum += s;
+    st_sq += q;
   }
   constexpr int NQ = C / 4;
   for (int idx = tid; idx < g.TH * g.TW * NQ; idx += kThreads) {

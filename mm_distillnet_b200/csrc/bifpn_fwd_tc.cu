@@ -63,15 +63,15 @@ __device__ __forceinline__ void tile_epilogue_tc(uint32_t tmem_base, const float
   tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
   __syncthreads();
   if (train && tid < C) {
-    float s = 0.f, q = 0.f;
+    double s = 0.0, q = 0.0;
     for (int ty = 0; ty < th; ++ty)
       for (int tx = 0; tx < tw; ++tx) {
-        const float v = __bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
+        const double v = (double)__bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
         s += v;
-        q = fmaf(v, v, q);
+        q = fma(v, v, q);
       }
-    st_sum += (double)s;
-    st_sq += (double)q;
+    st_sum += s;
+    st_sq += q;
   }
   for (int idx = tid; idx < g.TH * g.TW * NG; idx += kThreads) {
     const int p = idx / NG, gq = idx - p * NG;
