@@ -76,6 +76,17 @@ def test_plan_structure():
             spans.append((op.out.off, op.out.off + plan.B * op.out.H * op.out.W * 112 * 4))
     spans.sort()
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    # regression: references that an op does not use must be NULL (base -1), never "forward arena + 0";
+    # with inputs that need no gradient the projection backward must not get a dx destination
+    ng = bifpn._Plan(cells, "cells", shapes, torch.float32, True, True, [False] * 3)
+    for o in ng.bwd_ops:
+        if o.kind == _lib.OP_PROJ_BWD:
+            assert o.dx.base == -1 and o.du.base == -1 and o.g_dw.base == -1
+        if o.kind == _lib.OP_NODE_BWD:
+            assert o.dx.base == -1
+        for c in range(o.n_cons, 3):
+            assert o.cons[c].slot.base == -1 and o.cons[c].du.data.base == -1
+    assert all(o.dx.base == -1 and o.du.base == -1 for o in ng.fwd_ops)
     # eval plan: no deferred BatchNorm, outputs written in place by the last cell
     ev = bifpn._Plan(cells, "cells", shapes, torch.float32, False, False, [False] * 3)
     assert all(o.out.bn.base < 0 for o in ev.fwd_ops) and ev.bwd_ops is None
