@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a_tc_kernel(const __grid
   cons_weights(P, cw);
   bn_bwd_coefs<C>(P, cw, s_coef);
   // B operand of GEMM 1: B[n = i][k = o] = W[o][i]  ->  bf16 [o/8][i][o%8]
+#pragma unroll 7
   for (int idx = tid; idx < C * C; idx += kThreads) {
     const int o = idx / C, i = idx - o * C;
     s_b[(o >> 3) * (C * 8) + i * 8 + (o & 7)] = __float2bfloat16_rn(P.pw_w[idx]);

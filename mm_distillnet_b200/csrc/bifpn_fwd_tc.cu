@@ -10,6 +10,8 @@
 //               signalled through tcgen05.commit -> mbarrier
 //   epilogue  : all 8 warps read the accumulator with tcgen05.ld (32 lanes x 8 columns at a time), add the bias, round
 //               to bf16 into a staging tile; then per-channel sum / sum-of-squares (train) and 16-byte coalesced stores.
+#include <stdlib.h>
+
 #include "bifpn.cuh"
 #include "tc.cuh"
 
@@ -63,15 +65,17 @@ __device__ __forceinline__ void tile_epilogue_tc(uint32_t tmem_base, const float
   tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
   __syncthreads();
   if (train && tid < C) {
-    double s = 0.0, q = 0.0;
-    for (int ty = 0; ty < th; ++ty)
+    // fp32 partial sums over one tile row (<= 16 values), accumulated in double across rows / tiles
+    for (int ty = 0; ty < th; ++ty) {
+      float s = 0.f, q = 0.f;
       for (int tx = 0; tx < tw; ++tx) {
-        const double v = (double)__bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
+        const float v = __bfloat162float(s_y[(ty * g.TW + tx) * LDS + tid]);
         s += v;
-        q = fma(v, v, q);
+        q = fmaf(v, v, q);
       }
-    st_sum += s;
-    st_sq += q;
+      st_sum += (double)s;
+      st_sq += (double)q;
+    }
   }
   for (int idx = tid; idx < g.TH * g.TW * NG; idx += kThreads) {
     const int p = idx / NG, gq = idx - p * NG;
@@ -162,6 +166,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_c
     s_k[tap * C + c] = P.dw_w[idx];
   }
   // B operand: W[n][k] (native [out][in]) -> bf16 [k/8][n][k%8]; eval: fold the BatchNorm scale of channel n
+#pragma unroll 7
   for (int idx = tid; idx < C * C; idx += kThreads) {
     const int n = idx / C, k = idx - n * C;
     float w = P.pw_w[idx];
@@ -277,17 +282,281 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_c
   bn_finalize_tc<C>(P, st_sum, st_sq, &s_flag);
 }
 
+
+// =====================================================================================================================
+// v2: same data flow, restructured CUDA-core phases (the tensor-core GEMM made them the critical path).
+//   phase 1: a thread owns (8-channel group, halo column) and walks the halo rows: 16-byte loads, BatchNorm scale/shift
+//            pre-multiplied by the fusion weight (one FMA per element and input), swish via one MUFU.TANH, no div/mod.
+//   phase 2: a thread owns (4-channel quad, column) and walks the rows with three rolling accumulators: every halo
+//            element is read from shared memory once per column instead of three times, taps live in registers.
+// =====================================================================================================================
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  f[4] = __uint_as_float(r.z << 16); f[5] = __uint_as_float(r.z & 0xffff0000u);
+  f[6] = __uint_as_float(r.w << 16); f[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack4(const uint2& r, float (&f)[4]) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float swish_fast(float x) {   // x * sigmoid(x) = 0.5 x (1 + tanh(x/2))
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 2) node_fwd_tc2_kernel(const __grid_constant__ NodeFwdP P) {
+  using S = FwdTcSmem<C>;
+  constexpr int NQ = C / 4, NG = C / 8;
+  constexpr uint32_t kTmemCols = 128;
+  constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  bf16* s_v = reinterpret_cast<bf16*>(smem_raw + S::offV);
+  bf16* s_y = s_v;
+  bf16* s_a = reinterpret_cast<bf16*>(smem_raw + S::offA);
+  bf16* s_b = reinterpret_cast<bf16*>(smem_raw + S::offB);
+  float* s_k = reinterpret_cast<float*>(smem_raw + S::offK);
+  float* s_bias = reinterpret_cast<float*>(smem_raw + S::offBias);
+  float* s_insc = reinterpret_cast<float*>(smem_raw + S::offInSc);   // [input][scale*w | shift*w][C] (pool: unweighted)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + S::offBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + S::offBar + 8);
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const TileGeom g = P.g;
+  const bool train = P.train != 0;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+
+  if (warp == 0) tc::tmem_alloc(s_tmem, kTmemCols);
+  if (tid == 32) {
+    tc::mbar_init(s_bar, 1);
+    tc::fence_mbar_init();
+  }
+  float wgt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
+  for (int idx = tid; idx < 9 * C; idx += kThreads) {
+    const int c = idx / 9, tap = idx - c * 9;
+    s_k[tap * C + c] = P.dw_w[idx];
+  }
+#pragma unroll 7
+  for (int idx = tid; idx < C * C; idx += kThreads) {
+    const int n = idx / C, k = idx - n * C;
+    float w = P.pw_w[idx];
+    if (!train) w *= P.bn_w[n] * rsqrtf(P.bn_rv[n] + P.bn_eps);
+    s_b[(k >> 3) * (C * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
+  }
+  if (tid < C) {
+    float bia = P.pw_b[tid];
+    if (!train) {
+      const float sc = P.bn_w[tid] * rsqrtf(P.bn_rv[tid] + P.bn_eps);
+      bia = (bia - P.bn_rm[tid]) * sc + P.bn_b[tid];
+    }
+    s_bias[tid] = bia;
+  }
+  for (int idx = tid; idx < 3 * C; idx += kThreads) {
+    const int i = idx / C, c = idx - i * C;
+    const float* bn = (i < P.n_in) ? P.in[i].bn : nullptr;
+    const float w = (i < P.n_in && P.mode[i] != MMD_IN_POOL) ? wgt[i] : 1.f;   // pool: the weight is applied after the max
+    s_insc[(2 * i) * C + c] = (bn ? bn[c] : 1.f) * w;
+    s_insc[(2 * i + 1) * C + c] = (bn ? bn[C + c] : 0.f) * w;
+  }
+  for (int idx = tid; idx < kTileP * C / 8; idx += kThreads) reinterpret_cast<uint4*>(s_a)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t a_addr = tc::smem_u32(s_a), b_addr = tc::smem_u32(s_b);
+
+  double st_sum = 0.0, st_sq = 0.0;
+  const int HW2 = g.TW + 2, HH2 = g.TH + 2;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    const int b = tile / (g.tiles_x * g.tiles_y);
+    const int rem = tile - b * (g.tiles_x * g.tiles_y);
+    const int ty0 = (rem / g.tiles_x) * g.TH, tx0 = (rem % g.tiles_x) * g.TW;
+    const int th = min(g.TH, g.H - ty0), tw = min(g.TW, g.W - tx0);
+
+    // ---- phase 1: fused inputs -> halo tile v (bf16)
+    for (int item = tid; item < NG * HW2; item += kThreads) {
+      const int col = item / NG, cg = item - col * NG;
+      const int x = tx0 - 1 + col;
+      const bool col_in = (x >= 0) && (x < g.W);
+      const bool col_center = (col >= 1) && (col <= tw);
+      for (int hy = 0; hy < HH2; ++hy) {
+        const int y = ty0 - 1 + hy;
+        uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+        if (col_in && y >= 0 && y < g.H) {
+          float u[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) u[e] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            if (i >= P.n_in) break;
+            const TensorP& t = P.in[i];
+            const bf16* base = reinterpret_cast<const bf16*>(t.data);
+            float sc[8], sh[8];
+            *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(s_insc + (2 * i) * C + 8 * cg);
+            *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(s_insc + (2 * i) * C + 8 * cg + 4);
+            *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(s_insc + (2 * i + 1) * C + 8 * cg);
+            *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(s_insc + (2 * i + 1) * C + 8 * cg + 4);
+            if (P.mode[i] != MMD_IN_POOL) {
+              const int sy = (P.mode[i] == MMD_IN_UP2) ? (y >> 1) : y;
+              const int sx = (P.mode[i] == MMD_IN_UP2) ? (x >> 1) : x;
+              const uint4 r = *reinterpret_cast<const uint4*>(base + (((long long)b * t.H + sy) * t.W + sx) * C + 8 * cg);
+              float f[8];
+              unpack8(r, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) u[e] += fmaf(f[e], sc[e], sh[e]);
+            } else {
+              const int top = pool_pad_before(t.H), left = pool_pad_before(t.W);
+              float m[8];
+              unsigned a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; a[e] = 9u; }
+#pragma unroll
+              for (int wy = 0; wy < 3; ++wy) {
+                const int fy = 2 * y - top + wy;
+#pragma unroll
+                for (int wx = 0; wx < 3; ++wx) {
+                  const int fx = 2 * x - left + wx;
+                  const bool inside = (fy >= 0) && (fy < t.H) && (fx >= 0) && (fx < t.W);
+                  float vv[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) vv[e] = 0.f;
+                  if (inside) {
+                    const uint4 r = *reinterpret_cast<const uint4*>(base + (((long long)b * t.H + fy) * t.W + fx) * C + 8 * cg);
+                    float f[8];
+                    unpack8(r, f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vv[e] = fmaf(f[e], sc[e], sh[e]);
+                  }
+                  const unsigned id = inside ? (unsigned)(wy * 3 + wx) : 9u;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (vv[e] > m[e]) { m[e] = vv[e]; a[e] = id; }
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) u[e] = fmaf(wgt[i], m[e], u[e]);
+              if (col_center && hy >= 1 && hy <= th && P.pidx[i] != nullptr) {
+                uint2 pk;
+                pk.x = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
+                pk.y = a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24);
+                *reinterpret_cast<uint2*>(P.pidx[i] + (((long long)b * g.H + y) * g.W + x) * C + 8 * cg) = pk;
+              }
+            }
+          }
+          if (P.swish) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[e] = swish_fast(u[e]);
+          }
+          packed.x = pack2(u[0], u[1]); packed.y = pack2(u[2], u[3]);
+          packed.z = pack2(u[4], u[5]); packed.w = pack2(u[6], u[7]);
+        }
+        *reinterpret_cast<uint4*>(s_v + (hy * HW2 + col) * C + 8 * cg) = packed;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: depthwise 3x3 with rolling accumulators -> A operand
+    for (int item = tid; item < NQ * g.TW; item += kThreads) {
+      const int c = item / NQ, q = item - c * NQ;
+      float4 wk[9];
+#pragma unroll
+      for (int t9 = 0; t9 < 9; ++t9) wk[t9] = *reinterpret_cast<const float4*>(s_k + t9 * C + 4 * q);
+      float4 acc0 = f4_zero(), acc1 = f4_zero(), acc2 = f4_zero();
+      const bf16* vcol = s_v + c * C + 4 * q;
+      const int a_off = (q >> 1) * (kTileP * 8) + (q & 1) * 4;
+      bf16* dsave = (P.save_d != nullptr)
+                        ? reinterpret_cast<bf16*>(P.save_d) + (((long long)b * g.H + ty0) * g.W + tx0 + c) * C + 4 * q
+                        : nullptr;
+      auto row_step = [&](int r, float4& a_new, float4& a_mid, float4& a_old) {
+        // input halo row r: tap row 0 of output r (a_new), tap row 1 of output r-1 (a_mid), tap row 2 of output r-2 (a_old)
+        float4 v[3];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(vcol + (r * HW2 + dx) * C);
+          float f[4];
+          unpack4(raw, f);
+          v[dx] = make_float4(f[0], f[1], f[2], f[3]);
+        }
+        a_new = f4_mul(v[0], wk[0]);
+        a_new = f4_fma(v[1], wk[1], a_new);
+        a_new = f4_fma(v[2], wk[2], a_new);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          a_mid = f4_fma(v[dx], wk[3 + dx], a_mid);
+          a_old = f4_fma(v[dx], wk[6 + dx], a_old);
+        }
+        const int ty = r - 2;
+        if (ty >= 0 && ty < th && c < tw) {
+          uint2 pk;
+          pk.x = pack2(a_old.x, a_old.y);
+          pk.y = pack2(a_old.z, a_old.w);
+          *reinterpret_cast<uint2*>(s_a + a_off + (ty * g.TW + c) * 8) = pk;
+          if (dsave) *reinterpret_cast<uint2*>(dsave + (long long)ty * g.W * C) = pk;
+        }
+      };
+      for (int r0 = 0; r0 < HH2; r0 += 3) {
+        row_step(r0, acc0, acc2, acc1);
+        if (r0 + 1 < HH2) row_step(r0 + 1, acc1, acc0, acc2);
+        if (r0 + 2 < HH2) row_step(r0 + 2, acc2, acc1, acc0);
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) {
+        const uint64_t adesc = tc::make_desc(a_addr + j * 2 * (kTileP * 16), kTileP * 16, 128);
+        const uint64_t bdesc = tc::make_desc(b_addr + j * 2 * (C * 16), C * 16, 128);
+        tc::umma_bf16(tmem_base, adesc, bdesc, kIdesc, j > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(s_bar);
+    }
+    tc::mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+    tile_epilogue_tc<C>(tmem_base, s_bias, s_y, out, g, b, ty0, tx0, th, tw, train, st_sum, st_sq);
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (!train) return;
+  bn_finalize_tc<C>(P, st_sum, st_sq, &s_flag);
+}
+
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   constexpr int CC = 112;
   const size_t smem = FwdTcSmem<CC>::kBytes;
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("MMD_FWD_V1");
+    use_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
   MMD_CUDA(cudaFuncSetAttribute(node_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMD_CUDA(cudaFuncSetAttribute(node_fwd_tc2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.g.ntiles < 2 * sms ? p.g.ntiles : 2 * sms;
   ProfScope prof(PK_NODE_FWD, node_algo_bytes(p.in, p.n_in, p.g, C, 2), s);
-  node_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p);
+  if (use_v1) node_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p);
+  else node_fwd_tc2_kernel<CC><<<grid, kThreads, smem, s>>>(p);
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -324,6 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
     tc::mbar_init(s_bar, 1);
     tc::fence_mbar_init();
   }
+#pragma unroll 8
   for (int idx = tid; idx < C * Kp; idx += kThreads) {
     const int n = idx / Kp, k = idx - n * Kp;
     float w = 0.f;
