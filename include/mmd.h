@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 100
+#define MMD_VERSION 101
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -135,6 +135,8 @@ typedef struct {
   MmdTensor out;          /* fwd: produced tensor; bwd: the same tensor (its raw values are read again) */
   MmdRef save_d;          /* NODE train: depthwise output kept for the pointwise weight gradient */
   MmdRef pidx[3];         /* NODE / BNAPPLY train: arg-max indices written for pooled inputs */
+  MmdRef packed;          /* NODE / PROJ: this op's packed parameter block (written by mmd_bifpn_prep, layout below); */
+                          /* NULL: the kernels convert the fp32 parameters themselves (slow path)                 */
   MmdRef stats;           /* double[2*C] accumulators, zero on entry, re-zeroed by the kernel */
   MmdRef counter;         /* uint32, zero on entry, re-zeroed by the kernel */
   /* backward only */
@@ -146,6 +148,21 @@ typedef struct {
   MmdRef dx;              /* PROJ_BWD: dL/d(input) [B][H][W][Cin]; PULL: gathered dL/d(out) */
   MmdRef g_dw, g_pw, g_pb, g_bn_w, g_bn_b, g_fw; /* fp32 parameter gradients (zero on entry; accumulated) */
 } MmdOp;
+
+/* Packed parameter block of one NODE / PROJ op (bf16 storage only; every section starts 128-byte aligned):
+ *   [0, Kp*C*2)          forward B operand: bf16 [Kp/8][C][8] = W[n][k] (k < Cin, zero padded to Kp = ceil16(Cin)),
+ *                         eval mode: W[n][k] * gamma[n] / sqrt(running_var[n] + eps)
+ *   then  float bias[C]   (eval: (b - running_mean) * gamma / sqrt(running_var + eps) + beta)
+ *   then  float taps[9][C] (NODE only: depthwise weights, tap-major)
+ *   then  (NODE, train)   backward B operand: bf16 [C/8][C][8] = W[o][i] stored as [o/8][i][o%8]
+ * mmd_packed_bytes(kind, Cin, C) returns the block size the host must reserve. */
+size_t mmd_packed_bytes(int32_t kind, int32_t Cin, int32_t C);
+
+/* (Re)build the packed blocks of every NODE_FWD / PROJ_FWD op in `ops` whose `packed` reference is non-NULL, from the
+ * current fp32 parameters (and, in eval mode, the running statistics).  One or two launches for a whole stack.  Call it
+ * whenever the parameters may have changed since the last call (every training step; once for frozen teachers). */
+int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases, int32_t C, int32_t dtype,
+                   mmd_stream_t stream);
 
 /* Run `n_ops` ops in order on `stream`.  `C` is the pyramid channel count (112 for EfficientDet-D2). */
 int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases,

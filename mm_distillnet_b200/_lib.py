@@ -10,7 +10,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
-SOURCES = ("api.cu", "mta.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu", "bifpn_run.cu")
+SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v3.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu",
+           "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1
@@ -55,7 +56,7 @@ class Op(C.Structure):
         ("in_bn_w", C.c_void_p * 3), ("in_bn_b", C.c_void_p * 3),
         ("Cin", C.c_int32), ("accumulate_dx", C.c_int32), ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
         ("out", Tensor),
-        ("save_d", Ref), ("pidx", Ref * 3), ("stats", Ref), ("counter", Ref),
+        ("save_d", Ref), ("pidx", Ref * 3), ("packed", Ref), ("stats", Ref), ("counter", Ref),
         ("n_cons", C.c_int32), ("pad_", C.c_int32),
         ("cons", Cons * 3),
         ("du", Ref), ("dd", Ref), ("in_slot", Ref * 3), ("dx", Ref),
@@ -111,6 +112,10 @@ def lib():
     L.mmd_bifpn_run.restype = C.c_int
     L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.mmd_bifpn_prep.restype = C.c_int
+    L.mmd_bifpn_prep.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.mmd_packed_bytes.restype = C.c_size_t
+    L.mmd_packed_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     L.mmd_prof_enable.argtypes = [C.c_int]
     L.mmd_prof_enable.restype = None
     L.mmd_prof_num_kinds.restype = C.c_int
@@ -150,5 +155,6 @@ def prof_collect():
 
 
 EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run",
+           "mmd_bifpn_prep", "mmd_packed_bytes",
            "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
            "mmd_prof_collect")

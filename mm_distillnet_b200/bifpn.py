@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 
+_STATS_EPOCH = 0     # bumped by every train-mode forward (running statistics change behind PyTorch's version counters)
 BN_MOMENTUM = 0.01   # src/YetAnotherEfficientDet.py:176
 BN_EPS = 1e-3
 _ALIGN = 256
@@ -170,7 +171,7 @@ class _Tn:
 
 class _OpN:
     __slots__ = ("kind", "ins", "modes", "conv", "bn", "dw", "fw", "fw_eps", "swish", "out", "save_d", "pidx",
-                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref")
+                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed")
 
     def __init__(self, kind):
         self.kind = kind
@@ -186,6 +187,7 @@ class _OpN:
         self.glike = None      # BNAPPLY: (base, off) of the gradient of its output
         self.cin = 0
         self.gref = {}
+        self.packed = None     # (base, off) of the packed parameter block (bf16 plans)
 
 
 # fixed base indices
@@ -246,6 +248,7 @@ class _Plan:
         self.ops = []
         self.Cc = None
         self.params = self._collect_params(mods)
+        self.state_tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
         self.grad_off = {}
         if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
             off = 0
@@ -279,7 +282,14 @@ class _Plan:
             t.bn = (B_FWD, self.fwd_arena.alloc(4 * self.Cc * 4))
         return t
 
+    def _packed_storage(self, op):
+        """bf16 plans: room for the op's packed parameter block (written by mmd_bifpn_prep)."""
+        if self.dtype == torch.bfloat16:
+            n = _lib.lib().mmd_packed_bytes(op.kind, op.cin if op.kind == _lib.OP_PROJ_FWD else self.Cc, self.Cc)
+            op.packed = (B_PERSIST, self.persist.alloc(n))
+
     def _train_storage(self, op):
+        self._packed_storage(op)
         if self.train:
             op.stats = (B_PERSIST, self.persist.alloc(2 * self.Cc * 8))
             op.counter = (B_PERSIST, self.persist.alloc(4))
@@ -437,6 +447,7 @@ class _Plan:
         o.Cin = op.cin
         o.out = _tensor(op.out)
         o.save_d = _ref(op.save_d)
+        o.packed = _ref(op.packed)
         for i in range(3):
             o.pidx[i] = _ref(op.pidx[i])
             o.in_slot[i] = _ref(op.slots[i])
@@ -686,6 +697,26 @@ class _Runner:
                                           _lib.MMD_F32 if plan.dtype == torch.float32 else _lib.MMD_BF16, stream)
         _lib.check(rc, "mmd_bifpn_run")
 
+    def _prep(self, plan, bases):
+        """(Re)build the packed parameter blocks when the parameters may have changed: every training forward (the
+        optimiser updates the weights between steps); for eval plans (frozen teachers) only when a parameter / buffer
+        version or the global running-statistics epoch moved."""
+        global _STATS_EPOCH
+        if plan.dtype != torch.bfloat16:
+            return
+        if plan.train:
+            _STATS_EPOCH += 1     # this forward updates running statistics through raw pointers
+        else:
+            sig = (_STATS_EPOCH, tuple(t._version for t in plan.state_tensors))
+            if getattr(plan, "_prep_sig", None) == sig:
+                return
+            plan._prep_sig = sig
+        arr = (C.c_void_p * len(bases))(*bases)
+        with torch.cuda.device(plan.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = _lib.lib().mmd_bifpn_prep(plan.fwd_ops, len(plan.fwd_ops), arr, len(bases), plan.Cc, _lib.MMD_BF16, stream)
+        _lib.check(rc, "mmd_bifpn_prep")
+
     def _forward(self, plan, inputs):
         dev = plan.device
         xs = [x.detach().contiguous(memory_format=torch.channels_last) for x in inputs]
@@ -698,6 +729,7 @@ class _Runner:
             bases[B_EXT + i] = x.data_ptr()
         for k, o in enumerate(outs):
             bases[plan.B_OUT + k] = o.data_ptr()
+        self._prep(plan, bases)
         self._call(plan, plan.fwd_ops, bases)
         return outs, (xs, arena, outs)
 

@@ -51,6 +51,24 @@ inline double node_algo_bytes(const TensorP* in, int n_in, const TileGeom& g, in
   return pos * g.B * C * (double)esize;
 }
 
+// Layout of one op's packed parameter block (include/mmd.h, written by prep.cu).
+struct PackedLayout {
+  int Kp;              // K of the forward GEMM, padded to a multiple of 16
+  int offBias, offTaps, offBwd, fwdBytes, bytes;
+};
+inline PackedLayout packed_layout(int kind, int Cin, int C) {
+  PackedLayout L;
+  const bool node = (kind == MMD_OP_NODE_FWD || kind == MMD_OP_NODE_BWD);
+  if (node) Cin = C;
+  L.Kp = (Cin + 15) / 16 * 16;
+  L.offBias = (L.Kp * C * 2 + 127) / 128 * 128;
+  L.offTaps = L.offBias + C * 4;
+  L.fwdBytes = node ? L.offTaps + 9 * C * 4 : L.offTaps;   // what the forward kernel copies into shared memory
+  L.offBwd = (L.fwdBytes + 127) / 128 * 128;
+  L.bytes = node ? L.offBwd + (C * C * 2 + 127) / 128 * 128 : L.offBwd;
+  return L;
+}
+
 struct NodeFwdP {
   TensorP in[3];
   int mode[3];
@@ -63,6 +81,7 @@ struct NodeFwdP {
   void* out;
   float* out_bn;
   void* save_d;
+  const unsigned char* packed;  // packed parameter block (nullptr: convert in the kernel)
   unsigned char* pidx[3];
   double* stats;
   unsigned* counter;
@@ -94,6 +113,7 @@ struct NodeBwdP {
   const void* out;      // raw forward output of this op
   const float* out_bn;  // its scale/shift/mean/invstd
   const void* save_d;
+  const unsigned char* packed;   // packed parameter block of the forward op (nullptr: convert in the kernel)
   const unsigned char* pidx[3];  // arg-max indices written by the forward for pooled inputs
   int n_cons;
   ConsP cons[3];
@@ -156,6 +176,8 @@ __device__ __forceinline__ void load_input(const TensorP& t, int mode, int b, in
 // kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)
 int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, tcgen05 pointwise conv
+int launch_node_fwd_v3(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, packed parameters + bulk-copy staging
+bool fwd_v3_usable(const NodeFwdP& p);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead

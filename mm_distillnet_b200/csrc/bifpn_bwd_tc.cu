@@ -25,12 +25,12 @@ struct BwdATcSmem {
   static constexpr int kBBytes = C * C * 2;
   static constexpr int offCoef = offB + ((kBBytes + 127) / 128) * 128;
   static constexpr int offBar = offCoef + 3 * C * 4;
-  static constexpr int kBytes = offBar + 16;
+  static constexpr int kBytes = offBar + 32;
   static_assert(kTileP * LDS * 2 <= 2 * kTileBytes, "staging tile must fit in the two operand tiles");
 };
 
 template <int C>
-__global__ void __launch_bounds__(kThreads, 2) node_bwd_a_tc_kernel(const __grid_constant__ NodeBwdP P) {
+__global__ void __launch_bounds__(kThreads, 2) node_bwd_a_tc_kernel(const __grid_constant__ NodeBwdP P, int packed_off_bwd) {
   using S = BwdATcSmem<C>;
   constexpr int NQ = C / 4, NG = C / 8, LDS = S::LDS;
   constexpr uint32_t kTmemCols = 256;   // [0,128): dL/dd accumulator, [128,256): dW accumulator
@@ -56,11 +56,22 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a_tc_kernel(const __grid
   float cw[3];
   cons_weights(P, cw);
   bn_bwd_coefs<C>(P, cw, s_coef);
-  // B operand of GEMM 1: B[n = i][k = o] = W[o][i]  ->  bf16 [o/8][i][o%8]
+  // B operand of GEMM 1: B[n = i][k = o] = W[o][i]  ->  bf16 [o/8][i][o%8]: one bulk copy of the block prepared by
+  // mmd_bifpn_prep, or (no packed block) converted here from the fp32 parameter
+  uint64_t* s_bar_w = s_bar + 2;
+  if (P.packed != nullptr) {
+    if (tid == 32) {
+      tc::mbar_init(s_bar_w, 1);
+      tc::fence_mbar_init();
+      tc::mbar_expect_tx(s_bar_w, C * C * 2);
+      tc::bulk_g2s(s_b, P.packed + packed_off_bwd, C * C * 2, s_bar_w);
+    }
+  } else {
 #pragma unroll 7
-  for (int idx = tid; idx < C * C; idx += kThreads) {
-    const int o = idx / C, i = idx - o * C;
-    s_b[(o >> 3) * (C * 8) + i * 8 + (o & 7)] = __float2bfloat16_rn(P.pw_w[idx]);
+    for (int idx = tid; idx < C * C; idx += kThreads) {
+      const int o = idx / C, i = idx - o * C;
+      s_b[(o >> 3) * (C * 8) + i * 8 + (o & 7)] = __float2bfloat16_rn(P.pw_w[idx]);
+    }
   }
   tc::fence_async_smem();
   tc::fence_before_sync();
@@ -106,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a_tc_kernel(const __grid
     __syncthreads();
 
     if (tid == 0) {
+      if (iter == 0 && P.packed != nullptr) tc::mbar_wait(s_bar_w, 0u);   // W^T has landed (only the MMAs read it)
       tc::fence_after_sync();
 #pragma unroll
       for (int j = 0; j < C / 16; ++j) {   // GEMM 1: K runs over the output channels o
@@ -191,7 +203,7 @@ int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.g.ntiles < 2 * sms ? p.g.ntiles : 2 * sms;
   ProfScope prof(PK_NODE_BWD_A, node_algo_bytes(p.in, p.n_in, p.g, C, 2), s);
-  node_bwd_a_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p);
+  node_bwd_a_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p, packed_layout(MMD_OP_NODE_FWD, C, C).offBwd);
   MMD_LAUNCH_CHECK();
   return 0;
 }

@@ -542,6 +542,12 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc2_kernel(const __grid_
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   constexpr int CC = 112;
+  static int no_v3 = -1;
+  if (no_v3 < 0) {
+    const char* e = getenv("MMD_NO_V3");
+    no_v3 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!no_v3 && fwd_v3_usable(p)) return launch_node_fwd_v3(p, C, s);
   const size_t smem = FwdTcSmem<CC>::kBytes;
   static int use_v1 = -1;
   if (use_v1 < 0) {
@@ -566,7 +572,7 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
 // A = the input tile itself: a 16-byte global chunk (position p, channels 8k..8k+7) IS one row of core matrix k, so the
 // NHWC -> UMMA layout change costs nothing.  K is padded to a multiple of 16 with zero chunks (Cin = 120 -> 128).
 template <int C>
-__global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_constant__ NodeFwdP P, int Kp) {
+__global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_constant__ NodeFwdP P, int Kp, int packed_off_bias) {
   constexpr int LDS = C + 8;
   constexpr uint32_t kTmemCols = 128;
   constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
@@ -593,23 +599,34 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
     tc::mbar_init(s_bar, 1);
     tc::fence_mbar_init();
   }
+  uint64_t* s_bar_w = s_bar + 2;
+  if (P.packed != nullptr) {   // B operand + bias prepared by mmd_bifpn_prep: two bulk copies
+    if (tid == 32) {
+      tc::mbar_init(s_bar_w, 1);
+      tc::fence_mbar_init();
+      tc::mbar_expect_tx(s_bar_w, (uint32_t)(Kp * C * 2 + C * 4));
+      tc::bulk_g2s(s_b, P.packed, (uint32_t)(Kp * C * 2), s_bar_w);
+      tc::bulk_g2s(s_bias, P.packed + packed_off_bias, C * 4, s_bar_w);
+    }
+  } else {
 #pragma unroll 8
-  for (int idx = tid; idx < C * Kp; idx += kThreads) {
-    const int n = idx / Kp, k = idx - n * Kp;
-    float w = 0.f;
-    if (k < Cin) {
-      w = P.pw_w[(long long)n * Cin + k];
-      if (!train) w *= P.bn_w[n] * rsqrtf(P.bn_rv[n] + P.bn_eps);
+    for (int idx = tid; idx < C * Kp; idx += kThreads) {
+      const int n = idx / Kp, k = idx - n * Kp;
+      float w = 0.f;
+      if (k < Cin) {
+        w = P.pw_w[(long long)n * Cin + k];
+        if (!train) w *= P.bn_w[n] * rsqrtf(P.bn_rv[n] + P.bn_eps);
+      }
+      s_b[(k >> 3) * (C * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
     }
-    s_b[(k >> 3) * (C * 8) + n * 8 + (k & 7)] = __float2bfloat16_rn(w);
-  }
-  if (tid < C) {
-    float bia = P.pw_b[tid];
-    if (!train) {
-      const float sc = P.bn_w[tid] * rsqrtf(P.bn_rv[tid] + P.bn_eps);
-      bia = (bia - P.bn_rm[tid]) * sc + P.bn_b[tid];
+    if (tid < C) {
+      float bia = P.pw_b[tid];
+      if (!train) {
+        const float sc = P.bn_w[tid] * rsqrtf(P.bn_rv[tid] + P.bn_eps);
+        bia = (bia - P.bn_rm[tid]) * sc + P.bn_b[tid];
+      }
+      s_bias[tid] = bia;
     }
-    s_bias[tid] = bia;
   }
   tc::fence_async_smem();
   tc::fence_before_sync();
@@ -619,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
   const uint32_t a_addr = tc::smem_u32(s_a), b_addr = tc::smem_u32(s_b);
   double st_sum = 0.0, st_sq = 0.0;
   uint32_t phase = 0;
+  bool first_tile = true;
 
   for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
     const int b = tile / (g.tiles_x * g.tiles_y);
@@ -635,6 +653,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
     }
     tc::fence_async_smem();
     __syncthreads();
+    if (first_tile && P.packed != nullptr) tc::mbar_wait(s_bar_w, 0u);   // weights + bias have landed
+    first_tile = false;
     if (tid == 0) {
       tc::fence_after_sync();
       for (int j = 0; j < Kp / 16; ++j) {
@@ -661,7 +681,7 @@ int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   MMD_CHECK_ARG(p.Cin % 8 == 0, "bf16 projection needs Cin %% 8 == 0, got %d", p.Cin);
   constexpr int CC = 112;
   const int Kp = (p.Cin + 15) / 16 * 16, KG = Kp / 8;
-  const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 16;
+  const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 32;
   MMD_CHECK_ARG(smem <= 227 * 1024, "projection with Cin=%d does not fit in shared memory", p.Cin);
   MMD_CUDA(cudaFuncSetAttribute(proj_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
@@ -670,7 +690,7 @@ int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int grid = p.g.ntiles < per_sm * sms ? p.g.ntiles : per_sm * sms;
   ProfScope prof(PK_PROJ_FWD, (double)p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2, s);
-  proj_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p, Kp);
+  proj_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p, Kp, packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBias);
   MMD_LAUNCH_CHECK();
   return 0;
 }

@@ -31,6 +31,7 @@ static int fill_fwd(const MmdOp& op, const Bases& B, int batch, NodeFwdP& p) {
   p.out = B.get<void>(op.out.data);
   p.out_bn = B.get<float>(op.out.bn);
   p.save_d = B.get<void>(op.save_d);
+  p.packed = B.get<unsigned char>(op.packed);
   p.stats = B.get<double>(op.stats);
   p.counter = B.get<unsigned>(op.counter);
   p.bn_eps = op.bn_eps;
@@ -63,6 +64,7 @@ static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
   p.out = B.get<void>(op.out.data);
   p.out_bn = B.get<float>(op.out.bn);
   p.save_d = B.get<void>(op.save_d);
+  p.packed = B.get<unsigned char>(op.packed);
   p.n_cons = op.n_cons;
   MMD_CHECK_ARG(op.n_cons >= 0 && op.n_cons <= 3, "op: n_cons=%d", op.n_cons);
   for (int c = 0; c < 3; ++c) {

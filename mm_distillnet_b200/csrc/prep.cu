@@ -1,0 +1,133 @@
+// mmd_bifpn_prep: build the packed parameter blocks (include/mmd.h) of every NODE / PROJ op of a stack in one or two
+// launches.  The per-tile kernels then fetch their B operands / bias / depthwise taps with ONE bulk copy into shared
+// memory instead of every CTA re-reading and re-formatting ~50 KB of fp32 parameters.
+//
+//   forward B operand : bf16 [Kp/8][C][8], W[n][k] (eval: BatchNorm scale folded: src/YetAnotherEfficientDet.py:176 with
+//                       running statistics), zero padded in k up to Kp = ceil16(Cin)
+//   bias              : fp32 [C] (eval: folded)
+//   taps              : fp32 [9][C] (depthwise [C,1,3,3] transposed to tap-major)
+//   backward B operand: bf16 [C/8][C][8], element (o, i) of W stored at [o/8][i][o%8]  (dL/dd = dy * W)
+#include "bifpn.cuh"
+
+namespace mmd {
+
+struct PrepDesc {
+  const float *pw_w, *pw_b, *bn_w, *bn_b, *bn_rm, *bn_rv, *dw_w;
+  unsigned char* dst;
+  int Cin, Kp, train, node;
+  int offBias, offTaps, offBwd;
+  float eps;
+};
+constexpr int kPrepMax = 24;   // descriptors per launch (kernel parameter space is 4 KB)
+struct PrepArgs {
+  PrepDesc d[kPrepMax];
+};
+
+__device__ __forceinline__ uint32_t prep_pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepArgs A) {
+  const PrepDesc& D = A.d[blockIdx.x];
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nthr = gridDim.y * blockDim.x;
+  const int KG = D.Kp / 8;
+  // forward B operand: one 16-byte chunk (kg, n) per item
+  for (int item = tid; item < KG * C; item += nthr) {
+    const int kg = item / C, n = item - kg * C;
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * kg + j;
+      w[j] = (k < D.Cin) ? D.pw_w[(long long)n * D.Cin + k] : 0.f;
+    }
+    if (!D.train) {
+      const float sc = D.bn_w[n] * rsqrtf(D.bn_rv[n] + D.eps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] *= sc;
+    }
+    uint4 r;
+    r.x = prep_pack2(w[0], w[1]); r.y = prep_pack2(w[2], w[3]);
+    r.z = prep_pack2(w[4], w[5]); r.w = prep_pack2(w[6], w[7]);
+    *reinterpret_cast<uint4*>(D.dst + ((size_t)kg * C + n) * 16) = r;
+  }
+  if (blockIdx.y == 0 && threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float bia = D.pw_b[c];
+    if (!D.train) {
+      const float sc = D.bn_w[c] * rsqrtf(D.bn_rv[c] + D.eps);
+      bia = (bia - D.bn_rm[c]) * sc + D.bn_b[c];
+    }
+    reinterpret_cast<float*>(D.dst + D.offBias)[c] = bia;
+  }
+  if (!D.node) return;
+  float* taps = reinterpret_cast<float*>(D.dst + D.offTaps);
+  for (int idx = tid; idx < 9 * C; idx += nthr) {
+    const int tap = idx / C, c = idx - tap * C;
+    taps[idx] = D.dw_w[c * 9 + tap];
+  }
+  if (!D.train) return;
+  // backward B operand: chunk (og, i) holds W[8*og + j][i], j = 0..7
+  for (int item = tid; item < (C / 8) * C; item += nthr) {
+    const int og = item / C, i = item - og * C;
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = D.pw_w[(long long)(8 * og + j) * C + i];
+    uint4 r;
+    r.x = prep_pack2(w[0], w[1]); r.y = prep_pack2(w[2], w[3]);
+    r.z = prep_pack2(w[4], w[5]); r.w = prep_pack2(w[6], w[7]);
+    *reinterpret_cast<uint4*>(D.dst + D.offBwd + ((size_t)og * C + i) * 16) = r;
+  }
+}
+
+}  // namespace mmd
+
+using namespace mmd;
+
+extern "C" size_t mmd_packed_bytes(int32_t kind, int32_t Cin, int32_t C) {
+  if (kind != MMD_OP_NODE_FWD && kind != MMD_OP_PROJ_FWD) return 0;
+  return (size_t)packed_layout(kind, Cin, C).bytes;
+}
+
+extern "C" int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases, int32_t C,
+                              int32_t dtype, mmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMD_CHECK_ARG(ops != nullptr && n_ops >= 0 && bases != nullptr, "mmd_bifpn_prep: null arguments");
+  MMD_CHECK_ARG(C == 112, "mmd_bifpn_prep: kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  if (dtype != MMD_BF16) return 0;   // the fp32 parity kernels read the fp32 parameters directly
+  Bases B{bases, n_bases};
+  PrepArgs args;
+  int n = 0;
+  auto flush = [&]() -> int {
+    if (n == 0) return 0;
+    prep_kernel<112><<<dim3(n, 4), 256, 0, stream>>>(args);
+    MMD_LAUNCH_CHECK();
+    n = 0;
+    return 0;
+  };
+  for (int i = 0; i < n_ops; ++i) {
+    const MmdOp& op = ops[i];
+    if (op.kind != MMD_OP_NODE_FWD && op.kind != MMD_OP_PROJ_FWD) continue;
+    unsigned char* dst = B.get<unsigned char>(op.packed);
+    if (dst == nullptr) continue;
+    const bool node = op.kind == MMD_OP_NODE_FWD;
+    MMD_CHECK_ARG(op.pw_w && op.pw_b && op.bn_w && op.bn_b && op.bn_rm && op.bn_rv, "prep: op %d misses parameters", i);
+    MMD_CHECK_ARG(!node || op.dw_w != nullptr, "prep: node op %d has no depthwise weight", i);
+    const int Cin = node ? C : op.Cin;
+    MMD_CHECK_ARG(Cin >= 4, "prep: op %d has Cin=%d", i, Cin);
+    const PackedLayout L = packed_layout(op.kind, Cin, C);
+    PrepDesc& D = args.d[n++];
+    D.pw_w = op.pw_w; D.pw_b = op.pw_b; D.bn_w = op.bn_w; D.bn_b = op.bn_b;
+    D.bn_rm = op.bn_rm; D.bn_rv = op.bn_rv; D.dw_w = op.dw_w;
+    D.dst = dst;
+    D.Cin = Cin; D.Kp = L.Kp; D.train = op.train; D.node = node ? 1 : 0;
+    D.offBias = L.offBias; D.offTaps = L.offTaps; D.offBwd = L.offBwd;
+    D.eps = op.bn_eps;
+    if (n == kPrepMax) {
+      int rc = flush();
+      if (rc) return rc;
+    }
+  }
+  return flush();
+}

@@ -55,6 +55,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- bulk asynchronous copies global -> shared (cp.async.bulk, SASS UBLKCP), completion on an mbarrier -------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// `bytes` must be a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(__cvta_generic_to_global(src_gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2) and bf16 <-> fp32 helpers -----------------------------
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {   // two bf16 in one word -> two floats
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float swish1(float x) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (one MUFU.TANH)
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+__device__ __forceinline__ float2 swish2(float2 x) {
+  const float2 h = mul2(x, make_float2(0.5f, 0.5f));
+  float tx, ty;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+  return fma2(h, make_float2(tx, ty), h);
+}
+
 // TMEM allocation: executed by ONE full warp; the base address is written to shared memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
