@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 101
+#define MMD_VERSION 102
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -106,7 +106,10 @@ enum {
   MMD_OP_NODE_BWD = 4,  /* backward of NODE_FWD (two kernels: pointwise/BN part, depthwise/fusion part)                              */
   MMD_OP_PROJ_BWD = 5,  /* backward of PROJ_FWD                                                                                      */
   MMD_OP_PULL = 6,      /* dx = gathered gradient of `out` from its consumers (stack inputs, P6/P7 synthesis)                        */
-  MMD_OP_SLOT = 7       /* slot = (sum G, sum G*xhat) for a deferred tensor consumed by a BNAPPLY op                                 */
+  MMD_OP_SLOT = 7,      /* slot = (sum G, sum G*xhat) for a deferred tensor consumed by a BNAPPLY op                                 */
+  MMD_OP_POOLFUSE = 8   /* bf16 plans: out = w_a * pool3x3s2(bn(in[0])) [+ w_b * bn(in[1])], final values; the pre-pass that turns a  */
+                        /* node's pooled input (and its second same-resolution input) into ONE same-resolution operand, so that   */
+                        /* every NODE_FWD stages at most two inputs.  pidx[0]: arg-max bytes, save_d: raw value at the arg-max    */
 };
 
 typedef struct {
@@ -147,6 +150,9 @@ typedef struct {
   MmdRef in_slot[3];      /* NODE_BWD: double[2*C] per input edge (zero on entry) */
   MmdRef dx;              /* PROJ_BWD: dL/d(input) [B][H][W][Cin]; PULL: gathered dL/d(out) */
   MmdRef g_dw, g_pw, g_pb, g_bn_w, g_bn_b, g_fw; /* fp32 parameter gradients (zero on entry; accumulated) */
+  /* fusion-weight selection for ops that see only part of a node's inputs (NODE_FWD fed by a POOLFUSE, POOLFUSE itself):  */
+  int32_t fw_n;           /* number of entries of `fw`; 0: fw has n_in entries and input i uses entry i                      */
+  int32_t fw_idx[3];      /* entry of `fw` that weighs input i; -1: the input is already weighted (weight 1)                 */
 } MmdOp;
 
 /* Packed parameter block of one NODE / PROJ op (bf16 storage only; every section starts 128-byte aligned):

@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
-SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v3.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu",
+SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu",
            "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
@@ -19,7 +19,7 @@ MTA_MAX_LEVELS, MTA_MAX_TEACHERS = 8, 4
 
 IN_SAME, IN_UP2, IN_POOL = 0, 1, 2
 CONS_SAME, CONS_UP2, CONS_POOL = 0, 1, 2
-OP_NODE_FWD, OP_PROJ_FWD, OP_BNAPPLY, OP_NODE_BWD, OP_PROJ_BWD, OP_PULL, OP_SLOT = 1, 2, 3, 4, 5, 6, 7
+OP_NODE_FWD, OP_PROJ_FWD, OP_BNAPPLY, OP_NODE_BWD, OP_PROJ_BWD, OP_PULL, OP_SLOT, OP_POOLFUSE = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class MtaArgs(C.Structure):
@@ -61,6 +61,7 @@ class Op(C.Structure):
         ("cons", Cons * 3),
         ("du", Ref), ("dd", Ref), ("in_slot", Ref * 3), ("dx", Ref),
         ("g_dw", Ref), ("g_pw", Ref), ("g_pb", Ref), ("g_bn_w", Ref), ("g_bn_b", Ref), ("g_fw", Ref),
+        ("fw_n", C.c_int32), ("fw_idx", C.c_int32 * 3),
     ]
 
 

@@ -171,7 +171,7 @@ class _Tn:
 
 class _OpN:
     __slots__ = ("kind", "ins", "modes", "conv", "bn", "dw", "fw", "fw_eps", "swish", "out", "save_d", "pidx",
-                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed")
+                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed", "aux", "praw")
 
     def __init__(self, kind):
         self.kind = kind
@@ -188,6 +188,8 @@ class _OpN:
         self.cin = 0
         self.gref = {}
         self.packed = None     # (base, off) of the packed parameter block (bf16 plans)
+        self.aux = None        # bf16 plans, nodes with a pooled input: (base, off) of the POOLFUSE pre-pass output
+        self.praw = None       # ... and of the raw value at each pooling arg-max (kept for the backward)
 
 
 # fixed base indices
@@ -316,6 +318,11 @@ class _Plan:
         op.out = self._new_raw(H, W, sep.bn)
         op.out.producer = op
         self._train_storage(op)
+        if self.dtype == torch.bfloat16 and _lib.IN_POOL in op.modes:
+            n = self.B * H * W * self.Cc
+            op.aux = (B_FWD, self.fwd_arena.alloc(n * self.esize))
+            if self.need_grad:
+                op.praw = (B_FWD, self.fwd_arena.alloc(n * self.esize))
         if self.need_grad:
             n = self.B * H * W * self.Cc
             op.save_d = (B_FWD, self.fwd_arena.alloc(n * self.esize))
@@ -453,14 +460,56 @@ class _Plan:
             o.in_slot[i] = _ref(op.slots[i])
 
     def _emit_fwd(self):
-        arr = (_lib.Op * len(self.ops))()
-        for o, op in zip(arr, self.ops):
-            _null_refs(o)
+        out = []
+        for op in self.ops:
+            o = _new_op()
             o.kind = op.kind
             o.train = 1 if self.train else 0
             self._fill_common(o, op)
             o.stats, o.counter = _ref(op.stats), _ref(op.counter)
+            if op.aux is not None:
+                out.append(self._split_pooled(o, op))
+            out.append(o)
+        arr = (_lib.Op * len(out))()
+        for i, o in enumerate(out):
+            arr[i] = o
+        self._fwd_keep = out
         return arr
+
+    def _split_pooled(self, o, op):
+        """bf16 plans: a node with a pooled input runs as POOLFUSE (pooled input [+ the other non-first input] -> one
+        pre-weighted operand `aux`) followed by the node kernel on (input 0, aux).  Rewrites `o` in place and returns the
+        POOLFUSE op."""
+        n = len(op.ins)
+        pi = op.modes.index(_lib.IN_POOL)
+        rest = [i for i in range(1, n) if i != pi]
+        if pi == 0 or len(rest) > 1 or any(op.modes[i] != _lib.IN_SAME for i in rest):
+            raise RuntimeError("internal: unsupported pooled node layout")
+        pf = _new_op()
+        pf.kind = _lib.OP_POOLFUSE
+        pf.train = o.train
+        srcs = [pi] + rest
+        pf.n_in = len(srcs)
+        for k, i in enumerate(srcs):
+            pf.inp[k] = _tensor(op.ins[i])
+            pf.mode[k] = op.modes[i]
+            pf.fw_idx[k] = i
+        pf.fw, pf.fw_eps, pf.fw_n = _ptr(op.fw), op.fw_eps, n
+        aux = _lib.Tensor(_ref(op.aux), _ref(None), op.out.H, op.out.W, self.Cc, 0)
+        pf.out = aux
+        pf.pidx[0] = _ref(op.pidx[pi])
+        pf.save_d = _ref(op.praw)
+        # the node itself: (input 0, aux)
+        o.n_in = 2
+        o.inp[1] = aux
+        o.mode[1] = _lib.IN_SAME
+        o.inp[2] = _lib.Tensor(_ref(None), _ref(None), 0, 0, 0, 0)
+        o.mode[2] = 0
+        o.fw_n = n
+        o.fw_idx[0], o.fw_idx[1], o.fw_idx[2] = 0, -1, -1
+        for i in range(3):
+            o.pidx[i] = _ref(None)
+        return pf
 
     def _cons_of(self, t):
         """MmdCons entries for every consumer edge of tensor `t`."""

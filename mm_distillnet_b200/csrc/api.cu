@@ -22,7 +22,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
 static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",
-                                           "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot"};
+                                           "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot",
+                                           "poolfuse"};
 struct ProfRec { cudaEvent_t a, b; int kind; double bytes; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;

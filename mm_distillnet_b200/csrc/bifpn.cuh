@@ -87,6 +87,14 @@ struct NodeFwdP {
   unsigned* counter;
   float bn_eps, bn_mom;
   TileGeom g;
+  int fw_n;        // 0: `fw` has n_in entries, input i uses entry i
+  int fw_idx[3];   // entry of `fw` weighing input i; -1: weight 1 (operand produced by a POOLFUSE pre-pass)
+};
+
+// up to 4 networks (student + teachers) run the same node in ONE launch: blockIdx.y selects the network
+constexpr int kMaxBatchNets = 4;
+struct NodeFwdBatch {
+  NodeFwdP p[kMaxBatchNets];
 };
 
 struct ConsP {
@@ -125,6 +133,15 @@ struct NodeBwdP {
   unsigned* counter;
   TileGeom g;
 };
+
+// fusion weight of kernel input i (ops fed by a POOLFUSE pre-pass see only part of the node's inputs)
+__device__ __forceinline__ float in_weight(const NodeFwdP& P, int i) {
+  if (P.fw == nullptr) return 1.f;
+  const int n = P.fw_n > 0 ? P.fw_n : P.n_in;
+  const int k = P.fw_n > 0 ? P.fw_idx[i] : i;
+  if (k < 0) return 1.f;
+  return fusion_weight(P.fw, n, k, P.fw_eps);
+}
 
 // ---- fused input loader -------------------------------------------------------------------------------------
 // Loads 4 channels of input `t` as seen by an output position (y, x) of a node:
@@ -176,8 +193,10 @@ __device__ __forceinline__ void load_input(const TensorP& t, int mode, int b, in
 // kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)
 int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, tcgen05 pointwise conv
-int launch_node_fwd_v3(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, packed parameters + bulk-copy staging
-bool fwd_v3_usable(const NodeFwdP& p);
+// bf16, compile-time tile geometry (bifpn_fwd_v4.cu); `n` networks share one launch
+bool fwd_v4_usable(const NodeFwdP& p);
+int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s);
+int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) node_fwd_kernel(const __grid_cons
   // ---- per-CTA constants: fusion weights, depthwise taps (tap-major), pointwise weights transposed to [k][n]
   float wgt[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
+  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? in_weight(P, i) : 0.f;
   for (int idx = tid; idx < 9 * C; idx += kThreads) {
     const int c = idx / 9, tap = idx - c * 9;
     s_k[tap * C + c] = P.dw_w[idx];

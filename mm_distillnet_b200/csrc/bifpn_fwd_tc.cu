@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc_kernel(const __grid_c
   }
   float wgt[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
+  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? in_weight(P, i) : 0.f;
   for (int idx = tid; idx < 9 * C; idx += kThreads) {
     const int c = idx / 9, tap = idx - c * 9;
     s_k[tap * C + c] = P.dw_w[idx];
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc2_kernel(const __grid_
   }
   float wgt[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
+  for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? in_weight(P, i) : 0.f;
   for (int idx = tid; idx < 9 * C; idx += kThreads) {
     const int c = idx / 9, tap = idx - c * 9;
     s_k[tap * C + c] = P.dw_w[idx];
@@ -542,12 +542,12 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_tc2_kernel(const __grid_
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   constexpr int CC = 112;
-  static int no_v3 = -1;
-  if (no_v3 < 0) {
-    const char* e = getenv("MMD_NO_V3");
-    no_v3 = (e && e[0] == '1') ? 1 : 0;
+  static int no_v4 = -1;
+  if (no_v4 < 0) {
+    const char* e = getenv("MMD_NO_V4");
+    no_v4 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (!no_v3 && fwd_v3_usable(p)) return launch_node_fwd_v3(p, C, s);
+  if (!no_v4 && fwd_v4_usable(p)) return launch_node_fwd_v4(&p, 1, C, s);
   const size_t smem = FwdTcSmem<CC>::kBytes;
   static int use_v1 = -1;
   if (use_v1 < 0) {

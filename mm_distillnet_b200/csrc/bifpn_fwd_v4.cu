@@ -1,0 +1,686 @@
+// BiFPN fusion node, forward, bf16 storage — v4 (sm_100a): compile-time tile geometry.
+//
+// Same fusion as the earlier bf16 kernels (BN-on-load + nearest-x2 resampling + fast-normalised weighted sum + swish ->
+// depthwise 3x3 -> pointwise 1x1 on tcgen05 with the accumulator in TMEM -> bias / BatchNorm statistics), but
+//   * the tile shape <TW, TH> is a template parameter and only full tiles exist (W % TW == 0, H % TH == 0): the ncu source
+//     view of v3 showed ~60 executed instructions per output element, 85 % of them runtime index arithmetic, divisions and
+//     bounds checks.  Here every shared-memory offset is a constant, both CUDA-core phases are fully unrolled straight-line
+//     code (out-of-image halo positions are computed and then replaced by zero with a select), so the compiler interleaves
+//     the rows of one thread;
+//   * a node stages at most TWO inputs by bulk copies: pooled inputs (3x3 stride-2 windows over a tensor with 4x the
+//     positions, impossible to stage) are folded, together with a third same-resolution input, into one operand by the
+//     streaming pre-pass poolfuse_kernel below (MMD_OP_POOLFUSE);
+//   * the output tile leaves through bulk shared->global copies (one per tile row, a tile row of an NHWC tensor is
+//     contiguous) from a dense staging tile: no per-element store instructions;
+//   * the raw input tiles of the NEXT tile are requested as soon as their shared-memory regions are free (input 1 right
+//     after the MMA has consumed the A operand, input 0 after the output tile has been read by the bulk store);
+//   * up to four networks (student + the three teachers) run the same node in one launch (blockIdx.y): the small pyramid
+//     levels have fewer tiles than the GPU has SMs.
+// Shared memory (2 CTAs / SM):  region 0 = raw input 0 -> v (in place) -> output staging;  region 1 = raw input 1 -> UMMA
+// A operand;  packed parameter block (B operand in UMMA layout, bias, taps: one bulk copy);  folded BN/fusion coefficients.
+#include "bifpn.cuh"
+#include "tc.cuh"
+
+namespace mmd {
+namespace v4 {
+
+typedef __nv_bfloat16 bf16;
+using tc::add2;
+using tc::bf2_to_f2;
+using tc::f2_to_bf2;
+using tc::fma2;
+using tc::mul2;
+
+constexpr int C = 112, NG = C / 8, NQ = C / 4, POS = C * 2;
+constexpr int M1_NONE = 0, M1_SAME = 1, M1_UP2 = 2;
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int up128(int a) { return (a + 127) / 128 * 128; }
+
+template <int TW, int TH>
+struct Cfg {
+  static_assert(TW % 2 == 0 && TH % 2 == 0, "nearest-x2 inputs need even tiles");
+  static constexpr int HW2 = TW + 2, HH2 = TH + 2, NH = HW2 * HH2, NP = TW * TH;
+  static constexpr int UW = TW / 2 + 2, UH = TH / 2 + 2;      // staged source rectangle of a nearest-x2 input
+  static constexpr int kAStride = 128 * 16 + 16;               // bytes between channel groups of the A operand (padded)
+  static constexpr int kABytes = NG * kAStride;                // 28 896
+  static constexpr int kStage = 128 * POS;                     // dense output staging tile (rows >= NP unused)
+  static constexpr int kR0 = up128(cmax(NH * POS, kStage));
+  static constexpr int kR1 = up128(cmax(NH * POS, kABytes));
+  static constexpr int kWBytes = C * C * 2;
+  static constexpr int kPackBytes = kWBytes + C * 4 + 9 * C * 4;   // 29 568
+  static constexpr int offR0 = 0, offR1 = kR0, offPack = kR0 + kR1, offCoef = offPack + kPackBytes;
+  static constexpr int offBar = offCoef + 3 * C * 4;
+  static constexpr int kBytes = offBar + 64;
+  static constexpr int kP1Threads = NG * HW2, kP2Threads = NQ * (TW / 2);
+  static_assert(NP <= 128 && kP1Threads <= kThreads && kP2Threads <= kThreads && HH2 <= 32, "tile too large");
+  static_assert(offPack % 128 == 0 && offCoef % 16 == 0 && offBar % 8 == 0, "alignment");
+  static_assert(2 * (kBytes + 1024) <= 233472, "two CTAs per SM");
+};
+
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst_gmem)),
+               "r"(tc::smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct TilePos {
+  int b, ty0, tx0;
+};
+__device__ __forceinline__ TilePos tile_pos(int tile, int tiles_x, int tiles_y, int TW, int TH) {
+  TilePos t;
+  const int per = tiles_x * tiles_y;
+  t.b = tile / per;
+  const int rem = tile - t.b * per;
+  const int ry = rem / tiles_x;
+  t.ty0 = ry * TH;
+  t.tx0 = (rem - ry * tiles_x) * TW;
+  return t;
+}
+
+// ---- bulk row copies of one raw input tile (executed by one warp, one row per lane) ------------------------------
+// SAME inputs land at their halo coordinates; a nearest-x2 input lands as its (TH/2+2) x (TW/2+2) source rectangle.
+// Rows / columns outside the image are simply not copied (the consumer replaces those positions by zero).
+template <int TW, int TH>
+__device__ __forceinline__ void issue_input(unsigned char* dst, const bf16* src, bool up2, const TilePos t, int H, int W,
+                                            int lane, uint64_t* bar) {
+  using S = Cfg<TW, TH>;
+  int rows_lo, rows_hi, col_lo, col_hi, pitch, gy0, gx0, SH, SW;
+  if (!up2) {
+    rows_lo = (t.ty0 == 0) ? 1 : 0;
+    rows_hi = (t.ty0 + TH >= H) ? S::HH2 - 2 : S::HH2 - 1;
+    col_lo = (t.tx0 == 0) ? 1 : 0;
+    col_hi = (t.tx0 + TW >= W) ? S::HW2 - 2 : S::HW2 - 1;
+    pitch = S::HW2;
+    gy0 = t.ty0 - 1; gx0 = t.tx0 - 1; SH = H; SW = W;
+  } else {
+    SH = H >> 1; SW = W >> 1;
+    rows_lo = (t.ty0 == 0) ? 1 : 0;
+    rows_hi = ((t.ty0 >> 1) + TH / 2 >= SH) ? S::UH - 2 : S::UH - 1;
+    col_lo = (t.tx0 == 0) ? 1 : 0;
+    col_hi = ((t.tx0 >> 1) + TW / 2 >= SW) ? S::UW - 2 : S::UW - 1;
+    pitch = S::UW;
+    gy0 = (t.ty0 >> 1) - 1; gx0 = (t.tx0 >> 1) - 1;
+  }
+  const uint32_t rb = (uint32_t)(col_hi - col_lo + 1) * POS;
+  const int nrows = rows_hi - rows_lo + 1;
+  if (lane == 0) tc::mbar_expect_tx(bar, (uint32_t)nrows * rb);
+  __syncwarp();
+  if (lane < nrows) {
+    const int r = rows_lo + lane;
+    tc::bulk_g2s(dst + (r * pitch + col_lo) * POS, src + (((long long)t.b * SH + gy0 + r) * SW + gx0 + col_lo) * C, rb, bar);
+  }
+}
+
+// ---- phase 1: v = swish(a0 * x0 + a1 * resample(x1) + shift), written in place over raw input 0 ------------------
+template <int TW, int TH, int M1, bool SW>
+__device__ __forceinline__ void phase1(unsigned char* r0, const unsigned char* r1, const float* s_coef, int tid,
+                                       const TilePos t, int H, int W) {
+  using S = Cfg<TW, TH>;
+  if (tid >= S::kP1Threads) return;
+  const int cg = tid % NG, hx = tid / NG;
+  float2 a0[4], a1[4], sh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    a0[e] = *reinterpret_cast<const float2*>(s_coef + 8 * cg + 2 * e);
+    a1[e] = *reinterpret_cast<const float2*>(s_coef + C + 8 * cg + 2 * e);
+    sh[e] = *reinterpret_cast<const float2*>(s_coef + 2 * C + 8 * cg + 2 * e);
+  }
+  const int x = t.tx0 - 1 + hx;
+  const bool x_ok = (x >= 0) && (x < W);
+  const bool top_ok = t.ty0 > 0, bot_ok = t.ty0 + TH < H;
+  unsigned char* cell = r0 + hx * POS + cg * 16;
+  const unsigned char* src1 = r1 + ((M1 == M1_UP2) ? ((hx + 1) >> 1) : hx) * POS + cg * 16;
+  uint4 s1 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int hy = 0; hy < S::HH2; ++hy) {
+    const bool ok = x_ok && (hy == 0 ? top_ok : (hy == S::HH2 - 1 ? bot_ok : true));
+    const uint4 r = *reinterpret_cast<const uint4*>(cell + hy * (S::HW2 * POS));
+    float2 u[4];
+    u[0] = fma2(bf2_to_f2(r.x), a0[0], sh[0]);
+    u[1] = fma2(bf2_to_f2(r.y), a0[1], sh[1]);
+    u[2] = fma2(bf2_to_f2(r.z), a0[2], sh[2]);
+    u[3] = fma2(bf2_to_f2(r.w), a0[3], sh[3]);
+    if (M1 != M1_NONE) {
+      if (M1 == M1_SAME) {
+        s1 = *reinterpret_cast<const uint4*>(src1 + hy * (S::HW2 * POS));
+      } else if (hy == 0 || (hy & 1)) {   // halo rows 2k-1 and 2k share source row k
+        s1 = *reinterpret_cast<const uint4*>(src1 + ((hy + 1) >> 1) * (S::UW * POS));
+      }
+      u[0] = fma2(bf2_to_f2(s1.x), a1[0], u[0]);
+      u[1] = fma2(bf2_to_f2(s1.y), a1[1], u[1]);
+      u[2] = fma2(bf2_to_f2(s1.z), a1[2], u[2]);
+      u[3] = fma2(bf2_to_f2(s1.w), a1[3], u[3]);
+    }
+    if (SW) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) u[e] = tc::swish2(u[e]);
+    }
+    uint4 pk;
+    pk.x = ok ? f2_to_bf2(u[0]) : 0u;
+    pk.y = ok ? f2_to_bf2(u[1]) : 0u;
+    pk.z = ok ? f2_to_bf2(u[2]) : 0u;
+    pk.w = ok ? f2_to_bf2(u[3]) : 0u;
+    *reinterpret_cast<uint4*>(cell + hy * (S::HW2 * POS)) = pk;
+  }
+}
+
+// ---- phase 2: depthwise 3x3 over the v halo tile -> UMMA A operand (+ the saved depthwise output in training) ------
+template <int TW, int TH>
+__device__ __forceinline__ void phase2(const unsigned char* r0, unsigned char* r1, const float* s_k, int tid, bf16* dsave,
+                                       int W) {
+  using S = Cfg<TW, TH>;
+  if (tid >= S::kP2Threads) return;
+  const int q = tid % NQ, c0 = 2 * (tid / NQ);
+  float2 wk[9][2];
+#pragma unroll
+  for (int t9 = 0; t9 < 9; ++t9) {
+    const float4 k4 = *reinterpret_cast<const float4*>(s_k + t9 * C + 4 * q);
+    wk[t9][0] = make_float2(k4.x, k4.y);
+    wk[t9][1] = make_float2(k4.z, k4.w);
+  }
+  const unsigned char* vcol = r0 + c0 * POS + q * 8;
+  unsigned char* arow = r1 + (q >> 1) * S::kAStride + (q & 1) * 8 + c0 * 16;
+  if (dsave != nullptr) dsave += c0 * C + 4 * q;
+  float2 acc[3][2][2];   // [output row mod 3][column][channel pair]
+#pragma unroll
+  for (int r = 0; r < S::HH2; ++r) {
+    float2 v[4][2];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(vcol + (r * S::HW2 + dx) * POS);
+      v[dx][0] = bf2_to_f2(raw.x);
+      v[dx][1] = bf2_to_f2(raw.y);
+    }
+    // halo row r is tap row 0 of output row r, tap row 1 of r-1, tap row 2 of r-2
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (r < TH) {
+          float2 a = mul2(v[c][h], wk[0][h]);
+          a = fma2(v[c + 1][h], wk[1][h], a);
+          acc[r % 3][c][h] = fma2(v[c + 2][h], wk[2][h], a);
+        }
+        if (r >= 1 && r - 1 < TH) {
+          float2 a = acc[(r + 2) % 3][c][h];
+          a = fma2(v[c][h], wk[3][h], a);
+          a = fma2(v[c + 1][h], wk[4][h], a);
+          acc[(r + 2) % 3][c][h] = fma2(v[c + 2][h], wk[5][h], a);
+        }
+        if (r >= 2) {
+          float2 a = acc[(r + 1) % 3][c][h];
+          a = fma2(v[c][h], wk[6][h], a);
+          a = fma2(v[c + 1][h], wk[7][h], a);
+          acc[(r + 1) % 3][c][h] = fma2(v[c + 2][h], wk[8][h], a);
+        }
+      }
+    if (r >= 2) {
+      const int o = r - 2;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint2 pk;
+        pk.x = f2_to_bf2(acc[(r + 1) % 3][c][0]);
+        pk.y = f2_to_bf2(acc[(r + 1) % 3][c][1]);
+        *reinterpret_cast<uint2*>(arow + (o * TW + c) * 16) = pk;
+        if (dsave != nullptr) *reinterpret_cast<uint2*>(dsave + ((long long)o * W + c) * C) = pk;
+      }
+    }
+  }
+}
+
+template <int TW, int TH>
+__global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+  using S = Cfg<TW, TH>;
+  constexpr uint32_t kTmemCols = 128;
+  constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
+  const NodeFwdP& P = BATCH.p[blockIdx.y];
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* r0 = smem + S::offR0;
+  unsigned char* r1 = smem + S::offR1;
+  unsigned char* s_pack = smem + S::offPack;
+  const float* s_bias = reinterpret_cast<const float*>(s_pack + S::kWBytes);
+  const float* s_k = s_bias + C;
+  float* s_coef = reinterpret_cast<float*>(smem + S::offCoef);
+  uint64_t* bar_pack = reinterpret_cast<uint64_t*>(smem + S::offBar);
+  uint64_t* bar_in0 = bar_pack + 1;
+  uint64_t* bar_in1 = bar_pack + 2;
+  uint64_t* bar_mma = bar_pack + 3;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_pack + 4);
+  __shared__ int s_flag;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = P.g.H, W = P.g.W;
+  const int tiles_x = W / TW, tiles_y = H / TH, ntiles = P.g.B * tiles_x * tiles_y;
+  const bool train = P.train != 0;
+  const int m1 = (P.n_in < 2) ? M1_NONE : (P.mode[1] == MMD_IN_UP2 ? M1_UP2 : M1_SAME);
+  const bool sw = P.swish != 0;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+  const bf16* __restrict__ in0 = reinterpret_cast<const bf16*>(P.in[0].data);
+  const bf16* __restrict__ in1 = reinterpret_cast<const bf16*>(P.in[1].data);
+
+  // ---- per-CTA setup ---------------------------------------------------------------------------------------------
+  if (warp == 0) tc::tmem_alloc(s_tmem, kTmemCols);
+  if (tid == 32) {
+    tc::mbar_init(bar_pack, 1);
+    tc::mbar_init(bar_in0, 1);
+    tc::mbar_init(bar_in1, 1);
+    tc::mbar_init(bar_mma, 1);
+    tc::fence_mbar_init();
+    tc::mbar_expect_tx(bar_pack, S::kPackBytes);
+    tc::bulk_g2s(s_pack, P.packed, S::kPackBytes, bar_pack);
+  }
+  if (tid < C) {
+    const float w0 = in_weight(P, 0), w1 = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
+    const float* bn0 = P.in[0].bn;
+    const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
+    const float sc0 = bn0 ? bn0[tid] : 1.f, sh0 = bn0 ? bn0[C + tid] : 0.f;
+    const float sc1 = bn1 ? bn1[tid] : 1.f, sh1 = bn1 ? bn1[C + tid] : 0.f;
+    s_coef[tid] = sc0 * w0;
+    s_coef[C + tid] = sc1 * w1;
+    s_coef[2 * C + tid] = fmaf(sh1, w1, sh0 * w0);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t a_addr = tc::smem_u32(r1), b_addr = tc::smem_u32(s_pack);
+
+  // first tile's inputs
+  int tile = blockIdx.x;
+  if (warp == 1 && tile < ntiles) {
+    const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
+    issue_input<TW, TH>(r0, in0, false, t, H, W, lane, bar_in0);
+    if (m1 != M1_NONE) issue_input<TW, TH>(r1, in1, m1 == M1_UP2, t, H, W, lane, bar_in1);
+  }
+
+  // statistics role: channel pair sp of row slice ss (32 staging rows)
+  const int sp = tid % (C / 2), ss = tid / (C / 2);
+  double st[4] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t ph = 0;
+  bool pack_ready = false;
+
+  for (; tile < ntiles; tile += gridDim.x) {
+    const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
+    const int next = tile + gridDim.x;
+
+    // ---- (1) raw inputs have landed
+    tc::mbar_wait(bar_in0, ph);
+    if (m1 != M1_NONE) tc::mbar_wait(bar_in1, ph);
+
+    // ---- (2) phase 1
+    if (sw) {
+      if (m1 == M1_UP2) phase1<TW, TH, M1_UP2, true>(r0, r1, s_coef, tid, t, H, W);
+      else if (m1 == M1_SAME) phase1<TW, TH, M1_SAME, true>(r0, r1, s_coef, tid, t, H, W);
+      else phase1<TW, TH, M1_NONE, true>(r0, r1, s_coef, tid, t, H, W);
+    } else {
+      if (m1 == M1_UP2) phase1<TW, TH, M1_UP2, false>(r0, r1, s_coef, tid, t, H, W);
+      else if (m1 == M1_SAME) phase1<TW, TH, M1_SAME, false>(r0, r1, s_coef, tid, t, H, W);
+      else phase1<TW, TH, M1_NONE, false>(r0, r1, s_coef, tid, t, H, W);
+    }
+    __syncthreads();
+    if (!pack_ready) {   // taps / bias / B operand have landed (first tile only)
+      tc::mbar_wait(bar_pack, 0u);
+      pack_ready = true;
+    }
+
+    // ---- (3) phase 2
+    {
+      bf16* dsave = (P.save_d != nullptr)
+                        ? reinterpret_cast<bf16*>(P.save_d) + (((long long)t.b * H + t.ty0) * W + t.tx0) * C
+                        : nullptr;
+      phase2<TW, TH>(r0, r1, s_k, tid, dsave, W);
+    }
+    tc::fence_async_smem();   // the A operand was written through the generic proxy
+    __syncthreads();
+
+    // ---- (4) pointwise 1x1 on the tensor cores
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) {
+        const uint64_t adesc = tc::make_desc(a_addr + j * 2 * S::kAStride, S::kAStride, 128);
+        const uint64_t bdesc = tc::make_desc(b_addr + j * 2 * (C * 16), C * 16, 128);
+        tc::umma_bf16(tmem_base, adesc, bdesc, kIdesc, j > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(bar_mma);
+    }
+    tc::mbar_wait(bar_mma, ph);
+    tc::fence_after_sync();
+    // region 1 is free: request the next tile's input 1 while the epilogue runs
+    if (warp == 1 && next < ntiles && m1 != M1_NONE) {
+      const TilePos tn = tile_pos(next, tiles_x, tiles_y, TW, TH);
+      issue_input<TW, TH>(r1, in1, m1 == M1_UP2, tn, H, W, lane, bar_in1);
+    }
+
+    // ---- (5) epilogue: TMEM -> +bias -> dense bf16 staging tile (region 0)
+    bf16* s_y = reinterpret_cast<bf16*>(r0);
+    {
+      const int row = 32 * (warp & 3) + lane;
+      const int col0 = (warp >> 2) * (C / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+      float acc[C / 16][8];
+#pragma unroll
+      for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+      tc::tmem_ld_wait();
+      if (row < S::NP) {
+#pragma unroll
+        for (int j = 0; j < C / 16; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j + 4);
+          uint4 pk;
+          pk.x = f2_to_bf2(add2(make_float2(acc[j][0], acc[j][1]), make_float2(b0.x, b0.y)));
+          pk.y = f2_to_bf2(add2(make_float2(acc[j][2], acc[j][3]), make_float2(b0.z, b0.w)));
+          pk.z = f2_to_bf2(add2(make_float2(acc[j][4], acc[j][5]), make_float2(b1.x, b1.y)));
+          pk.w = f2_to_bf2(add2(make_float2(acc[j][6], acc[j][7]), make_float2(b1.z, b1.w)));
+          *reinterpret_cast<uint4*>(s_y + row * C + col0 + 8 * j) = pk;
+        }
+      }
+    }
+    tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
+    tc::fence_async_smem();    // staging tile -> visible to the bulk store engine
+    __syncthreads();
+
+    // ---- (6) output tile: one bulk copy per tile row; BatchNorm statistics from the staging tile
+    if (warp == 1) {
+      if (lane < TH)
+        bulk_s2g(out + (((long long)t.b * H + t.ty0 + lane) * W + t.tx0) * C, r0 + lane * (TW * POS), TW * POS);
+      bulk_commit();
+    }
+    if (train && ss < 4) {
+      constexpr int NP = S::NP;
+      const int p0 = ss * 32, p1 = (p0 + 32 < NP) ? p0 + 32 : NP;
+      float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+      const bf16* colp = s_y + 2 * sp;
+#pragma unroll 8
+      for (int p = p0; p < p1; ++p) {
+        const float2 v = bf2_to_f2(*reinterpret_cast<const uint32_t*>(colp + p * C));
+        s = add2(s, v);
+        q = fma2(v, v, q);
+      }
+      st[0] += (double)s.x; st[1] += (double)s.y; st[2] += (double)q.x; st[3] += (double)q.y;
+    }
+    tc::fence_async_smem();   // generic accesses to region 0 are ordered before the next tile's bulk copies
+    __syncthreads();
+    if (warp == 1) {
+      bulk_wait_read0();      // the bulk stores have read the staging tile
+      __syncwarp();
+      if (next < ntiles) {
+        const TilePos tn = tile_pos(next, tiles_x, tiles_y, TW, TH);
+        issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
+      }
+    }
+    ph ^= 1u;
+  }
+
+  // ---- teardown + BatchNorm finalisation (last CTA of this network)
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (!train) return;
+  double* s_red = reinterpret_cast<double*>(r1);   // [4 slices][C/2 pairs][4]
+  if (ss < 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s_red[(ss * (C / 2) + sp) * 4 + e] = st[e];
+  }
+  __syncthreads();
+  if (tid < C) {
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += s_red[(k * (C / 2) + (tid >> 1)) * 4 + (tid & 1)];
+      q += s_red[(k * (C / 2) + (tid >> 1)) * 4 + 2 + (tid & 1)];
+    }
+    atomicAdd(P.stats + tid, s);
+    atomicAdd(P.stats + C + tid, q);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(P.counter, 1u);
+    s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flag == 0) return;
+  __threadfence();
+  if (tid < C) {
+    const double n = (double)P.g.B * H * W;
+    const double mean = __ldcg(P.stats + tid) / n;
+    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
+    const float scale = P.bn_w[tid] * invstd;
+    P.out_bn[tid] = scale;
+    P.out_bn[C + tid] = P.bn_b[tid] - (float)mean * scale;
+    P.out_bn[2 * C + tid] = (float)mean;
+    P.out_bn[3 * C + tid] = invstd;
+    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+    P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
+    P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
+    P.stats[tid] = 0.0;
+    P.stats[C + tid] = 0.0;
+  }
+  if (tid == 0) {
+    *P.counter = 0u;
+    if (P.bn_nbt) *P.bn_nbt += 1;
+  }
+}
+
+// ---- pooling pre-pass ------------------------------------------------------------------------------------------------
+// out = w_a * maxpool3x3s2(bn_a(in[0]))  [+ w_b * bn_b(in[1])]   (final bf16 values at the node's resolution)
+// MaxPool2dStaticSamePadding (src/YetAnotherEfficientNet.py:90-104): the zero padding takes part in the max of the
+// NORMALISED values.  scale*x+shift is monotonic in x, so the window is searched on the raw bf16 values (sign flipped
+// where the scale is negative): each value is expanded to fp32 with (15 - window index) in its 4 lowest mantissa bits
+// (those bits are zero after the expansion), so ONE fmaxf per element yields the maximum and its position.
+constexpr int kPoolThreads = 224;   // 16 positions x 14 channel groups
+
+__device__ __forceinline__ void pool_keys(const uint4 r, const uint32_t tag, const uint32_t (&sgn)[8], float (&best)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t lo = __byte_perm(w[e], tag, 0x1054) ^ sgn[2 * e];
+    const uint32_t hi = ((w[e] & 0xffff0000u) | tag) ^ sgn[2 * e + 1];
+    best[2 * e] = fmaxf(best[2 * e], __uint_as_float(lo));
+    best[2 * e + 1] = fmaxf(best[2 * e + 1], __uint_as_float(hi));
+  }
+}
+
+__global__ void __launch_bounds__(kPoolThreads) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+  const NodeFwdP& P = BATCH.p[blockIdx.y];
+  const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
+  const int H = P.g.H, W = P.g.W, SH = P.in[0].H, SWd = P.in[0].W;
+  const int npos = P.g.B * H * W;
+  const bf16* __restrict__ src = reinterpret_cast<const bf16*>(P.in[0].data);
+  const bf16* __restrict__ same = (P.n_in >= 2) ? reinterpret_cast<const bf16*>(P.in[1].data) : nullptr;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+  bf16* __restrict__ praw = reinterpret_cast<bf16*>(P.save_d);
+  unsigned char* __restrict__ pidx = P.pidx[0];
+
+  const float wa = in_weight(P, 0), wb = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
+  float sc[8], sh[8], a1[8], b1[8];
+  uint32_t sgn[8];
+  {
+    const float* bn0 = P.in[0].bn;
+    const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = 8 * cg + e;
+      sc[e] = bn0 ? bn0[c] : 1.f;
+      sh[e] = bn0 ? bn0[C + c] : 0.f;
+      sgn[e] = (sc[e] < 0.f) ? 0x80000000u : 0u;
+      a1[e] = (bn1 ? bn1[c] : 1.f) * wb;
+      b1[e] = (bn1 ? bn1[C + c] : 0.f) * wb;
+    }
+  }
+  const int top = pool_pad_before(SH), left = pool_pad_before(SWd);
+
+  for (int pos = blockIdx.x * (kPoolThreads / NG) + pl; pos < npos; pos += gridDim.x * (kPoolThreads / NG)) {
+    const int b = pos / (H * W);
+    const int rem = pos - b * (H * W);
+    const int y = rem / W, x = rem - y * W;
+    const int fy0 = 2 * y - top, fx0 = 2 * x - left;
+    float best[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    bool has_pad = false;
+#pragma unroll
+    for (int wy = 0; wy < 3; ++wy) {
+      const int fy = fy0 + wy;
+#pragma unroll
+      for (int wx = 0; wx < 3; ++wx) {
+        const int fx = fx0 + wx;
+        if (fy >= 0 && fy < SH && fx >= 0 && fx < SWd) {
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(src + (((long long)b * SH + fy) * SWd + fx) * C + 8 * cg));
+          pool_keys(r, 15u - (uint32_t)(wy * 3 + wx), sgn, best);
+        } else {
+          has_pad = true;
+        }
+      }
+    }
+    const bool pad_first = (fy0 < 0) || (fx0 < 0);   // the padding precedes the real elements in scan order
+    float u[8];
+    uint32_t idx[8], rawb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t bits = __float_as_uint(best[e]);
+      idx[e] = 15u - (bits & 15u);
+      rawb[e] = (bits ^ sgn[e]) & 0xffff0000u;
+      float val = fmaf(__uint_as_float(rawb[e]), sc[e], sh[e]);
+      if (has_pad && (pad_first ? (0.f >= val) : (0.f > val))) {
+        val = 0.f;
+        idx[e] = 9u;
+        rawb[e] = 0u;
+      }
+      u[e] = wa * val;
+    }
+    const long long o = (long long)pos * C + 8 * cg;
+    if (same != nullptr) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + o));
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = bf2_to_f2(w[e]);
+        u[2 * e] += fmaf(f.x, a1[2 * e], b1[2 * e]);
+        u[2 * e + 1] += fmaf(f.y, a1[2 * e + 1], b1[2 * e + 1]);
+      }
+    }
+    uint4 pk;
+    pk.x = f2_to_bf2(make_float2(u[0], u[1]));
+    pk.y = f2_to_bf2(make_float2(u[2], u[3]));
+    pk.z = f2_to_bf2(make_float2(u[4], u[5]));
+    pk.w = f2_to_bf2(make_float2(u[6], u[7]));
+    *reinterpret_cast<uint4*>(out + o) = pk;
+    if (pidx != nullptr) {
+      uint2 ip;
+      ip.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+      ip.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+      *reinterpret_cast<uint2*>(pidx + o) = ip;
+    }
+    if (praw != nullptr) {
+      uint4 rp;
+      rp.x = (rawb[0] >> 16) | rawb[1];
+      rp.y = (rawb[2] >> 16) | rawb[3];
+      rp.z = (rawb[4] >> 16) | rawb[5];
+      rp.w = (rawb[6] >> 16) | rawb[7];
+      *reinterpret_cast<uint4*>(praw + o) = rp;
+    }
+  }
+}
+
+template <int TW, int TH>
+static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
+  using S = Cfg<TW, TH>;
+  static bool configured = false;
+  if (!configured) {
+    MMD_CUDA(cudaFuncSetAttribute(node_fwd_v4_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const NodeFwdP& p = batch.p[0];
+  const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
+  int per_net = (2 * sms) / n;
+  if (per_net < 1) per_net = 1;
+  const int gx = ntiles < per_net ? ntiles : per_net;
+  node_fwd_v4_kernel<TW, TH><<<dim3(gx, n), kThreads, S::kBytes, s>>>(batch);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+// tile shapes, tried in this order (exact fits only; anything else runs on the generic kernel of bifpn_fwd_tc.cu)
+static int pick_geom(int H, int W) {
+  if (W % 16 == 0 && H % 8 == 0) return 0;
+  if (W % 12 == 0 && H % 8 == 0) return 1;
+  if (W % 8 == 0 && H % 8 == 0) return 2;
+  if (W % 12 == 0 && H % 6 == 0) return 3;
+  if (W % 6 == 0 && H % 6 == 0) return 4;
+  return -1;
+}
+
+}  // namespace v4
+
+bool fwd_v4_usable(const NodeFwdP& p) {
+  if (p.packed == nullptr || p.n_in < 1 || p.n_in > 2 || p.mode[0] != MMD_IN_SAME) return false;
+  if (p.n_in == 2 && p.mode[1] == MMD_IN_POOL) return false;
+  if (p.n_in == 2 && p.mode[1] == MMD_IN_UP2 && (2 * p.in[1].H != p.g.H || 2 * p.in[1].W != p.g.W)) return false;
+  for (int i = 0; i < p.n_in; ++i)
+    if (((uintptr_t)p.in[i].data & 15u) != 0) return false;
+  if (((uintptr_t)p.out & 15u) != 0) return false;
+  return v4::pick_geom(p.g.H, p.g.W) >= 0;
+}
+
+int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "node_fwd_v4: %d networks in one launch", n);
+  NodeFwdBatch batch;
+  double bytes = 0.0;
+  for (int i = 0; i < n; ++i) {
+    batch.p[i] = p[i];
+    MMD_CHECK_ARG(p[i].g.H == p[0].g.H && p[i].g.W == p[0].g.W && p[i].g.B == p[0].g.B,
+                  "node_fwd_v4: batched networks must share the geometry");
+    // a node fed by a POOLFUSE pre-pass: the reads of its pooled / third input are charged to the pre-pass
+    const bool aux = p[i].fw_n > 0 && p[i].n_in == 2 && p[i].fw_idx[1] < 0;
+    bytes += node_algo_bytes(p[i].in, aux ? 1 : p[i].n_in, p[i].g, C, 2);
+  }
+  for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
+  ProfScope prof(PK_NODE_FWD, bytes, s);
+  switch (v4::pick_geom(p[0].g.H, p[0].g.W)) {
+    case 0: return v4::launch_geom<16, 8>(batch, n, s);
+    case 1: return v4::launch_geom<12, 8>(batch, n, s);
+    case 2: return v4::launch_geom<8, 8>(batch, n, s);
+    case 3: return v4::launch_geom<12, 6>(batch, n, s);
+    case 4: return v4::launch_geom<6, 6>(batch, n, s);
+  }
+  set_error("node_fwd_v4: no tile shape fits %dx%d", p[0].g.H, p[0].g.W);
+  return MMD_E_ARG;
+}
+
+int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "poolfuse: %d networks in one launch", n);
+  NodeFwdBatch batch;
+  double bytes = 0.0;
+  for (int i = 0; i < n; ++i) {
+    batch.p[i] = p[i];
+    MMD_CHECK_ARG(p[i].g.H == p[0].g.H && p[i].g.W == p[0].g.W && p[i].g.B == p[0].g.B,
+                  "poolfuse: batched networks must share the geometry");
+    MMD_CHECK_ARG(p[i].mode[0] == MMD_IN_POOL && (p[i].n_in == 1 || (p[i].n_in == 2 && p[i].mode[1] == MMD_IN_SAME)),
+                  "poolfuse: inputs must be (POOL[, SAME])");
+    // algorithmic bytes of the node's pooled + third input (each read once at its own resolution)
+    for (int k = 0; k < p[i].n_in; ++k) bytes += (double)p[i].g.B * p[i].in[k].H * p[i].in[k].W * C * 2.0;
+  }
+  for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
+  const int npos = p[0].g.B * p[0].g.H * p[0].g.W;
+  const int per = v4::kPoolThreads / v4::NG;
+  int gx = (npos + per - 1) / per;
+  if (gx > 148 * 8) gx = 148 * 8;
+  ProfScope prof(PK_POOLFUSE, bytes, s);
+  v4::poolfuse_kernel<<<dim3(gx, n), v4::kPoolThreads, 0, s>>>(batch);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mmd

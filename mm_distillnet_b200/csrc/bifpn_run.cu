@@ -26,6 +26,8 @@ static int fill_fwd(const MmdOp& op, const Bases& B, int batch, NodeFwdP& p) {
   p.Cin = op.Cin;
   p.fw = op.fw;
   p.fw_eps = op.fw_eps;
+  p.fw_n = op.fw_n;
+  for (int i = 0; i < 3; ++i) p.fw_idx[i] = op.fw_idx[i];
   p.dw_w = op.dw_w; p.pw_w = op.pw_w; p.pw_b = op.pw_b; p.bn_w = op.bn_w; p.bn_b = op.bn_b;
   p.bn_rm = op.bn_rm; p.bn_rv = op.bn_rv; p.bn_nbt = (long long*)op.bn_nbt;
   p.out = B.get<void>(op.out.data);
@@ -38,7 +40,7 @@ static int fill_fwd(const MmdOp& op, const Bases& B, int batch, NodeFwdP& p) {
   p.bn_mom = op.bn_momentum;
   p.g = make_geom(batch, op.out.H, op.out.W);
   MMD_CHECK_ARG(p.out != nullptr, "op: no output");
-  if (op.kind != MMD_OP_BNAPPLY) {
+  if (op.kind != MMD_OP_BNAPPLY && op.kind != MMD_OP_POOLFUSE) {
     MMD_CHECK_ARG(p.pw_w && p.pw_b && p.bn_w && p.bn_b && p.bn_rm && p.bn_rv, "op: missing conv/bn parameters");
     if (op.train) MMD_CHECK_ARG(p.out_bn && p.stats && p.counter, "train op: missing bn/stats/counter storage");
   }
@@ -111,6 +113,7 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
     switch (op.kind) {
       case MMD_OP_NODE_FWD:
       case MMD_OP_PROJ_FWD:
+      case MMD_OP_POOLFUSE:
       case MMD_OP_BNAPPLY: {
         NodeFwdP p;
         if ((rc = fill_fwd(op, B, batch, p))) return rc;
@@ -121,6 +124,9 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
         } else if (op.kind == MMD_OP_PROJ_FWD) {
           MMD_CHECK_ARG(op.Cin >= 4 && op.Cin % 4 == 0, "proj op %d: Cin=%d must be a positive multiple of 4", i, op.Cin);
           rc = launch_proj_fwd(p, C, dtype, stream);
+        } else if (op.kind == MMD_OP_POOLFUSE) {
+          MMD_CHECK_ARG(dtype == MMD_BF16, "poolfuse op %d: bf16 plans only", i);
+          rc = launch_poolfuse(&p, 1, C, stream);
         } else {
           rc = launch_bnapply(p, C, dtype, stream);
         }

@@ -39,7 +39,7 @@ void count_launch();
 // ---- optional per-kernel CUDA-event timing (mmd_prof_*), used by bench.py for the live roofline number ---------
 enum ProfKind {
   PK_MTA_POOL = 0, PK_MTA_LEVEL, PK_MTA_FINISH, PK_MTA_BWD, PK_NODE_FWD, PK_PROJ_FWD, PK_BNAPPLY, PK_NODE_BWD_A,
-  PK_NODE_BWD_B, PK_PROJ_BWD, PK_PULL, PK_SLOT, PK_COUNT
+  PK_NODE_BWD_B, PK_PROJ_BWD, PK_PULL, PK_SLOT, PK_POOLFUSE, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

@@ -44,6 +44,10 @@ def line_map(cubin, func_substr):
     return res
 
 
+import os
+SORTCOL = int(os.environ.get("NCU_SORT", "1"))
+
+
 def main():
     rep, regex, idx, cubin = sys.argv[1:5]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
@@ -64,7 +68,7 @@ def main():
     ts = sum(a[1] for a in agg.values()) or 1
     print("kernel:", name, "| warp instructions:", ti, "| stall samples:", ts)
     src = {}
-    for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][1] if kv[0] else 0)[:top]:
+    for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][SORTCOL] if kv[0] else 0)[:top]:
         if f not in src:
             try:
                 import glob
