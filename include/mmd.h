@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 102
+#define MMD_VERSION 103
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -153,6 +153,9 @@ typedef struct {
   /* fusion-weight selection for ops that see only part of a node's inputs (NODE_FWD fed by a POOLFUSE, POOLFUSE itself):  */
   int32_t fw_n;           /* number of entries of `fw`; 0: fw has n_in entries and input i uses entry i                      */
   int32_t fw_idx[3];      /* entry of `fw` that weighs input i; -1: the input is already weighted (weight 1)                 */
+  /* NODE_BWD of a bf16 node whose forward ran as POOLFUSE + NODE_FWD: what the pre-pass left behind                       */
+  MmdRef aux;             /* the pre-weighted operand (pooled input [+ second same-resolution input]), final values         */
+  MmdRef praw;            /* raw value of the pooled input at each arg-max (0 where the padding won)                         */
 } MmdOp;
 
 /* Packed parameter block of one NODE / PROJ op (bf16 storage only; every section starts 128-byte aligned):

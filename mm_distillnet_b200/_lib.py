@@ -10,7 +10,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
-SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu",
+SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu",
            "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
@@ -62,6 +62,7 @@ class Op(C.Structure):
         ("du", Ref), ("dd", Ref), ("in_slot", Ref * 3), ("dx", Ref),
         ("g_dw", Ref), ("g_pw", Ref), ("g_pb", Ref), ("g_bn_w", Ref), ("g_bn_b", Ref), ("g_fw", Ref),
         ("fw_n", C.c_int32), ("fw_idx", C.c_int32 * 3),
+        ("aux", Ref), ("praw", Ref),
     ]
 
 

@@ -254,7 +254,8 @@ class _Plan:
         self.grad_off = {}
         if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
             off = 0
-            for p in self.params:
+            for p in self.params:   # every gradient starts 16-byte aligned (the kernels use 16-byte vector reductions)
+                off = (off + 15) // 16 * 16
                 self.grad_off[id(p)] = (off, p.numel(), tuple(p.shape))
                 off += p.numel() * 4
             self.grad_floats = off // 4
@@ -578,6 +579,7 @@ class _Plan:
             elif op.kind == _lib.OP_NODE_FWD:
                 o = new(_lib.OP_NODE_BWD, op)
                 set_cons(o, op.out)
+                o.aux, o.praw = _ref(op.aux), _ref(op.praw)
                 o.du = _ref((op.du.base, op.du.off))
                 o.dd = _ref(dd)
                 o.g_dw = _ref(self._galloc(op.dw.weight))

@@ -123,6 +123,8 @@ struct NodeBwdP {
   const void* save_d;
   const unsigned char* packed;   // packed parameter block of the forward op (nullptr: convert in the kernel)
   const unsigned char* pidx[3];  // arg-max indices written by the forward for pooled inputs
+  const void* aux;               // bf16 nodes with a pooled input: the POOLFUSE operand (final values) ...
+  const void* praw;              // ... and the raw pooled-input value at each arg-max
   int n_cons;
   ConsP cons[3];
   void* du;
@@ -197,6 +199,9 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16,
 bool fwd_v4_usable(const NodeFwdP& p);
 int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s);
 int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s);
+// bf16 backward, compile-time tile geometry (bifpn_bwd_v4.cu)
+bool bwd_v4_usable(const NodeBwdP& p);
+int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead

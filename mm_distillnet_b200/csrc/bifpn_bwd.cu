@@ -13,6 +13,8 @@
 //                dL/du = dL/dv * swish'(u) -> written once; per-input slots; the last CTA forms the fusion-weight
 //                gradient (relu / normalise backward, src/YetAnotherEfficientDet.py:338-339).
 //   proj_bwd   : first-cell projections; pull_kernel / slot_kernel: P6/P7 synthesis and the stack boundary.
+#include <stdlib.h>
+
 #include "bifpn_bwd_common.cuh"
 
 namespace mmd {
@@ -615,6 +617,12 @@ static int launch_node_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   MMD_CUDA(cudaFuncSetAttribute(node_bwd_b_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
   const int grid = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();
   const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, sizeof(T));
+  static int no_v4 = -1;
+  if (no_v4 < 0) {
+    const char* e = getenv("MMD_NO_BWD_V4");
+    no_v4 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (sizeof(T) == 2 && !tc_disabled() && !no_v4 && bwd_v4_usable(p)) return launch_node_bwd_v4(p, C, s);
   if (sizeof(T) == 2 && !tc_disabled()) {
     int rc = launch_node_bwd_a_tc(p, C, s);
     if (rc) return rc;

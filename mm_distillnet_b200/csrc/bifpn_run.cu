@@ -67,6 +67,8 @@ static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
   p.out_bn = B.get<float>(op.out.bn);
   p.save_d = B.get<void>(op.save_d);
   p.packed = B.get<unsigned char>(op.packed);
+  p.aux = B.get<void>(op.aux);
+  p.praw = B.get<void>(op.praw);
   p.n_cons = op.n_cons;
   MMD_CHECK_ARG(op.n_cons >= 0 && op.n_cons <= 3, "op: n_cons=%d", op.n_cons);
   for (int c = 0; c < 3; ++c) {

@@ -61,7 +61,11 @@ def test_plan_structure():
     assert kinds.count(_lib.OP_NODE_FWD) == 40 and kinds.count(_lib.OP_PROJ_FWD) == 6
     assert kinds.count(_lib.OP_BNAPPLY) == 2 + 5
     assert plan.out_shapes == [(16, 112, 96 >> i, 96 >> i) for i in range(5)]
-    assert plan.grad_floats == sum(p.numel() for c in cells for p in c.parameters()) == 708159
+    n_par = sum(p.numel() for c in cells for p in c.parameters())
+    assert n_par == 708159
+    # one flat fp32 buffer, parameter order, each gradient 16-byte aligned (<= 3 floats of padding per tensor)
+    assert n_par <= plan.grad_floats <= n_par + 3 * len(plan.params)
+    assert all(off % 16 == 0 for off, _, _ in plan.grad_off.values())
     bk = [o.kind for o in plan.bwd_ops]
     assert bk.count(_lib.OP_NODE_BWD) == 40 and bk.count(_lib.OP_PROJ_BWD) == 6
     assert all(0 <= o.n_cons <= 3 for o in plan.bwd_ops)

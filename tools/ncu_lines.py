@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line instruction / stall-sample table for one kernel of an .ncu-rep (needs -lineinfo at compile time).
 
-    python tools/ncu_lines.py gpurun_out/prof.ncu-rep <kernel regex> <launch index> <cubin> [top N]
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep <kernel regex> <launch index> <cubin> [top N] [mangled-name substring]
 
 ncu's CSV source page is SASS-level only; nvdisasm -g gives the line of every SASS instruction of the same cubin.
 The two listings are matched by instruction order inside the function.
@@ -52,12 +52,12 @@ def main():
     rep, regex, idx, cubin = sys.argv[1:5]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
     name, hdr, rows = sass_rows(rep, regex, idx)
-    func = re.sub(r"[^A-Za-z0-9_]", "", regex)
+    func = sys.argv[6] if len(sys.argv) > 6 else re.sub(r"[^A-Za-z0-9_]", "", regex)
     lm = line_map(cubin, func)
     ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
     agg = collections.defaultdict(lambda: [0, 0])
-    rows = [r for r in rows if len(r) > ci]
+    rows = [r for r in rows if len(r) > ci and (r[ci] or "0").replace(".", "").isdigit()]
     if len(rows) != len(lm):
         print("warning: %d SASS rows in the report vs %d instructions in the cubin" % (len(rows), len(lm)))
     for r, l in zip(rows, lm):
