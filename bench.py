@@ -120,44 +120,84 @@ WORKLOAD = ("cfg2: MTA loss + 5-cell EfficientDet-D2 BiFPN fwd/bwd microbench on
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is read in-process from a background thread
+    (a polling `nvidia-smi -lms 100` child was measured to slow this launch-bound step 3-4x through driver contention);
+    falls back to one nvidia-smi query per second when pynvml is unavailable."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.05):
+        import threading
+        self.sm, self.smax, self.reasons, self.src = [], None, set(), None
+        self._stop = threading.Event()
+        self._thr = None
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {
+                "hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap,
+            }
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, b in bits.items():
+                            if r & b:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    self._stop.wait(period_s)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+            self.src = "nvml"
+        except Exception:
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
+                                           "--format=csv,noheader,nounits", "-lms", "1000"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.src = "nvidia-smi"
+            except OSError:
+                self.p = None
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-            out, _ = self.p.communicate()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join(timeout=2)
+        elif self.p is not None:
+            time.sleep(0.15)
+            self.p.terminate()
             try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                out, _ = self.p.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+                out, _ = self.p.communicate()
+            for ln in out.strip().splitlines():
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.sm.append(float(f[1]))
+                    self.smax = float(f[2])
+                except ValueError:
+                    continue
+                for n, v in zip(self.NAMES, f[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.src}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -214,17 +254,31 @@ def run_ours(args, rank, world, local_rank):
             ms = t.item()
         return ms
 
-    def resident_step():
+    def eager_step():
         for x in dev_s:
             x.grad = None
         return step(dev_s, dev_t)
 
+    # The whole step is captured once into a CUDA graph (DistillStep.capture) and replayed: ~400 launches of a few
+    # microseconds each are host-bound otherwise.  --no-graph times the eager path instead.
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture(dev_s, dev_t, warmup=max(args.warmup, 3))
+
+    def resident_step():
+        if use_graph:
+            return step.replay()
+        return eager_step()
+
     host_loss = torch.empty(N_TEACHERS, 5, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        xs = [x.to(dev, non_blocking=True).requires_grad_(True) for x in host_s]
-        kd = step(xs, host_t)                       # teacher inputs are copied host->device inside the call
-        host_loss.copy_(kd, non_blocking=False)     # device->host read of the step's result
+        if use_graph:
+            kd = step.replay(host_s, host_t)            # pinned host -> static device buffers, then the graph
+        else:
+            xs = [x.to(dev, non_blocking=True).requires_grad_(True) for x in host_s]
+            kd = step(xs, host_t)                       # teacher inputs are copied host->device inside the call
+        host_loss.copy_(kd, non_blocking=False)         # device->host read of the step's result
         return host_loss
 
     for _ in range(max(args.warmup, 3)):
@@ -234,6 +288,12 @@ def run_ours(args, rank, world, local_rank):
     ms = timed(resident_step, args.steps)
     launches = mmd.launch_count() - l0
     clocks = sampler.stop() if sampler else None
+    if use_graph:   # replayed launches never pass through the library's host-side counter: count one eager step
+        torch.cuda.synchronize()
+        l0 = mmd.launch_count()
+        eager_step()
+        torch.cuda.synchronize()
+        launches = (mmd.launch_count() - l0) * args.steps
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -246,7 +306,7 @@ def run_ours(args, rank, world, local_rank):
         _lib.prof_collect()
         nprof = min(args.steps, 5)
         for _ in range(nprof):
-            resident_step()
+            eager_step()
         prof = _lib.prof_collect()
         _lib.prof_enable(False)
         peak, peak_src = peaks()
@@ -284,7 +344,8 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": "dp%d (flat-gradient NCCL all-reduce)" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: the step streams ~%.1f GB of activations (L2 = 126 MB); no flush needed"
                              % (3 * B * 30016512 * esize * 2 / 1e9),
-                       "optimizer": "none (the microbench ends at the averaged gradients)"},
+                       "optimizer": "none (the microbench ends at the averaged gradients)",
+                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": N_TEACHERS * 5 * 4, "ms_per_step": ms_e2e / args.steps},
@@ -302,6 +363,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (cfg2: 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -625,8 +625,9 @@ class _Plan:
 
 
 class _Lease:
-    """A pooled device buffer: returned to its plan's pool when the last reference (e.g. the autograd context of the
-    forward that used it) goes away, so steady-state steps never touch the CUDA allocator."""
+    """A pooled device buffer.  It goes back to its plan's pool on release() — called as soon as the work that needs it
+    has been enqueued (stream order protects the contents) — or, as a safety net, when the last reference goes away
+    (a forward whose backward never runs).  Steady-state steps therefore never touch the CUDA allocator."""
     __slots__ = ("buf", "pool")
 
     def __init__(self, pool, nbytes, device):
@@ -634,12 +635,18 @@ class _Lease:
         self.buf = pool.pop() if pool else torch.empty(max(nbytes, _ALIGN), dtype=torch.uint8, device=device)
 
     def data_ptr(self):
+        if self.buf is None:
+            raise RuntimeError("mm_distillnet_b200.BiFPN: this forward's workspace was already released (backward twice?)")
         return self.buf.data_ptr()
+
+    def release(self):
+        buf, self.buf = self.buf, None
+        if buf is not None and len(self.pool) < 4:
+            self.pool.append(buf)
 
     def __del__(self):
         try:
-            if len(self.pool) < 4:
-                self.pool.append(self.buf)
+            self.release()
         except Exception:  # interpreter shutdown
             pass
 
@@ -660,6 +667,7 @@ class _StackFunction(torch.autograd.Function):
             raise RuntimeError("mm_distillnet_b200.BiFPN: backward through an eval-mode (folded BatchNorm) forward is "
                                "not supported; call .train() on the student")
         gin, gflat = ctx.runner._backward(plan, ctx.saved, gouts)
+        ctx.saved[1].release()   # the forward arena: every kernel that reads it is enqueued
         grads = [None, None, None]
         for i in range(ctx.n_in):
             grads.append(gin[i] if ctx.needs_input_grad[3 + i] else None)
@@ -729,7 +737,8 @@ class _Runner:
             outs = _StackFunction.apply(self, plan, len(inputs), *inputs, *params)
         else:
             with torch.no_grad():
-                outs, _ = self._forward(plan, inputs)
+                outs, saved = self._forward(plan, inputs)
+            saved[1].release()
             outs = tuple(outs)
         return outs
 
@@ -808,4 +817,5 @@ class _Runner:
             bases[plan.B_OUT + k] = o.data_ptr()
             bases[plan.B_GOUT + k] = g.data_ptr()
         self._call(plan, plan.bwd_ops, bases)
+        bwd.release()
         return gin, zero

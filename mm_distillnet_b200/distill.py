@@ -72,3 +72,48 @@ class DistillStep:
         loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
         loss.backward()                                              # :182
         return kd.detach()
+
+    # ---- CUDA-graph replay of the whole step -----------------------------------------------------------------------
+    def capture(self, student_inputs, teacher_inputs, warmup=3):
+        """Capture one full step (teacher forwards on their side streams, student forward, MTA, backward, gradient
+        all-reduce) into a CUDA graph over static device copies of the inputs.  The step is ~400 kernel launches of a
+        few microseconds each: replaying it as one graph takes the host (and any driver contention, e.g. a clock
+        monitor) out of the critical path.  Returns self; use replay()."""
+        dev = self.device
+        self._g_xs = [x.detach().to(dev).clone().requires_grad_(bool(x.requires_grad)) for x in student_inputs]
+        self._g_xt = [[x.detach().to(dev).clone() for x in xs] for xs in teacher_inputs]
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):      # plans, arenas and packed blocks exist before the capture starts
+                for x in self._g_xs:
+                    x.grad = None
+                self(self._g_xs, self._g_xt)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for x in self._g_xs:
+            x.grad = None
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self(self._g_xs, self._g_xt)
+        return self
+
+    def replay(self, student_inputs=None, teacher_inputs=None):
+        """Copy new inputs (host or device tensors; pinned host memory makes the copies asynchronous) into the static
+        buffers and replay the captured step.  Returns the static [n_teachers, n_levels] loss tensor; the student's
+        parameter gradients are in `flat_grad` / `.grad`, input gradients in `graph_inputs()[i].grad`."""
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("DistillStep.replay() needs capture() first")
+        if student_inputs is not None:
+            for d, x in zip(self._g_xs, student_inputs):
+                d.detach().copy_(x, non_blocking=True)
+        if teacher_inputs is not None:
+            for ds, xs in zip(self._g_xt, teacher_inputs):
+                for d, x in zip(ds, xs):
+                    d.copy_(x, non_blocking=True)
+        self._graph.replay()
+        return self._g_out
+
+    def graph_inputs(self):
+        return self._g_xs
