@@ -94,6 +94,10 @@ class DistillStep:
         torch.cuda.synchronize(dev)
         for x in self._g_xs:
             x.grad = None
+        try:   # the static inputs' AccumulateGrad nodes were created on another stream than the capture stream
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._g_out = self(self._g_xs, self._g_xt)
