@@ -177,6 +177,13 @@ int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t 
 int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases,
                   int32_t B, int32_t C, int32_t dtype, mmd_stream_t stream);
 
+/* Run `n_lists` op lists (e.g. the student's and the three teachers' forward) in lockstep on ONE stream: ops at the same
+ * index that have the same kind and geometry share a launch (blockIdx.y = network), which matters for the small pyramid
+ * levels (fewer tiles than SMs) and cuts the launch count by the number of networks; anything that does not line up
+ * runs as in mmd_bifpn_run.  Every list must use the same batch size B.  n_lists <= 4. */
+int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops, void* const* const* bases, const int32_t* n_bases,
+                        int32_t n_lists, int32_t B, int32_t C, int32_t dtype, mmd_stream_t stream);
+
 /* Optional profiler: while enabled, every kernel launch of this library is bracketed by a CUDA-event pair on its
  * stream.  mmd_prof_collect synchronises the device and ADDS, per kernel kind, the elapsed milliseconds, the number
  * of launches and the algorithmic bytes into the caller's arrays of length mmd_prof_num_kinds(). */

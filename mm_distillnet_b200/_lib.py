@@ -114,6 +114,9 @@ def lib():
     L.mmd_bifpn_run.restype = C.c_int
     L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.mmd_bifpn_run_multi.restype = C.c_int
+    L.mmd_bifpn_run_multi.argtypes = [C.POINTER(C.POINTER(Op)), C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_void_p)),
+                                      C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.mmd_bifpn_prep.restype = C.c_int
     L.mmd_bifpn_prep.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.mmd_packed_bytes.restype = C.c_size_t
@@ -156,7 +159,7 @@ def prof_collect():
             for i in range(n) if cnt[i] > 0}
 
 
-EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run",
+EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run", "mmd_bifpn_run_multi",
            "mmd_bifpn_prep", "mmd_packed_bytes",
            "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
            "mmd_prof_collect")

@@ -134,11 +134,14 @@ class BiFPNStack(nn.Sequential):
         super().__init__(*cells)
         self._runner = _Runner()
 
+    def fusable(self):
+        cells = list(self)
+        return len(cells) > 0 and all(isinstance(c, BiFPN) for c in cells) and len({c.training for c in cells}) == 1 and \
+            all(not c.first_time for c in cells[1:])
+
     def forward(self, inputs):
         cells = list(self)
-        fusable = all(isinstance(c, BiFPN) for c in cells) and len({c.training for c in cells}) == 1 and \
-            all(not c.first_time for c in cells[1:])
-        if not fusable:
+        if not self.fusable():
             for c in cells:
                 inputs = c(inputs)
             return inputs
@@ -624,6 +627,41 @@ class _Plan:
         return arr
 
 
+def forward_multi(items):
+    """items = [(BiFPNStack, inputs), ...] (<= 4 fusable stacks sharing batch size and dtype, e.g. the student and its
+    three frozen teachers): all forwards are enqueued by ONE mmd_bifpn_run_multi call on the current stream, so that
+    nodes of the same pyramid level share a launch.  Returns the per-stack output tuples; a train-mode stack under grad
+    mode gets its usual autograd node (the backward is unchanged)."""
+    L = _lib.lib()
+    prepared = []
+    for stack, inputs in items:
+        cells = list(stack)
+        inputs = tuple(inputs)
+        plan, params, need_grad = stack._runner._plan_for(cells, inputs, cells[0].training, "cells")
+        with torch.no_grad():
+            bases, outs, saved = stack._runner._forward_prepare(plan, inputs)
+        prepared.append((stack, inputs, plan, bases, outs, saved))
+    p0 = prepared[0][2]
+    if any(p[2].B != p0.B or p[2].dtype != p0.dtype or p[2].device != p0.device for p in prepared):
+        raise ValueError("forward_multi: stacks must share batch size, dtype and device")
+    n = len(prepared)
+    ops = (C.POINTER(_lib.Op) * n)(*[C.cast(p[2].fwd_ops, C.POINTER(_lib.Op)) for p in prepared])
+    n_ops = (C.c_int32 * n)(*[len(p[2].fwd_ops) for p in prepared])
+    base_arrs = [(C.c_void_p * len(p[3]))(*p[3]) for p in prepared]
+    bases = (C.POINTER(C.c_void_p) * n)(*[C.cast(a, C.POINTER(C.c_void_p)) for a in base_arrs])
+    n_bases = (C.c_int32 * n)(*[len(p[3]) for p in prepared])
+    with torch.cuda.device(p0.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = L.mmd_bifpn_run_multi(ops, n_ops, bases, n_bases, n, p0.B, p0.Cc,
+                                   _lib.MMD_F32 if p0.dtype == torch.float32 else _lib.MMD_BF16, stream)
+    _lib.check(rc, "mmd_bifpn_run_multi")
+    results = []
+    for stack, inputs, plan, _, outs, saved in prepared:
+        cells = list(stack)
+        results.append(stack._runner.run(cells, inputs, cells[0].training, "cells", pre=(outs, saved)))
+    return results
+
+
 class _Lease:
     """A pooled device buffer.  It goes back to its plan's pool on release() — called as soon as the work that needs it
     has been enqueued (stream order protects the contents) — or, as a safety net, when the last reference goes away
@@ -653,9 +691,9 @@ class _Lease:
 
 class _StackFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, plan, n_in, *tensors):
+    def forward(ctx, runner, plan, n_in, pre, *tensors):
         inputs, params = tensors[:n_in], tensors[n_in:]
-        outs, saved = runner._forward(plan, inputs)
+        outs, saved = pre if pre is not None else runner._forward(plan, inputs)
         ctx.runner, ctx.plan, ctx.saved, ctx.n_in = runner, plan, saved, n_in
         ctx.param_list = params
         return tuple(outs)
@@ -668,15 +706,15 @@ class _StackFunction(torch.autograd.Function):
                                "not supported; call .train() on the student")
         gin, gflat = ctx.runner._backward(plan, ctx.saved, gouts)
         ctx.saved[1].release()   # the forward arena: every kernel that reads it is enqueued
-        grads = [None, None, None]
+        grads = [None, None, None, None]
         for i in range(ctx.n_in):
-            grads.append(gin[i] if ctx.needs_input_grad[3 + i] else None)
+            grads.append(gin[i] if ctx.needs_input_grad[4 + i] else None)
         if ctx.runner.grad_sink is not None:
             # flat-gradient mode (DistillStep): hand over the one contiguous fp32 buffer holding every parameter
             # gradient and make each .grad a view of it, instead of ~360 per-parameter AccumulateGrad kernels
             flat = gflat[:plan.grad_floats]
             for j, p in enumerate(ctx.param_list):
-                if ctx.needs_input_grad[3 + ctx.n_in + j]:
+                if ctx.needs_input_grad[4 + ctx.n_in + j]:
                     off, n, shape = plan.grad_off[id(plan.params[j])]
                     p.grad = flat[off // 4: off // 4 + n].view(shape)
             ctx.runner.grad_sink(flat)
@@ -684,7 +722,7 @@ class _StackFunction(torch.autograd.Function):
             return tuple(grads)
         for j, p in enumerate(ctx.param_list):
             ent = plan.grad_off.get(id(plan.params[j]))
-            if ent is None or not ctx.needs_input_grad[3 + ctx.n_in + j]:
+            if ent is None or not ctx.needs_input_grad[4 + ctx.n_in + j]:
                 grads.append(None)
             else:
                 off, n, shape = ent
@@ -697,9 +735,10 @@ class _Runner:
 
     def __init__(self):
         self.plans = {}
+        self._param_cache = None
         self.grad_sink = None   # callable(flat_fp32_grad) -> None; see DistillStep
 
-    def run(self, mods, inputs, training, kind):
+    def _plan_for(self, mods, inputs, training, kind):
         if len(inputs) == 0:
             raise ValueError("BiFPN: empty input tuple")
         x0 = inputs[0]
@@ -710,7 +749,10 @@ class _Runner:
         for x in inputs:
             if x.dim() != 4 or x.shape[0] != x0.shape[0] or x.dtype != x0.dtype or x.device != x0.device:
                 raise ValueError("BiFPN: inputs must be [B,C,H,W] tensors sharing batch, dtype and device")
-        params = [p for m in mods for p in m.parameters()]
+        ck = tuple(id(m) for m in mods)
+        if self._param_cache is None or self._param_cache[0] != ck:   # walking 5 cells' modules costs ~1 ms per call
+            self._param_cache = (ck, [p for m in mods for p in m.parameters()])
+        params = self._param_cache[1]
         if any(p.dtype != torch.float32 for p in params):
             raise TypeError("BiFPN parameters must stay float32 (master weights); cast activations, not the module")
         if any(p.device != x0.device for p in params):
@@ -733,11 +775,16 @@ class _Runner:
             self.plans[key] = plan
             if len(self.plans) > 16:
                 self.plans.pop(next(iter(self.plans)))
+        return plan, params, need_grad
+
+    def run(self, mods, inputs, training, kind, pre=None):
+        """`pre` = (outs, saved) of a forward that forward_multi() has already enqueued for this plan."""
+        plan, params, need_grad = self._plan_for(mods, inputs, training, kind)
         if need_grad:
-            outs = _StackFunction.apply(self, plan, len(inputs), *inputs, *params)
+            outs = _StackFunction.apply(self, plan, len(inputs), pre, *inputs, *params)
         else:
             with torch.no_grad():
-                outs, saved = self._forward(plan, inputs)
+                outs, saved = pre if pre is not None else self._forward(plan, inputs)
             saved[1].release()
             outs = tuple(outs)
         return outs
@@ -777,7 +824,8 @@ class _Runner:
             rc = _lib.lib().mmd_bifpn_prep(plan.fwd_ops, len(plan.fwd_ops), arr, len(bases), plan.Cc, _lib.MMD_BF16, stream)
         _lib.check(rc, "mmd_bifpn_prep")
 
-    def _forward(self, plan, inputs):
+    def _forward_prepare(self, plan, inputs):
+        """Everything of a forward except the kernel launches: arena lease, outputs, base table, packed parameters."""
         dev = plan.device
         xs = [x.detach().contiguous(memory_format=torch.channels_last) for x in inputs]
         arena = _Lease(plan.pool_fwd, plan.fwd_arena.size, dev)
@@ -790,8 +838,12 @@ class _Runner:
         for k, o in enumerate(outs):
             bases[plan.B_OUT + k] = o.data_ptr()
         self._prep(plan, bases)
+        return bases, outs, (xs, arena, outs)
+
+    def _forward(self, plan, inputs):
+        bases, outs, saved = self._forward_prepare(plan, inputs)
         self._call(plan, plan.fwd_ops, bases)
-        return outs, (xs, arena, outs)
+        return outs, saved
 
     def _backward(self, plan, saved, gouts):
         xs, arena, outs = saved

@@ -101,6 +101,53 @@ static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
 
 using namespace mmd;
 
+static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream);
+
+extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops, void* const* const* bases,
+                                   const int32_t* n_bases, int32_t n_lists, int32_t batch, int32_t C, int32_t dtype,
+                                   mmd_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MMD_CHECK_ARG(ops && n_ops && bases && n_bases && n_lists >= 1 && n_lists <= kMaxBatchNets, "mmd_bifpn_run_multi: bad arguments");
+  MMD_CHECK_ARG(batch >= 1 && C == 112, "mmd_bifpn_run_multi: batch=%d C=%d", batch, C);
+  MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run_multi: dtype %d", dtype);
+  int max_n = 0;
+  for (int l = 0; l < n_lists; ++l) max_n = n_ops[l] > max_n ? n_ops[l] : max_n;
+  for (int i = 0; i < max_n; ++i) {
+    bool done[kMaxBatchNets] = {false, false, false, false};
+    for (int l = 0; l < n_lists; ++l) {
+      if (done[l] || i >= n_ops[l]) continue;
+      const MmdOp& op = ops[l][i];
+      const bool batchable = dtype == MMD_BF16 && (op.kind == MMD_OP_NODE_FWD || op.kind == MMD_OP_POOLFUSE);
+      NodeFwdP ps[kMaxBatchNets];
+      int members[kMaxBatchNets], n = 0;
+      if (batchable) {
+        for (int m = l; m < n_lists; ++m) {
+          if (done[m] || i >= n_ops[m]) continue;
+          const MmdOp& om = ops[m][i];
+          if (om.kind != op.kind || om.out.H != op.out.H || om.out.W != op.out.W) continue;
+          Bases Bm{bases[m], n_bases[m]};
+          int rc = fill_fwd(om, Bm, batch, ps[n]);
+          if (rc) return rc;
+          if (op.kind == MMD_OP_NODE_FWD && !fwd_v4_usable(ps[n])) continue;
+          members[n++] = m;
+        }
+      }
+      if (n >= 2) {
+        int rc = (op.kind == MMD_OP_NODE_FWD) ? launch_node_fwd_v4(ps, n, C, stream) : launch_poolfuse(ps, n, C, stream);
+        if (rc) return rc;
+        for (int k = 0; k < n; ++k) done[members[k]] = true;
+      }
+      if (!done[l]) {
+        Bases Bl{bases[l], n_bases[l]};
+        int rc = run_one(op, i, Bl, batch, C, dtype, stream);
+        if (rc) return rc;
+        done[l] = true;
+      }
+    }
+  }
+  return 0;
+}
+
 extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases, int32_t batch,
                              int32_t C, int32_t dtype, mmd_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -110,57 +157,61 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
   Bases B{bases, n_bases};
   for (int i = 0; i < n_ops; ++i) {
-    const MmdOp& op = ops[i];
-    int rc = 0;
-    switch (op.kind) {
-      case MMD_OP_NODE_FWD:
-      case MMD_OP_PROJ_FWD:
-      case MMD_OP_POOLFUSE:
-      case MMD_OP_BNAPPLY: {
-        NodeFwdP p;
-        if ((rc = fill_fwd(op, B, batch, p))) return rc;
-        if (op.kind == MMD_OP_NODE_FWD) {
-          MMD_CHECK_ARG(p.dw_w != nullptr, "node op %d: no depthwise weight", i);
-          for (int k = 0; k < op.n_in; ++k) MMD_CHECK_ARG(op.in[k].C == C, "node op %d: input %d has C=%d", i, k, op.in[k].C);
-          rc = launch_node_fwd(p, C, dtype, stream);
-        } else if (op.kind == MMD_OP_PROJ_FWD) {
-          MMD_CHECK_ARG(op.Cin >= 4 && op.Cin % 4 == 0, "proj op %d: Cin=%d must be a positive multiple of 4", i, op.Cin);
-          rc = launch_proj_fwd(p, C, dtype, stream);
-        } else if (op.kind == MMD_OP_POOLFUSE) {
-          MMD_CHECK_ARG(dtype == MMD_BF16, "poolfuse op %d: bf16 plans only", i);
-          rc = launch_poolfuse(&p, 1, C, stream);
-        } else {
-          rc = launch_bnapply(p, C, dtype, stream);
-        }
-        break;
-      }
-      case MMD_OP_NODE_BWD:
-      case MMD_OP_PROJ_BWD:
-      case MMD_OP_PULL:
-      case MMD_OP_SLOT: {
-        NodeBwdP p;
-        if ((rc = fill_bwd(op, B, batch, p))) return rc;
-        if (op.kind == MMD_OP_NODE_BWD) {
-          MMD_CHECK_ARG(p.out && p.out_bn && p.save_d && p.du && p.dd && p.g_pw && p.counter, "node bwd op %d: missing storage", i);
-          rc = launch_node_bwd(p, C, dtype, stream);
-        } else if (op.kind == MMD_OP_PROJ_BWD) {
-          MMD_CHECK_ARG(p.out && p.out_bn && p.g_pw && p.in[0].data, "proj bwd op %d: missing storage", i);
-          rc = launch_proj_bwd(p, C, dtype, stream);
-        } else if (op.kind == MMD_OP_PULL) {
-          MMD_CHECK_ARG(p.dx != nullptr, "pull op %d: no destination", i);
-          rc = launch_pull(p, C, dtype, stream);
-        } else {
-          MMD_CHECK_ARG(p.in[0].data && p.in[0].bn && p.in_slot[0] && op.n_cons == 1, "slot op %d: missing storage", i);
-          if (op.mode[0] == MMD_IN_POOL) MMD_CHECK_ARG(p.pidx[0] != nullptr, "slot op %d: no arg-max indices", i);
-          rc = launch_slot(p, C, dtype, stream);
-        }
-        break;
-      }
-      default:
-        set_error("mmd_bifpn_run: op %d has unknown kind %d", i, op.kind);
-        return MMD_E_ARG;
-    }
+    int rc = run_one(ops[i], i, B, batch, C, dtype, stream);
     if (rc) return rc;
   }
   return 0;
+}
+
+static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream) {
+  int rc = 0;
+    switch (op.kind) {
+    case MMD_OP_NODE_FWD:
+    case MMD_OP_PROJ_FWD:
+    case MMD_OP_POOLFUSE:
+    case MMD_OP_BNAPPLY: {
+      NodeFwdP p;
+      if ((rc = fill_fwd(op, B, batch, p))) return rc;
+      if (op.kind == MMD_OP_NODE_FWD) {
+        MMD_CHECK_ARG(p.dw_w != nullptr, "node op %d: no depthwise weight", i);
+        for (int k = 0; k < op.n_in; ++k) MMD_CHECK_ARG(op.in[k].C == C, "node op %d: input %d has C=%d", i, k, op.in[k].C);
+        rc = launch_node_fwd(p, C, dtype, stream);
+      } else if (op.kind == MMD_OP_PROJ_FWD) {
+        MMD_CHECK_ARG(op.Cin >= 4 && op.Cin % 4 == 0, "proj op %d: Cin=%d must be a positive multiple of 4", i, op.Cin);
+        rc = launch_proj_fwd(p, C, dtype, stream);
+      } else if (op.kind == MMD_OP_POOLFUSE) {
+        MMD_CHECK_ARG(dtype == MMD_BF16, "poolfuse op %d: bf16 plans only", i);
+        rc = launch_poolfuse(&p, 1, C, stream);
+      } else {
+        rc = launch_bnapply(p, C, dtype, stream);
+      }
+      break;
+    }
+    case MMD_OP_NODE_BWD:
+    case MMD_OP_PROJ_BWD:
+    case MMD_OP_PULL:
+    case MMD_OP_SLOT: {
+      NodeBwdP p;
+      if ((rc = fill_bwd(op, B, batch, p))) return rc;
+      if (op.kind == MMD_OP_NODE_BWD) {
+        MMD_CHECK_ARG(p.out && p.out_bn && p.save_d && p.du && p.dd && p.g_pw && p.counter, "node bwd op %d: missing storage", i);
+        rc = launch_node_bwd(p, C, dtype, stream);
+      } else if (op.kind == MMD_OP_PROJ_BWD) {
+        MMD_CHECK_ARG(p.out && p.out_bn && p.g_pw && p.in[0].data, "proj bwd op %d: missing storage", i);
+        rc = launch_proj_bwd(p, C, dtype, stream);
+      } else if (op.kind == MMD_OP_PULL) {
+        MMD_CHECK_ARG(p.dx != nullptr, "pull op %d: no destination", i);
+        rc = launch_pull(p, C, dtype, stream);
+      } else {
+        MMD_CHECK_ARG(p.in[0].data && p.in[0].bn && p.in_slot[0] && op.n_cons == 1, "slot op %d: missing storage", i);
+        if (op.mode[0] == MMD_IN_POOL) MMD_CHECK_ARG(p.pidx[0] != nullptr, "slot op %d: no arg-max indices", i);
+        rc = launch_slot(p, C, dtype, stream);
+      }
+      break;
+    }
+    default:
+      set_error("mmd_bifpn_run: op %d has unknown kind %d", i, op.kind);
+      return MMD_E_ARG;
+  }
+  return rc;
 }

@@ -11,7 +11,7 @@ student's flat fp32 gradient buffer (mean over ranks = DDP semantics; BatchNorm 
 import torch
 import torch.distributed as dist
 
-from .bifpn import BiFPN, BiFPNStack
+from .bifpn import BiFPN, BiFPNStack, forward_multi
 from .mta import MTALoss
 
 
@@ -23,7 +23,8 @@ class DistillStep:
     every student parameter's `.grad` is a view into `self.flat_grad` (already averaged over the process group).
     """
 
-    def __init__(self, student, teachers, criterion=None, w_kd=0.005, process_group=None, device=None):
+    def __init__(self, student, teachers, criterion=None, w_kd=0.005, process_group=None, device=None,
+                 batch_networks=True):
         if not isinstance(student, (BiFPN, BiFPNStack)):
             raise TypeError("DistillStep drives mm_distillnet_b200 BiFPN / BiFPNStack modules")
         self.student, self.teachers = student, list(teachers)
@@ -33,7 +34,8 @@ class DistillStep:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.device = device if device is not None else next(student.parameters()).device
         self.flat_grad = None
-        # the frozen teachers and the student are independent until the MTA loss: each teacher stack runs on its own
+        self.batch_networks = bool(batch_networks)
+        # multi-stream fallback (stacks that cannot share launches): the frozen teachers and the student are independent until the MTA loss: each teacher stack runs on its own
         # CUDA stream so the small pyramid levels (P5-P7: fewer CTAs than SMs) of different networks overlap
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.teachers] if self.device.type == "cuda" else []
         student._runner.grad_sink = self._on_flat_grad
@@ -52,22 +54,36 @@ class DistillStep:
     def _to_device(self, xs):
         return tuple(x if x.device == self.device else x.to(self.device, non_blocking=True) for x in xs)
 
+    def _batchable(self, xs, xts):
+        stacks = [self.student] + self.teachers
+        if len(stacks) > 4 or not all(isinstance(m, BiFPNStack) and m.fusable() for m in stacks):
+            return False
+        return all(x.dtype == torch.bfloat16 for x in xs) and all(x.dtype == torch.bfloat16 for t in xts for x in t) and \
+            all(t[0].shape[0] == xs[0].shape[0] for t in xts)
+
     def __call__(self, student_inputs, teacher_inputs):
-        main = torch.cuda.current_stream(self.device)
-        feats_t_all = []
-        for teacher, tin, st in zip(self.teachers, teacher_inputs, self.streams):   # train_methods.py:320-336
-            st.wait_stream(main)
-            with torch.cuda.stream(st), torch.no_grad():
-                feats_t = teacher(self._to_device(tin))
-                for f in feats_t:
-                    f.record_stream(main)
-            feats_t_all.append(feats_t)
         xs = self._to_device(student_inputs)
-        feats_s = self.student(xs)                                   # :318
-        kd = []
-        for feats_t, st in zip(feats_t_all, self.streams):           # :351-358
-            main.wait_stream(st)
-            kd.append(self.criterion(feats_s, [f.detach() for f in feats_t]))
+        xts = [self._to_device(t) for t in teacher_inputs]
+        if self.batch_networks and self._batchable(xs, xts):
+            # one lockstep pass: the same node of the student and of every teacher shares a launch
+            outs = forward_multi([(self.student, xs)] + [(t, x) for t, x in zip(self.teachers, xts)])
+            feats_s, feats_t_all = outs[0], outs[1:]
+            kd = [self.criterion(feats_s, [f.detach() for f in ft]) for ft in feats_t_all]       # :351-358
+        else:
+            main = torch.cuda.current_stream(self.device)
+            feats_t_all = []
+            for teacher, tin, st in zip(self.teachers, xts, self.streams):   # train_methods.py:320-336
+                st.wait_stream(main)
+                with torch.cuda.stream(st), torch.no_grad():
+                    feats_t = teacher(tin)
+                    for f in feats_t:
+                        f.record_stream(main)
+                feats_t_all.append(feats_t)
+            feats_s = self.student(xs)                                   # :318
+            kd = []
+            for feats_t, st in zip(feats_t_all, self.streams):           # :351-358
+                main.wait_stream(st)
+                kd.append(self.criterion(feats_s, [f.detach() for f in feats_t]))
         kd = torch.stack(kd)
         loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
         loss.backward()                                              # :182
