@@ -51,6 +51,18 @@ inline double node_algo_bytes(const TensorP* in, int n_in, const TileGeom& g, in
   return pos * g.B * C * (double)esize;
 }
 
+// Input-channel chunking of the tensor-core projection backward (bifpn_bwd_v4.cu): chunk width NC in {48, 128, 176}
+// (accumulator columns in TMEM and operand tiles in shared memory bound it), n chunks cover Cin.
+struct ProjChunks {
+  int NC, n;
+};
+inline ProjChunks proj_chunks(int Cin) {
+  ProjChunks c;
+  c.NC = Cin <= 48 ? 48 : (Cin <= 128 ? 128 : 176);
+  c.n = (Cin + c.NC - 1) / c.NC;
+  return c;
+}
+
 // Layout of one op's packed parameter block (include/mmd.h, written by prep.cu).
 struct PackedLayout {
   int Kp;              // K of the forward GEMM, padded to a multiple of 16
@@ -65,7 +77,12 @@ inline PackedLayout packed_layout(int kind, int Cin, int C) {
   L.offTaps = L.offBias + C * 4;
   L.fwdBytes = node ? L.offTaps + 9 * C * 4 : L.offTaps;   // what the forward kernel copies into shared memory
   L.offBwd = (L.fwdBytes + 127) / 128 * 128;
-  L.bytes = node ? L.offBwd + (C * C * 2 + 127) / 128 * 128 : L.offBwd;
+  if (node) {
+    L.bytes = L.offBwd + (C * C * 2 + 127) / 128 * 128;
+  } else {   // projection backward operand: [chunk][C/8][NC][8] bf16, element (o, i) = W[o][chunk*NC + i] (zero padded)
+    const ProjChunks pc = proj_chunks(Cin);
+    L.bytes = L.offBwd + (pc.n * (C / 8) * pc.NC * 16 + 127) / 128 * 128;
+  }
   return L;
 }
 
@@ -202,6 +219,8 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s);
 // bf16 backward, compile-time tile geometry (bifpn_bwd_v4.cu)
 bool bwd_v4_usable(const NodeBwdP& p);
 int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
+bool proj_bwd_v4_usable(const NodeBwdP& p);
+int launch_proj_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead

@@ -644,6 +644,7 @@ static int launch_node_bwd_t(const NodeBwdP& p, cudaStream_t s) {
 template <typename T>
 static int launch_proj_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   constexpr int C = 112;
+  if (sizeof(T) == 2 && !tc_disabled() && proj_bwd_v4_usable(p)) return launch_proj_bwd_v4(p, C, s);
   const size_t smem = ProjBSmem<C>::kFloats * sizeof(float);
   MMD_CUDA(cudaFuncSetAttribute(proj_bwd_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int gx = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();

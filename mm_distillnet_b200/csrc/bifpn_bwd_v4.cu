@@ -98,6 +98,61 @@ __device__ __forceinline__ void acc8_match(float2 (&acc)[4], uint4 w, const uint
   acc8(acc, w, cw2);
 }
 
+// G[r] += sum over the consumers of (edge weight) * (their dL/du as seen by rows ty0 + tyc + r, column x, channel group cg)
+template <int RC>
+__device__ __forceinline__ void gather_rows(const NodeBwdP& P, const float (&cw)[3], const TilePos t, const int tyc, const int x,
+                                            const int cg, const int H, const int W, float2 (&G)[RC][4]) {
+  for (int c = 0; c < P.n_cons; ++c) {
+    const ConsP& cs = P.cons[c];
+    const bf16* du = reinterpret_cast<const bf16*>(cs.du);
+    const float2 cw2 = make_float2(cw[c], cw[c]);
+    if (cs.mode == MMD_CONS_SAME) {
+      const bf16* src = du + (((long long)t.b * H + t.ty0 + tyc) * W + x) * C + 8 * cg;
+#pragma unroll
+      for (int r = 0; r < RC; ++r) acc8(G[r], ldg16(src + (long long)r * W * C), cw2);
+    } else if (cs.mode == MMD_CONS_UP2) {
+      const int W2 = 2 * W;
+      const bf16* src = du + (((long long)t.b * 2 * H + 2 * (t.ty0 + tyc)) * W2 + 2 * x) * C + 8 * cg;
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        const bf16* s0 = src + (long long)(2 * r) * W2 * C;
+        acc8(G[r], ldg16(s0), cw2);
+        acc8(G[r], ldg16(s0 + C), cw2);
+        acc8(G[r], ldg16(s0 + (long long)W2 * C), cw2);
+        acc8(G[r], ldg16(s0 + (long long)W2 * C + C), cw2);
+      }
+    } else {
+      // consumer pooled this tensor (3x3 stride 2, even sizes: no top / left padding): position (y, x) lies in
+      // window rows i = y/2 (wy 0) and y/2 - 1 (wy 2) when y is even, (y-1)/2 (wy 1) when odd; same for columns
+      const int cH = H >> 1, cW = W >> 1;
+      const bool xodd = (x & 1) != 0;
+      const int j0 = x >> 1;
+#pragma unroll
+      for (int r = 0; r < RC; ++r) {
+        const int y = t.ty0 + tyc + r;
+        const bool yodd = ((tyc + r) & 1) != 0;   // ty0 is even
+        const int i0 = y >> 1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (a == 1 && (yodd || i0 == 0)) continue;
+          const int i = i0 - a;
+          const uint32_t wy = yodd ? 1u : (a == 0 ? 0u : 2u);
+          const long long rowoff = ((long long)t.b * cH + i) * cW;
+          {
+            const long long off = (rowoff + j0) * C + 8 * cg;
+            acc8_match(G[r], ldg16(du + off), __ldg(reinterpret_cast<const uint2*>(cs.pidx + off)),
+                       wy * 3u + (xodd ? 1u : 0u), cw2);
+          }
+          if (!xodd && j0 > 0) {
+            const long long off = (rowoff + j0 - 1) * C + 8 * cg;
+            acc8_match(G[r], ldg16(du + off), __ldg(reinterpret_cast<const uint2*>(cs.pidx + off)), wy * 3u + 2u, cw2);
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int TW, int TH>
 __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_constant__ NodeBwdP P, int packed_off_bwd) {
   using S = CfgA<TW, TH>;
@@ -179,55 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
         for (int r = 0; r < RC; ++r)
 #pragma unroll
           for (int e = 0; e < 4; ++e) G[r][e] = make_float2(0.f, 0.f);
-        for (int c = 0; c < P.n_cons; ++c) {
-          const ConsP& cs = P.cons[c];
-          const bf16* du = reinterpret_cast<const bf16*>(cs.du);
-          const float2 cw2 = make_float2(cw[c], cw[c]);
-          if (cs.mode == MMD_CONS_SAME) {
-            const bf16* src = du + (((long long)t.b * H + t.ty0 + tyc) * W + x) * C + 8 * cg;
-#pragma unroll
-            for (int r = 0; r < RC; ++r) acc8(G[r], ldg16(src + (long long)r * W * C), cw2);
-          } else if (cs.mode == MMD_CONS_UP2) {
-            const int W2 = 2 * W;
-            const bf16* src = du + (((long long)t.b * 2 * H + 2 * (t.ty0 + tyc)) * W2 + 2 * x) * C + 8 * cg;
-#pragma unroll
-            for (int r = 0; r < RC; ++r) {
-              const bf16* s0 = src + (long long)(2 * r) * W2 * C;
-              acc8(G[r], ldg16(s0), cw2);
-              acc8(G[r], ldg16(s0 + C), cw2);
-              acc8(G[r], ldg16(s0 + (long long)W2 * C), cw2);
-              acc8(G[r], ldg16(s0 + (long long)W2 * C + C), cw2);
-            }
-          } else {
-            // consumer pooled this tensor (3x3 stride 2, even sizes: no top / left padding): position (y, x) lies in
-            // window rows i = y/2 (wy 0) and y/2 - 1 (wy 2) when y is even, (y-1)/2 (wy 1) when odd; same for columns
-            const int cH = H >> 1, cW = W >> 1;
-            const bool xodd = (x & 1) != 0;
-            const int j0 = x >> 1;
-#pragma unroll
-            for (int r = 0; r < RC; ++r) {
-              const int y = t.ty0 + tyc + r;
-              const bool yodd = ((tyc + r) & 1) != 0;   // ty0 is even
-              const int i0 = y >> 1;
-#pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                if (a == 1 && (yodd || i0 == 0)) continue;
-                const int i = i0 - a;
-                const uint32_t wy = yodd ? 1u : (a == 0 ? 0u : 2u);
-                const long long rowoff = ((long long)t.b * cH + i) * cW;
-                {
-                  const long long off = (rowoff + j0) * C + 8 * cg;
-                  acc8_match(G[r], ldg16(du + off), __ldg(reinterpret_cast<const uint2*>(cs.pidx + off)),
-                             wy * 3u + (xodd ? 1u : 0u), cw2);
-                }
-                if (!xodd && j0 > 0) {
-                  const long long off = (rowoff + j0 - 1) * C + 8 * cg;
-                  acc8_match(G[r], ldg16(du + off), __ldg(reinterpret_cast<const uint2*>(cs.pidx + off)), wy * 3u + 2u, cw2);
-                }
-              }
-            }
-          }
-        }
+        gather_rows<RC>(P, cw, t, tyc, x, cg, H, W, G);
         // BatchNorm backward + operand tiles
         const long long off0 = (((long long)t.b * H + t.ty0 + tyc) * W + x) * C + 8 * cg;
 #pragma unroll
@@ -316,6 +323,217 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =====================================================================================================================
+// first-cell projection backward (1x1 conv Cin -> C + BatchNorm), tensor cores
+// =====================================================================================================================
+// Same skeleton as part A: dy tile from the gathered gradient, then  dx[p][i] = sum_o dy[p][o] W[o][i]  (GEMM 1, N = one
+// chunk of NC input channels) and  dW[o][i] += sum_p dy[p][o] x[p][i]  (GEMM 2, the x tile carries an all-ones column for
+// the bias gradient).  blockIdx.y = input-channel chunk (see proj_chunks()).
+template <int TW, int TH, int NC>
+struct CfgP {
+  static constexpr int NP = TW * TH;
+  static constexpr int kGroup = 128 * 16;
+  static constexpr int kXStride = kGroup + 16;             // padded: the tile loader writes consecutive channel groups
+  static constexpr int NXG = NC / 8 + 2;                   // x tile groups: NC/8 data, one all-ones column group, one zero
+  static constexpr int N2 = NC + 16;
+  static constexpr int offGy = 0;
+  static constexpr int offX = NG * kGroup;                 // must follow dy (GEMM 2 reads 16 channel groups of "dy")
+  static constexpr int offB = up128(offX + NXG * kXStride);
+  static constexpr int kBBytes = (C / 8) * NC * 16;
+  static constexpr int offCoef = up128(offB + kBBytes);
+  static constexpr int offBar = offCoef + 3 * C * 4;
+  static constexpr int kBytes = offBar + 64;
+  static constexpr uint32_t kTmemCols = (NC + N2 <= 128) ? 128u : 512u;
+  static constexpr uint32_t kColW = kTmemCols / 2;         // [0, NC): dx accumulator, [kColW, kColW + N2): [dW | db]
+  static constexpr int kLoadThreads = NG * TW;
+  static constexpr int RC = (TH % 4 == 0) ? 4 : 2;
+  static_assert(NP <= 128 && NC % 16 == 0 && N2 <= 256 && NC <= (int)kColW && N2 <= (int)kColW, "shape");
+  static_assert(kBytes <= 232448, "shared memory");
+};
+
+template <int TW, int TH, int NC>
+__global__ void __launch_bounds__(kThreads, 1) proj_bwd4_kernel(const __grid_constant__ NodeBwdP P, int packed_off_bwd) {
+  using S = CfgP<TW, TH, NC>;
+  constexpr int RC = S::RC;
+  constexpr uint32_t kIdesc1 = tc::make_idesc_bf16(128, NC, false, false);
+  constexpr uint32_t kIdesc2 = tc::make_idesc_bf16(128, S::N2, true, true);
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_gy = smem + S::offGy;
+  unsigned char* s_x = smem + S::offX;
+  unsigned char* s_b = smem + S::offB;
+  float* s_coef = reinterpret_cast<float*>(smem + S::offCoef);
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + S::offBar);
+  uint64_t* bar_w = bar_mma + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = P.g.H, W = P.g.W, Cin = P.Cin;
+  const int chunk = blockIdx.y, cbase = chunk * NC;
+  const int valid = (Cin - cbase < NC) ? Cin - cbase : NC;     // real input channels of this chunk (multiple of 8)
+  const int tiles_x = W / TW, tiles_y = H / TH, ntiles = P.g.B * tiles_x * tiles_y;
+
+  if (warp == 0) tc::tmem_alloc(s_tmem, S::kTmemCols);
+  if (tid == 32) {
+    tc::mbar_init(bar_mma, 1);
+    tc::mbar_init(bar_w, 1);
+    tc::fence_mbar_init();
+    tc::mbar_expect_tx(bar_w, S::kBBytes);
+    tc::bulk_g2s(s_b, P.packed + packed_off_bwd + (size_t)chunk * S::kBBytes, S::kBBytes, bar_w);
+  }
+  float cw[3];
+  cons_weights(P, cw);
+  bn_bwd_coefs<C>(P, cw, s_coef);
+  // constant parts: dy rows >= NP are zero; x tile: rows >= NP zero, channels >= valid zero, ones column, zero group
+  for (int idx = tid; idx < NG * 128; idx += kThreads) {
+    const int grp = idx >> 7, row = idx & 127;
+    if (row >= S::NP) *reinterpret_cast<uint4*>(s_gy + grp * S::kGroup + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int idx = tid; idx < S::NXG * 128; idx += kThreads) {
+    const int grp = idx >> 7, row = idx & 127;
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    if (grp == NC / 8 && row < S::NP) z.x = 0x00003f80u;   // bf16 1.0 in column NC
+    if (grp >= valid / 8 || row >= S::NP) *reinterpret_cast<uint4*>(s_x + grp * S::kXStride + row * 16) = z;
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t gy_addr = tc::smem_u32(s_gy), x_addr = tc::smem_u32(s_x), b_addr = tc::smem_u32(s_b);
+
+  const bf16* __restrict__ yraw = reinterpret_cast<const bf16*>(P.out);
+  const bf16* __restrict__ xin = reinterpret_cast<const bf16*>(P.in[0].data);
+  bf16* __restrict__ dx = reinterpret_cast<bf16*>(P.dx);
+
+  const bool loader = tid < S::kLoadThreads;
+  const int cg = tid % NG, tx = tid / NG;
+  float2 cA[4], cB[4], cC[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    cA[e] = *reinterpret_cast<const float2*>(s_coef + 8 * cg + 2 * e);
+    cB[e] = *reinterpret_cast<const float2*>(s_coef + C + 8 * cg + 2 * e);
+    cC[e] = *reinterpret_cast<const float2*>(s_coef + 2 * C + 8 * cg + 2 * e);
+  }
+  uint32_t phase = 0;
+  int iter = 0;
+  const int vg = valid / 8;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
+    const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
+    // x tile: [channel group][tile position][8]
+    for (int idx = tid; idx < S::NP * vg; idx += kThreads) {
+      const int p = idx / vg, g = idx - p * vg;
+      const int ty = p / TW, txx = p - ty * TW;
+      const uint4 v = ldg16(xin + (((long long)t.b * H + t.ty0 + ty) * W + t.tx0 + txx) * Cin + cbase + 8 * g);
+      *reinterpret_cast<uint4*>(s_x + g * S::kXStride + p * 16) = v;
+    }
+    if (loader) {
+      const int x = t.tx0 + tx;
+#pragma unroll
+      for (int tyc = 0; tyc < TH; tyc += RC) {
+        float2 G[RC][4];
+#pragma unroll
+        for (int r = 0; r < RC; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) G[r][e] = make_float2(0.f, 0.f);
+        gather_rows<RC>(P, cw, t, tyc, x, cg, H, W, G);
+        const long long off0 = (((long long)t.b * H + t.ty0 + tyc) * W + x) * C + 8 * cg;
+#pragma unroll
+        for (int r = 0; r < RC; ++r) {
+          const uint4 yr = ldg16(yraw + off0 + (long long)r * W * C);
+          uint4 pk;
+          pk.x = f2_to_bf2(fma2(cA[0], G[r][0], fma2(cB[0], bf2_to_f2(yr.x), cC[0])));
+          pk.y = f2_to_bf2(fma2(cA[1], G[r][1], fma2(cB[1], bf2_to_f2(yr.y), cC[1])));
+          pk.z = f2_to_bf2(fma2(cA[2], G[r][2], fma2(cB[2], bf2_to_f2(yr.z), cC[2])));
+          pk.w = f2_to_bf2(fma2(cA[3], G[r][3], fma2(cB[3], bf2_to_f2(yr.w), cC[3])));
+          *reinterpret_cast<uint4*>(s_gy + cg * S::kGroup + ((tyc + r) * TW + tx) * 16) = pk;
+        }
+      }
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+      if (iter == 0) tc::mbar_wait(bar_w, 0u);
+      tc::fence_after_sync();
+      if (dx != nullptr) {
+#pragma unroll
+        for (int j = 0; j < C / 16; ++j) {   // GEMM 1: K runs over the output channels o
+          const uint64_t adesc = tc::make_desc(gy_addr + j * 2 * S::kGroup, S::kGroup, 128);
+          const uint64_t bdesc = tc::make_desc(b_addr + j * 2 * (NC * 16), NC * 16, 128);
+          tc::umma_bf16(tmem_base, adesc, bdesc, kIdesc1, j > 0 ? 1u : 0u);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 128 / 16; ++s) {   // GEMM 2: K runs over the 128 tile rows (MN-major views)
+        const uint64_t adesc = tc::make_desc(gy_addr + s * 256, 128, S::kGroup);
+        const uint64_t bdesc = tc::make_desc(x_addr + s * 256, 128, S::kXStride);
+        tc::umma_bf16(tmem_base + S::kColW, adesc, bdesc, kIdesc2, (iter > 0 || s > 0) ? 1u : 0u);
+      }
+      tc::umma_commit(bar_mma);
+    }
+    tc::mbar_wait(bar_mma, phase);
+    phase ^= 1u;
+    tc::fence_after_sync();
+
+    if (dx != nullptr) {   // dx accumulator -> bf16 -> HBM (row = tile position, NC/2 input channels per thread)
+      const int row = 32 * (warp & 3) + lane;
+      const int col0 = (warp >> 2) * (NC / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+      float acc[NC / 16][8];
+#pragma unroll
+      for (int j = 0; j < NC / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+      tc::tmem_ld_wait();
+      if (row < S::NP) {
+        const int ty = row / TW, txx = row - ty * TW;
+        bf16* dst = dx + (((long long)t.b * H + t.ty0 + ty) * W + t.tx0 + txx) * Cin + cbase + col0;
+#pragma unroll
+        for (int j = 0; j < NC / 16; ++j) {
+          if (col0 + 8 * j < valid) {
+            if (P.accumulate_dx) {
+              const uint4 old = *reinterpret_cast<const uint4*>(dst + 8 * j);
+              const float2 o0 = bf2_to_f2(old.x), o1 = bf2_to_f2(old.y), o2 = bf2_to_f2(old.z), o3 = bf2_to_f2(old.w);
+              acc[j][0] += o0.x; acc[j][1] += o0.y; acc[j][2] += o1.x; acc[j][3] += o1.y;
+              acc[j][4] += o2.x; acc[j][5] += o2.y; acc[j][6] += o3.x; acc[j][7] += o3.y;
+            }
+            *reinterpret_cast<uint4*>(dst + 8 * j) = tc::pack8_bf16(acc[j]);
+          }
+        }
+      }
+    }
+    tc::fence_before_sync();
+  }
+
+  // ---- flush [dW | db]: TMEM lane = output channel o, column = input channel of this chunk (column NC = bias gradient)
+  __syncthreads();
+  tc::fence_after_sync();
+  if (iter > 0) {
+    const int o = 32 * (warp & 3) + lane;
+    const int col0 = (warp >> 2) * (S::N2 / 2);
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + S::kColW + (uint32_t)col0;
+    float acc[S::N2 / 16][8];
+#pragma unroll
+    for (int j = 0; j < S::N2 / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+    tc::tmem_ld_wait();
+    if (o < C) {
+#pragma unroll
+      for (int j = 0; j < S::N2 / 16; ++j) {
+        const int i0 = col0 + 8 * j;
+        if (i0 < valid) {
+          float* dst = P.g_pw + (long long)o * Cin + cbase + i0;
+          red_add_v4(dst, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+          red_add_v4(dst + 4, acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        } else if (i0 == NC && chunk == 0 && P.g_pb) {
+          atomicAdd(P.g_pb + o, acc[j][0]);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, S::kTmemCols);
 }
 
 // =====================================================================================================================
@@ -731,6 +949,34 @@ static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
   }
 }
 
+template <int TW, int TH, int NC>
+static int launch_proj(const NodeBwdP& p, int nchunks, cudaStream_t s) {
+  using S = CfgP<TW, TH, NC>;
+  static bool configured = false;
+  if (!configured) {
+    MMD_CUDA(cudaFuncSetAttribute(proj_bwd4_kernel<TW, TH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    configured = true;
+  }
+  const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
+  int gx = sm_count() / nchunks;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  ProfScope prof(PK_PROJ_BWD, 2.0 * p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2.0, s);
+  proj_bwd4_kernel<TW, TH, NC><<<dim3(gx, nchunks), kThreads, S::kBytes, s>>>(p, packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBwd);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int TW, int TH>
+static int launch_proj_geom(const NodeBwdP& p, cudaStream_t s) {
+  const ProjChunks pc = proj_chunks(p.Cin);
+  switch (pc.NC) {
+    case 48: return launch_proj<TW, TH, 48>(p, pc.n, s);
+    case 128: return launch_proj<TW, TH, 128>(p, pc.n, s);
+    default: return launch_proj<TW, TH, 176>(p, pc.n, s);
+  }
+}
+
 static int pick_geom(int H, int W) {
   if (W % 16 == 0 && H % 8 == 0) return 0;
   if (W % 12 == 0 && H % 8 == 0) return 1;
@@ -763,6 +1009,32 @@ bool bwd_v4_usable(const NodeBwdP& p) {
     if (cs.mode == MMD_CONS_POOL && (2 * cs.H != p.g.H || 2 * cs.W != p.g.W || cs.pidx == nullptr)) return false;
   }
   return p.out && p.out_bn && p.save_d && p.du && p.dd && p.g_pw && p.counter;
+}
+
+bool proj_bwd_v4_usable(const NodeBwdP& p) {
+  if (p.packed == nullptr || p.Cin < 8 || p.Cin % 8 != 0 || b4::pick_geom(p.g.H, p.g.W) < 0) return false;
+  if (p.in[0].data == nullptr || p.out == nullptr || p.out_bn == nullptr || p.g_pw == nullptr) return false;
+  if ((((uintptr_t)p.g_pw) & 15u) != 0 || ((p.Cin * 4) & 15) != 0) return false;
+  for (int c = 0; c < p.n_cons; ++c) {
+    const ConsP& cs = p.cons[c];
+    if (cs.mode == MMD_CONS_SAME && (cs.H != p.g.H || cs.W != p.g.W)) return false;
+    if (cs.mode == MMD_CONS_UP2 && (cs.H != 2 * p.g.H || cs.W != 2 * p.g.W)) return false;
+    if (cs.mode == MMD_CONS_POOL && (2 * cs.H != p.g.H || 2 * cs.W != p.g.W || cs.pidx == nullptr)) return false;
+  }
+  return true;
+}
+
+int launch_proj_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  switch (b4::pick_geom(p.g.H, p.g.W)) {
+    case 0: return b4::launch_proj_geom<16, 8>(p, s);
+    case 1: return b4::launch_proj_geom<12, 8>(p, s);
+    case 2: return b4::launch_proj_geom<8, 8>(p, s);
+    case 3: return b4::launch_proj_geom<12, 6>(p, s);
+    case 4: return b4::launch_proj_geom<6, 6>(p, s);
+  }
+  set_error("proj_bwd_v4: no tile shape fits %dx%d", p.g.H, p.g.W);
+  return MMD_E_ARG;
 }
 
 int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s) {

@@ -472,119 +472,172 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
 // out = w_a * maxpool3x3s2(bn_a(in[0]))  [+ w_b * bn_b(in[1])]   (final bf16 values at the node's resolution)
 // MaxPool2dStaticSamePadding (src/YetAnotherEfficientNet.py:90-104): the zero padding takes part in the max of the
 // NORMALISED values.  scale*x+shift is monotonic in x, so the window is searched on the raw bf16 values (sign flipped
-// where the scale is negative): each value is expanded to fp32 with (15 - window index) in its 4 lowest mantissa bits
-// (those bits are zero after the expansion), so ONE fmaxf per element yields the maximum and its position.
-constexpr int kPoolThreads = 224;   // 16 positions x 14 channel groups
+// where the scale is negative): each value is expanded to fp32 with a 5-bit position tag in its lowest mantissa bits
+// (those bits are zero after the expansion), so ONE fmaxf per element yields the maximum AND its position (larger tag =
+// earlier in the row-major scan, so the first maximum wins for positive values).  A thread produces two horizontally
+// adjacent outputs: their windows share a column, the 3 x 5 raw vectors are loaded and tagged once.
+constexpr int kPoolThreads = 224;   // 16 output pairs x 14 channel groups
+constexpr int kPoolLanes = kPoolThreads / NG;
 
-__device__ __forceinline__ void pool_keys(const uint4 r, const uint32_t tag, const uint32_t (&sgn)[8], float (&best)[8]) {
+template <bool NEG>
+__device__ __forceinline__ void pool_key8(const uint4 r, const uint32_t tag, const uint32_t (&sgn)[8], float (&key)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const uint32_t lo = __byte_perm(w[e], tag, 0x1054) ^ sgn[2 * e];
-    const uint32_t hi = ((w[e] & 0xffff0000u) | tag) ^ sgn[2 * e + 1];
-    best[2 * e] = fmaxf(best[2 * e], __uint_as_float(lo));
-    best[2 * e + 1] = fmaxf(best[2 * e + 1], __uint_as_float(hi));
+    uint32_t lo = __byte_perm(w[e], tag, 0x1054);
+    uint32_t hi = (w[e] & 0xffff0000u) | tag;
+    if (NEG) { lo ^= sgn[2 * e]; hi ^= sgn[2 * e + 1]; }
+    key[2 * e] = __uint_as_float(lo);
+    key[2 * e + 1] = __uint_as_float(hi);
   }
 }
 
-__global__ void __launch_bounds__(kPoolThreads) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+// one output pair; BORDER: some window entries fall outside the source (zero padding)
+template <bool NEG, bool BORDER>
+__device__ __forceinline__ void pool_pair(const bf16* __restrict__ src, const int SH, const int SWd, const long long img,
+                                          const int fy0, const int fx0, const int cg, const uint32_t (&sgn)[8],
+                                          float (&bestA)[8], float (&bestB)[8], bool& padA, bool& padB) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bestA[e] = bestB[e] = -INFINITY;
+  padA = padB = false;
+#pragma unroll
+  for (int wy = 0; wy < 3; ++wy) {
+    const int fy = fy0 + wy;
+    const bool rok = !BORDER || (fy >= 0 && fy < SH);
+    const bf16* row = src + (img + (long long)(BORDER ? min(max(fy, 0), SH - 1) : fy) * SWd) * C + 8 * cg;
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) {
+      const int fx = fx0 + cc;
+      const bool ok = rok && (!BORDER || (fx >= 0 && fx < SWd));
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(row + (long long)(BORDER ? min(max(fx, 0), SWd - 1) : fx) * C));
+      float key[8];
+      pool_key8<NEG>(r, 31u - (uint32_t)(wy * 5 + cc), sgn, key);
+      if (BORDER && !ok) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) key[e] = -INFINITY;
+        if (cc <= 2) padA = true;
+        if (cc >= 2) padB = true;
+      }
+      if (cc <= 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bestA[e] = fmaxf(bestA[e], key[e]);
+      }
+      if (cc >= 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bestB[e] = fmaxf(bestB[e], key[e]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
   const NodeFwdP& P = BATCH.p[blockIdx.y];
+  __shared__ __align__(16) float s_c[4 * C];   // pooled input: scale | shift ; second input: w_b*scale | w_b*shift
   const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
   const int H = P.g.H, W = P.g.W, SH = P.in[0].H, SWd = P.in[0].W;
-  const int npos = P.g.B * H * W;
+  const int WP = (W + 1) >> 1;                  // output pairs per row
+  const int npairs = P.g.B * H * WP;
   const bf16* __restrict__ src = reinterpret_cast<const bf16*>(P.in[0].data);
   const bf16* __restrict__ same = (P.n_in >= 2) ? reinterpret_cast<const bf16*>(P.in[1].data) : nullptr;
   bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
   bf16* __restrict__ praw = reinterpret_cast<bf16*>(P.save_d);
   unsigned char* __restrict__ pidx = P.pidx[0];
 
-  const float wa = in_weight(P, 0), wb = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
-  float sc[8], sh[8], a1[8], b1[8];
-  uint32_t sgn[8];
-  {
+  const float wa = in_weight(P, 0);
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const float wb = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
     const float* bn0 = P.in[0].bn;
     const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
+    s_c[c] = bn0 ? bn0[c] : 1.f;
+    s_c[C + c] = bn0 ? bn0[C + c] : 0.f;
+    s_c[2 * C + c] = (bn1 ? bn1[c] : 1.f) * wb;
+    s_c[3 * C + c] = (bn1 ? bn1[C + c] : 0.f) * wb;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+  uint32_t sgn[8];
+  bool anyneg = false;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = 8 * cg + e;
-      sc[e] = bn0 ? bn0[c] : 1.f;
-      sh[e] = bn0 ? bn0[C + c] : 0.f;
-      sgn[e] = (sc[e] < 0.f) ? 0x80000000u : 0u;
-      a1[e] = (bn1 ? bn1[c] : 1.f) * wb;
-      b1[e] = (bn1 ? bn1[C + c] : 0.f) * wb;
-    }
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = s_c[8 * cg + e];
+    sh[e] = s_c[C + 8 * cg + e];
+    sgn[e] = (sc[e] < 0.f) ? 0x80000000u : 0u;
+    anyneg = anyneg || (sc[e] < 0.f);
   }
   const int top = pool_pad_before(SH), left = pool_pad_before(SWd);
 
-  for (int pos = blockIdx.x * (kPoolThreads / NG) + pl; pos < npos; pos += gridDim.x * (kPoolThreads / NG)) {
-    const int b = pos / (H * W);
-    const int rem = pos - b * (H * W);
-    const int y = rem / W, x = rem - y * W;
-    const int fy0 = 2 * y - top, fx0 = 2 * x - left;
-    float best[8];
+  for (int pp = blockIdx.x * kPoolLanes + pl; pp < npairs; pp += gridDim.x * kPoolLanes) {
+    const int b = pp / (H * WP);
+    const int rem = pp - b * (H * WP);
+    const int y = rem / WP, xp = rem - y * WP;
+    const int x0 = 2 * xp;
+    const bool second = (x0 + 1 < W);
+    const int fy0 = 2 * y - top, fx0 = 2 * x0 - left;
+    const long long img = (long long)b * SH * SWd;
+    const bool border = (fy0 < 0) || (fy0 + 2 >= SH) || (fx0 < 0) || (fx0 + 4 >= SWd);
+    float bestA[8], bestB[8];
+    bool padA, padB;
+    if (!border) {
+      if (anyneg) pool_pair<true, false>(src, SH, SWd, img, fy0, fx0, cg, sgn, bestA, bestB, padA, padB);
+      else pool_pair<false, false>(src, SH, SWd, img, fy0, fx0, cg, sgn, bestA, bestB, padA, padB);
+    } else {
+      pool_pair<true, true>(src, SH, SWd, img, fy0, fx0, cg, sgn, bestA, bestB, padA, padB);
+    }
+    const bool pad_first = (fy0 < 0) || (fx0 < 0);   // left / top padding precedes the real elements in scan order
 #pragma unroll
-    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
-    bool has_pad = false;
+    for (int o = 0; o < 2; ++o) {
+      if (o == 1 && !second) break;
+      const float* best = o ? bestB : bestA;
+      const bool has_pad = o ? padB : padA;
+      float u[8];
+      uint32_t idx[8], rawb[8];
 #pragma unroll
-    for (int wy = 0; wy < 3; ++wy) {
-      const int fy = fy0 + wy;
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t bits = __float_as_uint(best[e]);
+        const uint32_t t = 31u - (bits & 31u);
+        const uint32_t wy = (t * 52u) >> 8;            // t / 5 for t < 32
+        idx[e] = wy * 3u + (t - wy * 5u) - (o ? 2u : 0u);
+        rawb[e] = (bits ^ sgn[e]) & 0xffff0000u;
+        float val = fmaf(__uint_as_float(rawb[e]), sc[e], sh[e]);
+        if (has_pad && (pad_first ? (0.f >= val) : (0.f > val))) {
+          val = 0.f;
+          idx[e] = 9u;
+          rawb[e] = 0u;
+        }
+        u[e] = wa * val;
+      }
+      const long long oo = (((long long)b * H + y) * W + x0 + o) * C + 8 * cg;
+      if (same != nullptr) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + oo));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-      for (int wx = 0; wx < 3; ++wx) {
-        const int fx = fx0 + wx;
-        if (fy >= 0 && fy < SH && fx >= 0 && fx < SWd) {
-          const uint4 r = __ldg(reinterpret_cast<const uint4*>(src + (((long long)b * SH + fy) * SWd + fx) * C + 8 * cg));
-          pool_keys(r, 15u - (uint32_t)(wy * 3 + wx), sgn, best);
-        } else {
-          has_pad = true;
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = bf2_to_f2(w[e]);
+          u[2 * e] += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+          u[2 * e + 1] += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
         }
       }
-    }
-    const bool pad_first = (fy0 < 0) || (fx0 < 0);   // the padding precedes the real elements in scan order
-    float u[8];
-    uint32_t idx[8], rawb[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t bits = __float_as_uint(best[e]);
-      idx[e] = 15u - (bits & 15u);
-      rawb[e] = (bits ^ sgn[e]) & 0xffff0000u;
-      float val = fmaf(__uint_as_float(rawb[e]), sc[e], sh[e]);
-      if (has_pad && (pad_first ? (0.f >= val) : (0.f > val))) {
-        val = 0.f;
-        idx[e] = 9u;
-        rawb[e] = 0u;
+      uint4 pk;
+      pk.x = f2_to_bf2(make_float2(u[0], u[1]));
+      pk.y = f2_to_bf2(make_float2(u[2], u[3]));
+      pk.z = f2_to_bf2(make_float2(u[4], u[5]));
+      pk.w = f2_to_bf2(make_float2(u[6], u[7]));
+      *reinterpret_cast<uint4*>(out + oo) = pk;
+      if (pidx != nullptr) {
+        uint2 ip;
+        ip.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+        ip.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+        *reinterpret_cast<uint2*>(pidx + oo) = ip;
       }
-      u[e] = wa * val;
-    }
-    const long long o = (long long)pos * C + 8 * cg;
-    if (same != nullptr) {
-      const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + o));
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = bf2_to_f2(w[e]);
-        u[2 * e] += fmaf(f.x, a1[2 * e], b1[2 * e]);
-        u[2 * e + 1] += fmaf(f.y, a1[2 * e + 1], b1[2 * e + 1]);
+      if (praw != nullptr) {
+        uint4 rp;
+        rp.x = (rawb[0] >> 16) | rawb[1];
+        rp.y = (rawb[2] >> 16) | rawb[3];
+        rp.z = (rawb[4] >> 16) | rawb[5];
+        rp.w = (rawb[6] >> 16) | rawb[7];
+        *reinterpret_cast<uint4*>(praw + oo) = rp;
       }
-    }
-    uint4 pk;
-    pk.x = f2_to_bf2(make_float2(u[0], u[1]));
-    pk.y = f2_to_bf2(make_float2(u[2], u[3]));
-    pk.z = f2_to_bf2(make_float2(u[4], u[5]));
-    pk.w = f2_to_bf2(make_float2(u[6], u[7]));
-    *reinterpret_cast<uint4*>(out + o) = pk;
-    if (pidx != nullptr) {
-      uint2 ip;
-      ip.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-      ip.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-      *reinterpret_cast<uint2*>(pidx + o) = ip;
-    }
-    if (praw != nullptr) {
-      uint4 rp;
-      rp.x = (rawb[0] >> 16) | rawb[1];
-      rp.y = (rawb[2] >> 16) | rawb[3];
-      rp.z = (rawb[4] >> 16) | rawb[5];
-      rp.w = (rawb[6] >> 16) | rawb[7];
-      *reinterpret_cast<uint4*>(praw + o) = rp;
     }
   }
 }
@@ -673,10 +726,10 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
     for (int k = 0; k < p[i].n_in; ++k) bytes += (double)p[i].g.B * p[i].in[k].H * p[i].in[k].W * C * 2.0;
   }
   for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
-  const int npos = p[0].g.B * p[0].g.H * p[0].g.W;
-  const int per = v4::kPoolThreads / v4::NG;
-  int gx = (npos + per - 1) / per;
-  if (gx > 148 * 8) gx = 148 * 8;
+  const int npairs = p[0].g.B * p[0].g.H * ((p[0].g.W + 1) / 2);
+  int gx = (npairs + v4::kPoolLanes - 1) / v4::kPoolLanes;
+  const int cap = (148 * 4 + n - 1) / n;   // ~2 resident CTAs per SM and 2 waves over all networks
+  if (gx > cap) gx = cap;
   ProfScope prof(PK_POOLFUSE, bytes, s);
   v4::poolfuse_kernel<<<dim3(gx, n), v4::kPoolThreads, 0, s>>>(batch);
   MMD_LAUNCH_CHECK();

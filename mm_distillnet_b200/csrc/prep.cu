@@ -14,7 +14,7 @@ namespace mmd {
 struct PrepDesc {
   const float *pw_w, *pw_b, *bn_w, *bn_b, *bn_rm, *bn_rv, *dw_w;
   unsigned char* dst;
-  int Cin, Kp, train, node;
+  int Cin, Kp, train, node, NC, nchunks;
   int offBias, offTaps, offBwd;
   float eps;
 };
@@ -61,7 +61,22 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepA
     }
     reinterpret_cast<float*>(D.dst + D.offBias)[c] = bia;
   }
-  if (!D.node) return;
+  if (!D.node) {
+    if (!D.train) return;
+    // projection backward operand: chunk (ch, og, i) holds W[8*og + j][ch*NC + i], j = 0..7 (zero beyond Cin)
+    for (int item = tid; item < D.nchunks * (C / 8) * D.NC; item += nthr) {
+      const int i = item % D.NC, og = (item / D.NC) % (C / 8), ch = item / (D.NC * (C / 8));
+      const int ci = ch * D.NC + i;
+      float w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w[j] = (ci < D.Cin) ? D.pw_w[(long long)(8 * og + j) * D.Cin + ci] : 0.f;
+      uint4 r;
+      r.x = prep_pack2(w[0], w[1]); r.y = prep_pack2(w[2], w[3]);
+      r.z = prep_pack2(w[4], w[5]); r.w = prep_pack2(w[6], w[7]);
+      *reinterpret_cast<uint4*>(D.dst + D.offBwd + (size_t)item * 16) = r;
+    }
+    return;
+  }
   float* taps = reinterpret_cast<float*>(D.dst + D.offTaps);
   for (int idx = tid; idx < 9 * C; idx += nthr) {
     const int tap = idx / C, c = idx - tap * C;
@@ -124,6 +139,8 @@ extern "C" int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* base
     D.Cin = Cin; D.Kp = L.Kp; D.train = op.train; D.node = node ? 1 : 0;
     D.offBias = L.offBias; D.offTaps = L.offTaps; D.offBwd = L.offBwd;
     D.eps = op.bn_eps;
+    const ProjChunks pc = proj_chunks(Cin);
+    D.NC = pc.NC; D.nchunks = pc.n;
     if (n == kPrepMax) {
       int rc = flush();
       if (rc) return rc;
