@@ -125,7 +125,7 @@ class ClockSampler:
     falls back to one nvidia-smi query per second when pynvml is unavailable."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index, period_s=0.05):
+    def __init__(self, gpu_index, period_s=0.02):
         import threading
         self.sm, self.smax, self.reasons, self.src = [], None, set(), None
         self._stop = threading.Event()
@@ -345,6 +345,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs larger than L2: the step streams ~%.1f GB of activations (L2 = 126 MB); no flush needed"
                              % (3 * B * 30016512 * esize * 2 / 1e9),
                        "optimizer": "none (the microbench ends at the averaged gradients)",
+                       "precision": "activations stored as %s, all arithmetic fp32 (TMEM accumulators, BatchNorm statistics "
+                                    "in double, fp32 master weights and gradients)" % args.dtype,
                        "launch": "CUDA graph replay of the whole step" if use_graph else "eager"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
@@ -357,10 +359,12 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"],
+                    help="activation STORAGE type; arithmetic (accumulators, statistics, weights) is fp32 in both modes. "
+                         "bf16 is the tensor-core product path (BASELINE cfg 3), f32 the bit-level parity mode")
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (cfg2: 16)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")

@@ -1,5 +1,6 @@
 // C-ABI bookkeeping entry points of libmmd_b200.so (see include/mmd.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -19,6 +20,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMD_NO_PDL");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 // ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
 static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",

@@ -222,6 +222,7 @@ int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
 bool proj_bwd_v4_usable(const NodeBwdP& p);
 int launch_proj_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
+int launch_proj_fwd_tc_multi(const NodeFwdP* p, int n, int C, cudaStream_t s);   // n networks in one launch
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead
 int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);

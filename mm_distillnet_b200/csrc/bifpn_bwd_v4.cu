@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
     tc::mbar_expect_tx(bar_w, C * C * 2);
     tc::bulk_g2s(s_b, P.packed + packed_off_bwd, C * C * 2, bar_w);
   }
+  pdl_wait();
+  pdl_trigger();
   float cw[3];
   cons_weights(P, cw);
   bn_bwd_coefs<C>(P, cw, s_coef);
@@ -382,6 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_bwd4_kernel(const __grid_con
     tc::mbar_expect_tx(bar_w, S::kBBytes);
     tc::bulk_g2s(s_b, P.packed + packed_off_bwd + (size_t)chunk * S::kBBytes, S::kBBytes, bar_w);
   }
+  pdl_wait();
+  pdl_trigger();
   float cw[3];
   cons_weights(P, cw);
   bn_bwd_coefs<C>(P, cw, s_coef);
@@ -737,6 +741,8 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
     const int c = idx / 9, tap = idx - c * 9;
     s_taps[tap * C + c] = P.dw_w[idx];
   }
+  pdl_wait();
+  pdl_trigger();
   if (tid < C) {
     const float* bn0 = P.in[0].bn;
     const float sc0 = bn0 ? bn0[tid] : 1.f, sh0 = bn0 ? bn0[C + tid] : 0.f;
@@ -918,7 +924,7 @@ static int launch_b(const NodeBwdP& p, cudaStream_t s) {
   }
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
-  node_bwd_b4_kernel<TW, TH, X1M, SW><<<grid, S::kBlock, S::kBytes, s>>>(p);
+  MMD_CUDA(launch_pdl(node_bwd_b4_kernel<TW, TH, X1M, SW>, dim3(grid), dim3(S::kBlock), S::kBytes, s, p));
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -936,7 +942,8 @@ static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
   {
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
     ProfScope prof(PK_NODE_BWD_A, bytes, s);
-    node_bwd_a4_kernel<TW, TH><<<grid, kThreads, SA::kBytes, s>>>(p, packed_layout(MMD_OP_NODE_FWD, C, C).offBwd);
+    MMD_CUDA(launch_pdl(node_bwd_a4_kernel<TW, TH>, dim3(grid), dim3(kThreads), SA::kBytes, s, p,
+                        packed_layout(MMD_OP_NODE_FWD, C, C).offBwd));
     MMD_LAUNCH_CHECK();
   }
   ProfScope prof(PK_NODE_BWD_B, bytes, s);
@@ -962,7 +969,8 @@ static int launch_proj(const NodeBwdP& p, int nchunks, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   ProfScope prof(PK_PROJ_BWD, 2.0 * p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2.0, s);
-  proj_bwd4_kernel<TW, TH, NC><<<dim3(gx, nchunks), kThreads, S::kBytes, s>>>(p, packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBwd);
+  MMD_CUDA(launch_pdl(proj_bwd4_kernel<TW, TH, NC>, dim3(gx, nchunks), dim3(kThreads), S::kBytes, s, p,
+                      packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBwd));
   MMD_LAUNCH_CHECK();
   return 0;
 }

@@ -572,7 +572,8 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
 // A = the input tile itself: a 16-byte global chunk (position p, channels 8k..8k+7) IS one row of core matrix k, so the
 // NHWC -> UMMA layout change costs nothing.  K is padded to a multiple of 16 with zero chunks (Cin = 120 -> 128).
 template <int C>
-__global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_constant__ NodeFwdP P, int Kp, int packed_off_bias) {
+__global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_constant__ NodeFwdBatch BATCH, int Kp, int packed_off_bias) {
+  const NodeFwdP& P = BATCH.p[blockIdx.y];   // blockIdx.y = network (student / teachers share the launch)
   constexpr int LDS = C + 8;
   constexpr uint32_t kTmemCols = 128;
   constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
@@ -600,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
     tc::fence_mbar_init();
   }
   uint64_t* s_bar_w = s_bar + 2;
+  if (P.packed == nullptr) pdl_wait();   // slow path reads parameters that a preceding kernel may have produced
   if (P.packed != nullptr) {   // B operand + bias prepared by mmd_bifpn_prep: two bulk copies
     if (tid == 32) {
       tc::mbar_init(s_bar_w, 1);
@@ -628,6 +630,8 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
       s_bias[tid] = bia;
     }
   }
+  pdl_wait();
+  pdl_trigger();
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -676,23 +680,35 @@ __global__ void __launch_bounds__(kThreads, 1) proj_fwd_tc_kernel(const __grid_c
   bn_finalize_tc<C>(P, st_sum, st_sq, &s_flag);
 }
 
-int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
+int launch_proj_fwd_tc_multi(const NodeFwdP* ps, int n, int C, cudaStream_t s) {
+  const NodeFwdP& p = ps[0];
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(p.Cin % 8 == 0, "bf16 projection needs Cin %% 8 == 0, got %d", p.Cin);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "proj_fwd: %d networks in one launch", n);
   constexpr int CC = 112;
   const int Kp = (p.Cin + 15) / 16 * 16, KG = Kp / 8;
   const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 32;
   MMD_CHECK_ARG(smem <= 227 * 1024, "projection with Cin=%d does not fit in shared memory", p.Cin);
   MMD_CUDA(cudaFuncSetAttribute(proj_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NodeFwdBatch batch;
+  for (int i = 0; i < kMaxBatchNets; ++i) batch.p[i] = ps[i < n ? i : 0];
+  for (int i = 1; i < n; ++i)
+    MMD_CHECK_ARG(ps[i].Cin == p.Cin && ps[i].g.H == p.g.H && ps[i].g.W == p.g.W && ps[i].g.B == p.g.B,
+                  "proj_fwd: batched networks must share the shape");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-  const int grid = p.g.ntiles < per_sm * sms ? p.g.ntiles : per_sm * sms;
-  ProfScope prof(PK_PROJ_FWD, (double)p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2, s);
-  proj_fwd_tc_kernel<CC><<<grid, kThreads, smem, s>>>(p, Kp, packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBias);
+  int cap = per_sm * sms / n;
+  if (cap < 1) cap = 1;
+  const int grid = p.g.ntiles < cap ? p.g.ntiles : cap;
+  ProfScope prof(PK_PROJ_FWD, (double)n * p.g.B * p.g.H * p.g.W * (p.Cin + C) * 2, s);
+  MMD_CUDA(launch_pdl(proj_fwd_tc_kernel<CC>, dim3(grid, n), dim3(kThreads), smem, s, batch, Kp,
+                      packed_layout(MMD_OP_PROJ_FWD, p.Cin, C).offBias));
   MMD_LAUNCH_CHECK();
   return 0;
 }
+
+int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) { return launch_proj_fwd_tc_multi(&p, 1, C, s); }
 
 }  // namespace mmd

@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     tc::mbar_expect_tx(bar_pack, S::kPackBytes);
     tc::bulk_g2s(s_pack, P.packed, S::kPackBytes, bar_pack);
   }
+  pdl_wait();      // everything above overlaps the previous kernel; its outputs (inputs / BN vectors here) are visible now
+  pdl_trigger();
   if (tid < C) {
     const float w0 = in_weight(P, 0), w1 = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
     const float* bn0 = P.in[0].bn;
@@ -543,6 +545,8 @@ __global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_
   bf16* __restrict__ praw = reinterpret_cast<bf16*>(P.save_d);
   unsigned char* __restrict__ pidx = P.pidx[0];
 
+  pdl_wait();
+  pdl_trigger();
   const float wa = in_weight(P, 0);
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
@@ -658,7 +662,7 @@ static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   int per_net = (2 * sms) / n;
   if (per_net < 1) per_net = 1;
   const int gx = ntiles < per_net ? ntiles : per_net;
-  node_fwd_v4_kernel<TW, TH><<<dim3(gx, n), kThreads, S::kBytes, s>>>(batch);
+  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH>, dim3(gx, n), dim3(kThreads), S::kBytes, s, batch));
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -731,7 +735,7 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
   const int cap = (148 * 4 + n - 1) / n;   // ~2 resident CTAs per SM and 2 waves over all networks
   if (gx > cap) gx = cap;
   ProfScope prof(PK_POOLFUSE, bytes, s);
-  v4::poolfuse_kernel<<<dim3(gx, n), v4::kPoolThreads, 0, s>>>(batch);
+  MMD_CUDA(launch_pdl(v4::poolfuse_kernel, dim3(gx, n), dim3(v4::kPoolThreads), 0, s, batch));
   MMD_LAUNCH_CHECK();
   return 0;
 }

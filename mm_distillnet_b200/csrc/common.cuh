@@ -36,6 +36,32 @@ void count_launch();
     MMD_CUDA(cudaGetLastError());                \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The step is a chain of ~200 short dependent kernels.  Kernels launched through launch_pdl() may be scheduled while
+// their predecessor still runs: everything up to pdl_wait() (TMEM allocation, mbarrier init, the bulk copy of the packed
+// parameter block) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its
+// writes are visible.  pdl_trigger() (issued right after the wait, so that at most two kernels of the chain are ever in
+// flight) lets the NEXT kernel start being scheduled.  Without the launch attribute both are no-ops.  MMD_NO_PDL=1
+// disables the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- optional per-kernel CUDA-event timing (mmd_prof_*), used by bench.py for the live roofline number ---------
 enum ProfKind {
   PK_MTA_POOL = 0, PK_MTA_LEVEL, PK_MTA_FINISH, PK_MTA_BWD, PK_NODE_FWD, PK_PROJ_FWD, PK_BNAPPLY, PK_NODE_BWD_A,
