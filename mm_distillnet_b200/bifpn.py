@@ -16,7 +16,8 @@ import torch.nn as nn
 
 from . import _lib
 
-_STATS_EPOCH = 0     # bumped by every train-mode forward (running statistics change behind PyTorch's version counters)
+_STATS_EPOCH = {}    # id(module) -> count of train-mode forwards (they update running statistics through raw pointers,
+                     # behind PyTorch's version counters); eval plans of the same modules re-fold their BatchNorms after one
 BN_MOMENTUM = 0.01   # src/YetAnotherEfficientDet.py:176
 BN_EPS = 1e-3
 _ALIGN = 256
@@ -253,6 +254,7 @@ class _Plan:
         self.ops = []
         self.Cc = None
         self.params = self._collect_params(mods)
+        self.mod_ids = [id(m) for m in mods]
         self.state_tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
         self.grad_off = {}
         if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
@@ -808,13 +810,13 @@ class _Runner:
         """(Re)build the packed parameter blocks when the parameters may have changed: every training forward (the
         optimiser updates the weights between steps); for eval plans (frozen teachers) only when a parameter / buffer
         version or the global running-statistics epoch moved."""
-        global _STATS_EPOCH
         if plan.dtype != torch.bfloat16:
             return
         if plan.train:
-            _STATS_EPOCH += 1     # this forward updates running statistics through raw pointers
+            for mid in plan.mod_ids:   # this forward updates running statistics through raw pointers
+                _STATS_EPOCH[mid] = _STATS_EPOCH.get(mid, 0) + 1
         else:
-            sig = (_STATS_EPOCH, tuple(t._version for t in plan.state_tensors))
+            sig = (tuple(_STATS_EPOCH.get(mid, 0) for mid in plan.mod_ids), tuple(t._version for t in plan.state_tensors))
             if getattr(plan, "_prep_sig", None) == sig:
                 return
             plan._prep_sig = sig
