@@ -694,10 +694,15 @@ class _Lease:
 class _StackFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, plan, n_in, pre, *tensors):
+        """tensors = inputs + parameters, or (flat-gradient mode) inputs + one fresh anchor leaf: the parameter
+        gradients then reach `.grad` through the runner's sink, and the autograd graph has no edge to the parameters'
+        (possibly stale, created-on-another-stream) AccumulateGrad nodes, which keeps the backward CUDA-graph capturable."""
         inputs, params = tensors[:n_in], tensors[n_in:]
         outs, saved = pre if pre is not None else runner._forward(plan, inputs)
         ctx.runner, ctx.plan, ctx.saved, ctx.n_in = runner, plan, saved, n_in
-        ctx.param_list = params
+        ctx.sink_mode = runner.grad_sink is not None
+        ctx.param_list = plan.params if ctx.sink_mode else params
+        ctx.n_extra = len(params)
         return tuple(outs)
 
     @staticmethod
@@ -711,16 +716,17 @@ class _StackFunction(torch.autograd.Function):
         grads = [None, None, None, None]
         for i in range(ctx.n_in):
             grads.append(gin[i] if ctx.needs_input_grad[4 + i] else None)
-        if ctx.runner.grad_sink is not None:
+        if ctx.sink_mode:
             # flat-gradient mode (DistillStep): hand over the one contiguous fp32 buffer holding every parameter
             # gradient and make each .grad a view of it, instead of ~360 per-parameter AccumulateGrad kernels
             flat = gflat[:plan.grad_floats]
-            for j, p in enumerate(ctx.param_list):
-                if ctx.needs_input_grad[4 + ctx.n_in + j]:
-                    off, n, shape = plan.grad_off[id(plan.params[j])]
+            for p in ctx.param_list:
+                if p.requires_grad:
+                    off, n, shape = plan.grad_off[id(p)]
                     p.grad = flat[off // 4: off // 4 + n].view(shape)
-            ctx.runner.grad_sink(flat)
-            grads.extend([None] * len(ctx.param_list))
+            if ctx.runner.grad_sink is not None:
+                ctx.runner.grad_sink(flat)
+            grads.extend([None] * ctx.n_extra)
             return tuple(grads)
         for j, p in enumerate(ctx.param_list):
             ent = plan.grad_off.get(id(plan.params[j]))
@@ -783,7 +789,11 @@ class _Runner:
         """`pre` = (outs, saved) of a forward that forward_multi() has already enqueued for this plan."""
         plan, params, need_grad = self._plan_for(mods, inputs, training, kind)
         if need_grad:
-            outs = _StackFunction.apply(self, plan, len(inputs), pre, *inputs, *params)
+            if self.grad_sink is not None:
+                anchor = torch.empty((), dtype=torch.float32, device=plan.device, requires_grad=True)
+                outs = _StackFunction.apply(self, plan, len(inputs), pre, *inputs, anchor)
+            else:
+                outs = _StackFunction.apply(self, plan, len(inputs), pre, *inputs, *params)
         else:
             with torch.no_grad():
                 outs, saved = pre if pre is not None else self._forward(plan, inputs)

@@ -115,7 +115,7 @@ class DistillStep:
         except AttributeError:
             pass
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):   # the stream the warm-up ran on (autograd leaf streams match)
             self._g_out = self(self._g_xs, self._g_xt)
         return self
 

@@ -97,6 +97,34 @@ def test_plan_structure():
     assert [o.kind for o in ev.fwd_ops].count(_lib.OP_BNAPPLY) == 2
 
 
+def test_bf16_plan_splits_pooled_nodes():
+    """bf16 plans run every node with a pooled input as POOLFUSE + NODE_FWD(input 0, aux): 4 such nodes per cell; the
+    backward ops keep the node's original three inputs and get the pre-pass outputs (aux, raw arg-max values)."""
+    cells = [mmd.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(5)]
+    shapes = [(16, 48, 96, 96), (16, 120, 48, 48), (16, 352, 24, 24)]
+    plan = bifpn._Plan(cells, "cells", shapes, torch.bfloat16, True, True, [True] * 3)
+    kinds = [o.kind for o in plan.fwd_ops]
+    assert kinds.count(_lib.OP_POOLFUSE) == 20 and kinds.count(_lib.OP_NODE_FWD) == 40
+    for i, o in enumerate(plan.fwd_ops):
+        if o.kind == _lib.OP_POOLFUSE:
+            nxt = plan.fwd_ops[i + 1]
+            assert nxt.kind == _lib.OP_NODE_FWD and nxt.n_in == 2 and nxt.fw_idx[1] == -1 and nxt.fw_n == o.fw_n
+            assert o.mode[0] == _lib.IN_POOL and o.pidx[0].base == bifpn.B_FWD and o.save_d.base == bifpn.B_FWD
+            assert (nxt.inp[1].data.base, nxt.inp[1].data.off) == (o.out.data.base, o.out.data.off)
+            assert o.out.bn.base == -1                       # final values: no deferred BatchNorm on the operand
+    for o in plan.fwd_ops:
+        if o.kind == _lib.OP_NODE_FWD:
+            assert all(o.mode[k] != _lib.IN_POOL for k in range(o.n_in)) and o.packed.base == bifpn.B_PERSIST
+    pooled_bwd = [o for o in plan.bwd_ops if o.kind == _lib.OP_NODE_BWD and _lib.IN_POOL in list(o.mode)[:o.n_in]]
+    assert len(pooled_bwd) == 20 and all(o.aux.base == bifpn.B_FWD and o.praw.base == bifpn.B_FWD for o in pooled_bwd)
+    # fp32 (parity) plans keep the single fused node
+    p32 = bifpn._Plan(cells, "cells", shapes, torch.float32, True, True, [True] * 3)
+    assert [o.kind for o in p32.fwd_ops].count(_lib.OP_POOLFUSE) == 0
+    # eval bf16 plan: pre-pass without arg-max / raw outputs
+    ev = bifpn._Plan(cells, "cells", shapes, torch.bfloat16, False, False, [False] * 3)
+    assert all(o.pidx[0].base == -1 and o.save_d.base == -1 for o in ev.fwd_ops if o.kind == _lib.OP_POOLFUSE)
+
+
 def test_shape_validation_and_errors():
     cells = [mmd.BiFPN(112, [48, 120, 352], first_time=True)]
     with pytest.raises(ValueError):   # P4 is not exactly half of P3
