@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 103
+#define MMD_VERSION 104
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -59,6 +59,13 @@ typedef struct {
   int32_t dtype;  /* MMD_F32 / MMD_BF16 : element type of fs / ft / grad_fs */
   int32_t layout; /* MMD_NHWC / MMD_NCHW */
   float T, p;
+  int32_t separate; /* 0: ONE loss call against the product of all n_teachers (MTALoss.py:20-34).                 */
+                    /* 1: n_teachers independent single-teacher calls that share the student (what the step       */
+                    /*    wrappers do, train_methods.py:351-358: criterion_kd(features_s, features_t) per teacher) */
+                    /*    in one set of launches: the student maps are pooled once; loss / loss_b / ga_ws hold    */
+                    /*    n_teachers consecutive results ([call][level], [call][level][B], [call][B*sum HW]) and  */
+                    /*    mmd_mta_bwd takes grad_loss[call][level] and writes the SUM of the calls' gradients.    */
+  int32_t pad_;
   int32_t H[MMD_MTA_MAX_LEVELS], W[MMD_MTA_MAX_LEVELS];
   const void* fs[MMD_MTA_MAX_LEVELS];                       /* student features, one per level            */
   const void* ft[MMD_MTA_MAX_TEACHERS][MMD_MTA_MAX_LEVELS]; /* teacher features [teacher][level]          */

@@ -26,6 +26,7 @@ class MtaArgs(C.Structure):
     _fields_ = [
         ("n_levels", C.c_int32), ("n_teachers", C.c_int32), ("B", C.c_int32), ("C", C.c_int32),
         ("dtype", C.c_int32), ("layout", C.c_int32), ("T", C.c_float), ("p", C.c_float),
+        ("separate", C.c_int32), ("pad_", C.c_int32),
         ("H", C.c_int32 * MTA_MAX_LEVELS), ("W", C.c_int32 * MTA_MAX_LEVELS),
         ("fs", C.c_void_p * MTA_MAX_LEVELS),
         ("ft", (C.c_void_p * MTA_MAX_LEVELS) * MTA_MAX_TEACHERS),

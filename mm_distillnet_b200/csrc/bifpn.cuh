@@ -112,7 +112,14 @@ struct NodeFwdP {
 constexpr int kMaxBatchNets = 4;
 struct NodeFwdBatch {
   NodeFwdP p[kMaxBatchNets];
+  // 1-D grids (node_fwd_v4 / poolfuse): network k owns CTAs [cta_begin[k], cta_begin[k+1]) — a train-mode network
+  // (statistics, saved tensors, arg-max records) gets a larger share than a frozen one, see batch_shares()
+  int cta_begin[kMaxBatchNets + 1];
 };
+// split `budget` CTAs over the n networks of a lockstep launch: weight `train_w` for networks with p.train != 0, 1 for
+// the others; at least 1 and at most `max_per_net` CTAs each
+void batch_shares(NodeFwdBatch& batch, int n, int budget, int max_per_net, float train_w);
+float env_float(const char* name, float dflt);
 
 struct ConsP {
   const void* du;

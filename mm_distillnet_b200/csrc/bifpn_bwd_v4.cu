@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
   float wgt[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) wgt[i] = (i < P.n_in) ? fusion_weight(P.fw, P.n_in, i, P.fw_eps) : 0.f;
-  if (tid == 0) {
+  if (producer && lane == 0) {   // the producer warp owns the barriers: it can start loading right after pdl_wait()
     tc::mbar_init(bar_full, 1);
     tc::mbar_init(bar_full + 1, 1);
     tc::mbar_init(bar_ready, 1);
@@ -743,6 +743,12 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
   }
   pdl_wait();
   pdl_trigger();
+  if (producer) {   // first two tiles: in flight while the coefficients below are set up
+    __syncwarp();
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles && k < 2; tile += gridDim.x, ++k)
+      issue_tile_b<TW, TH>(smem + k * S::kBuf, P, X1M, x1src, tile_pos(tile, tiles_x, tiles_y, TW, TH), H, W, lane, bar_full + k);
+  }
   if (tid < C) {
     const float* bn0 = P.in[0].bn;
     const float sc0 = bn0 ? bn0[tid] : 1.f, sh0 = bn0 ? bn0[C + tid] : 0.f;
@@ -771,9 +777,6 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
     // ---- producer warp: bulk loads two tiles ahead, bulk stores of finished dL/du tiles
     bf16* duout = reinterpret_cast<bf16*>(P.du);
     int k = 0;
-    for (int tile = blockIdx.x; tile < ntiles && k < 2; tile += gridDim.x, ++k)
-      issue_tile_b<TW, TH>(smem + k * S::kBuf, P, X1M, x1src, tile_pos(tile, tiles_x, tiles_y, TW, TH), H, W, lane, bar_full + k);
-    k = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
       const int s = k & 1;
       const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);

@@ -18,6 +18,8 @@
 //     levels have fewer tiles than the GPU has SMs.
 // Shared memory (2 CTAs / SM):  region 0 = raw input 0 -> v (in place) -> output staging;  region 1 = raw input 1 -> UMMA
 // A operand;  packed parameter block (B operand in UMMA layout, bias, taps: one bulk copy);  folded BN/fusion coefficients.
+#include <stdlib.h>
+
 #include "bifpn.cuh"
 #include "tc.cuh"
 
@@ -236,7 +238,12 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   using S = Cfg<TW, TH>;
   constexpr uint32_t kTmemCols = 128;
   constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
-  const NodeFwdP& P = BATCH.p[blockIdx.y];
+  int net = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxBatchNets; ++k)
+    if ((int)blockIdx.x >= BATCH.cta_begin[k]) net = k;
+  const NodeFwdP& P = BATCH.p[net];
+  const int cta = (int)blockIdx.x - BATCH.cta_begin[net], nctas = BATCH.cta_begin[net + 1] - BATCH.cta_begin[net];
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* r0 = smem + S::offR0;
   unsigned char* r1 = smem + S::offR1;
@@ -274,6 +281,17 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   }
   pdl_wait();      // everything above overlaps the previous kernel; its outputs (inputs / BN vectors here) are visible now
   pdl_trigger();
+  // first tile's inputs: requested before the coefficient set-up below, whose dependent global loads (fusion weights,
+  // BatchNorm vectors) would otherwise delay them by a full round trip (warp 1 initialised the barriers itself)
+  int tile = cta;
+  if (warp == 1) {
+    __syncwarp();
+    if (tile < ntiles) {
+      const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
+      issue_input<TW, TH>(r0, in0, false, t, H, W, lane, bar_in0);
+      if (m1 != M1_NONE) issue_input<TW, TH>(r1, in1, m1 == M1_UP2, t, H, W, lane, bar_in1);
+    }
+  }
   if (tid < C) {
     const float w0 = in_weight(P, 0), w1 = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
     const float* bn0 = P.in[0].bn;
@@ -290,23 +308,15 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   const uint32_t tmem_base = *s_tmem;
   const uint32_t a_addr = tc::smem_u32(r1), b_addr = tc::smem_u32(s_pack);
 
-  // first tile's inputs
-  int tile = blockIdx.x;
-  if (warp == 1 && tile < ntiles) {
-    const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
-    issue_input<TW, TH>(r0, in0, false, t, H, W, lane, bar_in0);
-    if (m1 != M1_NONE) issue_input<TW, TH>(r1, in1, m1 == M1_UP2, t, H, W, lane, bar_in1);
-  }
-
   // statistics role: channel pair sp of row slice ss (32 staging rows)
   const int sp = tid % (C / 2), ss = tid / (C / 2);
   double st[4] = {0.0, 0.0, 0.0, 0.0};
   uint32_t ph = 0;
   bool pack_ready = false;
 
-  for (; tile < ntiles; tile += gridDim.x) {
+  for (; tile < ntiles; tile += nctas) {
     const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
-    const int next = tile + gridDim.x;
+    const int next = tile + nctas;
 
     // ---- (1) raw inputs have landed
     tc::mbar_wait(bar_in0, ph);
@@ -337,6 +347,13 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     }
     tc::fence_async_smem();   // the A operand was written through the generic proxy
     __syncthreads();
+    // a frozen network writes its output straight from the epilogue registers (no staging tile, no statistics): region 0
+    // is free as soon as the depthwise stage has consumed v, so the next tile's input 0 is already in flight during the
+    // MMA and the epilogue
+    if (!train && warp == 1 && next < ntiles) {
+      const TilePos tn = tile_pos(next, tiles_x, tiles_y, TW, TH);
+      issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
+    }
 
     // ---- (4) pointwise 1x1 on the tensor cores
     if (tid == 0) {
@@ -368,6 +385,9 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
       for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
       tc::tmem_ld_wait();
       if (row < S::NP) {
+        constexpr int kRowShift = (TW == 16) ? 4 : 0;
+        const int ty = kRowShift ? (row >> kRowShift) : (row / TW), txx = row - ty * TW;
+        bf16* gdst = out + (((long long)t.b * H + t.ty0 + ty) * W + t.tx0 + txx) * C + col0;
 #pragma unroll
         for (int j = 0; j < C / 16; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j);
@@ -377,11 +397,16 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
           pk.y = f2_to_bf2(add2(make_float2(acc[j][2], acc[j][3]), make_float2(b0.z, b0.w)));
           pk.z = f2_to_bf2(add2(make_float2(acc[j][4], acc[j][5]), make_float2(b1.x, b1.y)));
           pk.w = f2_to_bf2(add2(make_float2(acc[j][6], acc[j][7]), make_float2(b1.z, b1.w)));
-          *reinterpret_cast<uint4*>(s_y + row * C + col0 + 8 * j) = pk;
+          if (train) *reinterpret_cast<uint4*>(s_y + row * C + col0 + 8 * j) = pk;
+          else *reinterpret_cast<uint4*>(gdst + 8 * j) = pk;
         }
       }
     }
     tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
+    if (!train) {              // (the two barriers of the next tile's phases separate these reads from its MMAs)
+      ph ^= 1u;
+      continue;
+    }
     tc::fence_async_smem();    // staging tile -> visible to the bulk store engine
     __syncthreads();
 
@@ -442,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   __syncthreads();
   if (tid == 0) {
     const unsigned ticket = atomicAdd(P.counter, 1u);
-    s_flag = (ticket == gridDim.x - 1) ? 1 : 0;
+    s_flag = (ticket == (unsigned)nctas - 1u) ? 1 : 0;
   }
   __syncthreads();
   if (s_flag == 0) return;
@@ -532,8 +557,54 @@ __device__ __forceinline__ void pool_pair(const bf16* __restrict__ src, const in
   }
 }
 
+// Fast path for a pooled input that holds FINAL values and needs no arg-max record (frozen teachers: BatchNorm is folded
+// into the 1x1 weights, nothing is saved for a backward): the window maximum is taken on the packed bf16 pairs directly
+// (HMNMX2.BF16, one instruction per two channels, no expansion / tagging).
+__device__ __forceinline__ uint32_t bfmax2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <bool BORDER>
+__device__ __forceinline__ void pool_pair_final(const bf16* __restrict__ src, const int SH, const int SWd, const long long img,
+                                                const int fy0, const int fx0, const int cg, uint32_t (&bestA)[4],
+                                                uint32_t (&bestB)[4], bool& padA, bool& padB) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) bestA[e] = bestB[e] = 0xff80ff80u;   // (-inf, -inf)
+  padA = padB = false;
+#pragma unroll
+  for (int wy = 0; wy < 3; ++wy) {
+    const int fy = fy0 + wy;
+    const bool rok = !BORDER || (fy >= 0 && fy < SH);
+    const bf16* row = src + (img + (long long)(BORDER ? min(max(fy, 0), SH - 1) : fy) * SWd) * C + 8 * cg;
+#pragma unroll
+    for (int cc = 0; cc < 5; ++cc) {
+      const int fx = fx0 + cc;
+      const bool ok = rok && (!BORDER || (fx >= 0 && fx < SWd));
+      uint4 r = __ldg(reinterpret_cast<const uint4*>(row + (long long)(BORDER ? min(max(fx, 0), SWd - 1) : fx) * C));
+      if (BORDER && !ok) {
+        r = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+        if (cc <= 2) padA = true;
+        if (cc >= 2) padB = true;
+      }
+      if (cc <= 2) {
+        bestA[0] = bfmax2(bestA[0], r.x); bestA[1] = bfmax2(bestA[1], r.y);
+        bestA[2] = bfmax2(bestA[2], r.z); bestA[3] = bfmax2(bestA[3], r.w);
+      }
+      if (cc >= 2) {
+        bestB[0] = bfmax2(bestB[0], r.x); bestB[1] = bfmax2(bestB[1], r.y);
+        bestB[2] = bfmax2(bestB[2], r.z); bestB[3] = bfmax2(bestB[3], r.w);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
-  const NodeFwdP& P = BATCH.p[blockIdx.y];
+  int net = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxBatchNets; ++k)
+    if ((int)blockIdx.x >= BATCH.cta_begin[k]) net = k;
+  const NodeFwdP& P = BATCH.p[net];
+  const int cta = (int)blockIdx.x - BATCH.cta_begin[net], nctas = BATCH.cta_begin[net + 1] - BATCH.cta_begin[net];
   __shared__ __align__(16) float s_c[4 * C];   // pooled input: scale | shift ; second input: w_b*scale | w_b*shift
   const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
   const int H = P.g.H, W = P.g.W, SH = P.in[0].H, SWd = P.in[0].W;
@@ -570,8 +641,9 @@ __global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_
     anyneg = anyneg || (sc[e] < 0.f);
   }
   const int top = pool_pad_before(SH), left = pool_pad_before(SWd);
+  const bool final_in = (P.in[0].bn == nullptr) && (pidx == nullptr) && (praw == nullptr);
 
-  for (int pp = blockIdx.x * kPoolLanes + pl; pp < npairs; pp += gridDim.x * kPoolLanes) {
+  for (int pp = cta * kPoolLanes + pl; pp < npairs; pp += nctas * kPoolLanes) {
     const int b = pp / (H * WP);
     const int rem = pp - b * (H * WP);
     const int y = rem / WP, xp = rem - y * WP;
@@ -580,6 +652,36 @@ __global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_
     const int fy0 = 2 * y - top, fx0 = 2 * x0 - left;
     const long long img = (long long)b * SH * SWd;
     const bool border = (fy0 < 0) || (fy0 + 2 >= SH) || (fx0 < 0) || (fx0 + 4 >= SWd);
+    if (final_in) {
+      uint32_t bA[4], bB[4];
+      bool pA, pB;
+      if (!border) pool_pair_final<false>(src, SH, SWd, img, fy0, fx0, cg, bA, bB, pA, pB);
+      else pool_pair_final<true>(src, SH, SWd, img, fy0, fx0, cg, bA, bB, pA, pB);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        if (o == 1 && !second) break;
+        const uint32_t* best = o ? bB : bA;
+        const bool has_pad = o ? pB : pA;
+        const long long oo = (((long long)b * H + y) * W + x0 + o) * C + 8 * cg;
+        uint4 sm = make_uint4(0u, 0u, 0u, 0u);
+        if (same != nullptr) sm = __ldg(reinterpret_cast<const uint4*>(same + oo));
+        const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t m = has_pad ? bfmax2(best[e], 0u) : best[e];   // the zero padding takes part in the maximum
+          float2 u = mul2(bf2_to_f2(m), make_float2(wa, wa));
+          if (same != nullptr) {
+            const float2 f = bf2_to_f2(sw[e]);
+            u.x += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+            u.y += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
+          }
+          pk[e] = f2_to_bf2(u);
+        }
+        *reinterpret_cast<uint4*>(out + oo) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      continue;
+    }
     float bestA[8], bestB[8];
     bool padA, padB;
     if (!border) {
@@ -659,10 +761,10 @@ static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const NodeFwdP& p = batch.p[0];
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
-  int per_net = (2 * sms) / n;
-  if (per_net < 1) per_net = 1;
-  const int gx = ntiles < per_net ? ntiles : per_net;
-  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH>, dim3(gx, n), dim3(kThreads), S::kBytes, s, batch));
+  static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.5f);
+  NodeFwdBatch b2 = batch;
+  batch_shares(b2, n, 2 * sms, ntiles, train_w);
+  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH>, dim3(b2.cta_begin[n]), dim3(kThreads), S::kBytes, s, b2));
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -678,6 +780,30 @@ static int pick_geom(int H, int W) {
 }
 
 }  // namespace v4
+
+float env_float(const char* name, float dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr || *e == 0) return dflt;
+  const float v = (float)atof(e);
+  return v > 0.f ? v : dflt;
+}
+
+void batch_shares(NodeFwdBatch& batch, int n, int budget, int max_per_net, float train_w) {
+  float wsum = 0.f;
+  for (int i = 0; i < n; ++i) wsum += batch.p[i].train ? train_w : 1.f;
+  int begin = 0;
+  for (int i = 0; i < kMaxBatchNets; ++i) {
+    batch.cta_begin[i] = begin;
+    if (i < n) {
+      int c = (int)((float)budget * (batch.p[i].train ? train_w : 1.f) / wsum);
+      if (c > max_per_net) c = max_per_net;
+      if (c < 1) c = 1;
+      begin += c;
+    }
+  }
+  batch.cta_begin[kMaxBatchNets] = begin;
+  for (int i = n; i <= kMaxBatchNets; ++i) batch.cta_begin[i] = begin;
+}
 
 bool fwd_v4_usable(const NodeFwdP& p) {
   if (p.packed == nullptr || p.n_in < 1 || p.n_in > 2 || p.mode[0] != MMD_IN_SAME) return false;
@@ -731,11 +857,13 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
   }
   for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
   const int npairs = p[0].g.B * p[0].g.H * ((p[0].g.W + 1) / 2);
-  int gx = (npairs + v4::kPoolLanes - 1) / v4::kPoolLanes;
-  const int cap = (148 * 4 + n - 1) / n;   // ~2 resident CTAs per SM and 2 waves over all networks
-  if (gx > cap) gx = cap;
+  const int gx = (npairs + v4::kPoolLanes - 1) / v4::kPoolLanes;
+  // ~2 resident CTAs per SM and 2 waves over all networks; a training network (tagged arg-max search, two extra
+  // outputs) costs several times a frozen one (packed bf16 maxima)
+  static const float train_w = env_float("MMD_POOL_TRAIN_SHARE", 3.0f);
+  batch_shares(batch, n, 148 * 4, gx, train_w);
   ProfScope prof(PK_POOLFUSE, bytes, s);
-  MMD_CUDA(launch_pdl(v4::poolfuse_kernel, dim3(gx, n), dim3(v4::kPoolThreads), 0, s, batch));
+  MMD_CUDA(launch_pdl(v4::poolfuse_kernel, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
   MMD_LAUNCH_CHECK();
   return 0;
 }

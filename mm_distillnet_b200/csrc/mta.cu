@@ -26,17 +26,36 @@ struct MtaPoolP {
 
 __device__ __forceinline__ float powp(float v, float p, bool p_is_2) { return p_is_2 ? v * v : powf(v, p); }
 
-template <typename T>
+// sum over VEC consecutive channels of f^p: VEC = 4 (fp32: 16 B, bf16: 8 B per lane) or 8 (bf16 only: 16 B per lane)
+template <typename T, int VEC>
+__device__ __forceinline__ float pow_sum(const T* p, float pw, bool p2) {
+  if constexpr (VEC == 4) {
+    const float4 v = ld4<T>(p);
+    return powp(v.x, pw, p2) + powp(v.y, pw, p2) + powp(v.z, pw, p2) + powp(v.w, pw, p2);
+  } else {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+      a += powp(lo, pw, p2) + powp(hi, pw, p2);
+    }
+    return a;
+  }
+}
+
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) mta_pool_nhwc(const __grid_constant__ MtaPoolP P) {
   const MtaSeg s = P.seg[blockIdx.y];
   const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
-  const int C = P.C, NQ = C >> 2, G = P.group, PPW = 32 / G;
+  const int C = P.C, NQ = C / VEC, G = P.group, PPW = 32 / G;
   const bool p2 = (P.p == 2.0f);
   const int lane = threadIdx.x & 31, gl = lane % G, sub = lane / G;
   const int wpb = blockDim.x >> 5;
   const long long nw = (long long)gridDim.x * wpb;
   const float invC = 1.0f / (float)C;
-  constexpr int U = 4;  // pixel-chunks in flight per warp
+  constexpr int U = 2 * VEC;  // pixel-chunks in flight per warp
   for (long long chunk = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * U; chunk * PPW < s.npix; chunk += nw * U) {
     float acc[U];
 #pragma unroll
@@ -45,10 +64,7 @@ __global__ void __launch_bounds__(256) mta_pool_nhwc(const __grid_constant__ Mta
       long long pix = (chunk + u) * PPW + sub;
       if (pix < s.npix) {
         const T* row = f + pix * C;
-        for (int q = gl; q < NQ; q += G) {
-          float4 v = ld4<T>(row + 4 * q);
-          acc[u] += powp(v.x, P.p, p2) + powp(v.y, P.p, p2) + powp(v.z, P.p, p2) + powp(v.w, P.p, p2);
-        }
+        for (int q = gl; q < NQ; q += G) acc[u] += pow_sum<T, VEC>(row + VEC * q, P.p, p2);
       }
     }
 #pragma unroll
@@ -89,6 +105,8 @@ struct MtaLevelP {
   int HW[MMD_MTA_MAX_LEVELS];
   int B, nt;
   float T;
+  int separate;       // 1: blockIdx.z = independent single-teacher call (teacher z alone), see MmdMtaArgs.separate
+  int n_levels;
 };
 
 constexpr int kLvlThreads = 512;
@@ -126,12 +144,13 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], unsigned max_mask, 
 // the loss (= -ln N - 1/N + O(1e-4)) and its gradient (s * (g - <g,s>)) are differences of nearly equal numbers.
 __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_constant__ MtaLevelP P) {
   __shared__ double s_red[32 * 5];
-  const int b = blockIdx.x, l = blockIdx.y, n = P.HW[l], nt = P.nt;
+  const int b = blockIdx.x, l = blockIdx.y, n = P.HW[l], call = blockIdx.z;
+  const int nt = P.separate ? 1 : P.nt, t0 = P.separate ? call : 0;
   const long long off = (long long)P.B * P.cum[l] + (long long)b * n;
   const float* __restrict__ as = P.att + off;
   const float* __restrict__ at[MMD_MTA_MAX_TEACHERS];
 #pragma unroll
-  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) at[k] = P.att + (long long)(1 + (k < nt ? k : 0)) * P.Btot + off;
+  for (int k = 0; k < MMD_MTA_MAX_TEACHERS; ++k) at[k] = P.att + (long long)(1 + t0 + (k < nt ? k : 0)) * P.Btot + off;
   const double invT = 1.0 / (double)P.T;
 
   // pass 1: squared L2 norms of the student map and of every teacher map (F.normalize, eps 1e-12)
@@ -193,7 +212,7 @@ __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_con
     r4[1] += -t * invB * s;
   }
   block_reduce<2>(r4, 0u, s_red);
-  if (threadIdx.x == 0) P.loss_b[l * P.B + b] = (float)r4[0];
+  if (threadIdx.x == 0) P.loss_b[(call * P.n_levels + l) * P.B + b] = (float)r4[0];
   if (P.ga == nullptr) return;
 
   // pass 5: <a^, d a^> with d z = s (g - <g,s>), d a^ = d z / T
@@ -209,7 +228,7 @@ __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_con
   block_reduce<1>(r5, 0u, s_red);
   const bool clamped = !(nrm_s_raw > 1e-12);
   // pass 6: d a = (d a^ - a^ <a^, d a^>) / ||a||  (or d a^ / eps when the norm was clamped)
-  float* __restrict__ ga = P.ga + off;
+  float* __restrict__ ga = P.ga + (long long)call * P.Btot + off;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double ah = as[i] * inv_s;
     const double s = exp(ah * invT - max_zs) * inv_zs;
@@ -238,10 +257,46 @@ struct MtaBwdSeg {
 };
 struct MtaBwdP {
   MtaBwdSeg seg[MMD_MTA_MAX_LEVELS];
-  const float* grad_loss;
-  int C;
+  const float* grad_loss;   // [ncalls][n_levels]
+  long long Btot;           // stride between the ga maps of consecutive calls
+  int C, ncalls, n_levels;
   float p;
 };
+
+// per-pixel factor: sum over the calls of grad_loss[call][level] * (p / C) * d loss / d a
+__device__ __forceinline__ float bwd_coef(const MtaBwdP& P, const MtaBwdSeg& s, long long pix, const float (&coef)[MMD_MTA_MAX_TEACHERS]) {
+  float k = coef[0] * s.ga[pix];
+#pragma unroll
+  for (int c = 1; c < MMD_MTA_MAX_TEACHERS; ++c)
+    if (c < P.ncalls) k = fmaf(coef[c], s.ga[(long long)c * P.Btot + pix], k);
+  return k;
+}
+
+// bf16 NHWC, p == 2, C % 8 == 0: 16-byte vectors
+__global__ void __launch_bounds__(256) mta_bwd_bf16x8_kernel(const __grid_constant__ MtaBwdP P) {
+  const MtaBwdSeg s = P.seg[blockIdx.y];
+  const uint4* __restrict__ f = reinterpret_cast<const uint4*>(s.f);
+  uint4* __restrict__ g = reinterpret_cast<uint4*>(s.g);
+  const int NV = P.C >> 3;
+  float coef[MMD_MTA_MAX_TEACHERS];
+#pragma unroll
+  for (int c = 0; c < MMD_MTA_MAX_TEACHERS; ++c)
+    coef[c] = (c < P.ncalls) ? P.grad_loss[c * P.n_levels + s.level] * P.p / (float)P.C : 0.f;
+  const long long nvec = (long long)s.npix * NV;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
+    const float k = bwd_coef(P, s, v / NV, coef);
+    const uint4 x = __ldg(f + v);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+      __nv_bfloat162 h = __floats2bfloat162_rn(k * lo, k * hi);
+      o[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    g[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
 
 template <typename T, bool NCHW>
 __global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ MtaBwdP P) {
@@ -250,12 +305,15 @@ __global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ Mt
   T* __restrict__ g = reinterpret_cast<T*>(s.g);
   const int C = P.C;
   const bool p2 = (P.p == 2.0f);
-  const float coef = P.grad_loss[s.level] * P.p / (float)C;
+  float coef[MMD_MTA_MAX_TEACHERS];
+#pragma unroll
+  for (int c = 0; c < MMD_MTA_MAX_TEACHERS; ++c)
+    coef[c] = (c < P.ncalls) ? P.grad_loss[c * P.n_levels + s.level] * P.p / (float)C : 0.f;
   const long long nvec = (long long)s.npix * C / 4;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
     long long e = v * 4;
     if (!NCHW) {
-      float k = coef * s.ga[e / C];
+      float k = bwd_coef(P, s, e / C, coef);
       float4 x = ld4<T>(f + e);
       float4 r;
       if (p2) r = f4_scale(x, k);
@@ -267,7 +325,7 @@ __global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ Mt
         long long ee = e + j;
         int hw = (int)(ee % s.HW);
         int b = (int)(ee / ((long long)C * s.HW));
-        float k = coef * s.ga[(long long)b * s.HW + hw];
+        float k = bwd_coef(P, s, (long long)b * s.HW + hw, coef);
         float x = ld1<T>(f + ee);
         st1<T>(g + ee, p2 ? k * x : k * powf(x, P.p - 1.f));
       }
@@ -275,8 +333,8 @@ __global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ Mt
   }
 }
 
-static int group_lanes(int C) {
-  int nq = C / 4, g = 1;
+static int group_lanes(int C, int vec) {
+  int nq = C / vec, g = 1;
   while (g < nq && g < 32) g <<= 1;
   return g;
 }
@@ -318,8 +376,11 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
       s.HW = lp.HW[l];
       if (s.npix > maxpix) maxpix = s.npix;
     }
+  const bool vec8 = (a->dtype == MMD_BF16 && a->layout == MMD_NHWC && a->C % 8 == 0);
+  for (int i = 0; vec8 && i < nseg; ++i)
+    if (((uintptr_t)pp.seg[i].f & 15u) != 0) { set_error("mmd_mta_fwd: bf16 feature maps must be 16-byte aligned"); return MMD_E_ARG; }
   pp.C = a->C;
-  pp.group = group_lanes(a->C);
+  pp.group = group_lanes(a->C, vec8 ? 8 : 4);
   pp.p = a->p;
 
   double pool_bytes = 0.0;
@@ -327,12 +388,13 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   {
   ProfScope prof(PK_MTA_POOL, pool_bytes, stream);
   if (a->layout == MMD_NHWC) {
-    const int ppb = (32 / pp.group) * 8 * 4;  // pixels per block-iteration (8 warps, 4 chunks in flight)
+    const int ppb = (32 / pp.group) * 8 * (vec8 ? 16 : 8);  // pixels per block-iteration (8 warps, U chunks in flight)
     int gx = (maxpix + ppb - 1) / ppb;
     if (gx > 148 * 8) gx = 148 * 8;
     dim3 grid(gx, nseg);
-    if (a->dtype == MMD_F32) mta_pool_nhwc<float><<<grid, 256, 0, stream>>>(pp);
-    else mta_pool_nhwc<__nv_bfloat16><<<grid, 256, 0, stream>>>(pp);
+    if (a->dtype == MMD_F32) mta_pool_nhwc<float, 4><<<grid, 256, 0, stream>>>(pp);
+    else if (vec8) mta_pool_nhwc<__nv_bfloat16, 8><<<grid, 256, 0, stream>>>(pp);
+    else mta_pool_nhwc<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>(pp);
   } else {
     int gx = (maxpix + 255) / 256;
     if (gx > 148 * 8) gx = 148 * 8;
@@ -350,14 +412,17 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   lp.B = a->B;
   lp.nt = a->n_teachers;
   lp.T = a->T;
+  lp.separate = a->separate ? 1 : 0;
+  lp.n_levels = a->n_levels;
+  const int ncalls = a->separate ? a->n_teachers : 1;
   {
     ProfScope prof(PK_MTA_LEVEL, 0.0, stream);
-    mta_level_kernel<<<dim3(a->B, a->n_levels), kLvlThreads, 0, stream>>>(lp);
+    mta_level_kernel<<<dim3(a->B, a->n_levels, ncalls), kLvlThreads, 0, stream>>>(lp);
   }
   MMD_LAUNCH_CHECK();
   {
     ProfScope prof(PK_MTA_FINISH, 0.0, stream);
-    mta_finish_kernel<<<a->n_levels, 32, 0, stream>>>(a->loss_b, a->loss, a->B);
+    mta_finish_kernel<<<a->n_levels * ncalls, 32, 0, stream>>>(a->loss_b, a->loss, a->B);
   }
   MMD_LAUNCH_CHECK();
   return 0;
@@ -388,6 +453,13 @@ extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* co
   bp.grad_loss = grad_loss;
   bp.C = a->C;
   bp.p = a->p;
+  bp.ncalls = a->separate ? a->n_teachers : 1;
+  bp.n_levels = a->n_levels;
+  bp.Btot = (long long)a->B * cum;
+  bool vec8 = (a->dtype == MMD_BF16 && a->layout == MMD_NHWC && a->C % 8 == 0 && a->p == 2.0f);
+  for (int l = 0; vec8 && l < a->n_levels; ++l)
+    if ((((uintptr_t)bp.seg[l].f | (uintptr_t)bp.seg[l].g) & 15u) != 0) vec8 = false;
+  if (vec8) maxvec /= 2;
   long long gx = (maxvec + 255) / 256;
   if (gx > 148 * 16) gx = 148 * 16;
   dim3 grid((unsigned)gx, a->n_levels);
@@ -396,6 +468,7 @@ extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* co
   ProfScope prof(PK_MTA_BWD, bwd_bytes, stream);
   if (a->layout == MMD_NHWC) {
     if (a->dtype == MMD_F32) mta_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(bp);
+    else if (vec8) mta_bwd_bf16x8_kernel<<<grid, 256, 0, stream>>>(bp);
     else mta_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(bp);
   } else {
     if (a->dtype == MMD_F32) mta_bwd_kernel<float, true><<<grid, 256, 0, stream>>>(bp);

@@ -61,6 +61,13 @@ class DistillStep:
         return all(x.dtype == torch.bfloat16 for x in xs) and all(x.dtype == torch.bfloat16 for t in xts for x in t) and \
             all(t[0].shape[0] == xs[0].shape[0] for t in xts)
 
+    def _kd(self, feats_s, feats_t_all):
+        """criterion_kd(features_s, features_t) per teacher (train_methods.py:351-358) -> Tensor[n_teachers, n_levels]."""
+        teachers = [[f.detach() for f in ft] for ft in feats_t_all]
+        if isinstance(self.criterion, MTALoss) and 1 <= len(teachers) <= 4:
+            return self.criterion.forward_each(feats_s, teachers)      # one set of launches for all teachers
+        return torch.stack([self.criterion(feats_s, t) for t in teachers])
+
     def __call__(self, student_inputs, teacher_inputs):
         xs = self._to_device(student_inputs)
         xts = [self._to_device(t) for t in teacher_inputs]
@@ -68,7 +75,7 @@ class DistillStep:
             # one lockstep pass: the same node of the student and of every teacher shares a launch
             outs = forward_multi([(self.student, xs)] + [(t, x) for t, x in zip(self.teachers, xts)])
             feats_s, feats_t_all = outs[0], outs[1:]
-            kd = [self.criterion(feats_s, [f.detach() for f in ft]) for ft in feats_t_all]       # :351-358
+            kd = self._kd(feats_s, feats_t_all)                                                  # :351-358
         else:
             main = torch.cuda.current_stream(self.device)
             feats_t_all = []
@@ -80,11 +87,9 @@ class DistillStep:
                         f.record_stream(main)
                 feats_t_all.append(feats_t)
             feats_s = self.student(xs)                                   # :318
-            kd = []
-            for feats_t, st in zip(feats_t_all, self.streams):           # :351-358
+            for st in self.streams:
                 main.wait_stream(st)
-                kd.append(self.criterion(feats_s, [f.detach() for f in feats_t]))
-        kd = torch.stack(kd)
+            kd = self._kd(feats_s, feats_t_all)                          # :351-358
         loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
         loss.backward()                                              # :182
         return kd.detach()

@@ -36,10 +36,13 @@ def _check(feats):
 
 
 class _MTAFunction(torch.autograd.Function):
-    """loss[l] for all levels; feats = n_levels student maps followed by n_teachers * n_levels teacher maps."""
+    """loss[l] for all levels; feats = n_levels student maps followed by n_teachers * n_levels teacher maps.
+
+    `separate` (bool): n_teachers independent single-teacher calls sharing the student maps -> loss[n_teachers, n_levels]
+    (MmdMtaArgs.separate); otherwise one call against the product of the teachers -> loss[n_levels]."""
 
     @staticmethod
-    def forward(ctx, T, p, n_levels, n_teachers, *feats):
+    def forward(ctx, T, p, n_levels, n_teachers, separate, *feats):
         _check(feats)
         dtype = feats[0].dtype
         feats = [f.detach() if f.dtype == dtype else f.detach().to(dtype) for f in feats]
@@ -55,17 +58,19 @@ class _MTAFunction(torch.autograd.Function):
                     raise ValueError("MTALoss: level %d shapes differ: %s vs %s" % (l, tuple(t.shape), tuple(fs[l].shape)))
         dev = fs[0].device
         sum_hw = sum(f.shape[2] * f.shape[3] for f in fs)
-        need_grad = any(ctx.needs_input_grad[4:4 + n_levels])
+        need_grad = any(ctx.needs_input_grad[5:5 + n_levels])
+        ncalls = n_teachers if separate else 1
         att = torch.empty((1 + n_teachers) * B * sum_hw, dtype=torch.float32, device=dev)
-        ga = torch.empty(B * sum_hw, dtype=torch.float32, device=dev) if need_grad else None
-        loss_b = torch.empty(n_levels * B, dtype=torch.float32, device=dev)
-        loss = torch.empty(n_levels, dtype=torch.float32, device=dev)
+        ga = torch.empty(ncalls * B * sum_hw, dtype=torch.float32, device=dev) if need_grad else None
+        loss_b = torch.empty(ncalls * n_levels * B, dtype=torch.float32, device=dev)
+        loss = torch.empty(ncalls * n_levels, dtype=torch.float32, device=dev)
 
         a = _lib.MtaArgs()
         a.n_levels, a.n_teachers, a.B, a.C = n_levels, n_teachers, B, Cch
         a.dtype = _lib.MMD_F32 if dtype == torch.float32 else _lib.MMD_BF16
         a.layout = layout
         a.T, a.p = T, p
+        a.separate = 1 if separate else 0
         for l in range(n_levels):
             a.H[l], a.W[l] = fs[l].shape[2], fs[l].shape[3]
             a.fs[l] = fs[l].data_ptr()
@@ -80,7 +85,8 @@ class _MTAFunction(torch.autograd.Function):
         ctx.n_levels = n_levels
         ctx.keep = (fs, ga)          # keeps the pointers inside `a` alive until backward
         ctx.dev = dev
-        return loss     # always fp32: a bf16 loss could not even represent loss + ln(HW)
+        # always fp32: a bf16 loss could not even represent loss + ln(HW)
+        return loss.view(n_teachers, n_levels) if separate else loss
 
     @staticmethod
     def backward(ctx, grad_loss):
@@ -94,9 +100,9 @@ class _MTAFunction(torch.autograd.Function):
         with torch.cuda.device(ctx.dev):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().mmd_mta_bwd(C.byref(ctx.args), go.data_ptr(), ptrs, stream), "mmd_mta_bwd")
-        out = [None, None, None, None]
+        out = [None, None, None, None, None]
         for l in range(n):
-            out.append(grads[l] if ctx.needs_input_grad[4 + l] else None)
+            out.append(grads[l] if ctx.needs_input_grad[5 + l] else None)
         out.extend([None] * (len(ctx.needs_input_grad) - len(out)))
         return tuple(out)
 
@@ -109,7 +115,7 @@ class MTALoss(nn.Module):
         self.p = float(p)   # src/loss/MTALoss.py:12-13 (config passes strings)
         self.T = float(T)
 
-    def _run(self, g_s, teachers):
+    def _run(self, g_s, teachers, separate=False):
         n_levels = len(g_s)
         if not 1 <= n_levels <= _lib.MTA_MAX_LEVELS:
             raise ValueError("MTALoss supports 1..%d pyramid levels, got %d" % (_lib.MTA_MAX_LEVELS, n_levels))
@@ -118,7 +124,7 @@ class MTALoss(nn.Module):
         flat = list(g_s)
         for t in teachers:
             flat.extend(t[:n_levels])
-        return _MTAFunction.apply(self.T, self.p, n_levels, len(teachers), *flat)
+        return _MTAFunction.apply(self.T, self.p, n_levels, len(teachers), bool(separate), *flat)
 
     def forward(self, g_s, g_t):
         if torch.is_tensor(g_t[0]):                     # one teacher: list of level tensors (MTALoss.py:17-19)
@@ -126,6 +132,13 @@ class MTALoss(nn.Module):
             return self._run(list(g_s)[:n], [list(g_t)[:n]])
         n = len(g_s)                                    # list of teachers, each a list of levels (:20-34)
         return self._run(list(g_s), [list(t)[:n] for t in g_t])
+
+    def forward_each(self, g_s, teachers):
+        """`torch.stack([self(g_s, t) for t in teachers])` — the per-teacher calls of the reference's step wrappers
+        (train_methods.py:351-358) — in ONE set of launches: the student maps are pooled once, the backward writes the
+        sum of the calls' gradients in one pass.  Returns Tensor[len(teachers), len(g_s)]."""
+        n = len(g_s)
+        return self._run(list(g_s), [list(t)[:n] for t in teachers], separate=True)
 
     def mtaloss(self, out_s, out_t):
         """One level; `out_t` is a tensor or a list of teacher tensors (MTALoss.py:36-74)."""

@@ -237,3 +237,39 @@ def mta_random_case(B, C, sizes, n_teachers, dtype=torch.float32, channels_last=
         "ref32_grad": max(H.rel_l2(a.grad, b.grad) for a, b in zip(fs32, fs64)),
     }
     return m
+
+
+def mta_each_case(B, C, sizes, n_teachers, dtype=torch.float32, channels_last=True, seed=0):
+    """MTALoss.forward_each (n_teachers single-teacher calls sharing the student, one set of launches) vs the fp64
+    oracle run as the reference's step wrapper does: criterion_kd(features_s, features_t) per teacher
+    (train_methods.py:351-358), stacked, with a different upstream gradient for every (teacher, level) entry."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def feats():
+        return [(torch.randn(B, C, s, s, generator=gen) * torch.exp(1.5 * torch.randn(B, 1, s, s, generator=gen))).to(dtype).float()
+                for s in sizes]
+
+    fs = feats()
+    teachers = [feats() for _ in range(n_teachers)]
+    go = torch.rand(n_teachers, len(sizes), generator=gen) * 0.01 + 0.001
+    fs64 = [f.double().requires_grad_(True) for f in fs]
+    l64 = torch.stack([O.mta_loss(fs64, [f.double() for f in t]) for t in teachers])
+    (l64 * go.double()).sum().backward()
+
+    crit = mmd.MTALoss()
+    fd = [f.requires_grad_(True) for f in to_dev(fs, dtype, channels_last)]
+    td = [to_dev(t, dtype, channels_last) for t in teachers]
+    loss = crit.forward_each(fd, td)
+    (loss * go.to(DEV)).sum().backward()
+    g_each = [f.grad.clone() for f in fd]
+    for f in fd:
+        f.grad = None
+    loss_loop = torch.stack([crit(fd, t) for t in td])       # the same through n_teachers ordinary calls
+    (loss_loop * go.to(DEV)).sum().backward()
+    return {
+        "shape_ok": tuple(loss.shape) == (n_teachers, len(sizes)),
+        "loss_abs": float((loss.detach().double().cpu() - l64.detach()).abs().max()),
+        "grad": max(H.rel_l2(g.float().cpu(), b.grad) for g, b in zip(g_each, fs64)),
+        "loss_vs_loop": float((loss.detach() - loss_loop.detach()).abs().max()),
+        "grad_vs_loop": max(H.rel_l2(g.float(), f.grad.float()) for g, f in zip(g_each, fd)),
+    }

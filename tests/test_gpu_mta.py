@@ -27,6 +27,19 @@ def test_mta_vs_fp64_oracle(nt):
     assert m["grad"] <= 1e-4, m
 
 
+@pytest.mark.parametrize("nt,dtype,tol", [(1, torch.float32, 1e-4), (3, torch.float32, 1e-4), (4, torch.float32, 1e-4),
+                                          (3, torch.bfloat16, 4e-3)])
+def test_mta_forward_each_matches_per_teacher_calls(nt, dtype, tol):
+    """One batched launch set == the reference's per-teacher criterion_kd calls (train_methods.py:351-358)."""
+    m = G.mta_each_case(4, 112, [24, 12, 6, 3, 2], nt, dtype=dtype)
+    assert m["shape_ok"], m
+    assert m["loss_abs"] <= 2e-6 and m["loss_vs_loop"] <= 1e-6, m
+    assert m["grad"] <= tol, m
+    # fp32: the summed gradient equals the sum autograd forms from nt separate calls up to fp32 summation order;
+    # bf16: the loop rounds every call's gradient to bf16 before summing, the batched pass rounds once
+    assert m["grad_vs_loop"] <= (1e-5 if dtype == torch.float32 else 8e-3), m
+
+
 def test_mta_full_size_uniform_landmarks():
     """BASELINE sizes (B=16, P3..P7 of a 768^2 input), unstructured features: loss = -ln(HW) - 1/HW to 1e-3."""
     import mm_distillnet_b200 as mmd
