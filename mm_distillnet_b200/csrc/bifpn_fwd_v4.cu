@@ -347,14 +347,6 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     }
     tc::fence_async_smem();   // the A operand was written through the generic proxy
     __syncthreads();
-    // a frozen network writes its output straight from the epilogue registers (no staging tile, no statistics): region 0
-    // is free as soon as the depthwise stage has consumed v, so the next tile's input 0 is already in flight during the
-    // MMA and the epilogue
-    if (!train && warp == 1 && next < ntiles) {
-      const TilePos tn = tile_pos(next, tiles_x, tiles_y, TW, TH);
-      issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
-    }
-
     // ---- (4) pointwise 1x1 on the tensor cores
     if (tid == 0) {
       tc::fence_after_sync();
@@ -385,9 +377,6 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
       for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
       tc::tmem_ld_wait();
       if (row < S::NP) {
-        constexpr int kRowShift = (TW == 16) ? 4 : 0;
-        const int ty = kRowShift ? (row >> kRowShift) : (row / TW), txx = row - ty * TW;
-        bf16* gdst = out + (((long long)t.b * H + t.ty0 + ty) * W + t.tx0 + txx) * C + col0;
 #pragma unroll
         for (int j = 0; j < C / 16; ++j) {
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias + col0 + 8 * j);
@@ -397,16 +386,11 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
           pk.y = f2_to_bf2(add2(make_float2(acc[j][2], acc[j][3]), make_float2(b0.z, b0.w)));
           pk.z = f2_to_bf2(add2(make_float2(acc[j][4], acc[j][5]), make_float2(b1.x, b1.y)));
           pk.w = f2_to_bf2(add2(make_float2(acc[j][6], acc[j][7]), make_float2(b1.z, b1.w)));
-          if (train) *reinterpret_cast<uint4*>(s_y + row * C + col0 + 8 * j) = pk;
-          else *reinterpret_cast<uint4*>(gdst + 8 * j) = pk;
+          *reinterpret_cast<uint4*>(s_y + row * C + col0 + 8 * j) = pk;
         }
       }
     }
     tc::fence_before_sync();   // order the TMEM reads before the next tile's MMAs
-    if (!train) {              // (the two barriers of the next tile's phases separate these reads from its MMAs)
-      ph ^= 1u;
-      continue;
-    }
     tc::fence_async_smem();    // staging tile -> visible to the bulk store engine
     __syncthreads();
 
@@ -861,7 +845,8 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
   // ~2 resident CTAs per SM and 2 waves over all networks; a training network (tagged arg-max search, two extra
   // outputs) costs several times a frozen one (packed bf16 maxima)
   static const float train_w = env_float("MMD_POOL_TRAIN_SHARE", 3.0f);
-  batch_shares(batch, n, 148 * 4, gx, train_w);
+  static const float waves = env_float("MMD_POOL_WAVES", 2.0f);
+  batch_shares(batch, n, (int)(148 * 2 * waves), gx, train_w);
   ProfScope prof(PK_POOLFUSE, bytes, s);
   MMD_CUDA(launch_pdl(v4::poolfuse_kernel, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
   MMD_LAUNCH_CHECK();

@@ -18,7 +18,10 @@ struct MtaSeg {
   int HW;
 };
 struct MtaPoolP {
+  static constexpr int kU = 8;   // pixel-chunks in flight per warp (NHWC kernel)
   MtaSeg seg[kMaxSeg];
+  int item_begin[kMaxSeg + 1];   // NHWC kernel: prefix sums of the items (kU chunks each) per map
+  int nseg;
   int C;
   int group;  // lanes cooperating on one pixel (power of two <= 32)
   float p;
@@ -45,18 +48,27 @@ __device__ __forceinline__ float pow_sum(const T* p, float pw, bool p2) {
   }
 }
 
+// Persistent streaming kernel over ONE flattened work list (all feature maps of the call): an item is U consecutive
+// pixel-chunks of one map (a chunk = the 32/G pixels one warp-wide load covers), items are dealt round-robin to the
+// warps of a grid sized to the machine, so every warp keeps U independent 16-byte loads per lane in flight for several
+// iterations instead of one short-lived block per 256 pixels.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) mta_pool_nhwc(const __grid_constant__ MtaPoolP P) {
-  const MtaSeg s = P.seg[blockIdx.y];
-  const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
   const int C = P.C, NQ = C / VEC, G = P.group, PPW = 32 / G;
   const bool p2 = (P.p == 2.0f);
   const int lane = threadIdx.x & 31, gl = lane % G, sub = lane / G;
   const int wpb = blockDim.x >> 5;
-  const long long nw = (long long)gridDim.x * wpb;
+  const int nw = gridDim.x * wpb;
   const float invC = 1.0f / (float)C;
-  constexpr int U = 2 * VEC;  // pixel-chunks in flight per warp
-  for (long long chunk = ((long long)blockIdx.x * wpb + (threadIdx.x >> 5)) * U; chunk * PPW < s.npix; chunk += nw * U) {
+  constexpr int U = MtaPoolP::kU;
+  const int total = P.item_begin[P.nseg];
+  for (int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < total; item += nw) {
+    int si = 0;
+    for (int k = 1; k < P.nseg; ++k)
+      if (item >= P.item_begin[k]) si = k;
+    const MtaSeg& s = P.seg[si];
+    const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
+    const long long chunk = (long long)(item - P.item_begin[si]) * U;
     float acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -259,6 +271,7 @@ struct MtaBwdP {
   MtaBwdSeg seg[MMD_MTA_MAX_LEVELS];
   const float* grad_loss;   // [ncalls][n_levels]
   long long Btot;           // stride between the ga maps of consecutive calls
+  long long vec_begin[MMD_MTA_MAX_LEVELS + 1];   // bf16x8 kernel: prefix sums of the 16-byte vectors per level
   int C, ncalls, n_levels;
   float p;
 };
@@ -272,29 +285,54 @@ __device__ __forceinline__ float bwd_coef(const MtaBwdP& P, const MtaBwdSeg& s, 
   return k;
 }
 
-// bf16 NHWC, p == 2, C % 8 == 0: 16-byte vectors
+// bf16 NHWC, p == 2, C % 8 == 0: 16-byte vectors, one flattened index space over all levels (persistent grid, four
+// independent vectors per thread and iteration)
 __global__ void __launch_bounds__(256) mta_bwd_bf16x8_kernel(const __grid_constant__ MtaBwdP P) {
-  const MtaBwdSeg s = P.seg[blockIdx.y];
-  const uint4* __restrict__ f = reinterpret_cast<const uint4*>(s.f);
-  uint4* __restrict__ g = reinterpret_cast<uint4*>(s.g);
   const int NV = P.C >> 3;
-  float coef[MMD_MTA_MAX_TEACHERS];
+  const long long total = P.vec_begin[P.n_levels];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int UB = 4;
+  for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += UB * stride) {
+    uint4 x[UB];
+    float k[UB];
+    long long loc[UB];
+    int lv[UB];
 #pragma unroll
-  for (int c = 0; c < MMD_MTA_MAX_TEACHERS; ++c)
-    coef[c] = (c < P.ncalls) ? P.grad_loss[c * P.n_levels + s.level] * P.p / (float)P.C : 0.f;
-  const long long nvec = (long long)s.npix * NV;
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long long)gridDim.x * blockDim.x) {
-    const float k = bwd_coef(P, s, v / NV, coef);
-    const uint4 x = __ldg(f + v);
-    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-      __nv_bfloat162 h = __floats2bfloat162_rn(k * lo, k * hi);
-      o[e] = *reinterpret_cast<uint32_t*>(&h);
+    for (int u = 0; u < UB; ++u) {
+      const long long v = v0 + u * stride;
+      lv[u] = -1;
+      if (v < total) {
+        int l = 0;
+        for (int j = 1; j < P.n_levels; ++j)
+          if (v >= P.vec_begin[j]) l = j;
+        lv[u] = l;
+        loc[u] = v - P.vec_begin[l];
+        x[u] = __ldg(reinterpret_cast<const uint4*>(P.seg[l].f) + loc[u]);
+      }
     }
-    g[v] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (lv[u] < 0) continue;
+      const MtaBwdSeg& s = P.seg[lv[u]];
+      const long long pix = loc[u] / NV;
+      float kk = 0.f;
+      for (int c = 0; c < P.ncalls; ++c)
+        kk = fmaf(P.grad_loss[c * P.n_levels + s.level], s.ga[(long long)c * P.Btot + pix], kk);
+      k[u] = kk * P.p / (float)P.C;
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      if (lv[u] < 0) continue;
+      const uint32_t w[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+        __nv_bfloat162 h = __floats2bfloat162_rn(k[u] * lo, k[u] * hi);
+        o[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      reinterpret_cast<uint4*>(P.seg[lv[u]].g)[loc[u]] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -388,10 +426,17 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   {
   ProfScope prof(PK_MTA_POOL, pool_bytes, stream);
   if (a->layout == MMD_NHWC) {
-    const int ppb = (32 / pp.group) * 8 * (vec8 ? 16 : 8);  // pixels per block-iteration (8 warps, U chunks in flight)
-    int gx = (maxpix + ppb - 1) / ppb;
+    const int ppi = (32 / pp.group) * MtaPoolP::kU;   // pixels per item
+    int items = 0;
+    for (int i = 0; i < nseg; ++i) {
+      pp.item_begin[i] = items;
+      items += (pp.seg[i].npix + ppi - 1) / ppi;
+    }
+    pp.item_begin[nseg] = items;
+    pp.nseg = nseg;
+    int gx = (items + 7) / 8;
     if (gx > 148 * 8) gx = 148 * 8;
-    dim3 grid(gx, nseg);
+    dim3 grid(gx);
     if (a->dtype == MMD_F32) mta_pool_nhwc<float, 4><<<grid, 256, 0, stream>>>(pp);
     else if (vec8) mta_pool_nhwc<__nv_bfloat16, 8><<<grid, 256, 0, stream>>>(pp);
     else mta_pool_nhwc<__nv_bfloat16, 4><<<grid, 256, 0, stream>>>(pp);
@@ -459,10 +504,21 @@ extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* co
   bool vec8 = (a->dtype == MMD_BF16 && a->layout == MMD_NHWC && a->C % 8 == 0 && a->p == 2.0f);
   for (int l = 0; vec8 && l < a->n_levels; ++l)
     if ((((uintptr_t)bp.seg[l].f | (uintptr_t)bp.seg[l].g) & 15u) != 0) vec8 = false;
-  if (vec8) maxvec /= 2;
   long long gx = (maxvec + 255) / 256;
   if (gx > 148 * 16) gx = 148 * 16;
   dim3 grid((unsigned)gx, a->n_levels);
+  if (vec8) {
+    long long tot = 0;
+    for (int l = 0; l < a->n_levels; ++l) {
+      bp.vec_begin[l] = tot;
+      tot += (long long)bp.seg[l].npix * (a->C / 8);
+    }
+    bp.vec_begin[a->n_levels] = tot;
+    for (int l = a->n_levels + 1; l <= MMD_MTA_MAX_LEVELS; ++l) bp.vec_begin[l] = tot;
+    gx = (tot + 4 * 256 - 1) / (4 * 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    grid = dim3((unsigned)gx);
+  }
   double bwd_bytes = 0.0;
   for (int l = 0; l < a->n_levels; ++l) bwd_bytes += 2.0 * bp.seg[l].npix * a->C * (a->dtype == MMD_F32 ? 4 : 2);
   ProfScope prof(PK_MTA_BWD, bwd_bytes, stream);

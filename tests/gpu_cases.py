@@ -155,6 +155,7 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         if ref64:
             m["ref32_grad_in%d" % i] = H.rel_l2(xin32[i].grad, xin_ref[i].grad)
     worst, worst32 = {}, {}
+    fw_num = fw_den = fw_num32 = 0.0
     for k, p in stack.named_parameters():
         if k.endswith("conv.bias"):
             continue
@@ -167,6 +168,11 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
             m["zero_grad_abs"] = max(m.get("zero_grad_abs", 0.0), p.grad.abs().max().item())
             continue
         e = H.rel_l2(p.grad.cpu(), r)
+        if cls == "fw":   # all fusion-weight gradients of the stack as ONE vector (see check_fp32)
+            fw_num += float((p.grad.cpu().double() - r.double()).pow(2).sum())
+            fw_den += float(r.double().pow(2).sum())
+            if ref64:
+                fw_num32 += float((leaf32[k].grad.double() - r.double()).pow(2).sum())
         if e > worst.get(cls, 0.0):
             worst[cls] = e
             m["worstname_" + cls] = "%s |g|=%.3e" % (k, r.norm().item())
@@ -177,6 +183,10 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         m["pgrad_" + k] = v
     for k, v in worst32.items():
         m["ref32_pgrad_" + k] = v
+    if fw_den > 0.0:
+        m["pgrad_fwall"] = (fw_num / fw_den) ** 0.5
+        if ref64:
+            m["ref32_pgrad_fwall"] = (fw_num32 / fw_den) ** 0.5
     return m
 
 
