@@ -944,12 +944,12 @@ static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
   const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, 2);
   {
     const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
-    ProfScope prof(PK_NODE_BWD_A, bytes, s);
+    ProfScope prof((TW == 16 && TH == 8) ? PK_NODE_BWD_A_16x8 : PK_NODE_BWD_A, bytes, s);
     MMD_CUDA(launch_pdl(node_bwd_a4_kernel<TW, TH>, dim3(grid), dim3(kThreads), SA::kBytes, s, p,
                         packed_layout(MMD_OP_NODE_FWD, C, C).offBwd));
     MMD_LAUNCH_CHECK();
   }
-  ProfScope prof(PK_NODE_BWD_B, bytes, s);
+  ProfScope prof((TW == 16 && TH == 8) ? PK_NODE_BWD_B_16x8 : PK_NODE_BWD_B, bytes, s);
   const bool sw = p.swish != 0;
   switch (x1_mode(p)) {
     case X1_SAME: return sw ? launch_b<TW, TH, X1_SAME, true>(p, s) : launch_b<TW, TH, X1_SAME, false>(p, s);

@@ -582,7 +582,8 @@ __device__ __forceinline__ void pool_pair_final(const bf16* __restrict__ src, co
   }
 }
 
-__global__ void __launch_bounds__(kPoolThreads, 2) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+template <int MINB>
+__global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
   int net = 0;
 #pragma unroll
   for (int k = 1; k < kMaxBatchNets; ++k)
@@ -813,8 +814,9 @@ int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s) {
     bytes += node_algo_bytes(p[i].in, aux ? 1 : p[i].n_in, p[i].g, C, 2);
   }
   for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
-  ProfScope prof(PK_NODE_FWD, bytes, s);
-  switch (v4::pick_geom(p[0].g.H, p[0].g.W)) {
+  const int geom = v4::pick_geom(p[0].g.H, p[0].g.W);
+  ProfScope prof(geom == 0 ? PK_NODE_FWD_16x8 : PK_NODE_FWD, bytes, s);
+  switch (geom) {
     case 0: return v4::launch_geom<16, 8>(batch, n, s);
     case 1: return v4::launch_geom<12, 8>(batch, n, s);
     case 2: return v4::launch_geom<8, 8>(batch, n, s);
@@ -846,9 +848,12 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
   // outputs) costs several times a frozen one (packed bf16 maxima)
   static const float train_w = env_float("MMD_POOL_TRAIN_SHARE", 3.0f);
   static const float waves = env_float("MMD_POOL_WAVES", 2.0f);
-  batch_shares(batch, n, (int)(148 * 2 * waves), gx, train_w);
+  static const int minb = (int)env_float("MMD_POOL_MINB", 4.0f);   // resident CTAs per SM the kernel is compiled for
+  batch_shares(batch, n, (int)(148 * minb * waves), gx, train_w);
   ProfScope prof(PK_POOLFUSE, bytes, s);
-  MMD_CUDA(launch_pdl(v4::poolfuse_kernel, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
+  if (minb >= 4) MMD_CUDA(launch_pdl(v4::poolfuse_kernel<4>, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
+  else if (minb == 3) MMD_CUDA(launch_pdl(v4::poolfuse_kernel<3>, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
+  else MMD_CUDA(launch_pdl(v4::poolfuse_kernel<2>, dim3(batch.cta_begin[n]), dim3(v4::kPoolThreads), 0, s, batch));
   MMD_LAUNCH_CHECK();
   return 0;
 }

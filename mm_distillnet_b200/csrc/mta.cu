@@ -29,23 +29,38 @@ struct MtaPoolP {
 
 __device__ __forceinline__ float powp(float v, float p, bool p_is_2) { return p_is_2 ? v * v : powf(v, p); }
 
-// sum over VEC consecutive channels of f^p: VEC = 4 (fp32: 16 B, bf16: 8 B per lane) or 8 (bf16 only: 16 B per lane)
+// VEC consecutive channels: VEC = 4 (fp32: 16 B, bf16: 8 B per lane) or 8 (bf16 only: 16 B per lane).  The load and the
+// reduction are separate so that a warp can have all the loads of an item in flight before it consumes the first one.
 template <typename T, int VEC>
-__device__ __forceinline__ float pow_sum(const T* p, float pw, bool p2) {
-  if constexpr (VEC == 4) {
-    const float4 v = ld4<T>(p);
-    return powp(v.x, pw, p2) + powp(v.y, pw, p2) + powp(v.z, pw, p2) + powp(v.w, pw, p2);
+__device__ __forceinline__ uint4 ld_raw(const T* p) {
+  if constexpr (VEC == 8) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  } else if constexpr (sizeof(T) == 4) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
   } else {
-    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_uint4(r.x, r.y, 0u, 0u);
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ float pow_sum_raw(const uint4 r, float pw, bool p2) {
+  if constexpr (sizeof(T) == 4) {
+    return powp(__uint_as_float(r.x), pw, p2) + powp(__uint_as_float(r.y), pw, p2) + powp(__uint_as_float(r.z), pw, p2) +
+           powp(__uint_as_float(r.w), pw, p2);
+  } else {
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
     float a = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < VEC / 2; ++e) {
       const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
       a += powp(lo, pw, p2) + powp(hi, pw, p2);
     }
     return a;
   }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ float pow_sum(const T* p, float pw, bool p2) {
+  return pow_sum_raw<T, VEC>(ld_raw<T, VEC>(p), pw, p2);
 }
 
 // Persistent streaming kernel over ONE flattened work list (all feature maps of the call): an item is U consecutive
@@ -70,13 +85,25 @@ __global__ void __launch_bounds__(256) mta_pool_nhwc(const __grid_constant__ Mta
     const T* __restrict__ f = reinterpret_cast<const T*>(s.f);
     const long long chunk = (long long)(item - P.item_begin[si]) * U;
     float acc[U];
+    if (NQ <= G) {   // one vector per lane and pixel (C <= 32 * VEC): all U loads are issued before the first use
+      uint4 raw[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      acc[u] = 0.f;
-      long long pix = (chunk + u) * PPW + sub;
-      if (pix < s.npix) {
-        const T* row = f + pix * C;
-        for (int q = gl; q < NQ; q += G) acc[u] += pow_sum<T, VEC>(row + VEC * q, P.p, p2);
+      for (int u = 0; u < U; ++u) {
+        const long long pix = (chunk + u) * PPW + sub;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (pix < s.npix && gl < NQ) raw[u] = ld_raw<T, VEC>(f + pix * C + VEC * gl);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = (gl < NQ) ? pow_sum_raw<T, VEC>(raw[u], P.p, p2) : 0.f;   // 0^p of a lane without data
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u] = 0.f;
+        long long pix = (chunk + u) * PPW + sub;
+        if (pix < s.npix) {
+          const T* row = f + pix * C;
+          for (int q = gl; q < NQ; q += G) acc[u] += pow_sum<T, VEC>(row + VEC * q, P.p, p2);
+        }
       }
     }
 #pragma unroll

@@ -140,5 +140,45 @@ class DistillStep:
         self._graph.replay()
         return self._g_out
 
+    # ---- pipelined input feed for replay(): the host->device copy of step i+1 overlaps the replay of step i -----------
+    def prefetch(self, student_inputs, teacher_inputs):
+        """Start copying the NEXT step's inputs (host tensors, ideally pinned) into a device staging set on a side
+        stream.  The copy waits until the previous replay_prefetched() has consumed the staging set, so one call per
+        step is safe; it never blocks the host for pinned inputs."""
+        if getattr(self, "_graph", None) is None:
+            raise RuntimeError("DistillStep.prefetch() needs capture() first")
+        dev = self.device
+        if getattr(self, "_stage_xs", None) is None:
+            self._stage_xs = [torch.empty_like(x.detach()) for x in self._g_xs]
+            self._stage_xt = [[torch.empty_like(x) for x in xs] for xs in self._g_xt]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._ev_ready = torch.cuda.Event()
+            self._ev_consumed = torch.cuda.Event()
+            self._ev_consumed.record(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._ev_consumed)
+            for d, x in zip(self._stage_xs, student_inputs):
+                d.copy_(x, non_blocking=True)
+            for ds, xs in zip(self._stage_xt, teacher_inputs):
+                for d, x in zip(ds, xs):
+                    d.copy_(x, non_blocking=True)
+            self._ev_ready.record(self._copy_stream)
+        self._prefetched = True
+
+    def replay_prefetched(self):
+        """Replay the captured step on the inputs of the last prefetch(): waits for that copy, moves the staging set into
+        the graph's static inputs (device-to-device, ~0.1 ms for the D2 pyramid at B=16) and replays."""
+        if not getattr(self, "_prefetched", False):
+            raise RuntimeError("DistillStep.replay_prefetched() needs prefetch() first")
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._ev_ready)
+        with torch.no_grad():
+            torch._foreach_copy_([x.detach() for x in self._g_xs] + [d for ds in self._g_xt for d in ds],
+                                 list(self._stage_xs) + [s for ss in self._stage_xt for s in ss])
+        self._ev_consumed.record(cur)
+        self._prefetched = False
+        self._graph.replay()
+        return self._g_out
+
     def graph_inputs(self):
         return self._g_xs

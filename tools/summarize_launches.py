@@ -14,7 +14,8 @@ import os
 import re
 import sys
 
-KINDS = [("node_fwd", r"node_fwd"), ("poolfuse", r"poolfuse"), ("proj_fwd", r"proj_fwd"), ("bnapply", r"bnapply"),
+KINDS = [("node_fwd<16,8>", r"node_fwd_v4_kernel<\(?(int\))?16, \(?(int\))?8>"), ("node_bwd_a<16,8>", r"node_bwd_a4_kernel<\(?(int\))?16, \(?(int\))?8>"),
+         ("node_bwd_b<16,8>", r"node_bwd_b4_kernel<\(?(int\))?16, \(?(int\))?8"), ("node_fwd", r"node_fwd"), ("poolfuse", r"poolfuse"), ("proj_fwd", r"proj_fwd"), ("bnapply", r"bnapply"),
          ("node_bwd_a", r"node_bwd_a"), ("node_bwd_b", r"node_bwd_b"), ("proj_bwd", r"proj_bwd"), ("pull", r"pull_kernel"),
          ("slot", r"slot_kernel"), ("mta_pool", r"mta_pool"), ("mta_level", r"mta_level"), ("mta_bwd", r"mta_bwd"),
          ("mta_finish", r"mta_finish"), ("prep", r"prep_kernel")]
@@ -93,8 +94,13 @@ def main(argv):
     if "--traffic" in argv:
         out, dtype = argv[argv.index("--traffic") + 1], argv[argv.index("--traffic") + 2]
         kinds = {}
-        for kind, pat in KINDS:
-            sel = [L for L in seq if re.search(pat, L["name"]) and L["rd"] is not None]
+        def kind_of(name):   # first matching kind wins (the <16,8> instantiations are kinds of their own)
+            for kind, pat in KINDS:
+                if re.search(pat, name):
+                    return kind
+            return None
+        for kind, _ in KINDS:
+            sel = [L for L in seq if kind_of(L["name"]) == kind and L["rd"] is not None]
             if sel:
                 kinds[kind] = sum(L["rd"] + (L["wr"] or 0) for L in sel) / len(sel)
         cur = {}
