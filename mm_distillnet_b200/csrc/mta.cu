@@ -144,7 +144,7 @@ struct MtaLevelP {
   int HW[MMD_MTA_MAX_LEVELS];
   int B, nt;
   float T;
-  int separate;       // 1: blockIdx.z = independent single-teacher call (teacher z alone), see MmdMtaArgs.separate
+  int separate;       // 1: blockIdx.y = independent single-teacher call (that teacher alone), see MmdMtaArgs.separate
   int n_levels;
 };
 
@@ -183,7 +183,8 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], unsigned max_mask, 
 // the loss (= -ln N - 1/N + O(1e-4)) and its gradient (s * (g - <g,s>)) are differences of nearly equal numbers.
 __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_constant__ MtaLevelP P) {
   __shared__ double s_red[32 * 5];
-  const int b = blockIdx.x, l = blockIdx.y, n = P.HW[l], call = blockIdx.z;
+  // grid (sample, call, level): the CTAs of the largest level (level 0 of a pyramid) are scheduled first
+  const int b = blockIdx.x, l = blockIdx.z, n = P.HW[l], call = blockIdx.y;
   const int nt = P.separate ? 1 : P.nt, t0 = P.separate ? call : 0;
   const long long off = (long long)P.B * P.cum[l] + (long long)b * n;
   const float* __restrict__ as = P.att + off;
@@ -231,6 +232,65 @@ __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_con
   const double inv_l1 = (nt > 1) ? 1.0 / fmax(r2[0], 1e-12) : 1.0;  // F.normalize(p=1) (MTALoss.py:57)
   const double max_zs = r2[1] * invT, max_zt = r2[2] * inv_l1 * invT;
 
+  const double invB = 1.0 / (double)P.B;
+  constexpr int KC = 18;   // cached variant: <= 18 positions per thread (D2: P3 has 96*96 = 18 * 512 positions)
+  if (n <= KC * kLvlThreads && blockDim.x == kLvlThreads) {
+    // passes 3-6 with the two exponentials of every position kept in registers (8 -> 2 double exp per position)
+    double es[KC], et[KC];
+    double z[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int i = threadIdx.x + k * kLvlThreads;
+      es[k] = et[k] = 0.0;
+      if (i < n) {
+        es[k] = exp(as[i] * inv_s * invT - max_zs);
+        et[k] = exp(teacher_m(i) * inv_l1 * invT - max_zt);
+        z[0] += es[k];
+        z[1] += et[k];
+      }
+    }
+    block_reduce<2>(z, 0u, s_red);
+    const double inv_zs = 1.0 / z[0], inv_zt = 1.0 / z[1], log_zt = log(z[1]);
+    double r4[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int i = threadIdx.x + k * kLvlThreads;
+      if (i < n) {
+        const double s = es[k] * inv_zs, t = et[k] * inv_zt;
+        const double zt = teacher_m(i) * inv_l1 * invT - max_zt;
+        r4[0] += t * ((zt - log_zt) - s);
+        r4[1] += -t * invB * s;
+      }
+    }
+    block_reduce<2>(r4, 0u, s_red);
+    if (threadIdx.x == 0) P.loss_b[(call * P.n_levels + l) * P.B + b] = (float)r4[0];
+    if (P.ga == nullptr) return;
+    const double gs = r4[1];
+    double r5[1] = {0.0};
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int i = threadIdx.x + k * kLvlThreads;
+      if (i < n) {
+        const double ah = as[i] * inv_s;
+        const double dah = (es[k] * inv_zs) * (-(et[k] * inv_zt) * invB - gs) * invT;
+        es[k] = dah;   // d a^ replaces the exponential
+        r5[0] += ah * dah;
+      }
+    }
+    block_reduce<1>(r5, 0u, s_red);
+    const bool clamped = !(nrm_s_raw > 1e-12);
+    float* __restrict__ ga = P.ga + (long long)call * P.Btot + off;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int i = threadIdx.x + k * kLvlThreads;
+      if (i < n) {
+        const double ah = as[i] * inv_s;
+        ga[i] = (float)(clamped ? es[k] * inv_s : (es[k] - ah * r5[0]) * inv_s);
+      }
+    }
+    return;
+  }
+
   // pass 3: softmax denominators
   double z[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -241,7 +301,6 @@ __global__ void __launch_bounds__(kLvlThreads) mta_level_kernel(const __grid_con
   const double inv_zs = 1.0 / z[0], inv_zt = 1.0 / z[1], log_zt = log(z[1]);
 
   // pass 4: loss_b = sum t (log t - s)   (kl_div with a PROBABILITY input: MTALoss.py:62-72), and <g, s>
-  const double invB = 1.0 / (double)P.B;
   double r4[2] = {0.0, 0.0};
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double s = exp(as[i] * inv_s * invT - max_zs) * inv_zs;
@@ -489,7 +548,7 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   const int ncalls = a->separate ? a->n_teachers : 1;
   {
     ProfScope prof(PK_MTA_LEVEL, 0.0, stream);
-    mta_level_kernel<<<dim3(a->B, a->n_levels, ncalls), kLvlThreads, 0, stream>>>(lp);
+    mta_level_kernel<<<dim3(a->B, ncalls, a->n_levels), kLvlThreads, 0, stream>>>(lp);
   }
   MMD_LAUNCH_CHECK();
   {
