@@ -314,15 +314,17 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = timed(e2e_step, args.steps)
 
     # per-kernel CUDA-event timing of the same step (separate instrumented pass: event pairs around every launch)
+    # (every rank runs the instrumented steps: they contain the gradient all-reduce; rank 0 reports its own timings)
     roof = None
+    _lib.prof_enable(True)
+    _lib.prof_collect()
+    nprof = min(args.steps, 5)
+    for _ in range(nprof):
+        eager_step()
+    prof = _lib.prof_collect()
+    _lib.prof_enable(False)
+    barrier()
     if rank == 0:
-        _lib.prof_enable(True)
-        _lib.prof_collect()
-        nprof = min(args.steps, 5)
-        for _ in range(nprof):
-            eager_step()
-        prof = _lib.prof_collect()
-        _lib.prof_enable(False)
         peak, peak_src = peaks()
         total_ms = sum(v["ms"] for v in prof.values())
         dom = max(prof, key=lambda k: prof[k]["ms"])

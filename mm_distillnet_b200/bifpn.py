@@ -299,7 +299,7 @@ class _Plan:
     def _train_storage(self, op):
         self._packed_storage(op)
         if self.train:
-            op.stats = (B_PERSIST, self.persist.alloc(2 * self.Cc * 8))
+            op.stats = (B_PERSIST, self.persist.alloc(_lib.STATS_REPLICAS * 2 * self.Cc * 8))
             op.counter = (B_PERSIST, self.persist.alloc(4))
             op.bwd_counter = (B_PERSIST, self.persist.alloc(4))
 

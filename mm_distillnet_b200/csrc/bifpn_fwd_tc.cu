@@ -92,8 +92,9 @@ __device__ __forceinline__ void bn_finalize_tc(const NodeFwdP& P, double st_sum,
   const int tid = threadIdx.x;
   const TileGeom& g = P.g;
   if (tid < C) {
-    atomicAdd(P.stats + tid, st_sum);
-    atomicAdd(P.stats + C + tid, st_sq);
+    double* rep = P.stats + (blockIdx.x & (MMD_STATS_REPLICAS - 1)) * (2 * C);   // spread the same-address atomics
+    atomicAdd(rep + tid, st_sum);
+    atomicAdd(rep + C + tid, st_sq);
   }
   __threadfence();
   __syncthreads();
@@ -106,8 +107,14 @@ __device__ __forceinline__ void bn_finalize_tc(const NodeFwdP& P, double st_sum,
   __threadfence();
   if (tid < C) {
     const double n = (double)g.B * g.H * g.W;
-    const double mean = __ldcg(P.stats + tid) / n;
-    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
+    double sum = 0.0, sq = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      sum += __ldcg(P.stats + r * (2 * C) + tid);
+      sq += __ldcg(P.stats + r * (2 * C) + C + tid);
+    }
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
     const float scale = P.bn_w[tid] * invstd;
@@ -118,8 +125,11 @@ __device__ __forceinline__ void bn_finalize_tc(const NodeFwdP& P, double st_sum,
     const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
     P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
     P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
-    P.stats[tid] = 0.0;
-    P.stats[C + tid] = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      P.stats[r * (2 * C) + tid] = 0.0;
+      P.stats[r * (2 * C) + C + tid] = 0.0;
+    }
   }
   if (tid == 0) {
     *P.counter = 0u;

@@ -444,8 +444,9 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
       s += s_red[(k * (C / 2) + (tid >> 1)) * 4 + (tid & 1)];
       q += s_red[(k * (C / 2) + (tid >> 1)) * 4 + 2 + (tid & 1)];
     }
-    atomicAdd(P.stats + tid, s);
-    atomicAdd(P.stats + C + tid, q);
+    double* rep = P.stats + (cta & (MMD_STATS_REPLICAS - 1)) * (2 * C);   // spread the same-address atomics
+    atomicAdd(rep + tid, s);
+    atomicAdd(rep + C + tid, q);
   }
   __threadfence();
   __syncthreads();
@@ -458,8 +459,14 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   __threadfence();
   if (tid < C) {
     const double n = (double)P.g.B * H * W;
-    const double mean = __ldcg(P.stats + tid) / n;
-    double var = __ldcg(P.stats + C + tid) / n - mean * mean;
+    double sum = 0.0, sq = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      sum += __ldcg(P.stats + r * (2 * C) + tid);
+      sq += __ldcg(P.stats + r * (2 * C) + C + tid);
+    }
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)P.bn_eps));
     const float scale = P.bn_w[tid] * invstd;
@@ -470,8 +477,11 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
     P.bn_rm[tid] = (1.f - P.bn_mom) * P.bn_rm[tid] + P.bn_mom * (float)mean;
     P.bn_rv[tid] = (1.f - P.bn_mom) * P.bn_rv[tid] + P.bn_mom * (float)unbiased;
-    P.stats[tid] = 0.0;
-    P.stats[C + tid] = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      P.stats[r * (2 * C) + tid] = 0.0;
+      P.stats[r * (2 * C) + C + tid] = 0.0;
+    }
   }
   if (tid == 0) {
     *P.counter = 0u;
