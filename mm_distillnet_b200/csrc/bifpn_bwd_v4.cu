@@ -305,14 +305,17 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
     const int o = 32 * (warp & 3) + lane;
     const int col0 = (warp >> 2) * 64;
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 128u + (uint32_t)col0;
+    // every CTA adds into the same 112 x 113 gradient entries: each starts at another column group (rotation by the
+    // block index) so that concurrent CTAs hit different addresses of the L2 atomic units
+    const int rot = (int)(blockIdx.x & 7u);
     float acc[8][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
+    for (int j = 0; j < 8; ++j) tc::tmem_ld8(taddr + 8 * ((j + rot) & 7), acc[j]);
     tc::tmem_ld_wait();
     if (o < C) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int i0 = col0 + 8 * j;
+        const int i0 = col0 + 8 * ((j + rot) & 7);
         if (i0 < C) {
           red_add_v4(P.g_pw + o * C + i0, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
           red_add_v4(P.g_pw + o * C + i0 + 4, acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
@@ -838,14 +841,19 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
   }
   __syncthreads();
   const float* tot = s_red + S::kActive * S::NACC;
-  for (int idx = tid; idx < C * 9; idx += S::kBlock) {   // depthwise weight gradient [C][3][3]
+  // (all CTAs add into the same addresses: each starts at another offset so that concurrent CTAs spread over the L2
+  //  atomic units instead of queueing on one address)
+  const int rot9 = (int)((blockIdx.x * 131u) % (unsigned)(C * 9));
+  for (int k = tid; k < C * 9; k += S::kBlock) {   // depthwise weight gradient [C][3][3]
+    int idx = k + rot9;
+    if (idx >= C * 9) idx -= C * 9;
     const int c = idx / 9, t9 = idx - c * 9;
     if (P.g_dw) atomicAdd(P.g_dw + idx, tot[(c >> 1) * S::NACC + 2 * t9 + (c & 1)]);
   }
   if (tid < C) {
     // slots: (sum du*mask, sum du*mask*xhat) per input edge; xhat = (raw - mean) * invstd for a deferred-BN input,
     // the (final) value itself otherwise
-    const int c = tid;
+    const int c = (tid + (int)((blockIdx.x * 29u) % (unsigned)C)) % C;
     const float* tp = tot + (c >> 1) * S::NACC + (c & 1);
     const double s1 = tp[18], s2a = tp[20], s2b = tp[22], s1p = tp[24], s2p = tp[26], s2m = tp[28];
     for (int i = 0; i < P.n_in; ++i) {
