@@ -234,6 +234,7 @@ int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16,
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead
 int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
 int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
+int launch_bnapply_multi(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s);   // n networks in one launch
 int launch_node_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
 int launch_proj_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
 int launch_pull(const NodeBwdP& p, int C, int dtype, cudaStream_t s);

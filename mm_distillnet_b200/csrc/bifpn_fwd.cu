@@ -328,7 +328,20 @@ __global__ void __launch_bounds__(kThreads, 2) proj_fwd_kernel(const __grid_cons
 
 // ---- materialise [pool](scale*x + shift) -------------------------------------------------------------------
 template <typename T, int C>
+__device__ __forceinline__ void bnapply_body(const NodeFwdP& P);
+
+template <typename T, int C>
 __global__ void __launch_bounds__(kThreads) bnapply_kernel(const __grid_constant__ NodeFwdP P) {
+  bnapply_body<T, C>(P);
+}
+// the same op of up to 4 networks (student + teachers) in one launch: blockIdx.y selects the network
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads) bnapply_multi_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+  bnapply_body<T, C>(BATCH.p[blockIdx.y]);
+}
+
+template <typename T, int C>
+__device__ __forceinline__ void bnapply_body(const NodeFwdP& P) {
   constexpr int NQ = C / 4;
   const TileGeom g = P.g;
   const long long total = (long long)g.B * g.H * g.W * NQ;
@@ -407,6 +420,23 @@ static int launch_proj_fwd_t(const NodeFwdP& p, cudaStream_t s) {
 }
 
 template <typename T>
+static int launch_bnapply_multi_t(const NodeFwdP* p, int n, cudaStream_t s) {
+  constexpr int C = 112;
+  NodeFwdBatch batch;
+  double bytes = 0.0;
+  for (int i = 0; i < kMaxBatchNets; ++i) batch.p[i] = p[i < n ? i : 0];
+  for (int i = 0; i < n; ++i) bytes += node_algo_bytes(p[i].in, 1, p[i].g, C, sizeof(T));
+  long long total = (long long)p[0].g.B * p[0].g.H * p[0].g.W * (C / 4);
+  long long grid = (total + kThreads - 1) / kThreads;
+  if (grid > 8LL * num_sms() / n) grid = 8LL * num_sms() / n;
+  if (grid < 1) grid = 1;
+  ProfScope prof(PK_BNAPPLY, bytes, s);
+  bnapply_multi_kernel<T, C><<<dim3((unsigned)grid, n), kThreads, 0, s>>>(batch);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
 static int launch_bnapply_t(const NodeFwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   long long total = (long long)p.g.B * p.g.H * p.g.W * (C / 4);
@@ -443,5 +473,13 @@ int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) {
   MMD_DISPATCH(launch_proj_fwd_t)
 }
 int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_bnapply_t) }
+int launch_bnapply_multi(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "bnapply: %d networks in one launch", n);
+  if (dtype == MMD_F32) return launch_bnapply_multi_t<float>(p, n, s);
+  if (dtype == MMD_BF16) return launch_bnapply_multi_t<__nv_bfloat16>(p, n, s);
+  set_error("unsupported dtype %d", dtype);
+  return MMD_E_ARG;
+}
 
 }  // namespace mmd

@@ -117,9 +117,10 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
     for (int l = 0; l < n_lists; ++l) {
       if (done[l] || i >= n_ops[l]) continue;
       const MmdOp& op = ops[l][i];
-      const bool batchable = dtype == MMD_BF16 && !tc_disabled() &&
-                             (op.kind == MMD_OP_NODE_FWD || op.kind == MMD_OP_POOLFUSE ||
-                              (op.kind == MMD_OP_PROJ_FWD && op.Cin % 8 == 0));
+      const bool batchable = (dtype == MMD_BF16 && !tc_disabled() &&
+                              (op.kind == MMD_OP_NODE_FWD || op.kind == MMD_OP_POOLFUSE ||
+                               (op.kind == MMD_OP_PROJ_FWD && op.Cin % 8 == 0))) ||
+                             op.kind == MMD_OP_BNAPPLY;
       NodeFwdP ps[kMaxBatchNets];
       int members[kMaxBatchNets], n = 0;
       if (batchable) {
@@ -127,6 +128,7 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
           if (done[m] || i >= n_ops[m]) continue;
           const MmdOp& om = ops[m][i];
           if (om.kind != op.kind || om.out.H != op.out.H || om.out.W != op.out.W || om.Cin != op.Cin) continue;
+          if (op.kind == MMD_OP_BNAPPLY && (om.mode[0] != op.mode[0] || om.in[0].H != op.in[0].H || om.in[0].W != op.in[0].W)) continue;
           Bases Bm{bases[m], n_bases[m]};
           int rc = fill_fwd(om, Bm, batch, ps[n]);
           if (rc) return rc;
@@ -137,6 +139,7 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
       if (n >= 2) {
         int rc = (op.kind == MMD_OP_NODE_FWD)   ? launch_node_fwd_v4(ps, n, C, stream)
                  : (op.kind == MMD_OP_POOLFUSE) ? launch_poolfuse(ps, n, C, stream)
+                 : (op.kind == MMD_OP_BNAPPLY)  ? launch_bnapply_multi(ps, n, C, dtype, stream)
                                                 : launch_proj_fwd_tc_multi(ps, n, C, stream);
         if (rc) return rc;
         for (int k = 0; k < n; ++k) done[members[k]] = true;
