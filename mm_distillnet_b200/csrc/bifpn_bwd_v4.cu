@@ -68,10 +68,13 @@ __device__ __forceinline__ TilePos tile_pos(int tile, int tiles_x, int tiles_y, 
 template <int TW, int TH>
 struct CfgA {
   static constexpr int NP = TW * TH;
-  static constexpr int kGroup = 128 * 16;                 // one channel group of an operand tile: [128 rows][8] bf16
+  // one channel group of an operand tile: [128 rows][8] bf16, + 16 bytes of padding: the tile loader's lanes write
+  // consecutive channel groups of one row (2048-byte stride = the same banks for all 14 lanes: ncu counted 3.1 M
+  // conflict wavefronts of 3.8 M at P3)
+  static constexpr int kGroup = 128 * 16 + 16;
   static constexpr int offGy = 0;                          // dy tile, 14 groups
   static constexpr int offD = NG * kGroup;                 // d tile, 16 groups (14: all-ones column, 15: zeros); must follow dy
-  static constexpr int offB = offD + 16 * kGroup;
+  static constexpr int offB = up128(offD + 16 * kGroup);
   static constexpr int offCoef = offB + up128(C * C * 2);
   static constexpr int offBar = offCoef + 3 * C * 4;
   static constexpr int kBytes = offBar + 64;
@@ -339,8 +342,8 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
 template <int TW, int TH, int NC>
 struct CfgP {
   static constexpr int NP = TW * TH;
-  static constexpr int kGroup = 128 * 16;
-  static constexpr int kXStride = kGroup + 16;             // padded: the tile loader writes consecutive channel groups
+  static constexpr int kGroup = 128 * 16 + 16;             // dy tile: padded like CfgA::kGroup
+  static constexpr int kXStride = 128 * 16 + 16;           // padded: the tile loader writes consecutive channel groups
   static constexpr int NXG = NC / 8 + 2;                   // x tile groups: NC/8 data, one all-ones column group, one zero
   static constexpr int N2 = NC + 16;
   static constexpr int offGy = 0;
