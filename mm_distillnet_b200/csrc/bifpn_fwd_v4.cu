@@ -551,15 +551,6 @@ __device__ __forceinline__ void pool_pair(const bf16* __restrict__ src, const in
   }
 }
 
-// second-input coefficients of a channel group from the [scale | shift][half][group][4] layout (four float4 loads)
-__device__ __forceinline__ void load_b_coefs(const float* s_b, int cg, float (&bsc)[8], float (&bsh)[8]) {
-  const float4* b4 = reinterpret_cast<const float4*>(s_b);
-  const float4 s0 = b4[(0 * 2 + 0) * NG + cg], s1 = b4[(0 * 2 + 1) * NG + cg];
-  const float4 h0 = b4[(1 * 2 + 0) * NG + cg], h1 = b4[(1 * 2 + 1) * NG + cg];
-  bsc[0] = s0.x; bsc[1] = s0.y; bsc[2] = s0.z; bsc[3] = s0.w; bsc[4] = s1.x; bsc[5] = s1.y; bsc[6] = s1.z; bsc[7] = s1.w;
-  bsh[0] = h0.x; bsh[1] = h0.y; bsh[2] = h0.z; bsh[3] = h0.w; bsh[4] = h1.x; bsh[5] = h1.y; bsh[6] = h1.z; bsh[7] = h1.w;
-}
-
 // Fast path for a pooled input that holds FINAL values and needs no arg-max record (frozen teachers: BatchNorm is folded
 // into the 1x1 weights, nothing is saved for a backward): the window maximum is taken on the packed bf16 pairs directly
 // (HMNMX2.BF16, one instruction per two channels, no expansion / tagging).
@@ -630,12 +621,8 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
     const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
     s_c[c] = bn0 ? bn0[c] : 1.f;
     s_c[C + c] = bn0 ? bn0[C + c] : 0.f;
-    // second input: [scale | shift][channel half][channel group][4] so that the 14 channel groups of a warp read 14
-    // consecutive float4 (the plain [C] layout put every lane 32 bytes apart: 4-way bank conflicts on 16 scalar loads
-    // per output, 2.9 M conflict wavefronts in the P3 -> P4 launch)
-    const int cgc = c >> 3, hc = (c >> 2) & 1, kc = c & 3;
-    s_c[2 * C + ((0 * 2 + hc) * NG + cgc) * 4 + kc] = (bn1 ? bn1[c] : 1.f) * wb;
-    s_c[2 * C + ((1 * 2 + hc) * NG + cgc) * 4 + kc] = (bn1 ? bn1[C + c] : 0.f) * wb;
+    s_c[2 * C + c] = (bn1 ? bn1[c] : 1.f) * wb;
+    s_c[3 * C + c] = (bn1 ? bn1[C + c] : 0.f) * wb;
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -672,11 +659,7 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
         const bool has_pad = o ? pB : pA;
         const long long oo = (((long long)b * H + y) * W + x0 + o) * C + 8 * cg;
         uint4 sm = make_uint4(0u, 0u, 0u, 0u);
-        float bsc[8], bsh[8];
-        if (same != nullptr) {
-          sm = __ldg(reinterpret_cast<const uint4*>(same + oo));
-          load_b_coefs(s_c + 2 * C, cg, bsc, bsh);
-        }
+        if (same != nullptr) sm = __ldg(reinterpret_cast<const uint4*>(same + oo));
         const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
         uint32_t pk[4];
 #pragma unroll
@@ -685,8 +668,8 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
           float2 u = mul2(bf2_to_f2(m), make_float2(wa, wa));
           if (same != nullptr) {
             const float2 f = bf2_to_f2(sw[e]);
-            u.x += fmaf(f.x, bsc[2 * e], bsh[2 * e]);
-            u.y += fmaf(f.y, bsc[2 * e + 1], bsh[2 * e + 1]);
+            u.x += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+            u.y += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
           }
           pk[e] = f2_to_bf2(u);
         }
@@ -729,13 +712,11 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
       if (same != nullptr) {
         const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + oo));
         const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-        float bsc[8], bsh[8];
-        load_b_coefs(s_c + 2 * C, cg, bsc, bsh);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = bf2_to_f2(w[e]);
-          u[2 * e] += fmaf(f.x, bsc[2 * e], bsh[2 * e]);
-          u[2 * e + 1] += fmaf(f.y, bsc[2 * e + 1], bsh[2 * e + 1]);
+          u[2 * e] += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+          u[2 * e + 1] += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
         }
       }
       uint4 pk;
