@@ -216,6 +216,18 @@ __device__ __forceinline__ void load_input(const TensorP& t, int mode, int b, in
   arg = a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24);
 }
 
+// independent small ops of ONE network (the 5 output BNAPPLYs of a training stack, the 5 SLOT ops that open its
+// backward) share a launch: blockIdx.y selects the op, every op keeps its own geometry
+constexpr int kMaxGroupOps = 6;
+struct NodeFwdGroup {
+  NodeFwdP p[kMaxGroupOps];
+};
+struct NodeBwdGroup {
+  NodeBwdP p[kMaxGroupOps];
+};
+int launch_bnapply_group(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s);
+int launch_slot_group(const NodeBwdP* p, int n, int C, int dtype, cudaStream_t s);
+
 // kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)
 int launch_node_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);
 int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16, tcgen05 pointwise conv

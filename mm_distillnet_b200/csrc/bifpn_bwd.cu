@@ -533,7 +533,20 @@ __global__ void __launch_bounds__(kThreads) pull_kernel(const __grid_constant__ 
 // ---- slot for a deferred tensor consumed by a BNAPPLY op: (sum G, sum G * xhat) -------------------------------
 // P.g = geometry of G (the BNAPPLY output); P.in[0] = the deferred source, P.mode[0] how it was read; P.cons[0].du = G.
 template <typename T, int C>
+__device__ __forceinline__ void slot_body(const NodeBwdP& P);
+
+template <typename T, int C>
 __global__ void __launch_bounds__(kThreads) slot_kernel(const __grid_constant__ NodeBwdP P) {
+  slot_body<T, C>(P);
+}
+// the independent SLOT ops that open a backward in one launch: blockIdx.y selects the op
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads) slot_group_kernel(const __grid_constant__ NodeBwdGroup GROUP) {
+  slot_body<T, C>(GROUP.p[blockIdx.y]);
+}
+
+template <typename T, int C>
+__device__ __forceinline__ void slot_body(const NodeBwdP& P) {
   constexpr int NQ = C / 4;
   constexpr int ROWS = kThreads / NQ;
   __shared__ float s_red[ROWS * NQ * 8];
@@ -668,6 +681,27 @@ static int launch_pull_t(const NodeBwdP& p, cudaStream_t s) {
 }
 
 template <typename T>
+static int launch_slot_group_t(const NodeBwdP* p, int n, cudaStream_t s) {
+  constexpr int C = 112;
+  NodeBwdGroup group;
+  double bytes = 0.0;
+  long long maxpos = 0;
+  for (int i = 0; i < kMaxGroupOps; ++i) group.p[i] = p[i < n ? i : 0];
+  for (int i = 0; i < n; ++i) {
+    const long long npos = (long long)p[i].g.B * p[i].g.H * p[i].g.W;
+    bytes += 2.0 * npos * C * sizeof(T);
+    if (npos > maxpos) maxpos = npos;
+  }
+  long long grid = (maxpos + 9 * 8 - 1) / (9 * 8);
+  if (grid > 4LL * sm_count()) grid = 4LL * sm_count();
+  if (grid < 1) grid = 1;
+  ProfScope prof(PK_SLOT, bytes, s);
+  slot_group_kernel<T, C><<<dim3((unsigned)grid, n), kThreads, 0, s>>>(group);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
 static int launch_slot_t(const NodeBwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   long long npos = (long long)p.g.B * p.g.H * p.g.W;
@@ -691,5 +725,13 @@ int launch_node_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s) { MMD_D
 int launch_proj_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_proj_bwd_t) }
 int launch_pull(const NodeBwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_pull_t) }
 int launch_slot(const NodeBwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_slot_t) }
+int launch_slot_group(const NodeBwdP* p, int n, int C, int dtype, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxGroupOps, "slot group of %d ops", n);
+  if (dtype == MMD_F32) return launch_slot_group_t<float>(p, n, s);
+  if (dtype == MMD_BF16) return launch_slot_group_t<__nv_bfloat16>(p, n, s);
+  set_error("unsupported dtype %d", dtype);
+  return MMD_E_ARG;
+}
 
 }  // namespace mmd

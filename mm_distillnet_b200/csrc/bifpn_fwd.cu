@@ -340,6 +340,12 @@ __global__ void __launch_bounds__(kThreads) bnapply_multi_kernel(const __grid_co
   bnapply_body<T, C>(BATCH.p[blockIdx.y]);
 }
 
+// several independent ops of one network in one launch: blockIdx.y selects the op (each with its own geometry)
+template <typename T, int C>
+__global__ void __launch_bounds__(kThreads) bnapply_group_kernel(const __grid_constant__ NodeFwdGroup GROUP) {
+  bnapply_body<T, C>(GROUP.p[blockIdx.y]);
+}
+
 template <typename T, int C>
 __device__ __forceinline__ void bnapply_body(const NodeFwdP& P) {
   constexpr int NQ = C / 4;
@@ -437,6 +443,27 @@ static int launch_bnapply_multi_t(const NodeFwdP* p, int n, cudaStream_t s) {
 }
 
 template <typename T>
+static int launch_bnapply_group_t(const NodeFwdP* p, int n, cudaStream_t s) {
+  constexpr int C = 112;
+  NodeFwdGroup group;
+  double bytes = 0.0;
+  long long maxtotal = 0;
+  for (int i = 0; i < kMaxGroupOps; ++i) group.p[i] = p[i < n ? i : 0];
+  for (int i = 0; i < n; ++i) {
+    bytes += node_algo_bytes(p[i].in, 1, p[i].g, C, sizeof(T));
+    const long long total = (long long)p[i].g.B * p[i].g.H * p[i].g.W * (C / 4);
+    if (total > maxtotal) maxtotal = total;
+  }
+  long long grid = (maxtotal + kThreads - 1) / kThreads;
+  if (grid > 8LL * num_sms()) grid = 8LL * num_sms();
+  if (grid < 1) grid = 1;
+  ProfScope prof(PK_BNAPPLY, bytes, s);
+  bnapply_group_kernel<T, C><<<dim3((unsigned)grid, n), kThreads, 0, s>>>(group);
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
 static int launch_bnapply_t(const NodeFwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   long long total = (long long)p.g.B * p.g.H * p.g.W * (C / 4);
@@ -473,6 +500,14 @@ int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s) {
   MMD_DISPATCH(launch_proj_fwd_t)
 }
 int launch_bnapply(const NodeFwdP& p, int C, int dtype, cudaStream_t s) { MMD_DISPATCH(launch_bnapply_t) }
+int launch_bnapply_group(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxGroupOps, "bnapply group of %d ops", n);
+  if (dtype == MMD_F32) return launch_bnapply_group_t<float>(p, n, s);
+  if (dtype == MMD_BF16) return launch_bnapply_group_t<__nv_bfloat16>(p, n, s);
+  set_error("unsupported dtype %d", dtype);
+  return MMD_E_ARG;
+}
 int launch_bnapply_multi(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "bnapply: %d networks in one launch", n);

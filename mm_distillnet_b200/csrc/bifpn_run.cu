@@ -103,6 +103,43 @@ using namespace mmd;
 
 static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream);
 
+static bool same_ref(const MmdRef& a, const MmdRef& b) { return a.base >= 0 && a.base == b.base && a.off == b.off; }
+
+// Number of consecutive ops starting at `i` that may share ONE launch: BNAPPLY ops none of which reads the output of an
+// earlier one of the run (the 5 output normalisations of a training stack), or SLOT ops (always independent).
+static int group_len(const MmdOp* ops, int i, int n_ops) {
+  const int kind = ops[i].kind;
+  if (kind != MMD_OP_BNAPPLY && kind != MMD_OP_SLOT) return 1;
+  int n = 1;
+  while (i + n < n_ops && n < kMaxGroupOps && ops[i + n].kind == kind) {
+    bool dep = false;
+    if (kind == MMD_OP_BNAPPLY)
+      for (int k = 0; k < n; ++k) dep = dep || same_ref(ops[i + n].in[0].data, ops[i + k].out.data);
+    if (dep) break;
+    ++n;
+  }
+  return n;
+}
+
+// launches ops[i .. i+n) (n >= 2, from group_len) together
+static int run_group(const MmdOp* ops, int i, int n, const Bases& B, int batch, int C, int dtype, cudaStream_t stream) {
+  int rc = 0;
+  if (ops[i].kind == MMD_OP_BNAPPLY) {
+    NodeFwdP ps[kMaxGroupOps];
+    for (int k = 0; k < n; ++k)
+      if ((rc = fill_fwd(ops[i + k], B, batch, ps[k]))) return rc;
+    return launch_bnapply_group(ps, n, C, dtype, stream);
+  }
+  NodeBwdP ps[kMaxGroupOps];
+  for (int k = 0; k < n; ++k) {
+    const MmdOp& op = ops[i + k];
+    if ((rc = fill_bwd(op, B, batch, ps[k]))) return rc;
+    MMD_CHECK_ARG(ps[k].in[0].data && ps[k].in[0].bn && ps[k].in_slot[0] && op.n_cons == 1, "slot op %d: missing storage", i + k);
+    if (op.mode[0] == MMD_IN_POOL) MMD_CHECK_ARG(ps[k].pidx[0] != nullptr, "slot op %d: no arg-max indices", i + k);
+  }
+  return launch_slot_group(ps, n, C, dtype, stream);
+}
+
 extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops, void* const* const* bases,
                                    const int32_t* n_bases, int32_t n_lists, int32_t batch, int32_t C, int32_t dtype,
                                    mmd_stream_t stream_) {
@@ -112,10 +149,11 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run_multi: dtype %d", dtype);
   int max_n = 0;
   for (int l = 0; l < n_lists; ++l) max_n = n_ops[l] > max_n ? n_ops[l] : max_n;
+  int grouped_until[kMaxBatchNets] = {0, 0, 0, 0};   // ops below this index already ran as part of a group launch
   for (int i = 0; i < max_n; ++i) {
     bool done[kMaxBatchNets] = {false, false, false, false};
     for (int l = 0; l < n_lists; ++l) {
-      if (done[l] || i >= n_ops[l]) continue;
+      if (done[l] || i >= n_ops[l] || i < grouped_until[l]) continue;
       const MmdOp& op = ops[l][i];
       const bool batchable = (dtype == MMD_BF16 && !tc_disabled() &&
                               (op.kind == MMD_OP_NODE_FWD || op.kind == MMD_OP_POOLFUSE ||
@@ -125,7 +163,7 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
       int members[kMaxBatchNets], n = 0;
       if (batchable) {
         for (int m = l; m < n_lists; ++m) {
-          if (done[m] || i >= n_ops[m]) continue;
+          if (done[m] || i >= n_ops[m] || i < grouped_until[m]) continue;
           const MmdOp& om = ops[m][i];
           if (om.kind != op.kind || om.out.H != op.out.H || om.out.W != op.out.W || om.Cin != op.Cin) continue;
           if (op.kind == MMD_OP_BNAPPLY && (om.mode[0] != op.mode[0] || om.in[0].H != op.in[0].H || om.in[0].W != op.in[0].W)) continue;
@@ -146,8 +184,10 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
       }
       if (!done[l]) {
         Bases Bl{bases[l], n_bases[l]};
-        int rc = run_one(op, i, Bl, batch, C, dtype, stream);
+        const int g = group_len(ops[l], i, n_ops[l]);
+        int rc = (g >= 2) ? run_group(ops[l], i, g, Bl, batch, C, dtype, stream) : run_one(op, i, Bl, batch, C, dtype, stream);
         if (rc) return rc;
+        if (g >= 2) grouped_until[l] = i + g;
         done[l] = true;
       }
     }
@@ -163,9 +203,11 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
   MMD_CHECK_ARG(C == 112, "mmd_bifpn_run: kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
   Bases B{bases, n_bases};
-  for (int i = 0; i < n_ops; ++i) {
-    int rc = run_one(ops[i], i, B, batch, C, dtype, stream);
+  for (int i = 0; i < n_ops;) {
+    const int g = group_len(ops, i, n_ops);
+    int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream) : run_one(ops[i], i, B, batch, C, dtype, stream);
     if (rc) return rc;
+    i += g;
   }
   return 0;
 }
