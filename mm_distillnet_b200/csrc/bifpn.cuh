@@ -115,6 +115,9 @@ struct NodeFwdBatch {
   // 1-D grids (node_fwd_v4 / poolfuse): network k owns CTAs [cta_begin[k], cta_begin[k+1]) — a train-mode network
   // (statistics, saved tensors, arg-max records) gets a larger share than a frozen one, see batch_shares()
   int cta_begin[kMaxBatchNets + 1];
+  // node_fwd_v4 with the POOLFUSE pre-pass folded in (small pyramid levels, see launch_node_fwd_v4_pre): the pre-pass op
+  // of every network; its output tile is built in shared memory by the node kernel itself
+  NodeFwdP pre[kMaxBatchNets];
 };
 // split `budget` CTAs over the n networks of a lockstep launch: weight `train_w` for networks with p.train != 0, 1 for
 // the others; at least 1 and at most `max_per_net` CTAs each
@@ -235,6 +238,9 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);       // bf16,
 bool fwd_v4_usable(const NodeFwdP& p);
 int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s);
 int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s);
+// POOLFUSE + NODE_FWD of a small level (<= 24x24) as ONE launch: `pre[i]` is the pre-pass whose output is node[i].in[1]
+bool fwd_v4_pre_usable(const NodeFwdP& pre, const NodeFwdP& node);
+int launch_node_fwd_v4_pre(const NodeFwdP* node, const NodeFwdP* pre, int n, int C, cudaStream_t s);
 // bf16 backward, compile-time tile geometry (bifpn_bwd_v4.cu)
 bool bwd_v4_usable(const NodeBwdP& p);
 int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);

@@ -552,6 +552,12 @@ __device__ __forceinline__ void slot_body(const NodeBwdP& P) {
   __shared__ float s_red[ROWS * NQ * 8];
   const TileGeom g = P.g;
   const int tid = threadIdx.x;
+  // a group launch sizes the grid for its largest op: the blocks an op does not need leave at once (every block ends
+  // with 2*C double atomics onto the same addresses)
+  const long long npos = (long long)g.B * g.H * g.W;
+  const long long want = (npos + 9 * 8 - 1) / (9 * 8);
+  const int nblk = (int)(want < (long long)gridDim.x ? (want < 1 ? 1 : want) : (long long)gridDim.x);
+  if ((int)blockIdx.x >= nblk) return;
   const bool active = tid < ROWS * NQ;
   const int q = tid % NQ, prow = tid / NQ;
   const T* G = reinterpret_cast<const T*>(P.cons[0].du);
@@ -562,9 +568,8 @@ __device__ __forceinline__ void slot_body(const NodeBwdP& P) {
   if (active) {
     const float4 mu = *reinterpret_cast<const float4*>(bn + 2 * C + 4 * q);
     const float4 is = *reinterpret_cast<const float4*>(bn + 3 * C + 4 * q);
-    const long long npos = (long long)g.B * g.H * g.W;
     const int top = pool_pad_before(Hs), left = pool_pad_before(Ws);
-    for (long long pos = (long long)blockIdx.x * ROWS + prow; pos < npos; pos += (long long)gridDim.x * ROWS) {
+    for (long long pos = (long long)blockIdx.x * ROWS + prow; pos < npos; pos += (long long)nblk * ROWS) {
       const int x = (int)(pos % g.W);
       const int y = (int)((pos / g.W) % g.H);
       const int b = (int)(pos / ((long long)g.W * g.H));

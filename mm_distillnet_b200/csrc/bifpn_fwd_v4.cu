@@ -233,7 +233,100 @@ __device__ __forceinline__ void phase2(const unsigned char* r0, unsigned char* r
   }
 }
 
+// ---- inline pooling pre-pass (small levels): the POOLFUSE operand of one tile (+ halo) built straight in region 1 ------
+// out = w_a * maxpool3x3s2(bn_a(src)) [+ w_b * bn_b(same)], rounded to bf16 exactly as poolfuse_kernel stores it.  Window
+// scan in row-major order, strict '>' (first maximum wins), zero padding takes part with index 9 (MaxPool2dStaticSamePadding,
+// src/YetAnotherEfficientNet.py:90-104) — the comparison form of load_input().  In training the operand, the arg-max bytes
+// and the raw value at the arg-max of the tile's own positions also go to HBM for the backward.
 template <int TW, int TH>
+__device__ __forceinline__ void inline_pool_tile(const NodeFwdP& Q, const float* s_pc, unsigned char* r1, const TilePos t,
+                                                 const int H, const int W, const int tid, const float wa) {
+  using S = Cfg<TW, TH>;
+  const bf16* __restrict__ src = reinterpret_cast<const bf16*>(Q.in[0].data);
+  const bf16* __restrict__ same = (Q.n_in >= 2) ? reinterpret_cast<const bf16*>(Q.in[1].data) : nullptr;
+  const int SH = Q.in[0].H, SWd = Q.in[0].W;
+  bf16* __restrict__ aux = reinterpret_cast<bf16*>(Q.out);
+  unsigned char* __restrict__ pidx = Q.pidx[0];
+  bf16* __restrict__ praw = reinterpret_cast<bf16*>(Q.save_d);
+  const bool record = (pidx != nullptr) || (praw != nullptr);
+  const int top = pool_pad_before(SH), left = pool_pad_before(SWd);
+  for (int item = tid; item < S::NH * NG; item += kThreads) {
+    const int hp = item / NG, cg = item - hp * NG;
+    const int hy = hp / S::HW2, hx = hp - hy * S::HW2;
+    const int y = t.ty0 - 1 + hy, x = t.tx0 - 1 + hx;
+    if (y < 0 || y >= H || x < 0 || x >= W) continue;   // phase 1 replaces out-of-image positions by zero
+    float sc[8], sh[8], best[8], braw[8];
+    uint32_t bid[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sc[e] = s_pc[8 * cg + e];
+      sh[e] = s_pc[C + 8 * cg + e];
+      best[e] = -INFINITY;
+      braw[e] = 0.f;
+      bid[e] = 9u;
+    }
+#pragma unroll
+    for (int wy = 0; wy < 3; ++wy) {
+      const int fy = 2 * y - top + wy;
+#pragma unroll
+      for (int wx = 0; wx < 3; ++wx) {
+        const int fx = 2 * x - left + wx;
+        const bool inside = (fy >= 0) && (fy < SH) && (fx >= 0) && (fx < SWd);
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (inside) r = __ldcg(reinterpret_cast<const uint4*>(src + (((long long)t.b * SH + fy) * SWd + fx) * C + 8 * cg));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        const uint32_t id = inside ? (uint32_t)(wy * 3 + wx) : 9u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 raw = bf2_to_f2(w[e]);
+          const float v0 = inside ? fmaf(raw.x, sc[2 * e], sh[2 * e]) : 0.f;
+          const float v1 = inside ? fmaf(raw.y, sc[2 * e + 1], sh[2 * e + 1]) : 0.f;
+          if (v0 > best[2 * e]) { best[2 * e] = v0; braw[2 * e] = raw.x; bid[2 * e] = id; }
+          if (v1 > best[2 * e + 1]) { best[2 * e + 1] = v1; braw[2 * e + 1] = raw.y; bid[2 * e + 1] = id; }
+        }
+      }
+    }
+    float u[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = wa * best[e];
+    const long long oo = (((long long)t.b * H + y) * W + x) * C + 8 * cg;
+    if (same != nullptr) {
+      const uint4 r = __ldcg(reinterpret_cast<const uint4*>(same + oo));
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = bf2_to_f2(w[e]);
+        u[2 * e] += fmaf(f.x, s_pc[2 * C + 8 * cg + 2 * e], s_pc[3 * C + 8 * cg + 2 * e]);
+        u[2 * e + 1] += fmaf(f.y, s_pc[2 * C + 8 * cg + 2 * e + 1], s_pc[3 * C + 8 * cg + 2 * e + 1]);
+      }
+    }
+    uint4 pk;
+    pk.x = f2_to_bf2(make_float2(u[0], u[1]));
+    pk.y = f2_to_bf2(make_float2(u[2], u[3]));
+    pk.z = f2_to_bf2(make_float2(u[4], u[5]));
+    pk.w = f2_to_bf2(make_float2(u[6], u[7]));
+    *reinterpret_cast<uint4*>(r1 + hp * POS + cg * 16) = pk;
+    if (record && hy >= 1 && hy <= TH && hx >= 1 && hx <= TW) {   // the tile's own positions: what the backward reads
+      *reinterpret_cast<uint4*>(aux + oo) = pk;
+      if (pidx != nullptr) {
+        uint2 ip;
+        ip.x = bid[0] | (bid[1] << 8) | (bid[2] << 16) | (bid[3] << 24);
+        ip.y = bid[4] | (bid[5] << 8) | (bid[6] << 16) | (bid[7] << 24);
+        *reinterpret_cast<uint2*>(pidx + oo) = ip;
+      }
+      if (praw != nullptr) {
+        uint4 rp;
+        rp.x = f2_to_bf2(make_float2(braw[0], braw[1]));
+        rp.y = f2_to_bf2(make_float2(braw[2], braw[3]));
+        rp.z = f2_to_bf2(make_float2(braw[4], braw[5]));
+        rp.w = f2_to_bf2(make_float2(braw[6], braw[7]));
+        *reinterpret_cast<uint4*>(praw + oo) = rp;
+      }
+    }
+  }
+}
+
+template <int TW, int TH, bool PRE>
 __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
   using S = Cfg<TW, TH>;
   constexpr uint32_t kTmemCols = 128;
@@ -257,6 +350,8 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   uint64_t* bar_mma = bar_pack + 3;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_pack + 4);
   __shared__ int s_flag;
+  __shared__ __align__(16) float s_pc[PRE ? 4 * C : 4];   // PRE: the pre-pass coefficients (as poolfuse_kernel's s_c)
+  const NodeFwdP& Q = BATCH.pre[net];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = P.g.H, W = P.g.W;
@@ -289,7 +384,20 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     if (tile < ntiles) {
       const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
       issue_input<TW, TH>(r0, in0, false, t, H, W, lane, bar_in0);
-      if (m1 != M1_NONE) issue_input<TW, TH>(r1, in1, m1 == M1_UP2, t, H, W, lane, bar_in1);
+      if (!PRE && m1 != M1_NONE) issue_input<TW, TH>(r1, in1, m1 == M1_UP2, t, H, W, lane, bar_in1);
+    }
+  }
+  float pre_wa = 0.f;
+  if (PRE) {
+    pre_wa = in_weight(Q, 0);
+    if (tid < C) {
+      const float wb = (Q.n_in >= 2) ? in_weight(Q, 1) : 0.f;
+      const float* qb0 = Q.in[0].bn;
+      const float* qb1 = (Q.n_in >= 2) ? Q.in[1].bn : nullptr;
+      s_pc[tid] = qb0 ? qb0[tid] : 1.f;
+      s_pc[C + tid] = qb0 ? qb0[C + tid] : 0.f;
+      s_pc[2 * C + tid] = (qb1 ? qb1[tid] : 1.f) * wb;
+      s_pc[3 * C + tid] = (qb1 ? qb1[C + tid] : 0.f) * wb;
     }
   }
   if (tid < C) {
@@ -318,9 +426,15 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     const TilePos t = tile_pos(tile, tiles_x, tiles_y, TW, TH);
     const int next = tile + nctas;
 
+    // ---- (0) PRE: build the pooled operand of this tile in region 1 (free: the previous tile's MMA has completed)
+    if (PRE) {
+      inline_pool_tile<TW, TH>(Q, s_pc, r1, t, H, W, tid, pre_wa);
+      __syncthreads();
+    }
+
     // ---- (1) raw inputs have landed
     tc::mbar_wait(bar_in0, ph);
-    if (m1 != M1_NONE) tc::mbar_wait(bar_in1, ph);
+    if (!PRE && m1 != M1_NONE) tc::mbar_wait(bar_in1, ph);
 
     // ---- (2) phase 1
     if (sw) {
@@ -361,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     tc::mbar_wait(bar_mma, ph);
     tc::fence_after_sync();
     // region 1 is free: request the next tile's input 1 while the epilogue runs
-    if (warp == 1 && next < ntiles && m1 != M1_NONE) {
+    if (!PRE && warp == 1 && next < ntiles && m1 != M1_NONE) {
       const TilePos tn = tile_pos(next, tiles_x, tiles_y, TW, TH);
       issue_input<TW, TH>(r1, in1, m1 == M1_UP2, tn, H, W, lane, bar_in1);
     }
@@ -743,12 +857,12 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
   }
 }
 
-template <int TW, int TH>
+template <int TW, int TH, bool PRE = false>
 static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   using S = Cfg<TW, TH>;
   static bool configured = false;
   if (!configured) {
-    MMD_CUDA(cudaFuncSetAttribute(node_fwd_v4_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    MMD_CUDA(cudaFuncSetAttribute(node_fwd_v4_kernel<TW, TH, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     configured = true;
   }
   int dev = 0, sms = 148;
@@ -759,7 +873,7 @@ static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.5f);
   NodeFwdBatch b2 = batch;
   batch_shares(b2, n, 2 * sms, ntiles, train_w);
-  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH>, dim3(b2.cta_begin[n]), dim3(kThreads), S::kBytes, s, b2));
+  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH, PRE>, dim3(b2.cta_begin[n]), dim3(kThreads), S::kBytes, s, b2));
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -834,6 +948,51 @@ int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s) {
     case 4: return v4::launch_geom<6, 6>(batch, n, s);
   }
   set_error("node_fwd_v4: no tile shape fits %dx%d", p[0].g.H, p[0].g.W);
+  return MMD_E_ARG;
+}
+
+bool fwd_v4_pre_usable(const NodeFwdP& pre, const NodeFwdP& node) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("MMD_NO_INLINE_POOL");
+    off = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (off) return false;
+  if (!fwd_v4_usable(node) || node.n_in != 2 || node.mode[1] != MMD_IN_SAME) return false;
+  if (node.in[1].data != pre.out || pre.out == nullptr) return false;                     // the node consumes the pre-pass
+  if (pre.mode[0] != MMD_IN_POOL || (pre.n_in == 2 && pre.mode[1] != MMD_IN_SAME) || pre.n_in > 2) return false;
+  if (pre.g.H != node.g.H || pre.g.W != node.g.W || node.g.H * node.g.W > 24 * 24) return false;   // P5 and smaller
+  const int geom = v4::pick_geom(node.g.H, node.g.W);
+  if (geom != 1 && geom != 3 && geom != 4) return false;
+  for (int i = 0; i < pre.n_in; ++i)
+    if (((uintptr_t)pre.in[i].data & 15u) != 0) return false;
+  return (((uintptr_t)pre.out | (uintptr_t)pre.pidx[0] | (uintptr_t)pre.save_d) & 15u) == 0;
+}
+
+int launch_node_fwd_v4_pre(const NodeFwdP* node, const NodeFwdP* pre, int n, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "node_fwd_v4_pre: %d networks in one launch", n);
+  NodeFwdBatch batch;
+  double bytes = 0.0;
+  for (int i = 0; i < n; ++i) {
+    batch.p[i] = node[i];
+    batch.pre[i] = pre[i];
+    MMD_CHECK_ARG(node[i].g.H == node[0].g.H && node[i].g.W == node[0].g.W && node[i].g.B == node[0].g.B,
+                  "node_fwd_v4_pre: batched networks must share the geometry");
+    bytes += node_algo_bytes(node[i].in, 1, node[i].g, C, 2);   // input 0 + output; the pre-pass inputs:
+    for (int k = 0; k < pre[i].n_in; ++k) bytes += (double)pre[i].g.B * pre[i].in[k].H * pre[i].in[k].W * C * 2.0;
+  }
+  for (int i = n; i < kMaxBatchNets; ++i) {
+    batch.p[i] = node[0];
+    batch.pre[i] = pre[0];
+  }
+  ProfScope prof(PK_NODE_FWD, bytes, s);
+  switch (v4::pick_geom(node[0].g.H, node[0].g.W)) {
+    case 1: return v4::launch_geom<12, 8, true>(batch, n, s);
+    case 3: return v4::launch_geom<12, 6, true>(batch, n, s);
+    case 4: return v4::launch_geom<6, 6, true>(batch, n, s);
+  }
+  set_error("node_fwd_v4_pre: no tile shape fits %dx%d", node[0].g.H, node[0].g.W);
   return MMD_E_ARG;
 }
 

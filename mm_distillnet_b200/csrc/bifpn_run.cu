@@ -161,6 +161,33 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
                              op.kind == MMD_OP_BNAPPLY;
       NodeFwdP ps[kMaxBatchNets];
       int members[kMaxBatchNets], n = 0;
+      // POOLFUSE followed by the node that consumes it, small level: ONE launch (the node kernel pools inline)
+      if (dtype == MMD_BF16 && !tc_disabled() && op.kind == MMD_OP_POOLFUSE && i + 1 < n_ops[l] &&
+          ops[l][i + 1].kind == MMD_OP_NODE_FWD) {
+        NodeFwdP nodes[kMaxBatchNets];
+        for (int m = l; m < n_lists; ++m) {
+          if (done[m] || i + 1 >= n_ops[m] || i < grouped_until[m]) continue;
+          const MmdOp& om = ops[m][i];
+          const MmdOp& on = ops[m][i + 1];
+          if (om.kind != MMD_OP_POOLFUSE || on.kind != MMD_OP_NODE_FWD || om.out.H != op.out.H || om.out.W != op.out.W) continue;
+          Bases Bm{bases[m], n_bases[m]};
+          int rc = fill_fwd(om, Bm, batch, ps[n]);
+          if (rc) return rc;
+          if ((rc = fill_fwd(on, Bm, batch, nodes[n]))) return rc;
+          if (!fwd_v4_pre_usable(ps[n], nodes[n])) continue;
+          members[n++] = m;
+        }
+        if (n >= 1 && members[0] == l) {
+          int rc = launch_node_fwd_v4_pre(nodes, ps, n, C, stream);
+          if (rc) return rc;
+          for (int k = 0; k < n; ++k) {
+            done[members[k]] = true;
+            grouped_until[members[k]] = i + 2;
+          }
+          continue;
+        }
+        n = 0;
+      }
       if (batchable) {
         for (int m = l; m < n_lists; ++m) {
           if (done[m] || i >= n_ops[m] || i < grouped_until[m]) continue;
@@ -204,6 +231,17 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
   Bases B{bases, n_bases};
   for (int i = 0; i < n_ops;) {
+    if (dtype == MMD_BF16 && !tc_disabled() && ops[i].kind == MMD_OP_POOLFUSE && i + 1 < n_ops && ops[i + 1].kind == MMD_OP_NODE_FWD) {
+      NodeFwdP pre, node;
+      int rc = fill_fwd(ops[i], B, batch, pre);
+      if (rc) return rc;
+      if ((rc = fill_fwd(ops[i + 1], B, batch, node))) return rc;
+      if (fwd_v4_pre_usable(pre, node)) {
+        if ((rc = launch_node_fwd_v4_pre(&node, &pre, 1, C, stream))) return rc;
+        i += 2;
+        continue;
+      }
+    }
     const int g = group_len(ops, i, n_ops);
     int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream) : run_one(ops[i], i, B, batch, C, dtype, stream);
     if (rc) return rc;
