@@ -161,7 +161,27 @@ struct NodeBwdP {
   float *g_dw, *g_pw, *g_pb, *g_bn_w, *g_bn_b, *g_fw;
   unsigned* counter;
   TileGeom g;
+  int defer_fw;   // 1: node_bwd_b4 leaves the fusion-weight gradient to fwgrad_kernel (one launch per backward)
 };
+
+// Deferred fusion-weight gradients: the slots (sum du, sum du * xhat per input edge) of every node are complete when the
+// backward's last kernel has run, so ONE launch turns them into all g_fw vectors instead of a fence + ticket +
+// last-CTA epilogue at the end of each of the 40 part-B launches.
+struct FwGradEntry {
+  const double* slot[3];
+  const float* in_bn_w[3];
+  const float* in_bn_b[3];   // nullptr: the input was final (the slot holds sum du * x)
+  const float* fw;
+  float* g_fw;
+  float fw_eps;
+  int n_in;
+};
+constexpr int kFwGradPerLaunch = 24;
+struct FwGradBatch {
+  FwGradEntry e[kFwGradPerLaunch];
+};
+int launch_fwgrad(const FwGradEntry* entries, int n, int C, cudaStream_t s);
+bool fwgrad_deferral_enabled();
 
 // fusion weight of kernel input i (ops fed by a POOLFUSE pre-pass see only part of the node's inputs)
 __device__ __forceinline__ float in_weight(const NodeFwdP& P, int i) {

@@ -875,8 +875,8 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
   }
 
   // ---- the last CTA turns the slots into the fusion-weight gradient (relu / normalise backward,
-  //      src/YetAnotherEfficientDet.py:338-339)
-  if (P.fw == nullptr || P.g_fw == nullptr) return;
+  //      src/YetAnotherEfficientDet.py:338-339) — unless that is left to fwgrad_kernel at the end of the backward
+  if (P.fw == nullptr || P.g_fw == nullptr || P.defer_fw) return;
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -906,6 +906,34 @@ __global__ void __launch_bounds__(CfgB<TW, TH>::kBlock, 1) node_bwd_b4_kernel(co
     for (int j = 0; j < P.n_in; ++j) dot += fmaxf(P.fw[j], 0.f) / denom * s_gw[j];
     for (int k = 0; k < P.n_in; ++k) P.g_fw[k] = (P.fw[k] > 0.f) ? (s_gw[k] - dot) / denom : 0.f;
     *P.counter = 0u;
+  }
+}
+
+// ---- deferred fusion-weight gradients: one block per node --------------------------------------------------------------
+__global__ void __launch_bounds__(128) fwgrad_kernel(const __grid_constant__ FwGradBatch BATCH) {
+  const FwGradEntry& E = BATCH.e[blockIdx.x];
+  __shared__ float s_gw[3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  if (warp < E.n_in) {
+    const int i = warp;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const double s1 = __ldcg(E.slot[i] + c), s2 = __ldcg(E.slot[i] + C + c);
+      if (E.in_bn_b[i] != nullptr) acc += (float)((double)E.in_bn_w[i][c] * s2 + (double)E.in_bn_b[i][c] * s1);
+      else acc += (float)s2;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_gw[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ssum = 0.f;
+    for (int j = 0; j < E.n_in; ++j) ssum += fmaxf(E.fw[j], 0.f);
+    const float denom = ssum + E.fw_eps;
+    float dot = 0.f;
+    for (int j = 0; j < E.n_in; ++j) dot += fmaxf(E.fw[j], 0.f) / denom * s_gw[j];
+    for (int k = 0; k < E.n_in; ++k) E.g_fw[k] = (E.fw[k] > 0.f) ? (s_gw[k] - dot) / denom : 0.f;
   }
 }
 
@@ -1009,6 +1037,27 @@ static int pick_geom(int H, int W) {
 }
 
 }  // namespace b4
+
+bool fwgrad_deferral_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMD_NO_DEFER_FW");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+int launch_fwgrad(const FwGradEntry* entries, int n, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  for (int i0 = 0; i0 < n; i0 += kFwGradPerLaunch) {
+    const int m = (n - i0 < kFwGradPerLaunch) ? n - i0 : kFwGradPerLaunch;
+    FwGradBatch batch;
+    for (int k = 0; k < kFwGradPerLaunch; ++k) batch.e[k] = entries[i0 + (k < m ? k : 0)];
+    MMD_CUDA(launch_pdl(b4::fwgrad_kernel, dim3(m), dim3(128), 0, s, batch));
+    MMD_LAUNCH_CHECK();
+  }
+  return 0;
+}
 
 bool bwd_v4_usable(const NodeBwdP& p) {
   if (p.packed == nullptr || p.n_in < 1 || p.n_in > 3 || p.mode[0] != MMD_IN_SAME) return false;

@@ -94,14 +94,22 @@ static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
   p.g_bn_w = B.get<float>(op.g_bn_w); p.g_bn_b = B.get<float>(op.g_bn_b); p.g_fw = B.get<float>(op.g_fw);
   p.counter = B.get<unsigned>(op.counter);
   p.g = make_geom(batch, op.out.H, op.out.W);
+  p.defer_fw = 0;
   return 0;
 }
+
+// entries of the deferred fusion-weight gradient launch collected while an op list runs (see FwGradEntry)
+struct FwGradList {
+  FwGradEntry e[128];
+  int n = 0;
+};
 
 }  // namespace mmd
 
 using namespace mmd;
 
-static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream);
+static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream,
+                   FwGradList* fwl = nullptr);
 
 static bool same_ref(const MmdRef& a, const MmdRef& b) { return a.base >= 0 && a.base == b.base && a.off == b.off; }
 
@@ -230,6 +238,7 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
   MMD_CHECK_ARG(C == 112, "mmd_bifpn_run: kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
   Bases B{bases, n_bases};
+  FwGradList fwl;
   for (int i = 0; i < n_ops;) {
     if (dtype == MMD_BF16 && !tc_disabled() && ops[i].kind == MMD_OP_POOLFUSE && i + 1 < n_ops && ops[i + 1].kind == MMD_OP_NODE_FWD) {
       NodeFwdP pre, node;
@@ -243,14 +252,15 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
       }
     }
     const int g = group_len(ops, i, n_ops);
-    int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream) : run_one(ops[i], i, B, batch, C, dtype, stream);
+    int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream) : run_one(ops[i], i, B, batch, C, dtype, stream, &fwl);
     if (rc) return rc;
     i += g;
   }
+  if (fwl.n > 0) return launch_fwgrad(fwl.e, fwl.n, C, stream);   // all slots are complete: every g_fw in one launch
   return 0;
 }
 
-static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream) {
+static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream, FwGradList* fwl) {
   int rc = 0;
     switch (op.kind) {
     case MMD_OP_NODE_FWD:
@@ -282,6 +292,23 @@ static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int
       if ((rc = fill_bwd(op, B, batch, p))) return rc;
       if (op.kind == MMD_OP_NODE_BWD) {
         MMD_CHECK_ARG(p.out && p.out_bn && p.save_d && p.du && p.dd && p.g_pw && p.counter, "node bwd op %d: missing storage", i);
+        if (fwl != nullptr && fwl->n < 128 && dtype == MMD_BF16 && !tc_disabled() && fwgrad_deferral_enabled() &&
+            p.fw != nullptr && p.g_fw != nullptr && bwd_v4_usable(p)) {
+          FwGradEntry& e = fwl->e[fwl->n];
+          bool ok = true;
+          for (int k = 0; k < 3; ++k) {
+            e.slot[k] = (k < p.n_in) ? p.in_slot[k] : nullptr;
+            e.in_bn_w[k] = (k < p.n_in && p.in[k].bn != nullptr) ? p.in_bn_w[k] : nullptr;
+            e.in_bn_b[k] = (k < p.n_in && p.in[k].bn != nullptr) ? p.in_bn_b[k] : nullptr;
+            if (k < p.n_in && p.in_slot[k] == nullptr) ok = false;
+            if (k < p.n_in && p.in[k].bn != nullptr && (p.in_bn_w[k] == nullptr || p.in_bn_b[k] == nullptr)) ok = false;
+          }
+          e.fw = p.fw; e.g_fw = p.g_fw; e.fw_eps = p.fw_eps; e.n_in = p.n_in;
+          if (ok) {
+            p.defer_fw = 1;
+            ++fwl->n;
+          }
+        }
         rc = launch_node_bwd(p, C, dtype, stream);
       } else if (op.kind == MMD_OP_PROJ_BWD) {
         MMD_CHECK_ARG(p.out && p.out_bn && p.g_pw && p.in[0].data, "proj bwd op %d: missing storage", i);
