@@ -86,6 +86,16 @@ inline PackedLayout packed_layout(int kind, int Cin, int C) {
   return L;
 }
 
+// Where the BatchNorm vector (scale, shift) of a deferred-BN input can be rebuilt from when its producer leaves the
+// finalisation to bn_finalize_all_kernel (see NodeFwdP::defer_bn): the producer's raw statistics.
+struct BnSrc {
+  const double* stats;   // double[MMD_STATS_REPLICAS][2*C] sums / sums of squares; nullptr: read TensorP::bn
+  const float* gamma;
+  const float* beta;
+  double n;              // B * H * W of the producer's output
+  float eps;
+};
+
 struct NodeFwdP {
   TensorP in[3];
   int mode[3];
@@ -106,7 +116,52 @@ struct NodeFwdP {
   TileGeom g;
   int fw_n;        // 0: `fw` has n_in entries, input i uses entry i
   int fw_idx[3];   // entry of `fw` weighing input i; -1: weight 1 (operand produced by a POOLFUSE pre-pass)
+  // Deferred BatchNorm finalisation (training, bf16 path).  A producer with defer_bn = 1 only accumulates its statistics
+  // and returns: no fence, no ticket, no last-CTA pass at the end of the launch.  Its forward consumers rebuild
+  // (scale, shift) from the sums in their prologue (bnsrc[i].stats != nullptr, same arithmetic as the finaliser), and
+  // ONE bn_finalize_all launch at the end of the forward writes every out_bn vector for the backward, updates the running
+  // statistics and clears the accumulators.
+  BnSrc bnsrc[3];
+  int defer_bn;
 };
+
+// (scale, shift) of channel c of input `t`: from the finalised vector, or rebuilt from the producer's statistics
+template <int C>
+__device__ __forceinline__ void bn_coef(const TensorP& t, const BnSrc& b, int c, float& scale, float& shift) {
+  if (b.stats == nullptr) {
+    scale = t.bn ? t.bn[c] : 1.f;
+    shift = t.bn ? t.bn[C + c] : 0.f;
+    return;
+  }
+  double sum = 0.0, sq = 0.0;
+#pragma unroll
+  for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+    sum += __ldcg(b.stats + r * (2 * C) + c);
+    sq += __ldcg(b.stats + r * (2 * C) + C + c);
+  }
+  const double mean = sum / b.n;
+  double var = sq / b.n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)b.eps));
+  scale = b.gamma[c] * invstd;
+  shift = b.beta[c] - (float)mean * scale;
+}
+
+// one entry of the deferred finalisation launch
+struct BnFinalEntry {
+  double* stats;
+  const float *gamma, *beta;
+  float *rm, *rv, *out_bn;
+  long long* nbt;
+  double n;
+  float eps, mom;
+};
+constexpr int kBnFinalPerLaunch = 24;
+struct BnFinalBatch {
+  BnFinalEntry e[kBnFinalPerLaunch];
+};
+int launch_bn_finalize_all(const BnFinalEntry* entries, int n, int C, cudaStream_t s);
+bool bn_deferral_enabled();
 
 // up to 4 networks (student + teachers) run the same node in ONE launch: blockIdx.y selects the network
 constexpr int kMaxBatchNets = 4;
@@ -119,6 +174,7 @@ struct NodeFwdBatch {
   // of every network; its output tile is built in shared memory by the node kernel itself
   NodeFwdP pre[kMaxBatchNets];
 };
+static_assert(sizeof(NodeFwdBatch) <= 4096, "kernel parameter space (4 KB without the large-parameter opt-in)");
 // split `budget` CTAs over the n networks of a lockstep launch: weight `train_w` for networks with p.train != 0, 1 for
 // the others; at least 1 and at most `max_per_net` CTAs each
 void batch_shares(NodeFwdBatch& batch, int n, int budget, int max_per_net, float train_w);
@@ -248,6 +304,7 @@ struct NodeFwdGroup {
 struct NodeBwdGroup {
   NodeBwdP p[kMaxGroupOps];
 };
+static_assert(sizeof(NodeFwdGroup) <= 4096 && sizeof(NodeBwdGroup) <= 4096, "kernel parameter space");
 int launch_bnapply_group(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s);
 int launch_slot_group(const NodeBwdP* p, int n, int C, int dtype, cudaStream_t s);
 

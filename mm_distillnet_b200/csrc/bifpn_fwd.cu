@@ -351,7 +351,17 @@ __device__ __forceinline__ void bnapply_body(const NodeFwdP& P) {
   constexpr int NQ = C / 4;
   const TileGeom g = P.g;
   const long long total = (long long)g.B * g.H * g.W * NQ;
-  const float* bn = P.in[0].bn;
+  // (scale, shift) of the source, staged once per block (rebuilt from the producer's statistics when its BatchNorm
+  // finalisation is deferred, see NodeFwdP::defer_bn)
+  __shared__ __align__(16) float s_bn[2 * C];
+  if ((long long)blockIdx.x * blockDim.x >= total) return;
+  if (threadIdx.x < C) {
+    float sc1, sh1;
+    bn_coef<C>(P.in[0], P.bnsrc[0], threadIdx.x, sc1, sh1);
+    s_bn[threadIdx.x] = sc1;
+    s_bn[C + threadIdx.x] = sh1;
+  }
+  __syncthreads();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(idx % NQ);
     long long pos = idx / NQ;
@@ -359,11 +369,8 @@ __device__ __forceinline__ void bnapply_body(const NodeFwdP& P) {
     pos /= g.W;
     const int y = (int)(pos % g.H);
     const int b = (int)(pos / g.H);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = f4_zero();
-    if (bn) {
-      sc = *reinterpret_cast<const float4*>(bn + 4 * q);
-      sh = *reinterpret_cast<const float4*>(bn + C + 4 * q);
-    }
+    const float4 sc = *reinterpret_cast<const float4*>(s_bn + 4 * q);
+    const float4 sh = *reinterpret_cast<const float4*>(s_bn + C + 4 * q);
     float4 val, raw;
     unsigned arg;
     load_input<T, C>(P.in[0], P.mode[0], b, y, x, q, sc, sh, val, raw, arg);

@@ -96,6 +96,7 @@ __device__ __forceinline__ void bn_finalize_tc(const NodeFwdP& P, double st_sum,
     atomicAdd(rep + tid, st_sum);
     atomicAdd(rep + C + tid, st_sq);
   }
+  if (P.defer_bn) return;   // see NodeFwdP::defer_bn
   __threadfence();
   __syncthreads();
   if (tid == 0) {

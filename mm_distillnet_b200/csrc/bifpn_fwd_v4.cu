@@ -392,20 +392,20 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     pre_wa = in_weight(Q, 0);
     if (tid < C) {
       const float wb = (Q.n_in >= 2) ? in_weight(Q, 1) : 0.f;
-      const float* qb0 = Q.in[0].bn;
-      const float* qb1 = (Q.n_in >= 2) ? Q.in[1].bn : nullptr;
-      s_pc[tid] = qb0 ? qb0[tid] : 1.f;
-      s_pc[C + tid] = qb0 ? qb0[C + tid] : 0.f;
-      s_pc[2 * C + tid] = (qb1 ? qb1[tid] : 1.f) * wb;
-      s_pc[3 * C + tid] = (qb1 ? qb1[C + tid] : 0.f) * wb;
+      float qs0, qh0, qs1 = 1.f, qh1 = 0.f;
+      bn_coef<C>(Q.in[0], Q.bnsrc[0], tid, qs0, qh0);
+      if (Q.n_in >= 2) bn_coef<C>(Q.in[1], Q.bnsrc[1], tid, qs1, qh1);
+      s_pc[tid] = qs0;
+      s_pc[C + tid] = qh0;
+      s_pc[2 * C + tid] = qs1 * wb;
+      s_pc[3 * C + tid] = qh1 * wb;
     }
   }
   if (tid < C) {
     const float w0 = in_weight(P, 0), w1 = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
-    const float* bn0 = P.in[0].bn;
-    const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
-    const float sc0 = bn0 ? bn0[tid] : 1.f, sh0 = bn0 ? bn0[C + tid] : 0.f;
-    const float sc1 = bn1 ? bn1[tid] : 1.f, sh1 = bn1 ? bn1[C + tid] : 0.f;
+    float sc0, sh0, sc1 = 1.f, sh1 = 0.f;
+    bn_coef<C>(P.in[0], P.bnsrc[0], tid, sc0, sh0);
+    if (P.n_in >= 2) bn_coef<C>(P.in[1], P.bnsrc[1], tid, sc1, sh1);
     s_coef[tid] = sc0 * w0;
     s_coef[C + tid] = sc1 * w1;
     s_coef[2 * C + tid] = fmaf(sh1, w1, sh0 * w0);
@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     atomicAdd(rep + tid, s);
     atomicAdd(rep + C + tid, q);
   }
+  if (P.defer_bn) return;   // consumers rebuild (scale, shift) from the sums; bn_finalize_all does the rest
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -731,12 +732,13 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     const float wb = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
-    const float* bn0 = P.in[0].bn;
-    const float* bn1 = (P.n_in >= 2) ? P.in[1].bn : nullptr;
-    s_c[c] = bn0 ? bn0[c] : 1.f;
-    s_c[C + c] = bn0 ? bn0[C + c] : 0.f;
-    s_c[2 * C + c] = (bn1 ? bn1[c] : 1.f) * wb;
-    s_c[3 * C + c] = (bn1 ? bn1[C + c] : 0.f) * wb;
+    float ps0, ph0, ps1 = 1.f, ph1 = 0.f;
+    bn_coef<C>(P.in[0], P.bnsrc[0], c, ps0, ph0);
+    if (P.n_in >= 2) bn_coef<C>(P.in[1], P.bnsrc[1], c, ps1, ph1);
+    s_c[c] = ps0;
+    s_c[C + c] = ph0;
+    s_c[2 * C + c] = ps1 * wb;
+    s_c[3 * C + c] = ph1 * wb;
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -889,6 +891,66 @@ static int pick_geom(int H, int W) {
 }
 
 }  // namespace v4
+
+namespace v4 {
+// ---- deferred BatchNorm finalisation: one block per train-mode op of the forward ------------------------------------
+// Same arithmetic as the in-kernel finaliser (and as bn_coef()): out_bn = scale | shift | mean | invstd, running statistics
+// (momentum update with the unbiased variance, src/YetAnotherEfficientDet.py:176 semantics of nn.BatchNorm2d),
+// num_batches_tracked, accumulators cleared for the next forward.
+__global__ void __launch_bounds__(128) bn_finalize_all_kernel(const __grid_constant__ BnFinalBatch BATCH) {
+  const BnFinalEntry& E = BATCH.e[blockIdx.x];
+  const int tid = threadIdx.x;
+  pdl_wait();
+  if (tid < C) {
+    double sum = 0.0, sq = 0.0;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      sum += __ldcg(E.stats + r * (2 * C) + tid);
+      sq += __ldcg(E.stats + r * (2 * C) + C + tid);
+    }
+    const double n = E.n;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)E.eps));
+    const float scale = E.gamma[tid] * invstd;
+    E.out_bn[tid] = scale;
+    E.out_bn[C + tid] = E.beta[tid] - (float)mean * scale;
+    E.out_bn[2 * C + tid] = (float)mean;
+    E.out_bn[3 * C + tid] = invstd;
+    const double unbiased = var * (n / (n > 1.0 ? n - 1.0 : 1.0));
+    E.rm[tid] = (1.f - E.mom) * E.rm[tid] + E.mom * (float)mean;
+    E.rv[tid] = (1.f - E.mom) * E.rv[tid] + E.mom * (float)unbiased;
+#pragma unroll
+    for (int r = 0; r < MMD_STATS_REPLICAS; ++r) {
+      E.stats[r * (2 * C) + tid] = 0.0;
+      E.stats[r * (2 * C) + C + tid] = 0.0;
+    }
+  }
+  if (tid == 0 && E.nbt) *E.nbt += 1;
+}
+}  // namespace v4
+
+bool bn_deferral_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MMD_NO_DEFER_BN");
+    on = (e && e[0] == '1') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+int launch_bn_finalize_all(const BnFinalEntry* entries, int n, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  for (int i0 = 0; i0 < n; i0 += kBnFinalPerLaunch) {
+    const int m = (n - i0 < kBnFinalPerLaunch) ? n - i0 : kBnFinalPerLaunch;
+    BnFinalBatch batch;
+    for (int k = 0; k < kBnFinalPerLaunch; ++k) batch.e[k] = entries[i0 + (k < m ? k : 0)];
+    MMD_CUDA(launch_pdl(v4::bn_finalize_all_kernel, dim3(m), dim3(128), 0, s, batch));
+    MMD_LAUNCH_CHECK();
+  }
+  return 0;
+}
 
 float env_float(const char* name, float dflt) {
   const char* e = getenv(name);

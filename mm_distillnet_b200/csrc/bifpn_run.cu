@@ -1,4 +1,6 @@
 // mmd_bifpn_run: resolve an op list (include/mmd.h) into kernel arguments and enqueue it on the caller's stream.
+#include <vector>
+
 #include "bifpn.cuh"
 
 namespace mmd {
@@ -39,6 +41,8 @@ static int fill_fwd(const MmdOp& op, const Bases& B, int batch, NodeFwdP& p) {
   p.bn_eps = op.bn_eps;
   p.bn_mom = op.bn_momentum;
   p.g = make_geom(batch, op.out.H, op.out.W);
+  p.defer_bn = 0;
+  for (int i = 0; i < 3; ++i) p.bnsrc[i] = BnSrc{nullptr, nullptr, nullptr, 0.0, 0.f};
   MMD_CHECK_ARG(p.out != nullptr, "op: no output");
   if (op.kind != MMD_OP_BNAPPLY && op.kind != MMD_OP_POOLFUSE) {
     MMD_CHECK_ARG(p.pw_w && p.pw_b && p.bn_w && p.bn_b && p.bn_rm && p.bn_rv, "op: missing conv/bn parameters");
@@ -98,6 +102,64 @@ static int fill_bwd(const MmdOp& op, const Bases& B, int batch, NodeBwdP& p) {
   return 0;
 }
 
+// ---- deferred BatchNorm finalisation plan of one forward op list (see NodeFwdP::defer_bn) ------------------------------
+struct DeferPlan {
+  std::vector<char> defer;                 // per op: the producer skips its in-kernel finalisation
+  std::vector<BnSrc> src;                  // per op and input (3 per op): where a consumer rebuilds (scale, shift) from
+  std::vector<BnFinalEntry> fin;           // what bn_finalize_all has to do at the end of the list
+  bool any() const { return !fin.empty(); }
+};
+
+static bool ref_eq(const MmdRef& a, const MmdRef& b) { return a.base >= 0 && a.base == b.base && a.off == b.off; }
+
+// A train-mode NODE_FWD / PROJ_FWD op may defer when every later op that applies its BatchNorm on load runs on a kernel
+// that can rebuild the coefficients from the statistics: the v4 node kernel, the poolfuse pre-pass, bnapply.
+static int plan_defer(const MmdOp* ops, int n_ops, const Bases& B, int batch, int dtype, DeferPlan& D) {
+  D.defer.assign(n_ops, 0);
+  D.src.assign((size_t)n_ops * 3, BnSrc{nullptr, nullptr, nullptr, 0.0, 0.f});
+  D.fin.clear();
+  if (dtype != MMD_BF16 || tc_disabled() || !bn_deferral_enabled()) return 0;
+  for (int j = 0; j < n_ops; ++j) {
+    const MmdOp& op = ops[j];
+    if (!op.train || !(op.kind == MMD_OP_NODE_FWD || (op.kind == MMD_OP_PROJ_FWD && op.Cin % 8 == 0))) continue;
+    if (op.out.bn.base < 0 || op.stats.base < 0) continue;
+    bool ok = true;
+    for (int k = j + 1; k < n_ops && ok; ++k) {
+      const MmdOp& ck = ops[k];
+      bool reads = false;
+      for (int i = 0; i < ck.n_in && i < 3; ++i) reads = reads || ref_eq(ck.in[i].bn, op.out.bn);
+      if (!reads) continue;
+      if (ck.kind == MMD_OP_POOLFUSE || ck.kind == MMD_OP_BNAPPLY) continue;
+      if (ck.kind != MMD_OP_NODE_FWD) { ok = false; break; }
+      NodeFwdP cp;
+      int rc = fill_fwd(ck, B, batch, cp);
+      if (rc) return rc;
+      if (!fwd_v4_usable(cp)) ok = false;
+    }
+    if (!ok) continue;
+    BnFinalEntry e;
+    e.stats = B.get<double>(op.stats);
+    e.gamma = op.bn_w; e.beta = op.bn_b;
+    e.rm = op.bn_rm; e.rv = op.bn_rv; e.nbt = (long long*)op.bn_nbt;
+    e.out_bn = B.get<float>(op.out.bn);
+    e.n = (double)batch * op.out.H * op.out.W;
+    e.eps = op.bn_eps; e.mom = op.bn_momentum;
+    if (e.stats == nullptr || e.out_bn == nullptr || e.gamma == nullptr || e.beta == nullptr || e.rm == nullptr || e.rv == nullptr) continue;
+    D.defer[j] = 1;
+    D.fin.push_back(e);
+    for (int k = j + 1; k < n_ops; ++k)
+      for (int i = 0; i < ops[k].n_in && i < 3; ++i)
+        if (ref_eq(ops[k].in[i].bn, op.out.bn)) D.src[(size_t)k * 3 + i] = BnSrc{e.stats, e.gamma, e.beta, e.n, e.eps};
+  }
+  return 0;
+}
+
+static void apply_defer(const DeferPlan* D, int idx, NodeFwdP& p) {
+  if (D == nullptr || D->defer.empty()) return;
+  p.defer_bn = D->defer[idx];
+  for (int i = 0; i < 3; ++i) p.bnsrc[i] = D->src[(size_t)idx * 3 + i];
+}
+
 // entries of the deferred fusion-weight gradient launch collected while an op list runs (see FwGradEntry)
 struct FwGradList {
   FwGradEntry e[128];
@@ -109,7 +171,7 @@ struct FwGradList {
 using namespace mmd;
 
 static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream,
-                   FwGradList* fwl = nullptr);
+                   FwGradList* fwl = nullptr, const DeferPlan* dp = nullptr);
 
 static bool same_ref(const MmdRef& a, const MmdRef& b) { return a.base >= 0 && a.base == b.base && a.off == b.off; }
 
@@ -130,12 +192,15 @@ static int group_len(const MmdOp* ops, int i, int n_ops) {
 }
 
 // launches ops[i .. i+n) (n >= 2, from group_len) together
-static int run_group(const MmdOp* ops, int i, int n, const Bases& B, int batch, int C, int dtype, cudaStream_t stream) {
+static int run_group(const MmdOp* ops, int i, int n, const Bases& B, int batch, int C, int dtype, cudaStream_t stream,
+                     const DeferPlan* dp = nullptr) {
   int rc = 0;
   if (ops[i].kind == MMD_OP_BNAPPLY) {
     NodeFwdP ps[kMaxGroupOps];
-    for (int k = 0; k < n; ++k)
+    for (int k = 0; k < n; ++k) {
       if ((rc = fill_fwd(ops[i + k], B, batch, ps[k]))) return rc;
+      apply_defer(dp, i + k, ps[k]);
+    }
     return launch_bnapply_group(ps, n, C, dtype, stream);
   }
   NodeBwdP ps[kMaxGroupOps];
@@ -158,6 +223,12 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
   int max_n = 0;
   for (int l = 0; l < n_lists; ++l) max_n = n_ops[l] > max_n ? n_ops[l] : max_n;
   int grouped_until[kMaxBatchNets] = {0, 0, 0, 0};   // ops below this index already ran as part of a group launch
+  DeferPlan plans[kMaxBatchNets];
+  for (int l = 0; l < n_lists; ++l) {
+    Bases Bl{bases[l], n_bases[l]};
+    int rc = plan_defer(ops[l], n_ops[l], Bl, batch, dtype, plans[l]);
+    if (rc) return rc;
+  }
   for (int i = 0; i < max_n; ++i) {
     bool done[kMaxBatchNets] = {false, false, false, false};
     for (int l = 0; l < n_lists; ++l) {
@@ -182,6 +253,8 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
           int rc = fill_fwd(om, Bm, batch, ps[n]);
           if (rc) return rc;
           if ((rc = fill_fwd(on, Bm, batch, nodes[n]))) return rc;
+          apply_defer(&plans[m], i, ps[n]);
+          apply_defer(&plans[m], i + 1, nodes[n]);
           if (!fwd_v4_pre_usable(ps[n], nodes[n])) continue;
           members[n++] = m;
         }
@@ -205,6 +278,7 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
           Bases Bm{bases[m], n_bases[m]};
           int rc = fill_fwd(om, Bm, batch, ps[n]);
           if (rc) return rc;
+          apply_defer(&plans[m], i, ps[n]);
           if (op.kind == MMD_OP_NODE_FWD && !fwd_v4_usable(ps[n])) continue;
           members[n++] = m;
         }
@@ -220,13 +294,19 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
       if (!done[l]) {
         Bases Bl{bases[l], n_bases[l]};
         const int g = group_len(ops[l], i, n_ops[l]);
-        int rc = (g >= 2) ? run_group(ops[l], i, g, Bl, batch, C, dtype, stream) : run_one(op, i, Bl, batch, C, dtype, stream);
+        int rc = (g >= 2) ? run_group(ops[l], i, g, Bl, batch, C, dtype, stream, &plans[l])
+                          : run_one(op, i, Bl, batch, C, dtype, stream, nullptr, &plans[l]);
         if (rc) return rc;
         if (g >= 2) grouped_until[l] = i + g;
         done[l] = true;
       }
     }
   }
+  for (int l = 0; l < n_lists; ++l)   // every forward consumer has run: finalise the deferred BatchNorms of each list
+    if (plans[l].any()) {
+      int rc = launch_bn_finalize_all(plans[l].fin.data(), (int)plans[l].fin.size(), C, stream);
+      if (rc) return rc;
+    }
   return 0;
 }
 
@@ -239,12 +319,19 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
   MMD_CHECK_ARG(dtype == MMD_F32 || dtype == MMD_BF16, "mmd_bifpn_run: dtype %d", dtype);
   Bases B{bases, n_bases};
   FwGradList fwl;
+  DeferPlan plan;
+  {
+    int rc = plan_defer(ops, n_ops, B, batch, dtype, plan);
+    if (rc) return rc;
+  }
   for (int i = 0; i < n_ops;) {
     if (dtype == MMD_BF16 && !tc_disabled() && ops[i].kind == MMD_OP_POOLFUSE && i + 1 < n_ops && ops[i + 1].kind == MMD_OP_NODE_FWD) {
       NodeFwdP pre, node;
       int rc = fill_fwd(ops[i], B, batch, pre);
       if (rc) return rc;
       if ((rc = fill_fwd(ops[i + 1], B, batch, node))) return rc;
+      apply_defer(&plan, i, pre);
+      apply_defer(&plan, i + 1, node);
       if (fwd_v4_pre_usable(pre, node)) {
         if ((rc = launch_node_fwd_v4_pre(&node, &pre, 1, C, stream))) return rc;
         i += 2;
@@ -252,15 +339,20 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
       }
     }
     const int g = group_len(ops, i, n_ops);
-    int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream) : run_one(ops[i], i, B, batch, C, dtype, stream, &fwl);
+    int rc = (g >= 2) ? run_group(ops, i, g, B, batch, C, dtype, stream, &plan) : run_one(ops[i], i, B, batch, C, dtype, stream, &fwl, &plan);
     if (rc) return rc;
     i += g;
+  }
+  if (plan.any()) {   // every forward consumer has run: finalise the deferred BatchNorms
+    int rc = launch_bn_finalize_all(plan.fin.data(), (int)plan.fin.size(), C, stream);
+    if (rc) return rc;
   }
   if (fwl.n > 0) return launch_fwgrad(fwl.e, fwl.n, C, stream);   // all slots are complete: every g_fw in one launch
   return 0;
 }
 
-static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream, FwGradList* fwl) {
+static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int dtype, cudaStream_t stream, FwGradList* fwl,
+                   const DeferPlan* dp) {
   int rc = 0;
     switch (op.kind) {
     case MMD_OP_NODE_FWD:
@@ -269,6 +361,7 @@ static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int
     case MMD_OP_BNAPPLY: {
       NodeFwdP p;
       if ((rc = fill_fwd(op, B, batch, p))) return rc;
+      apply_defer(dp, i, p);
       if (op.kind == MMD_OP_NODE_FWD) {
         MMD_CHECK_ARG(p.dw_w != nullptr, "node op %d: no depthwise weight", i);
         for (int k = 0; k < op.n_in; ++k) MMD_CHECK_ARG(op.in[k].C == C, "node op %d: input %d has C=%d", i, k, op.in[k].C);
