@@ -51,7 +51,7 @@ unsigned long long mmd_launch_count(void);
  *   loss[l] = sum_b sum_i t (log t - s) / B  with s = softmax(a^_s/T), t = softmax(a^_t/T)   (reference quirk:
  *   probabilities, not log-probabilities, are the kl_div input — reproduced as is).
  * ---------------------------------------------------------------------------------------------------------- */
-#define MMD_STATS_REPLICAS 16
+#define MMD_STATS_REPLICAS 1
 #define MMD_MTA_MAX_LEVELS 8
 #define MMD_MTA_MAX_TEACHERS 4
 
@@ -148,9 +148,10 @@ typedef struct {
   MmdRef pidx[3];         /* NODE / BNAPPLY train: arg-max indices written for pooled inputs */
   MmdRef packed;          /* NODE / PROJ: this op's packed parameter block (written by mmd_bifpn_prep, layout below); */
                           /* NULL: the kernels convert the fp32 parameters themselves (slow path)                 */
-  MmdRef stats;           /* double[MMD_STATS_REPLICAS][2*C] accumulators, zero on entry, re-zeroed by the kernel.  CTAs spread */
-                          /* their partial sums over the replicas (296 CTAs adding into the same 2*C doubles serialise at the   */
-                          /* L2 atomic units); the finalising CTA adds the replicas up.  Kernels may use replica 0 only.        */
+  MmdRef stats;           /* double[MMD_STATS_REPLICAS][2*C] accumulators, zero on entry, re-zeroed by the finaliser.  CTAs may  */
+                          /* spread their partial sums over the replicas; whoever turns the sums into (scale, shift) adds the    */
+                          /* replicas up.  Measured on B200: 16 / 4 / 1 replicas make no difference to the producers, and every  */
+                          /* replica costs the consumers of a deferred BatchNorm two more L2 loads per channel: 1 replica.       */
   MmdRef counter;         /* uint32, zero on entry, re-zeroed by the kernel */
   /* backward only */
   int32_t n_cons, pad_;

@@ -16,7 +16,7 @@ SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bi
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1
 MTA_MAX_LEVELS, MTA_MAX_TEACHERS = 8, 4
-STATS_REPLICAS = 16   # MMD_STATS_REPLICAS
+STATS_REPLICAS = 1   # MMD_STATS_REPLICAS
 
 IN_SAME, IN_UP2, IN_POOL = 0, 1, 2
 CONS_SAME, CONS_UP2, CONS_POOL = 0, 1, 2
