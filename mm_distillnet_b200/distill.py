@@ -90,8 +90,12 @@ class DistillStep:
             for st in self.streams:
                 main.wait_stream(st)
             kd = self._kd(feats_s, feats_t_all)                          # :351-358
-        loss = self.w_kd * kd.sum()                                  # traditional.py:171-181 (KD term)
-        loss.backward()                                              # :182
+        # loss = w_kd * sum(stack(kd_losses)); loss.backward()  (traditional.py:171-182, KD term): d loss / d kd[t, l] is
+        # the constant w_kd, so the backward starts from that constant instead of three scalar kernels (sum, mul, expand)
+        g = getattr(self, "_kd_grad", None)
+        if g is None or g.shape != kd.shape or g.device != kd.device:
+            g = self._kd_grad = torch.full_like(kd.detach(), self.w_kd)
+        torch.autograd.backward([kd], [g])
         return kd.detach()
 
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------------------------
