@@ -403,11 +403,26 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"    # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world == 1:
+        run_ours(args, rank, world, local_rank)
+        return
+    # N > 1: the step's CUDA graph holds captured NCCL kernels; tearing the communicator down while it is alive was
+    # observed to hang the processes AFTER rank 0 had printed its line (destroy_process_group never returned).  Every
+    # rank has passed the last barrier by then, so: flush, synchronise, leave without the NCCL teardown.
+    code = 0
     try:
         run_ours(args, rank, world, local_rank)
-    finally:
-        if world > 1:
-            dist.destroy_process_group()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        code = 1
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        torch.cuda.synchronize()
+    except Exception:
+        code = code or 1
+    os._exit(code)
 
 
 if __name__ == "__main__":
