@@ -935,7 +935,8 @@ bool bn_deferral_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("MMD_NO_DEFER_BN");
-    on = (e && e[0] == '1') ? 0 : 1;
+    const char* v = getenv("MMD_NO_V4");   // the generic node kernels read the finalised vectors only
+    on = ((e && e[0] == '1') || (v && v[0] == '1')) ? 0 : 1;
   }
   return on == 1;
 }
