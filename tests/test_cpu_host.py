@@ -196,3 +196,31 @@ def test_flat_gradient_allreduce_gloo_world2():
         vals, w = res[r]
         assert w == 2
         assert vals == [1.5, 3.0, 4.5, 1.5]    # mean over ranks (DDP semantics, train_methods.py:957-961)
+
+
+def test_header_constants_match_python_mirrors():
+    """Constants shared between include/mmd.h and the ctypes side (array extents, accumulator replicas, version)."""
+    hdr = open(os.path.join(ROOT, "include", "mmd.h")).read()
+    defs = dict(re.findall(r"#define\s+(MMD_[A-Z_]+)\s+(\d+)", hdr))
+    assert int(defs["MMD_MTA_MAX_LEVELS"]) == _lib.MTA_MAX_LEVELS
+    assert int(defs["MMD_MTA_MAX_TEACHERS"]) == _lib.MTA_MAX_TEACHERS
+    assert int(defs["MMD_STATS_REPLICAS"]) == _lib.STATS_REPLICAS
+    assert _lib.lib().mmd_version() == int(defs["MMD_VERSION"])
+    # the per-teacher batching flag of the MTA call is part of the mirrored struct
+    assert "separate" in [f[0] for f in _lib.MtaArgs._fields_]
+
+
+def test_mta_forward_each_rejects_cpu_tensors_and_bad_shapes():
+    """No CPU fallback on the batched per-teacher entry either; argument checks happen before any launch."""
+    crit = mmd.MTALoss()
+    fs = [torch.randn(2, 112, 4, 4), torch.randn(2, 112, 2, 2)]
+    ts = [[torch.randn(2, 112, 4, 4), torch.randn(2, 112, 2, 2)] for _ in range(3)]
+    with pytest.raises(RuntimeError):
+        crit.forward_each(fs, ts)
+    with pytest.raises(ValueError):
+        crit.forward_each(fs, [ts[0]] * 5)          # more teachers than one call takes
+
+
+def test_distill_step_rejects_foreign_modules():
+    with pytest.raises(TypeError):
+        mmd.DistillStep(torch.nn.Linear(2, 2), [])
