@@ -345,10 +345,11 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        Bc = 4
-        ts = time_cpu(Bc, 2, 1)
+        Bc, Kc, Wc = 4, 25, 2    # ~10-12 s of CPU work on the box's host cores
+        ts = time_cpu(Bc, Kc, Wc)
         cpu = {"value": Bc * len(ts) / sum(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "2 timed steps (1 warm-up) of the same step at batch %d on the oracle port (torch CPU fp32)" % Bc}
+               "sample": "%d timed steps (%d warm-up) of the same step at batch %d on the oracle port (torch CPU fp32, "
+                         "all host threads)" % (Kc, Wc, Bc)}
 
     if rank == 0:
         h2d = (1 + N_TEACHERS) * B * sum(c * (S3 >> i) ** 2 for i, c in enumerate(CC)) * esize
