@@ -872,7 +872,7 @@ static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const NodeFwdP& p = batch.p[0];
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
-  static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.5f);
+  static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.0f);
   NodeFwdBatch b2 = batch;
   batch_shares(b2, n, 2 * sms, ntiles, train_w);
   MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH, PRE>, dim3(b2.cta_begin[n]), dim3(kThreads), S::kBytes, s, b2));
