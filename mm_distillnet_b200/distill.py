@@ -15,6 +15,22 @@ from .bifpn import BiFPN, BiFPNStack, forward_multi
 from .mta import MTALoss
 
 
+def _flat_channels_last(like, device):
+    """(flat uint8 buffer, views): one channels_last view per tensor of `like` (same logical [B,C,H,W] shape and dtype),
+    laid out back to back at 256-byte aligned offsets of ONE allocation."""
+    offs, total = [], 0
+    for x in like:
+        offs.append(total)
+        total += (x.numel() * x.element_size() + 255) // 256 * 256
+    flat = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+    views = []
+    for x, off in zip(like, offs):
+        B, C, H, W = x.shape
+        v = flat[off:off + x.numel() * x.element_size()].view(x.dtype).view(B, H, W, C).permute(0, 3, 1, 2)
+        views.append(v)
+    return flat, views
+
+
 class DistillStep:
     """step(student_inputs, teacher_inputs) -> detached fp32 tensor [n_teachers, n_levels] of MTA losses.
 
@@ -105,8 +121,20 @@ class DistillStep:
         few microseconds each: replaying it as one graph takes the host (and any driver contention, e.g. a clock
         monitor) out of the critical path.  Returns self; use replay()."""
         dev = self.device
-        self._g_xs = [x.detach().to(dev).clone().requires_grad_(bool(x.requires_grad)) for x in student_inputs]
-        self._g_xt = [[x.detach().to(dev).clone() for x in xs] for xs in teacher_inputs]
+        # all static inputs are channels_last views into ONE flat buffer: replay_prefetched() moves a whole staging set
+        # into them with a single device-to-device copy
+        srcs = list(student_inputs) + [x for xs in teacher_inputs for x in xs]
+        self._flat_static, views = _flat_channels_last(srcs, dev)
+        with torch.no_grad():
+            for v, x in zip(views, srcs):
+                v.copy_(x.detach())
+        ns = len(student_inputs)
+        self._g_xs = [v.requires_grad_(bool(x.requires_grad)) for v, x in zip(views[:ns], student_inputs)]
+        self._g_xt, k = [], ns
+        for xs in teacher_inputs:
+            self._g_xt.append(views[k:k + len(xs)])
+            k += len(xs)
+        self._stage_xs = None
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
@@ -153,8 +181,12 @@ class DistillStep:
             raise RuntimeError("DistillStep.prefetch() needs capture() first")
         dev = self.device
         if getattr(self, "_stage_xs", None) is None:
-            self._stage_xs = [torch.empty_like(x.detach()) for x in self._g_xs]
-            self._stage_xt = [[torch.empty_like(x) for x in xs] for xs in self._g_xt]
+            self._flat_stage, views = _flat_channels_last([x.detach() for x in self._g_xs] + [x for xs in self._g_xt for x in xs], dev)
+            ns = len(self._g_xs)
+            self._stage_xs, self._stage_xt, k = views[:ns], [], ns
+            for xs in self._g_xt:
+                self._stage_xt.append(views[k:k + len(xs)])
+                k += len(xs)
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._ev_ready = torch.cuda.Event()
             self._ev_consumed = torch.cuda.Event()
@@ -177,8 +209,7 @@ class DistillStep:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._ev_ready)
         with torch.no_grad():
-            torch._foreach_copy_([x.detach() for x in self._g_xs] + [d for ds in self._g_xt for d in ds],
-                                 list(self._stage_xs) + [s for ss in self._stage_xt for s in ss])
+            self._flat_static.copy_(self._flat_stage)       # one copy: both sets share the flat layout
         self._ev_consumed.record(cur)
         self._prefetched = False
         self._graph.replay()
