@@ -243,3 +243,21 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+
+
+def test_flat_channels_last_views():
+    """DistillStep's static / staging input sets: channels_last views of ONE allocation with identical layouts, so a
+    whole set moves with a single copy of the flat buffer."""
+    from mm_distillnet_b200.distill import _flat_channels_last
+    xs = [torch.randn(2, 48, 8, 8).to(torch.bfloat16), torch.randn(2, 120, 4, 4).to(torch.bfloat16), torch.randn(2, 352, 2, 2)]
+    flat_a, va = _flat_channels_last(xs, torch.device("cpu"))
+    flat_b, vb = _flat_channels_last(xs, torch.device("cpu"))
+    assert flat_a.numel() == flat_b.numel() and flat_a.dtype == torch.uint8
+    for v, x in zip(va, xs):
+        assert v.shape == x.shape and v.dtype == x.dtype and v.is_contiguous(memory_format=torch.channels_last)
+        assert v.data_ptr() % 16 == 0          # bulk copies / 16-byte vector loads of the kernels
+        v.copy_(x)
+    flat_b.copy_(flat_a)
+    assert all(torch.equal(b, x) for b, x in zip(vb, xs))
+    leaf = va[0].requires_grad_(True)
+    assert leaf.is_leaf and leaf.requires_grad
