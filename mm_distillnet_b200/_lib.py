@@ -71,25 +71,82 @@ class Op(C.Structure):
 NULL_REF = (-1, 0, 0)
 
 
+NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC")
+
+
 def nvcc_command(out_path=LIB_PATH, extra=()):
+    """The single-command equivalent of build() (documentation / manual builds)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-            "-Xcompiler", "-fPIC", "-shared", "-o", out_path, *extra, *srcs]
+    return ["nvcc", *NVCC_FLAGS, "-shared", "-o", out_path, *extra, *srcs]
+
+
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _deps():
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "mmd.h"))
+    return deps
+
+
+def source_hash():
+    """SHA-256 over every source / header the library is built from (content, not mtimes: the snapshot that carries the
+    tree to the GPU box does not have to preserve timestamps)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_stale():
+    """True when libmmd_b200.so is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA sources into mm_distillnet_b200/libmmd_b200.so (in-tree, sm_100a only)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(os.path.dirname(_HERE), "include", "mmd.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+    """Compile the CUDA sources into mm_distillnet_b200/libmmd_b200.so (in-tree, sm_100a only).  Skipped when the library
+    on disk was built from exactly the current sources (content hash in libmmd_b200.so.srchash)."""
+    if not force and not is_stale():
         return LIB_PATH
-    cmd = nvcc_command()
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    digest = source_hash()
+    # one nvcc process per translation unit (the v4 kernels are template-heavy), then one link
+    import concurrent.futures
+    import tempfile
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = tempfile.mkdtemp(prefix="mmd_build_")
+    objs = [os.path.join(tmp, os.path.splitext(os.path.basename(s))[0] + ".o") for s in srcs]
+
+    def cc(pair):
+        src, obj = pair
+        cmd = ["nvcc", *NVCC_FLAGS, "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        return subprocess.run(cmd, capture_output=True, text=True)
+
+    try:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(cc, zip(srcs, objs)))
+        bad = [r for r in results if r.returncode != 0]
+        if bad:
+            raise RuntimeError("nvcc failed:\n" + "\n".join(r.stdout + r.stderr for r in bad))
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    with open(HASH_PATH, "w") as f:
+        f.write(digest + "\n")
     return LIB_PATH
 
 
@@ -97,12 +154,12 @@ _lib = None
 
 
 def lib():
-    """Load the shared library (building it first if the sources are newer).  Raises if unavailable."""
+    """Load the shared library, (re)building it first when it is missing or was built from other sources than the tree
+    holds (content hash, see is_stale()).  Raises if unavailable: there is no fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        build()
+    build()
     L = C.CDLL(LIB_PATH)
     L.mmd_version.restype = C.c_int
     L.mmd_last_error.restype = C.c_char_p

@@ -16,8 +16,9 @@ import torch.nn as nn
 
 from . import _lib
 
-_STATS_EPOCH = {}    # id(module) -> count of train-mode forwards (they update running statistics through raw pointers,
-                     # behind PyTorch's version counters); eval plans of the same modules re-fold their BatchNorms after one
+_EPOCH_ATTR = "_mmd_stats_epoch"   # per-module count of train-mode forwards (they update running statistics through raw
+                                   # pointers, behind PyTorch's version counters); eval plans of the same modules re-fold
+                                   # their BatchNorms after one.  A plain attribute: id(module) can be reused after GC.
 BN_MOMENTUM = 0.01   # src/YetAnotherEfficientDet.py:176
 BN_EPS = 1e-3
 _ALIGN = 256
@@ -82,6 +83,9 @@ class BiFPN(nn.Module):
 
     def __init__(self, num_channels, conv_channels, first_time=False, epsilon=1e-4, onnx_export=False, attention=True):
         super(BiFPN, self).__init__()
+        if num_channels != KERNEL_CHANNELS:   # D0/D1/D3.. (src/YetAnotherEfficientDet.py:611-629): fail at construction
+            raise NotImplementedError("mm_distillnet_b200.BiFPN: the sm_100a kernels are built for num_channels=%d "
+                                      "(EfficientDet-D2, compound_coef=2), got %d" % (KERNEL_CHANNELS, num_channels))
         self.epsilon = epsilon
         self.num_channels = num_channels
         self.conv_channels = list(conv_channels) if conv_channels is not None else None
@@ -254,7 +258,7 @@ class _Plan:
         self.ops = []
         self.Cc = None
         self.params = self._collect_params(mods)
-        self.mod_ids = [id(m) for m in mods]
+        self.mods = list(mods)
         self.state_tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
         self.grad_off = {}
         if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
@@ -746,6 +750,17 @@ class _Runner:
         self._param_cache = None
         self.grad_sink = None   # callable(flat_fp32_grad) -> None; see DistillStep
 
+    # Plans hold ctypes op lists full of raw device pointers: they are a cache, never state.  copy.deepcopy(module),
+    # torch.save(module) and spawn-based workers therefore get a fresh, empty runner (plans are rebuilt on first use).
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return _Runner()
+
     def _plan_for(self, mods, inputs, training, kind):
         if len(inputs) == 0:
             raise ValueError("BiFPN: empty input tuple")
@@ -759,23 +774,37 @@ class _Runner:
                 raise ValueError("BiFPN: inputs must be [B,C,H,W] tensors sharing batch, dtype and device")
         ck = tuple(id(m) for m in mods)
         if self._param_cache is None or self._param_cache[0] != ck:   # walking 5 cells' modules costs ~1 ms per call
-            self._param_cache = (ck, [p for m in mods for p in m.parameters()])
-        params = self._param_cache[1]
+            self._param_cache = (ck, [p for m in mods for p in m.parameters()], [b for m in mods for b in m.buffers()])
+        params, buffers = self._param_cache[1], self._param_cache[2]
+        if len(params) == 0:
+            raise RuntimeError("mm_distillnet_b200.BiFPN: the module holds no parameters (an nn.DataParallel replica?); "
+                               "multi-GPU runs use one process per GPU, see mm_distillnet_b200.DistillStep")
         if any(p.dtype != torch.float32 for p in params):
             raise TypeError("BiFPN parameters must stay float32 (master weights); cast activations, not the module")
         if any(p.device != x0.device for p in params):
             raise RuntimeError("BiFPN: parameters and inputs live on different devices")
         grad_on = torch.is_grad_enabled()
         in_need = [grad_on and x.requires_grad for x in inputs]
-        need_grad = training and grad_on and (any(in_need) or any(p.requires_grad for p in params))
+        wants_grad = grad_on and (any(in_need) or any(p.requires_grad for p in params))
+        if wants_grad and not training:
+            # the eval-mode kernels fold the running statistics into the 1x1 weights and keep nothing for a backward;
+            # returning detached outputs would silently drop the gradients (reference BiFPN is differentiable in eval mode)
+            raise NotImplementedError(
+                "mm_distillnet_b200.BiFPN: backward through an eval-mode (folded BatchNorm) forward is not supported; "
+                "call .train() on the student, or run frozen / validation forwards under torch.no_grad() "
+                "(teachers: train_methods.py:321, validate: :1132-1142)")
+        need_grad = training and wants_grad
         Cc = mods[0].num_channels if kind == "cells" else inputs[0].shape[1]
         if Cc != KERNEL_CHANNELS:
             raise NotImplementedError("the sm_100a BiFPN kernels are built for %d channels (EfficientDet-D2), got %d"
                                       % (KERNEL_CHANNELS, Cc))
         if training and x0.shape[0] * min(x.shape[2] * x.shape[3] for x in inputs) < 1:
             raise ValueError("empty batch")
+        # the op lists hold the raw data_ptr() of EVERY parameter and BatchNorm buffer: all of them are part of the key
+        # (load_state_dict(assign=True), an EMA swap through p.data or a reassigned buffer must miss the cache)
+        ptrs = hash(tuple(t.data_ptr() for t in params) + tuple(t.data_ptr() for t in buffers))
         key = (kind, tuple(tuple(x.shape) for x in inputs), x0.dtype, bool(training), need_grad, tuple(in_need),
-               x0.device.index, len(params), params[0].data_ptr(), params[-1].data_ptr())
+               x0.device.index, len(params), ptrs)
         plan = self.plans.get(key)
         if plan is None:
             plan = _Plan(mods, kind, [tuple(x.shape) for x in inputs], x0.dtype, bool(training), need_grad, in_need)
@@ -823,10 +852,10 @@ class _Runner:
         if plan.dtype != torch.bfloat16:
             return
         if plan.train:
-            for mid in plan.mod_ids:   # this forward updates running statistics through raw pointers
-                _STATS_EPOCH[mid] = _STATS_EPOCH.get(mid, 0) + 1
+            for m in plan.mods:   # this forward updates running statistics through raw pointers
+                object.__setattr__(m, _EPOCH_ATTR, getattr(m, _EPOCH_ATTR, 0) + 1)
         else:
-            sig = (tuple(_STATS_EPOCH.get(mid, 0) for mid in plan.mod_ids), tuple(t._version for t in plan.state_tensors))
+            sig = (tuple(getattr(m, _EPOCH_ATTR, 0) for m in plan.mods), tuple(t._version for t in plan.state_tensors))
             if getattr(plan, "_prep_sig", None) == sig:
                 return
             plan._prep_sig = sig

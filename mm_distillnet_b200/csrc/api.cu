@@ -29,6 +29,45 @@ bool pdl_enabled() {
   return on == 1;
 }
 
+static thread_local bool g_pdl_fence = false;
+void pdl_fence_next() { g_pdl_fence = true; }
+bool pdl_take() {
+  const bool fenced = g_pdl_fence;
+  g_pdl_fence = false;
+  return pdl_enabled() && !fenced;
+}
+
+// ---- per-device launch configuration (see common.cuh) ----------------------------------------------------------------
+static std::mutex g_cfg_mu;
+static std::vector<std::pair<const void*, int>> g_cfg_done;   // (kernel, device) pairs whose smem attribute is set
+static int g_sm_count[64] = {0};
+int device_sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  int n = g_sm_count[dev];
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    g_sm_count[dev] = n;
+  }
+  return n;
+}
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    for (const auto& e : g_cfg_done)
+      if (e.first == kernel && e.second == dev) return 0;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
+  g_cfg_done.emplace_back(kernel, dev);
+  return 0;
+}
+
 // ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
 static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",
                                            "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot",

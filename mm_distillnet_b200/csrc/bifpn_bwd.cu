@@ -616,23 +616,14 @@ __device__ __forceinline__ void slot_body(const NodeBwdP& P) {
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 template <typename T>
 static int launch_node_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   const size_t smem_a = BwdASmem<C>::kFloats * sizeof(float), smem_b = BwdBSmem<C>::kFloats * sizeof(float);
-  MMD_CUDA(cudaFuncSetAttribute(node_bwd_a_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
-  MMD_CUDA(cudaFuncSetAttribute(node_bwd_b_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  MMD_SMEM((node_bwd_a_kernel<T, C>), smem_a);
+  MMD_SMEM((node_bwd_b_kernel<T, C>), smem_b);
   const int grid = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();
   const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, sizeof(T));
   static int no_v4 = -1;
@@ -664,7 +655,7 @@ static int launch_proj_bwd_t(const NodeBwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   if (sizeof(T) == 2 && !tc_disabled() && proj_bwd_v4_usable(p)) return launch_proj_bwd_v4(p, C, s);
   const size_t smem = ProjBSmem<C>::kFloats * sizeof(float);
-  MMD_CUDA(cudaFuncSetAttribute(proj_bwd_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMD_SMEM((proj_bwd_kernel<T, C>), smem);
   const int gx = p.g.ntiles < sm_count() ? p.g.ntiles : sm_count();
   const int gy = (p.Cin + kProjBC - 1) / kProjBC;
   ProfScope prof(PK_PROJ_BWD, 2.0 * p.g.B * p.g.H * p.g.W * (p.Cin + C) * sizeof(T), s);

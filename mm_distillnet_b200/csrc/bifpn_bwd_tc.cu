@@ -197,7 +197,7 @@ int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   constexpr int CC = 112;
   const size_t smem = BwdATcSmem<CC>::kBytes;
-  MMD_CUDA(cudaFuncSetAttribute(node_bwd_a_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMD_SMEM((node_bwd_a_tc_kernel<CC>), smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

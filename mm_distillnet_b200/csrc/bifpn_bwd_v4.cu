@@ -938,16 +938,7 @@ __global__ void __launch_bounds__(128) fwgrad_kernel(const __grid_constant__ FwG
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 static int x1_mode(const NodeBwdP& p) {
   if (p.n_in == 1) return X1_NONE;
@@ -959,11 +950,7 @@ static int x1_mode(const NodeBwdP& p) {
 template <int TW, int TH, int X1M, bool SW>
 static int launch_b(const NodeBwdP& p, cudaStream_t s) {
   using S = CfgB<TW, TH>;
-  static bool configured = false;
-  if (!configured) {
-    MMD_CUDA(cudaFuncSetAttribute(node_bwd_b4_kernel<TW, TH, X1M, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
-    configured = true;
-  }
+  MMD_SMEM((node_bwd_b4_kernel<TW, TH, X1M, SW>), S::kBytes);
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   const int grid = ntiles < sm_count() ? ntiles : sm_count();
   MMD_CUDA(launch_pdl(node_bwd_b4_kernel<TW, TH, X1M, SW>, dim3(grid), dim3(S::kBlock), S::kBytes, s, p));
@@ -974,11 +961,7 @@ static int launch_b(const NodeBwdP& p, cudaStream_t s) {
 template <int TW, int TH>
 static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
   using SA = CfgA<TW, TH>;
-  static bool configured = false;
-  if (!configured) {
-    MMD_CUDA(cudaFuncSetAttribute(node_bwd_a4_kernel<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SA::kBytes));
-    configured = true;
-  }
+  MMD_SMEM((node_bwd_a4_kernel<TW, TH>), SA::kBytes);
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, 2);
   {
@@ -1001,11 +984,7 @@ static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
 template <int TW, int TH, int NC>
 static int launch_proj(const NodeBwdP& p, int nchunks, cudaStream_t s) {
   using S = CfgP<TW, TH, NC>;
-  static bool configured = false;
-  if (!configured) {
-    MMD_CUDA(cudaFuncSetAttribute(proj_bwd4_kernel<TW, TH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
-    configured = true;
-  }
+  MMD_SMEM((proj_bwd4_kernel<TW, TH, NC>), S::kBytes);
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   int gx = sm_count() / nchunks;
   if (gx < 1) gx = 1;

@@ -381,33 +381,13 @@ __device__ __forceinline__ void bnapply_body(const NodeFwdP& P) {
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
-template <typename K>
-static int set_smem(K kernel, size_t bytes) {
-  MMD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return 0;
-}
+static int num_sms() { return device_sm_count(); }
 
 template <typename T>
 static int launch_node_fwd_t(const NodeFwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   const size_t smem = FwdSmem<C>::kFloats * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(node_fwd_kernel<T, C>, smem);
-    if (rc) return rc;
-    configured = true;
-  }
+  MMD_SMEM((node_fwd_kernel<T, C>), smem);
   int grid = p.g.ntiles < num_sms() ? p.g.ntiles : num_sms();
   ProfScope prof(PK_NODE_FWD, node_algo_bytes(p.in, p.n_in, p.g, C, sizeof(T)), s);
   node_fwd_kernel<T, C><<<grid, kThreads, smem, s>>>(p);
@@ -419,12 +399,7 @@ template <typename T>
 static int launch_proj_fwd_t(const NodeFwdP& p, cudaStream_t s) {
   constexpr int C = 112;
   const size_t smem = ProjSmem<C>::kFloats * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    int rc = set_smem(proj_fwd_kernel<T, C>, smem);
-    if (rc) return rc;
-    configured = true;
-  }
+  MMD_SMEM((proj_fwd_kernel<T, C>), smem);
   int grid = p.g.ntiles < 2 * num_sms() ? p.g.ntiles : 2 * num_sms();
   ProfScope prof(PK_PROJ_FWD, (double)p.g.B * p.g.H * p.g.W * (p.Cin + C) * sizeof(T), s);
   proj_fwd_kernel<T, C><<<grid, kThreads, smem, s>>>(p);

@@ -565,8 +565,8 @@ int launch_node_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s) {
     const char* e = getenv("MMD_FWD_V1");
     use_v1 = (e && e[0] == '1') ? 1 : 0;
   }
-  MMD_CUDA(cudaFuncSetAttribute(node_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MMD_CUDA(cudaFuncSetAttribute(node_fwd_tc2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMD_SMEM((node_fwd_tc_kernel<CC>), smem);
+  MMD_SMEM((node_fwd_tc2_kernel<CC>), smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -700,7 +700,7 @@ int launch_proj_fwd_tc_multi(const NodeFwdP* ps, int n, int C, cudaStream_t s) {
   const int Kp = (p.Cin + 15) / 16 * 16, KG = Kp / 8;
   const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 32;
   MMD_CHECK_ARG(smem <= 227 * 1024, "projection with Cin=%d does not fit in shared memory", p.Cin);
-  MMD_CUDA(cudaFuncSetAttribute(proj_fwd_tc_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MMD_SMEM((proj_fwd_tc_kernel<CC>), smem);
   NodeFwdBatch batch;
   for (int i = 0; i < kMaxBatchNets; ++i) batch.p[i] = ps[i < n ? i : 0];
   for (int i = 1; i < n; ++i)

@@ -862,14 +862,8 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
 template <int TW, int TH, bool PRE = false>
 static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   using S = Cfg<TW, TH>;
-  static bool configured = false;
-  if (!configured) {
-    MMD_CUDA(cudaFuncSetAttribute(node_fwd_v4_kernel<TW, TH, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
-    configured = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  MMD_SMEM((node_fwd_v4_kernel<TW, TH, PRE>), S::kBytes);
+  const int sms = device_sm_count();
   const NodeFwdP& p = batch.p[0];
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.0f);

@@ -36,6 +36,22 @@ void count_launch();
     MMD_CUDA(cudaGetLastError());                \
   } while (0)
 
+// ---- per-device launch configuration ------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel and the SM count is a per-device
+// number: both are tracked per device ordinal, so a process that touches several GPUs (one thread per GPU, or a test
+// that moves between devices) configures every kernel on each of them.
+int device_sm_count();                                    // SM count of the CURRENT device
+int ensure_dynamic_smem(const void* kernel, size_t bytes); // 0 or a cudaError_t; sets the attribute once per (kernel, device)
+#define MMD_SMEM(kernel, bytes)                                                          \
+  do {                                                                                   \
+    int rc_ = ::mmd::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (bytes)); \
+    if (rc_ != 0) {                                                                      \
+      ::mmd::set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s (%s:%d)", (size_t)(bytes), \
+                       cudaGetErrorString((cudaError_t)rc_), __FILE__, __LINE__);         \
+      return rc_;                                                                        \
+    }                                                                                    \
+  } while (0)
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
 // The step is a chain of ~200 short dependent kernels.  Kernels launched through launch_pdl() may be scheduled while
 // their predecessor still runs: everything up to pdl_wait() (TMEM allocation, mbarrier init, the bulk copy of the packed
@@ -44,6 +60,11 @@ void count_launch();
 // flight) lets the NEXT kernel start being scheduled.  Without the launch attribute both are no-ops.  MMD_NO_PDL=1
 // disables the attribute.
 bool pdl_enabled();
+// mmd_bifpn_prep rewrites the packed parameter blocks that the next forward kernel bulk-copies in its prologue, i.e.
+// BEFORE its griddepcontrol.wait: that one launch must not overlap its predecessor.  pdl_fence_next() (called by the
+// prep entry point after its launches) makes the next launch_pdl() of this thread a plain stream-ordered launch.
+void pdl_fence_next();
+bool pdl_take();   // pdl_enabled() and no pending fence (consumes the fence)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -56,7 +77,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_take() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -146,5 +146,7 @@ extern "C" int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* base
       if (rc) return rc;
     }
   }
-  return flush();
+  const int rc = flush();
+  pdl_fence_next();   // the next forward kernel reads these blocks in its prologue, before its griddepcontrol.wait
+  return rc;
 }

@@ -42,14 +42,25 @@ def same_pad(size, kernel, stride):
     return before, extra - before
 
 
-def maxpool_same(x):
+def maxpool_same(x, hint=None):
     """MaxPool2dStaticSamePadding(3, 2): zero-pad (NOT -inf) then 3x3/s2 max.
-    src/YetAnotherEfficientNet.py:90-104, instantiated at src/YetAnotherEfficientDet.py:228-231."""
+    src/YetAnotherEfficientNet.py:90-104, instantiated at src/YetAnotherEfficientDet.py:228-231.
+
+    `hint` (test-only, never part of the pinned path): a tensor shaped like `x` holding ANOTHER implementation's values
+    of the same tensor.  The window arg-max is then taken on `hint` (same zero padding, same first-maximum rule) and the
+    output gathers `x` there.  Forward values change by at most the top-2 gap of a window (~1e-7 where two fp32
+    executions disagree); the backward routes every gradient exactly like the implementation that produced `hint`, which
+    removes the arg-max-flip discontinuity from gradient comparisons (tests/test_gpu_bifpn.py)."""
     h, w = x.shape[-2:]
     top, bottom = same_pad(h, 3, 2)
     left, right = same_pad(w, 3, 2)
     x = F.pad(x, [left, right, top, bottom])
-    return F.max_pool2d(x, 3, 2)
+    if hint is None:
+        return F.max_pool2d(x, 3, 2)
+    assert hint.shape[-2:] == (h, w) and hint.shape[:2] == x.shape[:2]
+    hp = F.pad(hint.detach().to(torch.float64), [left, right, top, bottom])
+    _, idx = F.max_pool2d(hp, 3, 2, return_indices=True)
+    return x.flatten(-2).gather(-1, idx.flatten(-2)).view(idx.shape)
 
 
 def upsample2(x):
@@ -120,10 +131,12 @@ def fusion_weights(w, eps=FUSION_EPS):
 # BiFPN cell / stack
 # ----------------------------------------------------------------------------------------------
 def bifpn_cell(inputs, p, prefix="", first_time=False, training=False, attention=True,
-               eps=FUSION_EPS, stats_out=None):
+               eps=FUSION_EPS, stats_out=None, pool_hints=None):
     """One BiFPN cell.  src/YetAnotherEfficientDet.py:320-392 (attention=True) and :394-442
-    (attention=False: plain sums).  `p` holds the cell's tensors under `prefix`."""
+    (attention=False: plain sums).  `p` holds the cell's tensors under `prefix`.
+    `pool_hints` (test-only, see maxpool_same): {"p3_out" | "p4_out" | "p5_out" | "p6_out": tensor}."""
     q = prefix
+    hint = (pool_hints or {}).get
 
     def fw(name, n):
         if attention:
@@ -156,24 +169,26 @@ def bifpn_cell(inputs, p, prefix="", first_time=False, training=False, attention
         p5_in = projection(p5, p, q + "p5_down_channel_2", training, stats_out)          # :363
 
     w = fw("p4_w2", 3)
-    p4_out = sep(swish(w[0] * p4_in + w[1] * p4_up + w[2] * maxpool_same(p3_out)), "conv4_down")  # :366-370
+    p4_out = sep(swish(w[0] * p4_in + w[1] * p4_up + w[2] * maxpool_same(p3_out, hint("p3_out"))), "conv4_down")  # :366-370
     w = fw("p5_w2", 3)
-    p5_out = sep(swish(w[0] * p5_in + w[1] * p5_up + w[2] * maxpool_same(p4_out)), "conv5_down")  # :373-377
+    p5_out = sep(swish(w[0] * p5_in + w[1] * p5_up + w[2] * maxpool_same(p4_out, hint("p4_out"))), "conv5_down")  # :373-377
     w = fw("p6_w2", 3)
-    p6_out = sep(swish(w[0] * p6_in + w[1] * p6_up + w[2] * maxpool_same(p5_out)), "conv6_down")  # :380-384
+    p6_out = sep(swish(w[0] * p6_in + w[1] * p6_up + w[2] * maxpool_same(p5_out, hint("p5_out"))), "conv6_down")  # :380-384
     w = fw("p7_w2", 2)
-    p7_out = sep(swish(w[0] * p7_in + w[1] * maxpool_same(p6_out)), "conv7_down")        # :387-390
+    p7_out = sep(swish(w[0] * p7_in + w[1] * maxpool_same(p6_out, hint("p6_out"))), "conv7_down")        # :387-390
     return p3_out, p4_out, p5_out, p6_out, p7_out
 
 
 def bifpn_stack(inputs, p, n_cells, prefix="", first_cell_first_time=True, training=False,
-                attention=True, stats_out=None):
+                attention=True, stats_out=None, pool_hints=None):
     """nn.Sequential(*[BiFPN(..., first_time=(i == 0), attention=...)]) as built at
-    src/YetAnotherEfficientDet.py:639-644 and called at :668.  Keys are `<prefix><i>.<name>`."""
+    src/YetAnotherEfficientDet.py:639-644 and called at :668.  Keys are `<prefix><i>.<name>`.
+    `pool_hints` (test-only): one dict per cell, see bifpn_cell."""
     feats = inputs
     for i in range(n_cells):
         feats = bifpn_cell(feats, p, prefix + "%d." % i, first_time=(i == 0 and first_cell_first_time),
-                           training=training, attention=attention, stats_out=stats_out)
+                           training=training, attention=attention, stats_out=stats_out,
+                           pool_hints=None if pool_hints is None else pool_hints[i])
     return feats
 
 

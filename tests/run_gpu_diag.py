@@ -33,6 +33,16 @@ CASES = [
     ("stack_rand_5cells_s96", lambda: G.random_stack_case(5, True, 2, 96)),
     ("stack_rand_2cells_s48_oddP7", lambda: G.random_stack_case(2, True, 1, 48)),  # 48,24,12,6,3: odd P7
     ("stack_rand_3cells_s48_bf16", lambda: G.random_stack_case(3, True, 2, 48, dtype=BF)),
+    ("stack_rand_5cells_s96_bf16", lambda: G.random_stack_case(5, True, 2, 96, dtype=BF)),
+    ("stack_rand_2cells_s48_bf16_smoke", lambda: G.random_stack_case(2, True, 2, 48, dtype=BF, ref64=False)),
+    ("stack_golden_cell_c112_bf16", lambda: G.stack_golden_case("cell_c112", dtype=BF)),
+    ("stack_golden_stack2_c112_bf16", lambda: G.stack_golden_case("stack2_c112", dtype=BF)),
+    # the same fp32 cases WITHOUT the arg-max hints (what the max-pool flips cost), and repeated with hints (stability)
+    ("stack_rand_5cells_s96_nohint", lambda: G.random_stack_case(5, True, 2, 96, force_argmax=False)),
+    ("stack_rand_3cells_s48_mixedfw_nohint", lambda: G.random_stack_case(3, True, 2, 48, fw_mode="mixed", channels_last=True, force_argmax=False)),
+    ("stack_rand_5cells_s96_rep2", lambda: G.random_stack_case(5, True, 2, 96)),
+    ("stack_rand_5cells_s96_seed1", lambda: G.random_stack_case(5, True, 2, 96, seed=1)),
+    ("stack_rand_3cells_s48_mixedfw_seed1", lambda: G.random_stack_case(3, True, 2, 48, fw_mode="mixed", channels_last=True, seed=1)),
 ]
 
 

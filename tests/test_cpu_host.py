@@ -261,3 +261,91 @@ def test_flat_channels_last_views():
     assert all(torch.equal(b, x) for b, x in zip(vb, xs))
     leaf = va[0].requires_grad_(True)
     assert leaf.is_leaf and leaf.requires_grad
+
+
+def test_other_channel_counts_fail_at_construction():
+    """The reference builds D0..D7 (64/88/112/160.. channels, src/YetAnotherEfficientDet.py:611-629); the kernels exist for
+    D2 only, and a drop-in must say so when the model is built, not at its first forward."""
+    with pytest.raises(NotImplementedError):
+        mmd.BiFPN(64, [40, 112, 320], first_time=True)
+    with pytest.raises(NotImplementedError):
+        mmd.BiFPN(160, [48, 136, 384])
+
+
+def test_modules_with_cached_plans_deepcopy_and_pickle():
+    """A runner that holds plans (ctypes op lists full of device pointers) must not break copy.deepcopy / pickling of the
+    module (EMA copies, best-model snapshots, spawn-based workers): the copy gets a fresh, empty runner."""
+    import copy
+    import pickle
+    stack = mmd.BiFPNStack(*[mmd.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(2)])
+    shapes = [(2, 48, 16, 16), (2, 120, 8, 8), (2, 352, 4, 4)]
+    plan = bifpn._Plan(list(stack), "cells", shapes, torch.bfloat16, True, True, [False] * 3)
+    stack._runner.plans["k"] = plan
+    stack[0]._runner.plans["k"] = plan
+    stack._runner.grad_sink = lambda flat: None
+    dup = copy.deepcopy(stack)
+    assert dup._runner is not stack._runner and dup._runner.plans == {} and dup._runner.grad_sink is None
+    assert dup[0]._runner.plans == {} and len(stack._runner.plans) == 1
+    assert all(torch.equal(a, b) for a, b in zip(dup.state_dict().values(), stack.state_dict().values()))
+    stack._runner.grad_sink = None
+    back = pickle.loads(pickle.dumps(stack))
+    assert back._runner.plans == {} and set(back.state_dict()) == set(stack.state_dict())
+
+
+def test_library_staleness_is_a_content_hash():
+    """_lib.lib() rebuilds when the .so was built from other sources (hash of the sources, not mtimes)."""
+    assert os.path.exists(_lib.LIB_PATH) and not _lib.is_stale()
+    with open(_lib.HASH_PATH) as f:
+        saved = f.read()
+    try:
+        with open(_lib.HASH_PATH, "w") as f:
+            f.write("0" * 64 + "\n")
+        assert _lib.is_stale()
+    finally:
+        with open(_lib.HASH_PATH, "w") as f:
+            f.write(saved)
+    assert not _lib.is_stale() and saved.strip() == _lib.source_hash()
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="the reference tree exists in the build container only")
+def test_patch_reference_on_the_real_modules():
+    """patch_reference() on the REAL src.* modules (not fakes): the patched YetAnotherEfficientDet(D2) has the same
+    state_dict keys / shapes as the unpatched one, loads its state_dict strictly, holds a fused BiFPNStack, refuses CPU
+    tensors (no fallback), and other compound coefficients fail at construction."""
+    import importlib
+    import sys
+    sys.path.insert(0, REF)
+    try:
+        det = importlib.import_module("src.YetAnotherEfficientDet")
+        loss = importlib.import_module("src.loss.MTALoss")
+        orig_bifpn, orig_mta, orig_init = det.BiFPN, loss.MTALoss, det.YetAnotherEfficientDet.__init__
+        torch.manual_seed(0)
+        ref_model = det.YetAnotherEfficientDet(num_classes=20, compound_coef=2)
+        ref_sd = ref_model.state_dict()
+        try:
+            mmd.patch_reference()
+            assert det.BiFPN is mmd.BiFPN and loss.MTALoss is mmd.MTALoss
+            torch.manual_seed(0)
+            ours = det.YetAnotherEfficientDet(num_classes=20, compound_coef=2)
+            assert isinstance(ours.bifpn, mmd.BiFPNStack) and len(ours.bifpn) == 5
+            sd = ours.state_dict()
+            assert list(sd.keys()) == list(ref_sd.keys())
+            assert all(tuple(sd[k].shape) == tuple(ref_sd[k].shape) for k in sd)
+            # same construction order under the same seed -> identical initial weights
+            assert all(torch.equal(sd[k], ref_sd[k]) for k in sd if k.startswith("bifpn."))
+            ours.load_state_dict(ref_sd, strict=True)
+            with pytest.raises(RuntimeError):          # CPU tensors: the product path has no CPU fallback
+                ours.eval()(torch.zeros(1, 3, 768, 768))
+            with pytest.raises(NotImplementedError):   # D0: 64 channels
+                det.YetAnotherEfficientDet(num_classes=20, compound_coef=0)
+            crit = loss.MTALoss(T="9", p="2")
+            assert isinstance(crit, mmd.MTALoss)
+        finally:
+            det.BiFPN, loss.MTALoss = orig_bifpn, orig_mta
+            det.YetAnotherEfficientDet.__init__ = orig_init
+            det.YetAnotherEfficientDet._mmd_patched = False
+    finally:
+        sys.path.remove(REF)

@@ -101,3 +101,39 @@ def test_landmarks():
     assert abs(w[0].item() - 0.333322) < 1e-6
     x = -torch.ones(1, 1, 4, 4)
     assert O.maxpool_same(x).flatten().tolist() == [-1.0, 0.0, 0.0, 0.0]   # zero pad wins at the border
+
+
+def test_pool_hint_with_own_values_is_the_pinned_path():
+    """maxpool_same(x, hint=x) (the test-only arg-max forcing used by the fp32 GPU gradient checks) equals the pinned
+    maxpool_same(x) in value and gradient, including ties against the zero padding and first-maximum ties."""
+    x = O.synth((2, 5, 9, 12), 3).requires_grad_(True)
+    with torch.no_grad():
+        x[0, 0, :2, :2] = 0.25          # a 4-way tie inside one window: the first maximum takes the gradient
+        x[1, :, -1, :] = -1.0           # bottom windows: the padding zero wins
+    g = O.synth((2, 5, 5, 6), 4)
+    a = O.maxpool_same(x)
+    (ga,) = torch.autograd.grad((a * g).sum(), x)
+    b = O.maxpool_same(x, hint=x.detach().clone())
+    (gb,) = torch.autograd.grad((b * g).sum(), x)
+    assert torch.equal(a, b) and torch.equal(ga, gb)
+    # a hint that prefers another element of a window reroutes the gradient and moves the value by the top-2 gap only
+    h = x.detach().clone()
+    h[0, 1, 4, 4] += 10.0
+    c = O.maxpool_same(x, hint=h)
+    (gc,) = torch.autograd.grad((c * g).sum(), x)
+    assert gc[0, 1, 4, 4] != ga[0, 1, 4, 4] and (c - a).abs().max() <= 2.0
+
+
+def test_stack_pool_hints_reproduce_unhinted_stack():
+    name = "stack2_c16_odd"
+    C, cc, n_cells, first, B, s3, seed = H.STACK_CASES[name]
+    params, xs = H.stack_case_inputs(name)
+    with torch.no_grad():
+        feats, hints = tuple(xs), []
+        for i in range(n_cells):   # per-cell outputs of the same implementation as hints
+            feats = O.bifpn_cell(feats, params, "%d." % i, first_time=(i == 0 and first), training=True)
+            hints.append(dict(zip(("p3_out", "p4_out", "p5_out", "p6_out"), feats)))
+        a = O.bifpn_stack(tuple(xs), params, n_cells, first_cell_first_time=first, training=True)
+        b = O.bifpn_stack(tuple(xs), params, n_cells, first_cell_first_time=first, training=True, pool_hints=hints)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
