@@ -91,19 +91,32 @@ def time_cpu(B, steps, warmup):
 
 
 def run_reference(args, rank):
+    """The reference arm: the CPU port of the reference's own implementation of the path (oracle/, pinned against outputs
+    of the unmodified reference) on all host threads, SAME step and SAME batch as the CUDA arm.  If K + W steps at that
+    batch would not end within a few minutes on this host, the per-step sample is halved until they do (and the line
+    says so: config.batch_per_step / config.same_batch_as_cuda_arm)."""
     if rank != 0:
         return
-    B = 4   # bounded sample per step so the whole run ends within minutes; CPU samples/s is ~flat in B
-    ts = time_cpu(B, args.steps, args.warmup)
+    B = args.batch
+    budget_s = 240.0
+    t_probe = None
+    while True:
+        t_probe = sum(time_cpu(B, 1, 0))          # one untimed probe step (also warms the allocator / thread pool)
+        if t_probe * (args.steps + args.warmup) <= budget_s or B <= 2:
+            break
+        B //= 2
+    ts = time_cpu(B, args.steps, max(args.warmup - 1, 0))
     total = sum(ts)
     v = B * len(ts) / total
     cores = torch.get_num_threads()
-    sample = "each step = the full hot-path step at batch %d (student+3 teachers+3 MTA+backward), oracle port, torch CPU fp32" % B
+    sample = ("each step = the full hot-path step at batch %d (student fwd+bwd, 3 teacher fwd, 3 MTA calls), oracle port, "
+              "torch CPU fp32, %d threads" % (B, cores))
     line = {
         "impl": "reference", "metric": "distill samples/s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_step": B},
+        "config": {"workload": WORKLOAD, "batch_per_step": B, "batch_per_gpu": B, "cuda_arm_batch_per_gpu": args.batch,
+                   "same_batch_as_cuda_arm": B == args.batch},
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -111,9 +124,10 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-WORKLOAD = ("cfg2: MTA loss + 5-cell EfficientDet-D2 BiFPN fwd/bwd microbench on synthetic pyramid inputs "
-            "(C3 48@96^2, C4 120@48^2, C5 352@24^2 -> 112 ch P3-P7): student fwd+bwd (train BN) + 3 teacher fwd (eval) "
-            "+ 3 MTA calls")
+WORKLOAD = ("hot path of cfg3/cfg4 (3-teacher -> student distillation step, batch 32 per GPU, bf16) on the cfg2 microbench "
+            "inputs: MTA loss + 5-cell EfficientDet-D2 BiFPN on synthetic pyramid features (C3 48@96^2, C4 120@48^2, "
+            "C5 352@24^2 -> 112 ch P3-P7): student fwd+bwd (train BN) + 3 teacher fwd (eval) + 3 MTA calls "
+            "[+ flat-gradient NCCL all-reduce for N > 1]; the cfg2 batch (16) is measured in the same run (cfg2_b16)")
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -200,16 +214,22 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.src}
 
 
-def run_ours(args, rank, world, local_rank):
+def algo_bytes_per_step(B, esize, n_teachers=N_TEACHERS):
+    """Algorithmic HBM bytes of one step: student forward + backward = 3 x forward bytes, each teacher
+    forward = 1 x, MTA forward reads every student and teacher map once, MTA backward re-reads the student maps and
+    writes their gradient.  30 016 512 elements per sample and 5-cell forward; 12 276 * 112 per sample and pyramid."""
+    fwd = 30016512 * esize * B
+    pyr = POS_PER_SAMPLE * C * esize * B
+    return 3 * fwd + n_teachers * fwd + (1 + n_teachers) * pyr + 2 * pyr
+
+
+def measure(B, args, rank, world, dev, dtype, min_timed_s):
+    """Everything measured at one per-GPU batch size: resident (device-timed) step, end-to-end step, per-kernel
+    instrumented pass.  Timed regions are blocks of EXACTLY args.steps steps bracketed by barrier + synchronize; blocks are
+    repeated until >= min_timed_s seconds have been timed and the MEDIAN block is reported (max over ranks per block)."""
     import mm_distillnet_b200 as mmd
     from mm_distillnet_b200 import _lib
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     esize = 4 if dtype == torch.float32 else 2
-    B = args.batch
 
     torch.manual_seed(0)   # identical student init on every rank (DDP broadcast-at-start semantics)
     student = mmd.BiFPNStack(*[mmd.BiFPN(C, CC, first_time=(i == 0)) for i in range(N_CELLS)]).to(dev).train()
@@ -220,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
     step = mmd.DistillStep(student, teachers, mmd.MTALoss(T=9.0, p=2.0), w_kd=W_KD)
 
     gen = torch.Generator().manual_seed(1000 + rank)
+
     def pinned_nhwc(x):   # pinned host staging buffer already in the kernels' NHWC (channels_last) layout
         h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).contiguous(memory_format=torch.channels_last)
         if not h.is_pinned():
@@ -239,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed_block(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -254,12 +275,27 @@ def run_ours(args, rank, world, local_rank):
             ms = t.item()
         return ms
 
+    def timed(fn, steps, before_block=None):
+        blocks, total = [], 0.0
+        while True:
+            if before_block is not None:
+                before_block()
+            ms = timed_block(fn, steps)
+            blocks.append(ms)
+            total += ms
+            more = torch.tensor([1.0 if (total < 1e3 * min_timed_s and len(blocks) < 200) else 0.0], device=dev)
+            if world > 1:
+                dist.all_reduce(more, op=dist.ReduceOp.MIN)   # every rank times the same number of blocks
+            if more.item() == 0.0:
+                break
+        return statistics.median(blocks), blocks
+
     def eager_step():
         for x in dev_s:
             x.grad = None
         return step(dev_s, dev_t)
 
-    # The whole step is captured once into a CUDA graph (DistillStep.capture) and replayed: ~400 launches of a few
+    # The whole step is captured once into a CUDA graph (DistillStep.capture) and replayed: ~300 launches of a few
     # microseconds each are host-bound otherwise.  --no-graph times the eager path instead.
     use_graph = not args.no_graph
     if use_graph:
@@ -271,8 +307,7 @@ def run_ours(args, rank, world, local_rank):
         return eager_step()
 
     host_loss = torch.empty(N_TEACHERS, 5, dtype=torch.float32).pin_memory()
-
-    e2e_i = [0]
+    e2e_i, e2e_total = [0], [0]
 
     def e2e_step():
         if use_graph and not args.no_prefetch:
@@ -293,29 +328,59 @@ def run_ours(args, rank, world, local_rank):
         host_loss.copy_(kd, non_blocking=False)         # device->host read of the step's result
         return host_loss
 
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         resident_step()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    l0 = mmd.launch_count()
-    ms = timed(resident_step, args.steps)
-    launches = mmd.launch_count() - l0
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    ms, blocks = timed(resident_step, args.steps)
     clocks = sampler.stop() if sampler else None
-    if use_graph:   # replayed launches never pass through the library's host-side counter: count one eager step
-        torch.cuda.synchronize()
-        l0 = mmd.launch_count()
-        eager_step()
-        torch.cuda.synchronize()
-        launches = (mmd.launch_count() - l0) * args.steps
+    torch.cuda.synchronize()
+    l0 = mmd.launch_count()   # replayed launches never pass through the library's host-side counter: count one eager step
+    eager_step()
+    torch.cuda.synchronize()
+    launches_per_step = mmd.launch_count() - l0
 
-    e2e_total = [max(args.warmup, 3)]
-    for _ in range(max(args.warmup, 3)):
+    # gradient checksum (N > 1: the averaged flat gradient must be the same on every rank)
+    checksum = float(step.flat_grad.double().sum().item()) if step.flat_grad is not None else None
+    checks = [checksum]
+    if world > 1:
+        t = torch.tensor([checksum], dtype=torch.float64, device=dev)
+        ts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        checks = [float(x.item()) for x in ts]
+
+    def e2e_reset():
+        e2e_i[0], e2e_total[0] = 0, args.steps
+
+    e2e_total[0] = W
+    for _ in range(W):
         e2e_step()
-    e2e_i[0], e2e_total[0] = 0, args.steps
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e, blocks_e2e = timed(e2e_step, args.steps, before_block=e2e_reset)
 
-    # per-kernel CUDA-event timing of the same step (separate instrumented pass: event pairs around every launch)
-    # (every rank runs the instrumented steps: they contain the gradient all-reduce; rank 0 reports its own timings)
-    roof = None
+    # host->device feed alone (pinned host -> staging set on the copy stream), for the N > 1 e2e discussion
+    h2d = (1 + N_TEACHERS) * B * sum(c * (S3 >> i) ** 2 for i, c in enumerate(CC)) * esize
+    h2d_gbs = None
+    if use_graph and not args.no_prefetch:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cs = step._copy_stream
+        with torch.cuda.stream(cs):
+            e0.record(cs)
+        for _ in range(5):   # back to back on the copy stream (the staging set is free: no replay is pending)
+            step.prefetch(host_s, host_t)
+        with torch.cuda.stream(cs):
+            e1.record(cs)
+        barrier()
+        h2d_ms = e0.elapsed_time(e1) / 5
+        step._prefetched = False
+        if world > 1:
+            t = torch.tensor([h2d_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            h2d_ms = t.item()
+        h2d_gbs = h2d / (h2d_ms * 1e-3) / 1e9
+
+    # per-kernel CUDA-event timing of the same step (separate instrumented EAGER pass: an event pair around every launch;
+    # every rank runs it because the step contains the gradient all-reduce; rank 0 reports its own timings)
     _lib.prof_enable(True)
     _lib.prof_collect()
     nprof = min(args.steps, 5)
@@ -324,6 +389,7 @@ def run_ours(args, rank, world, local_rank):
     prof = _lib.prof_collect()
     _lib.prof_enable(False)
     barrier()
+    roof = None
     if rank == 0:
         peak, peak_src = peaks()
         total_ms = sum(v["ms"] for v in prof.values())
@@ -332,49 +398,97 @@ def run_ours(args, rank, world, local_rank):
         ach = d["algo_bytes"] / (d["ms"] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and B == 16:   # the committed ncu launch list was taken at the default batch
+        if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.dtype, {}).get(dom)
+                tj = json.load(f)
+            traffic = tj.get("%s_b%d" % (args.dtype, B), tj.get(args.dtype, {}) if B == 16 else {}).get(dom)
+        step_bytes = algo_bytes_per_step(B, esize)
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_us": 1e3 * d["ms"] / d["launches"], "algo_bytes_per_launch": d["algo_bytes"] / d["launches"],
                 "share_of_kernel_time": d["ms"] / total_ms,
+                # the WHOLE step against the same roofline: algorithmic bytes of the step / graph-replay time per step
+                "step": {"algo_bytes": step_bytes, "ms": ms / args.steps,
+                         "achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                         "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                "timing_note": ("per-kernel times: CUDA events around every launch of an eager pass (sum %.3f ms/step); the "
+                                "graph replay of the same launches takes %.3f ms/step (launch gaps and event overhead differ): "
+                                "shares are of the instrumented sum" % (total_ms / nprof, ms / args.steps)),
                 "all_kernels": {k: {"ms_per_step": v["ms"] / nprof, "launches_per_step": v["launches"] / nprof,
-                                    "GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
+                                    "GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None,
+                                    "frac": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9 / peak) if v["ms"] > 0 and v["algo_bytes"] > 0 else None}
                                 for k, v in prof.items()}}
+    res = {"B": B, "ms": ms, "blocks": blocks, "ms_e2e": ms_e2e, "blocks_e2e": blocks_e2e, "roof": roof, "clocks": clocks,
+           "launches_per_step": launches_per_step, "h2d": h2d, "h2d_gbs": h2d_gbs, "checksums": checks,
+           "use_graph": use_graph, "esize": esize}
+    # release this batch size's graph / arenas before the next one is measured
+    del step, student, teachers
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    B = args.batch
+    main_r = measure(B, args, rank, world, dev, dtype, args.min_seconds)
+    cfg2 = None
+    if B != 16 and not args.no_cfg2:   # BASELINE configs[1]: the microbench batch, same run, shorter timed region
+        cfg2 = measure(16, args, rank, world, dev, dtype, min(args.min_seconds, 1.0))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        Bc, Kc, Wc = 4, 25, 2    # ~10-12 s of CPU work on the box's host cores
+        Bc, Kc, Wc = B, 3, 1     # the same step at the same batch: ~10-30 s of CPU work on the box's host cores
         ts = time_cpu(Bc, Kc, Wc)
         cpu = {"value": Bc * len(ts) / sum(ts), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d timed steps (%d warm-up) of the same step at batch %d on the oracle port (torch CPU fp32, "
                          "all host threads)" % (Kc, Wc, Bc)}
 
-    if rank == 0:
-        h2d = (1 + N_TEACHERS) * B * sum(c * (S3 >> i) ** 2 for i, c in enumerate(CC)) * esize
-        line = {
-            "metric": "distill samples/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": "dp%d (flat-gradient NCCL all-reduce)" % world if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: the step streams ~%.1f GB of activations (L2 = 126 MB); no flush needed"
-                             % (3 * B * 30016512 * esize * 2 / 1e9),
-                       "optimizer": "none (the microbench ends at the averaged gradients)",
-                       "precision": "activations stored as %s, all arithmetic fp32 (TMEM accumulators, BatchNorm statistics "
-                                    "in double, fp32 master weights and gradients)" % args.dtype,
-                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager",
-                       "e2e_feed": ("pinned host inputs copied on a side stream into a staging set while the previous step "
-                                    "replays (DistillStep.prefetch / replay_prefetched); K copies, K replays, K loss "
-                                    "read-backs inside the timed region") if (use_graph and not args.no_prefetch)
-                                   else "inputs copied in front of every step"},
-            "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": B * world * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": N_TEACHERS * 5 * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
+    if rank != 0:
+        return
+    r = main_r
+    steps, ms, ms_e2e = args.steps, r["ms"], r["ms_e2e"]
+    line = {
+        "metric": "distill samples/s", "value": B * world * steps / (ms * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": "dp%d (flat-gradient NCCL all-reduce)" % world if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: the step streams ~%.1f GB of activations (L2 = 126 MB); no flush needed"
+                         % (algo_bytes_per_step(B, r["esize"]) / 1e9),
+                   "timed_region": "%d blocks of exactly %d steps each (%.2f s timed in total), median block reported; "
+                                   "min / max block %.3f / %.3f ms per step"
+                                   % (len(r["blocks"]), steps, sum(r["blocks"]) * 1e-3, min(r["blocks"]) / steps,
+                                      max(r["blocks"]) / steps),
+                   "optimizer": "none (the microbench ends at the averaged gradients)",
+                   "precision": "activations stored as %s, all arithmetic fp32 (TMEM accumulators, BatchNorm statistics "
+                                "in double, fp32 master weights and gradients)" % args.dtype,
+                   "launch": "CUDA graph replay of the whole step" if r["use_graph"] else "eager",
+                   "e2e_feed": ("pinned host inputs copied on a side stream into a staging set while the previous step "
+                                "replays (DistillStep.prefetch / replay_prefetched); K copies, K replays, K loss "
+                                "read-backs inside the timed region") if (r["use_graph"] and not args.no_prefetch)
+                               else "inputs copied in front of every step"},
+        "roofline": r["roof"], "cpu_baseline": cpu,
+        "e2e": {"value": B * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d"],
+                "d2h_bytes_per_step": N_TEACHERS * 5 * 4, "ms_per_step": ms_e2e / steps,
+                "h2d_feed_GBps_per_rank": r["h2d_gbs"],
+                "h2d_ms_per_step_alone": (r["h2d"] / (r["h2d_gbs"] * 1e9) * 1e3) if r["h2d_gbs"] else None,
+                "bound": ("host feed: the H2D copy of a step alone takes longer than the resident step"
+                          if r["h2d_gbs"] and r["h2d"] / (r["h2d_gbs"] * 1e9) * 1e3 > ms / steps else "device step")},
+        "gpu_launches": r["launches_per_step"] * steps, "gpu_launches_per_step": r["launches_per_step"],
+        "clocks": r["clocks"],
+        "grad_checksum": {"per_rank": r["checksums"], "equal_on_all_ranks": len(set(r["checksums"])) == 1},
+    }
+    if cfg2 is not None:
+        line["cfg2_b16"] = {"batch_per_gpu": 16, "value": 16 * world * steps / (cfg2["ms"] * 1e-3), "unit": "samples/s",
+                            "ms_per_step": cfg2["ms"] / steps,
+                            "e2e": {"value": 16 * world * steps / (cfg2["ms_e2e"] * 1e-3), "ms_per_step": cfg2["ms_e2e"] / steps},
+                            "roofline": cfg2["roof"], "gpu_launches_per_step": cfg2["launches_per_step"]}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -386,7 +500,11 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["f32", "bf16"],
                     help="activation STORAGE type; arithmetic (accumulators, statistics, weights) is fp32 in both modes. "
                          "bf16 is the tensor-core product path (BASELINE cfg 3), f32 the bit-level parity mode")
-    ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step (cfg2: 16)")
+    ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step (cfg3/cfg4: 32; cfg2's 16 is measured "
+                    "in the same run and reported as cfg2_b16)")
+    ap.add_argument("--min-seconds", type=float, default=2.0, help="repeat the timed block of K steps until this many "
+                    "seconds have been timed; the median block is reported")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the extra cfg2 (batch 16) measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-prefetch", action="store_true",

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 104
+#define MMD_VERSION 105
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -202,6 +202,13 @@ void mmd_prof_enable(int on);
 int mmd_prof_num_kinds(void);
 const char* mmd_prof_kind_name(int kind);
 int mmd_prof_collect(double* ms, long long* launches, double* algo_bytes);
+
+/* Runtime switches of the library (process-wide; each also has an environment default that is read once):
+ *   "chain_fwd"  0 / 1   run consecutive P5-P7 forward nodes of mmd_bifpn_run / _run_multi as ONE persistent launch with
+ *                        grid barriers between the nodes (cooperative launch).  Default 0 (env MMD_CHAIN=1): measured
+ *                        slower than separate launches on B200, see profiles/r2_chain_fwd.md.
+ * Returns 0, or MMD_E_ARG for an unknown name. */
+int mmd_set_option(const char* name, int32_t value);
 
 /* sizeof(MmdOp) / sizeof(MmdMtaArgs) as compiled, so a binding can verify its struct mirror */
 size_t mmd_sizeof_op(void);

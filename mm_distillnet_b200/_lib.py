@@ -180,6 +180,8 @@ def lib():
     L.mmd_bifpn_prep.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     L.mmd_packed_bytes.restype = C.c_size_t
     L.mmd_packed_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.mmd_set_option.restype = C.c_int
+    L.mmd_set_option.argtypes = [C.c_char_p, C.c_int32]
     L.mmd_prof_enable.argtypes = [C.c_int]
     L.mmd_prof_enable.restype = None
     L.mmd_prof_num_kinds.restype = C.c_int
@@ -200,6 +202,11 @@ def check(rc, what):
         raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
+def set_option(name, value):
+    """Runtime switch of the library (include/mmd.h: mmd_set_option), e.g. set_option("chain_fwd", 1)."""
+    check(lib().mmd_set_option(name.encode(), int(value)), "mmd_set_option")
+
+
 def launch_count():
     return int(lib().mmd_launch_count())
 
@@ -218,7 +225,7 @@ def prof_collect():
             for i in range(n) if cnt[i] > 0}
 
 
-EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run", "mmd_bifpn_run_multi",
+EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_set_option", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run", "mmd_bifpn_run_multi",
            "mmd_bifpn_prep", "mmd_packed_bytes",
            "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
            "mmd_prof_collect")

@@ -179,7 +179,7 @@ class _Tn:
 
 class _OpN:
     __slots__ = ("kind", "ins", "modes", "conv", "bn", "dw", "fw", "fw_eps", "swish", "out", "save_d", "pidx",
-                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed", "aux", "praw")
+                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed", "aux", "praw", "tag")
 
     def __init__(self, kind):
         self.kind = kind
@@ -198,6 +198,7 @@ class _OpN:
         self.packed = None     # (base, off) of the packed parameter block (bf16 plans)
         self.aux = None        # bf16 plans, nodes with a pooled input: (base, off) of the POOLFUSE pre-pass output
         self.praw = None       # ... and of the raw value at each pooling arg-max (kept for the backward)
+        self.tag = None        # (cell index, name) of the 3x3-s2 max-pool this op performs (debug_pool_argmax)
 
 
 # fixed base indices
@@ -306,9 +307,13 @@ class _Plan:
             op.stats = (B_PERSIST, self.persist.alloc(_lib.STATS_REPLICAS * 2 * self.Cc * 8))
             op.counter = (B_PERSIST, self.persist.alloc(4))
             op.bwd_counter = (B_PERSIST, self.persist.alloc(4))
+        elif self.dtype == torch.bfloat16:
+            # eval plans too: the persistent small-level chain keeps its grid-barrier words in the first node's counter
+            op.counter = (B_PERSIST, self.persist.alloc(4))
 
-    def _node(self, sep, ins, fw, fw_eps, swish=1):
+    def _node(self, sep, ins, fw, fw_eps, swish=1, tag=None):
         op = _OpN(_lib.OP_NODE_FWD)
+        op.tag = tag
         op.ins = [t for t, _ in ins]
         op.modes = [m for _, m in ins]
         op.conv, op.bn, op.dw = sep.pointwise_conv.conv, sep.bn, sep.depthwise_conv.conv
@@ -358,9 +363,10 @@ class _Plan:
         self.ops.append(op)
         return op.out
 
-    def _bnapply(self, src, mode, dst=None):
+    def _bnapply(self, src, mode, dst=None, tag=None):
         """dst = [pool](bn(src)); `dst` None allocates an arena tensor (P6/P7 synthesis)."""
         op = _OpN(_lib.OP_BNAPPLY)
+        op.tag = tag
         op.ins, op.modes = [src], [mode]
         H, W = (src.H, src.W) if mode == _lib.IN_SAME else ((src.H + 1) // 2, (src.W + 1) // 2)
         n = self.B * H * W * self.Cc
@@ -388,8 +394,8 @@ class _Plan:
             for t, cin in zip(ext, first.conv_channels):
                 if t.C != cin:
                     raise ValueError("BiFPN first cell: input has %d channels, expected %d" % (t.C, cin))
-            p6_in = self._bnapply(self._proj(first.p5_to_p6, c5), P)          # :324
-            p7_in = self._bnapply(p6_in, P)                                   # :325
+            p6_in = self._bnapply(self._proj(first.p5_to_p6, c5), P, tag=(0, "p6_in"))   # :324
+            p7_in = self._bnapply(p6_in, P, tag=(0, "p7_in"))                            # :325
             p3_in = self._proj(first.p3_down_channel, c3)                     # :327-329
             p4_in = self._proj(first.p4_down_channel, c4)
             p5_in = self._proj(first.p5_down_channel, c5)
@@ -412,10 +418,14 @@ class _Plan:
             p5_up = self._node(cell.conv5_up, [(p5_in, S), (p6_up, U)], fw("p5_w1"), e)            # :344-347
             p4_up = self._node(cell.conv4_up, [(p4_in, S), (p5_up, U)], fw("p4_w1"), e)            # :350-353
             p3_out = self._node(cell.conv3_up, [(p3_in, S), (p4_up, U)], fw("p3_w1"), e)           # :356-359
-            p4_out = self._node(cell.conv4_down, [(p4_in2, S), (p4_up, S), (p3_out, P)], fw("p4_w2"), e)  # :366-370
-            p5_out = self._node(cell.conv5_down, [(p5_in2, S), (p5_up, S), (p4_out, P)], fw("p5_w2"), e)  # :373-377
-            p6_out = self._node(cell.conv6_down, [(p6_in, S), (p6_up, S), (p5_out, P)], fw("p6_w2"), e)   # :380-384
-            p7_out = self._node(cell.conv7_down, [(p7_in, S), (p6_out, P)], fw("p7_w2"), e)               # :387-390
+            p4_out = self._node(cell.conv4_down, [(p4_in2, S), (p4_up, S), (p3_out, P)], fw("p4_w2"), e,
+                                tag=(ci, "p3_out"))                                                        # :366-370
+            p5_out = self._node(cell.conv5_down, [(p5_in2, S), (p5_up, S), (p4_out, P)], fw("p5_w2"), e,
+                                tag=(ci, "p4_out"))                                                        # :373-377
+            p6_out = self._node(cell.conv6_down, [(p6_in, S), (p6_up, S), (p5_out, P)], fw("p6_w2"), e,
+                                tag=(ci, "p5_out"))                                                        # :380-384
+            p7_out = self._node(cell.conv7_down, [(p7_in, S), (p6_out, P)], fw("p7_w2"), e,
+                                tag=(ci, "p6_out"))                                                        # :387-390
             p3_in, p4_in, p5_in, p6_in, p7_in = p3_out, p4_out, p5_out, p6_out, p7_out
             p4_in2, p5_in2 = p4_in, p5_in
         return [p3_in, p4_in, p5_in, p6_in, p7_in]
@@ -631,6 +641,31 @@ class _Plan:
             arr[i] = o
         self._bwd_keep = out
         return arr
+
+
+def debug_pool_argmax(output):
+    """TEST HOOK.  `output`: any tensor returned by a train-mode forward under grad whose backward has not run yet.
+    Returns one dict per cell: the window index (uint8 [B,C,Ho,Wo]; 0..8 row-major inside the 3x3 window, 9 = the zero
+    padding won) that the forward recorded for every 3x3-s2 max-pool — keyed "p3_out".."p6_out" by the pooled tensor of
+    the bottom-up path, "p6_in" / "p7_in" for the first cell's P6 / P7 synthesis.  The parity tests hand these to the
+    oracle (oracle.maxpool_same(hint=...)) so that both sides route the pooling gradients through the same elements."""
+    fn = output.grad_fn
+    plan, saved = getattr(fn, "plan", None), getattr(fn, "saved", None)
+    if plan is None or saved is None or not plan.need_grad:
+        raise RuntimeError("debug_pool_argmax needs an output of a train-mode forward that recorded a backward")
+    arena = saved[1]
+    res = {}
+    for op in plan.ops:
+        if op.tag is None:
+            continue
+        for ref in op.pidx:
+            if ref is None:
+                continue
+            H, W = op.out.H, op.out.W
+            n = plan.B * H * W * plan.Cc
+            res.setdefault(op.tag[0], {})[op.tag[1]] = \
+                arena.buf[ref[1]: ref[1] + n].view(plan.B, H, W, plan.Cc).permute(0, 3, 1, 2).contiguous().cpu()
+    return [res.get(i, {}) for i in range(max(res) + 1 if res else 0)]
 
 
 def forward_multi(items):

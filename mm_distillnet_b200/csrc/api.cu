@@ -1,6 +1,7 @@
 // C-ABI bookkeeping entry points of libmmd_b200.so (see include/mmd.h).
 #include <stdarg.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
@@ -39,7 +40,8 @@ bool pdl_take() {
 
 // ---- per-device launch configuration (see common.cuh) ----------------------------------------------------------------
 static std::mutex g_cfg_mu;
-static std::vector<std::pair<const void*, int>> g_cfg_done;   // (kernel, device) pairs whose smem attribute is set
+struct CfgDone { const void* kernel; int dev; size_t bytes; };
+static std::vector<CfgDone> g_cfg_done;   // largest dynamic shared memory size configured per (kernel, device)
 static int g_sm_count[64] = {0};
 int device_sm_count() {
   int dev = 0;
@@ -56,22 +58,22 @@ int device_sm_count() {
 int ensure_dynamic_smem(const void* kernel, size_t bytes) {
   int dev = 0;
   cudaGetDevice(&dev);
-  {
-    std::lock_guard<std::mutex> lk(g_cfg_mu);
-    for (const auto& e : g_cfg_done)
-      if (e.first == kernel && e.second == dev) return 0;
-  }
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
+  CfgDone* hit = nullptr;
+  for (auto& e : g_cfg_done)
+    if (e.kernel == kernel && e.dev == dev) hit = &e;
+  if (hit != nullptr && hit->bytes >= bytes) return 0;      // (a kernel may be launched with several sizes: keep the max)
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return (int)e;
-  std::lock_guard<std::mutex> lk(g_cfg_mu);
-  g_cfg_done.emplace_back(kernel, dev);
+  if (hit != nullptr) hit->bytes = bytes;
+  else g_cfg_done.push_back(CfgDone{kernel, dev, bytes});
   return 0;
 }
 
 // ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
 static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",
                                            "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot",
-                                           "poolfuse", "node_fwd<16,8>", "node_bwd_a<16,8>", "node_bwd_b<16,8>"};
+                                           "poolfuse", "node_fwd<16,8>", "node_bwd_a<16,8>", "node_bwd_b<16,8>", "chain_fwd", "chain_bwd"};
 struct ProfRec { cudaEvent_t a, b; int kind; double bytes; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -125,6 +127,17 @@ extern "C" int mmd_prof_collect(double* ms, long long* launches, double* bytes) 
   }
   mmd::g_prof_recs.clear();
   return 0;
+}
+
+namespace mmd { void set_chain_fwd(int on); }
+// Runtime switches (each also has an environment default, read once): returns 0, or MMD_E_ARG for an unknown name.
+extern "C" int mmd_set_option(const char* name, int value) {
+  if (name != nullptr && strcmp(name, "chain_fwd") == 0) {
+    mmd::set_chain_fwd(value);
+    return 0;
+  }
+  mmd::set_error("mmd_set_option: unknown option '%s'", name ? name : "(null)");
+  return MMD_E_ARG;
 }
 
 extern "C" int mmd_version(void) { return MMD_VERSION; }

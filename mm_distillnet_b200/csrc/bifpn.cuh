@@ -317,7 +317,20 @@ int launch_node_fwd_v4(const NodeFwdP* p, int n, int C, cudaStream_t s);
 int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s);
 // POOLFUSE + NODE_FWD of a small level (<= 24x24) as ONE launch: `pre[i]` is the pre-pass whose output is node[i].in[1]
 bool fwd_v4_pre_usable(const NodeFwdP& pre, const NodeFwdP& node);
+bool fwd_v4_pre_fusable(const NodeFwdP& pre, const NodeFwdP& node);   // the same without the MMD_INLINE_POOL switch
 int launch_node_fwd_v4_pre(const NodeFwdP* node, const NodeFwdP* pre, int n, int C, cudaStream_t s);
+// Persistent small-level chain (bifpn_fwd_v4.cu: chain_fwd_kernel): consecutive P5-P7 nodes of all lockstep networks in ONE
+// launch, separated by grid barriers.  One host-side step = the same node of n networks (+ its folded POOLFUSE pre-pass).
+constexpr int kMaxChainStepsH = 6;
+struct ChainStepH {
+  NodeFwdP node[kMaxBatchNets];
+  NodeFwdP pre[kMaxBatchNets];
+  int has_pre;
+};
+bool chain_fwd_enabled();                                          // MMD_CHAIN=1 / mmd_set_option("chain_fwd", 1); off by default
+void set_chain_fwd(int on);
+bool chain_fwd_step_usable(const NodeFwdP& node, const NodeFwdP* pre);   // small level, v4 body, deferred BN when training
+int launch_chain_fwd(const ChainStepH* steps, int n_steps, int n_nets, int C, cudaStream_t s);
 // bf16 backward, compile-time tile geometry (bifpn_bwd_v4.cu)
 bool bwd_v4_usable(const NodeBwdP& p);
 int launch_node_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);

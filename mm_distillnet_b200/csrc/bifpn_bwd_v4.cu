@@ -288,9 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_c
       const int col0 = (warp >> 2) * (C / 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
       float acc[C / 16][8];
-#pragma unroll
-      for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
-      tc::tmem_ld_wait();
+      tc::tmem_ld56(taddr, acc);
       if (row < S::NP) {
         const int ty = row / TW, txx = row - ty * TW;
         bf16* dst = ddout + (((long long)t.b * H + t.ty0 + ty) * W + t.tx0 + txx) * C + col0;

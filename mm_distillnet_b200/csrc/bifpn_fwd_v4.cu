@@ -39,6 +39,13 @@ constexpr int M1_NONE = 0, M1_SAME = 1, M1_UP2 = 2;
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int up128(int a) { return (a + 127) / 128 * 128; }
 
+// Shared-memory layout.  The mbarriers and the TMEM base address sit at FIXED offsets at the front (the same for every tile
+// shape): a persistent kernel that runs nodes of several shapes one after the other (chain_fwd_kernel) initialises them
+// once and carries their phases from node to node.
+constexpr int kOffBar = 0;          // bar_pack | bar_in0 | bar_in1 | bar_mma | tmem address   (64 bytes reserved)
+constexpr int kOffFlag = 64;        // int: "this CTA finalises" flag of the non-deferred BatchNorm epilogue
+constexpr int kFront = 128;
+
 template <int TW, int TH>
 struct Cfg {
   static_assert(TW % 2 == 0 && TH % 2 == 0, "nearest-x2 inputs need even tiles");
@@ -51,12 +58,13 @@ struct Cfg {
   static constexpr int kR1 = up128(cmax(NH * POS, kABytes));
   static constexpr int kWBytes = C * C * 2;
   static constexpr int kPackBytes = kWBytes + C * 4 + 9 * C * 4;   // 29 568
-  static constexpr int offR0 = 0, offR1 = kR0, offPack = kR0 + kR1, offCoef = offPack + kPackBytes;
-  static constexpr int offBar = offCoef + 3 * C * 4;
-  static constexpr int kBytes = offBar + 64;
+  static constexpr int offR0 = kFront, offR1 = offR0 + kR0, offPack = offR1 + kR1, offCoef = offPack + kPackBytes;
+  static constexpr int offPc = offCoef + 3 * C * 4;            // pre-pass coefficients (PRE kernels only)
+  static constexpr int kBytes = offPc;
+  static constexpr int kBytesPre = offPc + 4 * C * 4;
   static constexpr int kP1Threads = NG * HW2, kP2Threads = NQ * (TW / 2);
   static_assert(NP <= 128 && kP1Threads <= kThreads && kP2Threads <= kThreads && HH2 <= 32, "tile too large");
-  static_assert(offPack % 128 == 0 && offCoef % 16 == 0 && offBar % 8 == 0, "alignment");
+  static_assert(offPack % 128 == 0 && offCoef % 16 == 0 && offPc % 16 == 0, "alignment");
   static_assert(2 * (kBytes + 1024) <= 233472, "two CTAs per SM");
 };
 
@@ -326,32 +334,32 @@ __device__ __forceinline__ void inline_pool_tile(const NodeFwdP& Q, const float*
   }
 }
 
+// Per-CTA state that outlives one node: where TMEM is, and the phase of every mbarrier (each is used a different number of
+// times per node — bar_in1 only by nodes that stage a second input, bar_pack once per node — so each carries its own bit).
+struct FwdCtx {
+  uint32_t tmem_base;
+  uint32_t ph_pack, ph_in0, ph_in1, ph_mma;
+};
+
+// One fusion node for the CTAs [0, nctas) of one network.  Called by every thread of the CTA; all barriers inside are
+// CTA-wide.  `pdl`: this is the first node of its kernel, do the griddepcontrol handshake where the prologue allows.
 template <int TW, int TH, bool PRE>
-__global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+__device__ __forceinline__ void node_fwd_body(const NodeFwdP& P, const NodeFwdP& Q, const int cta, const int nctas,
+                                              unsigned char* smem, FwdCtx& X, const bool pdl) {
   using S = Cfg<TW, TH>;
-  constexpr uint32_t kTmemCols = 128;
   constexpr uint32_t kIdesc = tc::make_idesc_bf16(128, C, false, false);
-  int net = 0;
-#pragma unroll
-  for (int k = 1; k < kMaxBatchNets; ++k)
-    if ((int)blockIdx.x >= BATCH.cta_begin[k]) net = k;
-  const NodeFwdP& P = BATCH.p[net];
-  const int cta = (int)blockIdx.x - BATCH.cta_begin[net], nctas = BATCH.cta_begin[net + 1] - BATCH.cta_begin[net];
-  extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* r0 = smem + S::offR0;
   unsigned char* r1 = smem + S::offR1;
   unsigned char* s_pack = smem + S::offPack;
   const float* s_bias = reinterpret_cast<const float*>(s_pack + S::kWBytes);
   const float* s_k = s_bias + C;
   float* s_coef = reinterpret_cast<float*>(smem + S::offCoef);
-  uint64_t* bar_pack = reinterpret_cast<uint64_t*>(smem + S::offBar);
+  float* s_pc = reinterpret_cast<float*>(smem + S::offPc);   // PRE: the pre-pass coefficients (as poolfuse_kernel's s_c)
+  uint64_t* bar_pack = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_in0 = bar_pack + 1;
   uint64_t* bar_in1 = bar_pack + 2;
   uint64_t* bar_mma = bar_pack + 3;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_pack + 4);
-  __shared__ int s_flag;
-  __shared__ __align__(16) float s_pc[PRE ? 4 * C : 4];   // PRE: the pre-pass coefficients (as poolfuse_kernel's s_c)
-  const NodeFwdP& Q = BATCH.pre[net];
+  int* s_flag = reinterpret_cast<int*>(smem + kOffFlag);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = P.g.H, W = P.g.W;
@@ -363,21 +371,17 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   const bf16* __restrict__ in0 = reinterpret_cast<const bf16*>(P.in[0].data);
   const bf16* __restrict__ in1 = reinterpret_cast<const bf16*>(P.in[1].data);
 
-  // ---- per-CTA setup ---------------------------------------------------------------------------------------------
-  if (warp == 0) tc::tmem_alloc(s_tmem, kTmemCols);
-  if (tid == 32) {
-    tc::mbar_init(bar_pack, 1);
-    tc::mbar_init(bar_in0, 1);
-    tc::mbar_init(bar_in1, 1);
-    tc::mbar_init(bar_mma, 1);
-    tc::fence_mbar_init();
+  // ---- per-node setup ---------------------------------------------------------------------------------------------
+  if (tid == 32) {   // the packed parameter block: B operand, bias, depthwise taps (one bulk copy)
     tc::mbar_expect_tx(bar_pack, S::kPackBytes);
     tc::bulk_g2s(s_pack, P.packed, S::kPackBytes, bar_pack);
   }
-  pdl_wait();      // everything above overlaps the previous kernel; its outputs (inputs / BN vectors here) are visible now
-  pdl_trigger();
+  if (pdl) {
+    pdl_wait();      // everything above overlaps the previous kernel; its outputs (inputs / BN vectors here) are visible now
+    pdl_trigger();
+  }
   // first tile's inputs: requested before the coefficient set-up below, whose dependent global loads (fusion weights,
-  // BatchNorm vectors) would otherwise delay them by a full round trip (warp 1 initialised the barriers itself)
+  // BatchNorm vectors) would otherwise delay them by a full round trip (warp 1 owns the barriers)
   int tile = cta;
   if (warp == 1) {
     __syncwarp();
@@ -410,16 +414,13 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     s_coef[C + tid] = sc1 * w1;
     s_coef[2 * C + tid] = fmaf(sh1, w1, sh0 * w0);
   }
-  tc::fence_before_sync();
   __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = X.tmem_base;
   const uint32_t a_addr = tc::smem_u32(r1), b_addr = tc::smem_u32(s_pack);
 
   // statistics role: channel pair sp of row slice ss (32 staging rows)
   const int sp = tid % (C / 2), ss = tid / (C / 2);
   double st[4] = {0.0, 0.0, 0.0, 0.0};
-  uint32_t ph = 0;
   bool pack_ready = false;
 
   for (; tile < ntiles; tile += nctas) {
@@ -433,8 +434,12 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     }
 
     // ---- (1) raw inputs have landed
-    tc::mbar_wait(bar_in0, ph);
-    if (!PRE && m1 != M1_NONE) tc::mbar_wait(bar_in1, ph);
+    tc::mbar_wait(bar_in0, X.ph_in0);
+    X.ph_in0 ^= 1u;
+    if (!PRE && m1 != M1_NONE) {
+      tc::mbar_wait(bar_in1, X.ph_in1);
+      X.ph_in1 ^= 1u;
+    }
 
     // ---- (2) phase 1
     if (sw) {
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     }
     __syncthreads();
     if (!pack_ready) {   // taps / bias / B operand have landed (first tile only)
-      tc::mbar_wait(bar_pack, 0u);
+      tc::mbar_wait(bar_pack, X.ph_pack);
       pack_ready = true;
     }
 
@@ -472,7 +477,8 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
       }
       tc::umma_commit(bar_mma);
     }
-    tc::mbar_wait(bar_mma, ph);
+    tc::mbar_wait(bar_mma, X.ph_mma);
+    X.ph_mma ^= 1u;
     tc::fence_after_sync();
     // region 1 is free: request the next tile's input 1 while the epilogue runs
     if (!PRE && warp == 1 && next < ntiles && m1 != M1_NONE) {
@@ -487,9 +493,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
       const int col0 = (warp >> 2) * (C / 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
       float acc[C / 16][8];
-#pragma unroll
-      for (int j = 0; j < C / 16; ++j) tc::tmem_ld8(taddr + 8 * j, acc[j]);
-      tc::tmem_ld_wait();
+      tc::tmem_ld56(taddr, acc);
       if (row < S::NP) {
 #pragma unroll
         for (int j = 0; j < C / 16; ++j) {
@@ -537,13 +541,13 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
         issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
       }
     }
-    ph ^= 1u;
   }
+  if (!pack_ready) tc::mbar_wait(bar_pack, X.ph_pack);   // a CTA without tiles still consumes this node's pack phase
+  X.ph_pack ^= 1u;
 
-  // ---- teardown + BatchNorm finalisation (last CTA of this network)
+  // ---- BatchNorm statistics (+ finalisation by the last CTA of this network unless it is deferred)
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
   if (!train) return;
   double* s_red = reinterpret_cast<double*>(r1);   // [4 slices][C/2 pairs][4]
   if (ss < 4) {
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
     for (int e = 0; e < 4; ++e) s_red[(ss * (C / 2) + sp) * 4 + e] = st[e];
   }
   __syncthreads();
-  if (tid < C) {
+  if (tid < C && cta < ntiles) {
     double s = 0.0, q = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -567,10 +571,10 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   __syncthreads();
   if (tid == 0) {
     const unsigned ticket = atomicAdd(P.counter, 1u);
-    s_flag = (ticket == (unsigned)nctas - 1u) ? 1 : 0;
+    *s_flag = (ticket == (unsigned)nctas - 1u) ? 1 : 0;
   }
   __syncthreads();
-  if (s_flag == 0) return;
+  if (*s_flag == 0) return;
   __threadfence();
   if (tid < C) {
     const double n = (double)P.g.B * H * W;
@@ -601,6 +605,160 @@ __global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_c
   if (tid == 0) {
     *P.counter = 0u;
     if (P.bn_nbt) *P.bn_nbt += 1;
+  }
+}
+
+// per-CTA one-time setup shared by the single-node kernel and the chain kernel: TMEM allocation, mbarrier init
+__device__ __forceinline__ void fwd_ctx_init(unsigned char* smem, FwdCtx& X, const uint32_t tmem_cols) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc(s_tmem, tmem_cols);
+  if (tid == 32) {
+    tc::mbar_init(bar + 0, 1);
+    tc::mbar_init(bar + 1, 1);
+    tc::mbar_init(bar + 2, 1);
+    tc::mbar_init(bar + 3, 1);
+    tc::fence_mbar_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  X.tmem_base = *s_tmem;
+  X.ph_pack = X.ph_in0 = X.ph_in1 = X.ph_mma = 0u;
+}
+
+template <int TW, int TH, bool PRE>
+__global__ void __launch_bounds__(kThreads, 2) node_fwd_v4_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+  constexpr uint32_t kTmemCols = 128;
+  int net = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxBatchNets; ++k)
+    if ((int)blockIdx.x >= BATCH.cta_begin[k]) net = k;
+  const int cta = (int)blockIdx.x - BATCH.cta_begin[net], nctas = BATCH.cta_begin[net + 1] - BATCH.cta_begin[net];
+  extern __shared__ __align__(128) unsigned char smem[];
+  FwdCtx X;
+  fwd_ctx_init(smem, X, kTmemCols);
+  node_fwd_body<TW, TH, PRE>(BATCH.p[net], BATCH.pre[net], cta, nctas, smem, X, true);
+  tc::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(X.tmem_base, kTmemCols);
+}
+
+// ---- persistent small-level chain ---------------------------------------------------------------------------------------
+// The P5 - P7 nodes hold 6 % of the bytes of a cell but took 26 % of the step as separate launches: every launch costs
+// 12 - 20 us whatever it moves (launch -> prologue -> dependent parameter loads -> first tile -> drain).  Between two
+// blocks of large-level work the small nodes form a strict chain (p5_out, p6_out, p7_out of cell k, then p6_up, p5_up of
+// cell k + 1: src/YetAnotherEfficientDet.py:338-390), each needing its predecessor's complete output (tile halos, and in
+// training the batch-global BatchNorm sums).  chain_fwd_kernel runs such a chain — for all lockstep networks — as ONE
+// launch: the node bodies are the device functions above (TMEM allocated once, mbarrier phases carried from node to node,
+// pooled inputs built inline) separated by a grid barrier.  All CTAs are co-resident (grid <= 2 x SM count, 2 CTAs / SM).
+constexpr int kMaxChainSteps = 6;
+struct ChainStep {
+  NodeFwdP p[kMaxBatchNets];      // the node of every network
+  NodeFwdP pre[kMaxBatchNets];    // its POOLFUSE pre-pass (has_pre): folded into the node body
+  int cta_begin[kMaxBatchNets + 1];
+  int geom;                       // pick_geom() code of the node's tile shape: 1 <12,8>, 3 <12,6>, 4 <6,6>
+  int has_pre;
+};
+struct ChainFwd {
+  ChainStep step[kMaxChainSteps];
+  int n_steps;
+  unsigned* sync;                 // [0] barrier arrivals, [1] exit tickets; zero on entry, re-zeroed by the last CTA to leave
+  unsigned long long* dbg;        // MMD_CHAIN_DEBUG=1: [step][4] = min start, max body end, max barrier end, sum body ns (globaltimer)
+};
+static_assert(sizeof(ChainFwd) <= 32000, "kernel parameter space (32 764 bytes since CUDA 12.1)");
+
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Barrier over all CTAs of the grid.  Before arriving, everything this CTA wrote to global memory is made visible device
+// wide: bulk shared->global stores are complete (wait_group 0 by the issuing warp), generic and async-proxy accesses are
+// ordered against each other (the next node reads through bulk copies what this one wrote through generic stores, e.g.
+// the inline-pooled operand, and vice versa), __threadfence.  A CTA that waits longer than ~1 s traps (a grid that is
+// not co-resident would otherwise hang the GPU): the launch then fails loudly with a sticky CUDA error.
+__device__ __forceinline__ void grid_barrier(unsigned* sync, const unsigned nctas, unsigned& epoch) {
+  if ((threadIdx.x >> 5) == 1) bulk_wait_all();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  __syncthreads();
+  epoch += 1u;
+  if (threadIdx.x == 0) {
+    const unsigned target = epoch * nctas;
+    atomicAdd(sync, 1u);
+    unsigned seen, spins = 0u;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(sync) : "memory");
+      if (seen >= target) break;
+      __nanosleep(64);
+      if (++spins > (1u << 23)) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) chain_fwd_kernel(const __grid_constant__ ChainFwd CH) {
+  constexpr uint32_t kTmemCols = 128;
+  extern __shared__ __align__(128) unsigned char smem[];
+  FwdCtx X;
+  fwd_ctx_init(smem, X, kTmemCols);
+  unsigned epoch = 0u;
+  for (int s = 0; s < CH.n_steps; ++s) {
+    unsigned long long t0 = 0ull;
+    if (CH.dbg != nullptr && threadIdx.x == 0) {
+      t0 = gtimer();
+      atomicMin(CH.dbg + 4 * s, t0);
+    }
+    const ChainStep& S = CH.step[s];
+    int net = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxBatchNets; ++k)
+      if ((int)blockIdx.x >= S.cta_begin[k]) net = k;
+    const int cta = (int)blockIdx.x - S.cta_begin[net], nctas = S.cta_begin[net + 1] - S.cta_begin[net];
+    const bool active = (int)blockIdx.x < S.cta_begin[kMaxBatchNets];
+    const bool pdl = (s == 0);
+    if (active) {
+      const NodeFwdP& P = S.p[net];
+      const NodeFwdP& Q = S.pre[net];
+      if (S.has_pre) {
+        if (S.geom == 1) node_fwd_body<12, 8, true>(P, Q, cta, nctas, smem, X, pdl);
+        else if (S.geom == 3) node_fwd_body<12, 6, true>(P, Q, cta, nctas, smem, X, pdl);
+        else node_fwd_body<6, 6, true>(P, Q, cta, nctas, smem, X, pdl);
+      } else {
+        if (S.geom == 1) node_fwd_body<12, 8, false>(P, Q, cta, nctas, smem, X, pdl);
+        else if (S.geom == 3) node_fwd_body<12, 6, false>(P, Q, cta, nctas, smem, X, pdl);
+        else node_fwd_body<6, 6, false>(P, Q, cta, nctas, smem, X, pdl);
+      }
+    } else if (pdl) {
+      pdl_wait();
+      pdl_trigger();
+    }
+    if (CH.dbg != nullptr && threadIdx.x == 0) {
+      const unsigned long long t1 = gtimer();
+      atomicMax(CH.dbg + 4 * s + 1, t1);
+      atomicAdd(CH.dbg + 4 * s + 3, t1 - t0);
+    }
+    if (s + 1 < CH.n_steps) grid_barrier(CH.sync, gridDim.x, epoch);
+    if (CH.dbg != nullptr && threadIdx.x == 0) atomicMax(CH.dbg + 4 * s + 2, gtimer());
+  }
+  // ---- teardown: the last CTA to leave re-arms the barrier words for the next launch
+  tc::fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(X.tmem_base, kTmemCols);
+  if (threadIdx.x == 0 && CH.n_steps > 1) {
+    const unsigned ticket = atomicAdd(CH.sync + 1, 1u);
+    if (ticket == gridDim.x - 1u) {
+      CH.sync[0] = 0u;
+      CH.sync[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
@@ -862,14 +1020,14 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
 template <int TW, int TH, bool PRE = false>
 static int launch_geom(const NodeFwdBatch& batch, int n, cudaStream_t s) {
   using S = Cfg<TW, TH>;
-  MMD_SMEM((node_fwd_v4_kernel<TW, TH, PRE>), S::kBytes);
+  MMD_SMEM((node_fwd_v4_kernel<TW, TH, PRE>), (PRE ? S::kBytesPre : S::kBytes));
   const int sms = device_sm_count();
   const NodeFwdP& p = batch.p[0];
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   static const float train_w = env_float("MMD_FWD_TRAIN_SHARE", 1.0f);
   NodeFwdBatch b2 = batch;
   batch_shares(b2, n, 2 * sms, ntiles, train_w);
-  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH, PRE>, dim3(b2.cta_begin[n]), dim3(kThreads), S::kBytes, s, b2));
+  MMD_CUDA(launch_pdl(node_fwd_v4_kernel<TW, TH, PRE>, dim3(b2.cta_begin[n]), dim3(kThreads), PRE ? S::kBytesPre : S::kBytes, s, b2));
   MMD_LAUNCH_CHECK();
   return 0;
 }
@@ -1018,6 +1176,11 @@ bool fwd_v4_pre_usable(const NodeFwdP& pre, const NodeFwdP& node) {
     on = (e && e[0] == '1') ? 1 : 0;
   }
   if (!on) return false;
+  return fwd_v4_pre_fusable(pre, node);
+}
+
+// conditions under which the node body can build the pre-pass operand inline (PRE = true instantiations)
+bool fwd_v4_pre_fusable(const NodeFwdP& pre, const NodeFwdP& node) {
   if (!fwd_v4_usable(node) || node.n_in != 2 || node.mode[1] != MMD_IN_SAME) return false;
   if (node.in[1].data != pre.out || pre.out == nullptr) return false;                     // the node consumes the pre-pass
   if (pre.mode[0] != MMD_IN_POOL || (pre.n_in == 2 && pre.mode[1] != MMD_IN_SAME) || pre.n_in > 2) return false;
@@ -1027,6 +1190,157 @@ bool fwd_v4_pre_usable(const NodeFwdP& pre, const NodeFwdP& node) {
   for (int i = 0; i < pre.n_in; ++i)
     if (((uintptr_t)pre.in[i].data & 15u) != 0) return false;
   return (((uintptr_t)pre.out | (uintptr_t)pre.pidx[0] | (uintptr_t)pre.save_d) & 15u) == 0;
+}
+
+// Off by default.  Measured on B200 (profiles/r2_chain_fwd.md): the chain of one cell boundary (5 nodes, 4 lockstep
+// networks, B = 16) takes 120 - 160 us against 110 - 143 us for the same nodes as separate PDL launches — the time of a
+// small-level node is the latency of ONE tile through the body (parameter block + coefficient round trips, two CUDA-core
+// phases, MMA, epilogue, store drain: ~10 us), which a grid barrier (2.5 - 3 us incl. the bulk-store drain) does not
+// shorten compared with a PDL launch boundary.  MMD_CHAIN=1 or mmd_set_option("chain_fwd", 1) turns it on.
+static int g_chain_fwd = -1;
+void set_chain_fwd(int on) { g_chain_fwd = on ? 1 : 0; }
+bool chain_fwd_enabled() {
+  if (g_chain_fwd < 0) {
+    const char* e = getenv("MMD_CHAIN");
+    g_chain_fwd = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_chain_fwd == 1;
+}
+
+bool chain_fwd_step_usable(const NodeFwdP& node, const NodeFwdP* pre) {
+  if (!fwd_v4_usable(node) || node.g.H * node.g.W > 24 * 24) return false;
+  const int geom = v4::pick_geom(node.g.H, node.g.W);
+  if (geom != 1 && geom != 3 && geom != 4) return false;
+  if (node.train && !node.defer_bn) return false;     // the in-kernel finaliser is per launch, not per chain step
+  if (pre != nullptr && !fwd_v4_pre_fusable(*pre, node)) return false;
+  return true;
+}
+
+int launch_chain_fwd(const ChainStepH* steps, int n_steps, int n_nets, int C, cudaStream_t s) {
+  MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  MMD_CHECK_ARG(n_steps >= 1 && n_steps <= v4::kMaxChainSteps && n_nets >= 1 && n_nets <= kMaxBatchNets,
+                "chain_fwd: %d steps, %d networks", n_steps, n_nets);
+  static_assert(kMaxChainStepsH == v4::kMaxChainSteps, "host / device chain length");
+  unsigned* sync = steps[0].node[0].counter;
+  MMD_CHECK_ARG(sync != nullptr, "chain_fwd: the first node carries no counter storage (barrier words)");
+  // shared memory: the largest layout any step needs; all CTAs must be co-resident
+  size_t smem = 0;
+  int max_tiles = 1;
+  double bytes = 0.0;
+  for (int k = 0; k < n_steps; ++k) {
+    const NodeFwdP& p0 = steps[k].node[0];
+    const int geom = v4::pick_geom(p0.g.H, p0.g.W);
+    size_t need = 0;
+    int tiles = 0;
+    switch (geom) {
+      case 1: need = steps[k].has_pre ? v4::Cfg<12, 8>::kBytesPre : v4::Cfg<12, 8>::kBytes; tiles = p0.g.B * (p0.g.H / 8) * (p0.g.W / 12); break;
+      case 3: need = steps[k].has_pre ? v4::Cfg<12, 6>::kBytesPre : v4::Cfg<12, 6>::kBytes; tiles = p0.g.B * (p0.g.H / 6) * (p0.g.W / 12); break;
+      case 4: need = steps[k].has_pre ? v4::Cfg<6, 6>::kBytesPre : v4::Cfg<6, 6>::kBytes; tiles = p0.g.B * (p0.g.H / 6) * (p0.g.W / 6); break;
+      default: set_error("chain_fwd: step %d has no small-level tile shape (%dx%d)", k, p0.g.H, p0.g.W); return MMD_E_ARG;
+    }
+    smem = need > smem ? need : smem;
+    max_tiles = tiles * n_nets > max_tiles ? tiles * n_nets : max_tiles;
+    for (int i = 0; i < n_nets; ++i) {
+      const NodeFwdP& p = steps[k].node[i];
+      MMD_CHECK_ARG(p.g.H == p0.g.H && p.g.W == p0.g.W && p.g.B == p0.g.B, "chain_fwd: lockstep networks must share the geometry");
+      bytes += node_algo_bytes(p.in, steps[k].has_pre ? 1 : p.n_in, p.g, C, 2);
+      if (steps[k].has_pre) {
+        const NodeFwdP& q = steps[k].pre[i];
+        for (int j = 0; j < q.n_in; ++j) bytes += (double)q.g.B * q.in[j].H * q.in[j].W * C * 2.0;
+      }
+    }
+  }
+  MMD_SMEM(v4::chain_fwd_kernel, smem);
+  int per_sm = 0;
+  MMD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v4::chain_fwd_kernel, kThreads, smem));
+  if (per_sm > 2) per_sm = 2;
+  MMD_CHECK_ARG(per_sm >= 1, "chain_fwd: the kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  int grid = per_sm * device_sm_count();
+  if (grid > max_tiles) grid = max_tiles;
+  v4::ChainFwd ch;
+  ch.n_steps = n_steps;
+  ch.sync = sync;
+  ch.dbg = nullptr;
+  static int dbg_on = -1;
+  static unsigned long long* dbg_buf = nullptr;
+  if (dbg_on < 0) {
+    const char* e = getenv("MMD_CHAIN_DEBUG");
+    dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (dbg_on) cudaMalloc(&dbg_buf, 4 * v4::kMaxChainSteps * sizeof(unsigned long long));
+  }
+  if (dbg_on && dbg_buf != nullptr) {
+    unsigned long long init[4 * v4::kMaxChainSteps];
+    for (int k = 0; k < v4::kMaxChainSteps; ++k) { init[4 * k] = ~0ull; init[4 * k + 1] = init[4 * k + 2] = init[4 * k + 3] = 0ull; }
+    cudaMemcpyAsync(dbg_buf, init, sizeof(init), cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    ch.dbg = dbg_buf;
+  }
+  for (int k = 0; k < v4::kMaxChainSteps; ++k) {
+    const ChainStepH& src = steps[k < n_steps ? k : 0];
+    v4::ChainStep& d = ch.step[k];
+    NodeFwdBatch tmp;
+    for (int i = 0; i < kMaxBatchNets; ++i) {
+      d.p[i] = src.node[i < n_nets ? i : 0];
+      d.pre[i] = src.pre[i < n_nets ? i : 0];
+      tmp.p[i] = d.p[i];
+    }
+    const NodeFwdP& p0 = src.node[0];
+    d.geom = v4::pick_geom(p0.g.H, p0.g.W);
+    d.has_pre = src.has_pre;
+    const int tiles = (d.geom == 1) ? p0.g.B * (p0.g.H / 8) * (p0.g.W / 12)
+                                    : (d.geom == 3 ? p0.g.B * (p0.g.H / 6) * (p0.g.W / 12) : p0.g.B * (p0.g.H / 6) * (p0.g.W / 6));
+    batch_shares(tmp, n_nets, grid, tiles, 1.0f);
+    for (int i = 0; i <= kMaxBatchNets; ++i) d.cta_begin[i] = tmp.cta_begin[i];
+  }
+  ProfScope prof(PK_CHAIN_FWD, bytes, s);
+  // cooperative launch: the driver guarantees that all CTAs are co-resident (or refuses the launch), also when other
+  // streams keep SMs busy; programmatic dependent launch on top when the driver accepts the combination
+  static int coop_pdl = -1;   // -1: not probed yet, 1: both attributes, 0: cooperative only
+  static int no_coop = -1;
+  if (no_coop < 0) {
+    const char* e = getenv("MMD_CHAIN_NOCOOP");   // debugging aid: plain (PDL) launch; safe only while nothing else runs
+    no_coop = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (no_coop) {
+    MMD_CUDA(launch_pdl(v4::chain_fwd_kernel, dim3(grid), dim3(kThreads), smem, s, ch));
+    MMD_LAUNCH_CHECK();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_take() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = (coop_pdl == 0) ? 1 : 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, v4::chain_fwd_kernel, ch);
+  if (e != cudaSuccess && cfg.numAttrs == 2 && coop_pdl < 0) {   // the combination is not supported: cooperative only
+    cudaGetLastError();
+    coop_pdl = 0;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, v4::chain_fwd_kernel, ch);
+  } else if (e == cudaSuccess && coop_pdl < 0) {
+    coop_pdl = 1;
+  }
+  MMD_CUDA(e);
+  MMD_LAUNCH_CHECK();
+  if (dbg_on && dbg_buf != nullptr) {
+    unsigned long long h[4 * v4::kMaxChainSteps];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[chain_fwd] grid %d, coop_pdl %d, %d steps:", grid, coop_pdl, n_steps);
+    for (int k = 0; k < n_steps; ++k)
+      fprintf(stderr, "  [%dx%d%s start +%.1f body %.1f (avg %.1f) barrier %.1f us]", steps[k].node[0].g.H, steps[k].node[0].g.W,
+              steps[k].has_pre ? " pre" : "", (double)(h[4 * k] - h[0]) * 1e-3, (double)(h[4 * k + 1] - h[4 * k]) * 1e-3,
+              (double)h[4 * k + 3] * 1e-3 / grid, (double)(h[4 * k + 2] - h[4 * k + 1]) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+  return 0;
 }
 
 int launch_node_fwd_v4_pre(const NodeFwdP* node, const NodeFwdP* pre, int n, int C, cudaStream_t s) {

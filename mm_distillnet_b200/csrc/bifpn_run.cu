@@ -213,6 +213,59 @@ static int run_group(const MmdOp* ops, int i, int n, const Bases& B, int batch, 
   return launch_slot_group(ps, n, C, dtype, stream);
 }
 
+// ---- persistent small-level chains (bifpn.cuh: ChainStepH) -------------------------------------------------------------
+// Starting at op index i of every member list (lists whose ops line up), collect consecutive units — NODE_FWD, or POOLFUSE
+// followed by the NODE_FWD that consumes it — that the chain kernel can run (P5 and smaller, v4 bodies, deferred BatchNorm
+// when training) and launch them as ONE kernel.  Returns the number of op-list entries consumed (0: no chain, nothing
+// launched); *rc carries a launch error.
+static int try_chain_fwd(const MmdOp* const* ops, const int32_t* n_ops, void* const* const* bases, const int32_t* n_bases,
+                         const DeferPlan* plans, const int* members, int n_members, int i, int batch, int C, int dtype,
+                         cudaStream_t stream, int* rc) {
+  *rc = 0;
+  if (dtype != MMD_BF16 || tc_disabled() || !chain_fwd_enabled() || n_members < 1) return 0;
+  static thread_local ChainStepH steps[kMaxChainStepsH];
+  int n_steps = 0, j = i;
+  const int m0 = members[0];
+  while (n_steps < kMaxChainStepsH && j < n_ops[m0]) {
+    const MmdOp& a = ops[m0][j];
+    int len, node_at;
+    if (a.kind == MMD_OP_POOLFUSE && j + 1 < n_ops[m0] && ops[m0][j + 1].kind == MMD_OP_NODE_FWD) { len = 2; node_at = j + 1; }
+    else if (a.kind == MMD_OP_NODE_FWD) { len = 1; node_at = j; }
+    else break;
+    if (ops[m0][node_at].out.H * ops[m0][node_at].out.W > 24 * 24) break;
+    static const int max_pre_hw = (int)env_float("MMD_CHAIN_PRE_MAX_HW", 24.f * 24.f);   // largest level pooled inline
+    if (len == 2 && ops[m0][node_at].out.H * ops[m0][node_at].out.W > max_pre_hw) break;
+    ChainStepH& st = steps[n_steps];
+    st.has_pre = (len == 2) ? 1 : 0;
+    bool ok = true;
+    for (int k = 0; k < n_members && ok; ++k) {
+      const int m = members[k];
+      if (j + len > n_ops[m]) { ok = false; break; }
+      const MmdOp& om = ops[m][node_at];
+      if (om.kind != MMD_OP_NODE_FWD || om.out.H != ops[m0][node_at].out.H || om.out.W != ops[m0][node_at].out.W) { ok = false; break; }
+      if (len == 2 && ops[m][j].kind != MMD_OP_POOLFUSE) { ok = false; break; }
+      if (len == 1 && ops[m][j].kind != MMD_OP_NODE_FWD) { ok = false; break; }
+      Bases Bm{bases[m], n_bases[m]};
+      if (fill_fwd(om, Bm, batch, st.node[k]) != 0) { ok = false; break; }
+      apply_defer(&plans[m], node_at, st.node[k]);
+      if (len == 2) {
+        if (fill_fwd(ops[m][j], Bm, batch, st.pre[k]) != 0) { ok = false; break; }
+        apply_defer(&plans[m], j, st.pre[k]);
+      } else {
+        st.pre[k] = st.node[k];
+      }
+      if (!chain_fwd_step_usable(st.node[k], len == 2 ? &st.pre[k] : nullptr)) ok = false;
+    }
+    if (!ok) break;
+    if (n_steps == 0 && steps[0].node[0].counter == nullptr) break;   // the barrier words live in the first node's counter
+    ++n_steps;
+    j += len;
+  }
+  if (n_steps < 2) return 0;
+  *rc = launch_chain_fwd(steps, n_steps, n_members, C, stream);
+  return j - i;
+}
+
 extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops, void* const* const* bases,
                                    const int32_t* n_bases, int32_t n_lists, int32_t batch, int32_t C, int32_t dtype,
                                    mmd_stream_t stream_) {
@@ -240,6 +293,26 @@ extern "C" int mmd_bifpn_run_multi(const MmdOp* const* ops, const int32_t* n_ops
                              op.kind == MMD_OP_BNAPPLY;
       NodeFwdP ps[kMaxBatchNets];
       int members[kMaxBatchNets], n = 0;
+      // a run of small-level nodes of all lockstep networks: ONE persistent launch (try_chain_fwd)
+      if (op.kind == MMD_OP_NODE_FWD || op.kind == MMD_OP_POOLFUSE) {
+        for (int m = l; m < n_lists; ++m) {
+          if (done[m] || i >= n_ops[m] || i < grouped_until[m]) continue;
+          const MmdOp& om = ops[m][i];
+          if (om.kind != op.kind || om.out.H != op.out.H || om.out.W != op.out.W) continue;
+          members[n++] = m;
+        }
+        int rc = 0;
+        const int used = try_chain_fwd(ops, n_ops, bases, n_bases, plans, members, n, i, batch, C, dtype, stream, &rc);
+        if (rc) return rc;
+        if (used > 0) {
+          for (int k = 0; k < n; ++k) {
+            done[members[k]] = true;
+            grouped_until[members[k]] = i + used;
+          }
+          continue;
+        }
+        n = 0;
+      }
       // POOLFUSE followed by the node that consumes it, small level: ONE launch (the node kernel pools inline)
       if (dtype == MMD_BF16 && !tc_disabled() && op.kind == MMD_OP_POOLFUSE && i + 1 < n_ops[l] &&
           ops[l][i + 1].kind == MMD_OP_NODE_FWD) {
@@ -325,6 +398,20 @@ extern "C" int mmd_bifpn_run(const MmdOp* ops, int32_t n_ops, void* const* bases
     if (rc) return rc;
   }
   for (int i = 0; i < n_ops;) {
+    if (ops[i].kind == MMD_OP_NODE_FWD || ops[i].kind == MMD_OP_POOLFUSE) {   // a run of small-level nodes: one launch
+      const int member = 0;
+      const MmdOp* lists[1] = {ops};
+      const int32_t counts[1] = {n_ops};
+      void* const* blists[1] = {bases};
+      const int32_t bcounts[1] = {n_bases};
+      int rc = 0;
+      const int used = try_chain_fwd(lists, counts, blists, bcounts, &plan, &member, 1, i, batch, C, dtype, stream, &rc);
+      if (rc) return rc;
+      if (used > 0) {
+        i += used;
+        continue;
+      }
+    }
     if (dtype == MMD_BF16 && !tc_disabled() && ops[i].kind == MMD_OP_POOLFUSE && i + 1 < n_ops && ops[i + 1].kind == MMD_OP_NODE_FWD) {
       NodeFwdP pre, node;
       int rc = fill_fwd(ops[i], B, batch, pre);

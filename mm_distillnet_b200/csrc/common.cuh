@@ -89,7 +89,9 @@ enum ProfKind {
   PK_NODE_BWD_B, PK_PROJ_BWD, PK_PULL, PK_SLOT, PK_POOLFUSE,
   // the <16,8> instantiations (P3 / P4 of the D2 pyramid: 85 % of the bytes) are kernels of their own in the launch
   // list and are timed as such; the kinds above then hold the remaining tile shapes
-  PK_NODE_FWD_16x8, PK_NODE_BWD_A_16x8, PK_NODE_BWD_B_16x8, PK_COUNT
+  PK_NODE_FWD_16x8, PK_NODE_BWD_A_16x8, PK_NODE_BWD_B_16x8,
+  // persistent small-level chains (several P5-P7 nodes per launch)
+  PK_CHAIN_FWD, PK_CHAIN_BWD, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

@@ -46,21 +46,35 @@ def maxpool_same(x, hint=None):
     """MaxPool2dStaticSamePadding(3, 2): zero-pad (NOT -inf) then 3x3/s2 max.
     src/YetAnotherEfficientNet.py:90-104, instantiated at src/YetAnotherEfficientDet.py:228-231.
 
-    `hint` (test-only, never part of the pinned path): a tensor shaped like `x` holding ANOTHER implementation's values
-    of the same tensor.  The window arg-max is then taken on `hint` (same zero padding, same first-maximum rule) and the
-    output gathers `x` there.  Forward values change by at most the top-2 gap of a window (~1e-7 where two fp32
-    executions disagree); the backward routes every gradient exactly like the implementation that produced `hint`, which
-    removes the arg-max-flip discontinuity from gradient comparisons (tests/test_gpu_bifpn.py)."""
+    `hint` (test-only, never part of the pinned path) forces the window arg-max to ANOTHER implementation's choice, so
+    that both route the pooling gradients identically and the arg-max-flip discontinuity (a window whose two largest
+    entries differ by less than the two implementations' rounding) drops out of gradient comparisons
+    (tests/test_gpu_bifpn.py).  Forward values then differ from the true maximum by at most that top-2 gap.
+      * floating tensor shaped like `x`: the other implementation's VALUES of the pooled tensor; the arg-max is taken on
+        them (same zero padding, same first-maximum rule);
+      * integer tensor [B, C, Ho, Wo]: the other implementation's recorded window indices, 0..8 row-major inside the
+        3x3 window, 9 = the zero padding won (the encoding of the CUDA kernels' arg-max bytes)."""
     h, w = x.shape[-2:]
     top, bottom = same_pad(h, 3, 2)
     left, right = same_pad(w, 3, 2)
     x = F.pad(x, [left, right, top, bottom])
     if hint is None:
         return F.max_pool2d(x, 3, 2)
-    assert hint.shape[-2:] == (h, w) and hint.shape[:2] == x.shape[:2]
-    hp = F.pad(hint.detach().to(torch.float64), [left, right, top, bottom])
-    _, idx = F.max_pool2d(hp, 3, 2, return_indices=True)
-    return x.flatten(-2).gather(-1, idx.flatten(-2)).view(idx.shape)
+    wp = x.shape[-1]
+    ho, wo = (x.shape[-2] - 3) // 2 + 1, (wp - 3) // 2 + 1
+    if hint.is_floating_point():
+        assert hint.shape[-2:] == (h, w) and hint.shape[:2] == x.shape[:2]
+        hp = F.pad(hint.detach().to(torch.float64), [left, right, top, bottom])
+        _, idx = F.max_pool2d(hp, 3, 2, return_indices=True)
+        return x.flatten(-2).gather(-1, idx.flatten(-2)).view(idx.shape)
+    assert tuple(hint.shape) == (x.shape[0], x.shape[1], ho, wo), (tuple(hint.shape), (x.shape[0], x.shape[1], ho, wo))
+    k = hint.to(torch.int64)
+    pad_won = k >= 9
+    k = k.clamp(max=8)
+    iy = 2 * torch.arange(ho).view(1, 1, ho, 1) + k // 3
+    ix = 2 * torch.arange(wo).view(1, 1, 1, wo) + k % 3
+    out = x.flatten(-2).gather(-1, (iy * wp + ix).flatten(-2)).view(k.shape)
+    return torch.where(pad_won, torch.zeros((), dtype=x.dtype), out)
 
 
 def upsample2(x):
@@ -134,7 +148,9 @@ def bifpn_cell(inputs, p, prefix="", first_time=False, training=False, attention
                eps=FUSION_EPS, stats_out=None, pool_hints=None):
     """One BiFPN cell.  src/YetAnotherEfficientDet.py:320-392 (attention=True) and :394-442
     (attention=False: plain sums).  `p` holds the cell's tensors under `prefix`.
-    `pool_hints` (test-only, see maxpool_same): {"p3_out" | "p4_out" | "p5_out" | "p6_out": tensor}."""
+    `pool_hints` (test-only, see maxpool_same): {"p3_out" | "p4_out" | "p5_out" | "p6_out" | (first cell) "p6_in" |
+    "p7_in": tensor}, keyed by the name of the pooling's OUTPUT for the first-cell synthesis pools and of its INPUT for
+    the bottom-up path."""
     q = prefix
     hint = (pool_hints or {}).get
 
@@ -145,8 +161,8 @@ def bifpn_cell(inputs, p, prefix="", first_time=False, training=False, attention
 
     if first_time:
         p3, p4, p5 = inputs
-        p6_in = maxpool_same(projection(p5, p, q + "p5_to_p6", training, stats_out))     # :324
-        p7_in = maxpool_same(p6_in)                                                       # :325
+        p6_in = maxpool_same(projection(p5, p, q + "p5_to_p6", training, stats_out), hint("p6_in"))   # :324
+        p7_in = maxpool_same(p6_in, hint("p7_in"))                                                    # :325
         p3_in = projection(p3, p, q + "p3_down_channel", training, stats_out)            # :327
         p4_in = projection(p4, p, q + "p4_down_channel", training, stats_out)            # :328
         p5_in = projection(p5, p, q + "p5_down_channel", training, stats_out)            # :329

@@ -86,36 +86,19 @@ def param_class(k):
         "proj" if ".0.conv" in k else "bn"
 
 
-def cuda_pool_hints(stack, xs_dev, n_cells):
-    """The CUDA path's own values of every tensor that feeds a 3x3-s2 max-pool inside a cell (p3_out .. p6_out of every
-    cell), obtained by running the cells ONE AT A TIME in train mode (each cell's outputs are then user-visible).  In fp32
-    storage these equal the fused stack's internal values: a deferred-BatchNorm tensor is normalised with the same
-    fma(raw, scale, shift) whether a BNAPPLY op materialises it or a consumer applies it on load.  Fed to the oracle as
-    arg-max hints (oracle.maxpool_same) so that both route the pooling gradients identically.  The module's running
-    statistics are restored afterwards."""
-    sd0 = {k: v.clone() for k, v in stack.state_dict().items()}
-    was_training = stack.training
-    stack.train()
-    hints = []
-    with torch.no_grad():
-        feats = tuple(xs_dev)
-        for i in range(n_cells):
-            feats = stack[i](feats)
-            hints.append({n: t.detach().float().cpu() for n, t in zip(("p3_out", "p4_out", "p5_out", "p6_out"), feats)})
-    stack.load_state_dict(sd0)
-    stack.train(was_training)
-    return hints
-
-
 def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channels_last=False, ref64=True,
                       fw_mode="ones", force_argmax=None):
     """CUDA stack vs the oracle (fp64 and fp32) on D2-shaped random data.  Returns metrics for ours and, for
     calibration, for the fp32 oracle against the fp64 oracle.
-    force_argmax (default: on for fp32 storage): every oracle run takes its max-pool arg-max from the CUDA path's own
-    values (cuda_pool_hints), so a near-tie resolved differently by two fp32 summation orders no longer shows up as a
-    1e-4 .. 1e-3 jump of every gradient; the forward bounds are unaffected (values move by the top-2 gap, ~1e-7)."""
+    force_argmax (default on): every oracle run takes its max-pool arg-max from the window indices the CUDA forward itself
+    recorded (mm_distillnet_b200.bifpn.debug_pool_argmax -> oracle.maxpool_same(hint=...)), so a near-tie resolved
+    differently by two summation orders (fp32: 1e-4 .. 1e-3 jumps of every gradient; bf16 storage: the dominant part of
+    the gradient error) no longer hides the arithmetic error of the kernels.  The forward comparison of the train
+    outputs uses the hinted oracle too: its values differ from the true maxima by the top-2 gap of the flipped windows
+    only (~1e-7 fp32); the eval forward is always compared against the plain, unhinted oracle."""
     if force_argmax is None:
-        force_argmax = (dtype == torch.float32)
+        force_argmax = True
+    from mm_distillnet_b200.bifpn import debug_pool_argmax
     C, cc = 112, [48, 120, 352]
     gen = torch.Generator().manual_seed(seed)
     cells = [mmd.BiFPN(C, cc, first_time=(i == 0 and first)) for i in range(n_cells)]
@@ -144,7 +127,14 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         xs = [x.to(dtype).float() for x in xs]
     stack = stack.to(DEV)
     m = {}
-    hints = cuda_pool_hints(stack, to_dev(xs, dtype, channels_last), n_cells) if force_argmax else None
+    # CUDA first: eval forward, then the train forward whose recorded arg-max the oracle follows; its backward runs last
+    stack.eval()
+    with torch.no_grad():
+        ev = stack(tuple(to_dev(xs, dtype, channels_last)))
+    stack.train()
+    xd = [x.requires_grad_(True) for x in to_dev(xs, dtype, channels_last)]
+    tr = stack(tuple(xd))
+    hints = debug_pool_argmax(tr[0]) if force_argmax else None
 
     def oracle_run(dt, training):
         p = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in params.items()}
@@ -189,15 +179,9 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
         if fwd_ > 0.0:
             m["torchbf16_pgrad_fwall"] = (fwn / fwd_) ** 0.5
 
-    stack.eval()
-    with torch.no_grad():
-        ev = stack(tuple(to_dev(xs, dtype, channels_last)))
     for n, t, r in zip(H.LEVELS, ev, ev_ref):
         assert t.shape == r.shape
         m["eval_" + n] = H.max_rel(t.float().cpu(), r)
-    stack.train()
-    xd = [x.requires_grad_(True) for x in to_dev(xs, dtype, channels_last)]
-    tr = stack(tuple(xd))
     sum((t.float() * go.to(DEV)).sum() for t, go in zip(tr, gouts)).backward()
     for i, (n, t, r) in enumerate(zip(H.LEVELS, tr, tr_ref)):
         m["train_" + n] = H.max_rel(t.detach().float().cpu(), r.detach())

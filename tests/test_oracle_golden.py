@@ -124,6 +124,29 @@ def test_pool_hint_with_own_values_is_the_pinned_path():
     assert gc[0, 1, 4, 4] != ga[0, 1, 4, 4] and (c - a).abs().max() <= 2.0
 
 
+def test_pool_hint_as_window_indices():
+    """Integer hints (the CUDA kernels' arg-max bytes: 0..8 inside the window, 9 = padding) select exactly those elements."""
+    x = O.synth((1, 3, 6, 6), 5).requires_grad_(True)
+    with torch.no_grad():
+        x[0, 0, 4:, :] = -1.0       # the bottom windows of channel 0 hold only negative values: the padding zero wins
+    ref = O.maxpool_same(x)
+    # derive the indices of the natural arg-max, then check the index path reproduces value and gradient
+    xp = torch.nn.functional.pad(x.detach(), [0, 1, 0, 1])
+    _, flat = torch.nn.functional.max_pool2d(xp, 3, 2, return_indices=True)
+    iy, ix = flat // 7, flat % 7
+    oy = 2 * torch.arange(3).view(1, 1, 3, 1)
+    ox = 2 * torch.arange(3).view(1, 1, 1, 3)
+    k = (iy - oy) * 3 + (ix - ox)
+    k = torch.where((iy >= 6) | (ix >= 6), torch.full_like(k, 9), k).to(torch.uint8)
+    got = O.maxpool_same(x, hint=k)
+    assert torch.equal(got, ref)
+    g = O.synth((1, 3, 3, 3), 6)
+    (ga,) = torch.autograd.grad((ref * g).sum(), x, retain_graph=True)
+    (gb,) = torch.autograd.grad((got * g).sum(), x)
+    assert torch.equal(ga, gb)
+    assert (k == 9).any()          # the bottom-row windows of channel 0 are won by the padding
+
+
 def test_stack_pool_hints_reproduce_unhinted_stack():
     name = "stack2_c16_odd"
     C, cc, n_cells, first, B, s3, seed = H.STACK_CASES[name]
