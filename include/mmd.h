@@ -207,6 +207,8 @@ int mmd_prof_collect(double* ms, long long* launches, double* algo_bytes);
  *   "chain_fwd"  0 / 1   run consecutive P5-P7 forward nodes of mmd_bifpn_run / _run_multi as ONE persistent launch with
  *                        grid barriers between the nodes (cooperative launch).  Default 0 (env MMD_CHAIN=1): measured
  *                        slower than separate launches on B200, see profiles/r2_chain_fwd.md.
+ *   "mta_fast"   0 / 1   MTA pooling / backward of bf16 NHWC C = 112 p = 2 maps on the super-chunk kernels (7 fully coalesced
+ *                        warp loads per 16 pixels) instead of the generic ones.  Default 1 (env MMD_NO_MTA_FAST=1 -> 0).
  * Returns 0, or MMD_E_ARG for an unknown name. */
 int mmd_set_option(const char* name, int32_t value);
 

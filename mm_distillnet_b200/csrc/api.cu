@@ -129,11 +129,18 @@ extern "C" int mmd_prof_collect(double* ms, long long* launches, double* bytes) 
   return 0;
 }
 
-namespace mmd { void set_chain_fwd(int on); }
+namespace mmd {
+void set_chain_fwd(int on);
+void set_mta_fast(int on);
+}
 // Runtime switches (each also has an environment default, read once): returns 0, or MMD_E_ARG for an unknown name.
 extern "C" int mmd_set_option(const char* name, int value) {
   if (name != nullptr && strcmp(name, "chain_fwd") == 0) {
     mmd::set_chain_fwd(value);
+    return 0;
+  }
+  if (name != nullptr && strcmp(name, "mta_fast") == 0) {
+    mmd::set_mta_fast(value);
     return 0;
   }
   mmd::set_error("mmd_set_option: unknown option '%s'", name ? name : "(null)");

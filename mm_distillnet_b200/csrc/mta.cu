@@ -5,6 +5,8 @@
 //   mta_level  one CTA per (level, sample): norms, teacher product, two softmaxes, the KL-style sum and
 //              d loss / d a in a handful of block reductions over data that sits in L2;
 //   mta_bwd    re-reads f_s once and writes grad = go * (p/C) * f^(p-1) * (d loss / d a).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mmd {
@@ -457,6 +459,172 @@ __global__ void __launch_bounds__(256) mta_bwd_kernel(const __grid_constant__ Mt
   }
 }
 
+// ---- fast path of the D2 product configuration: bf16, NHWC, C = 112, p = 2 ---------------------------------------------
+// A pixel is 14 16-byte vectors (224 B).  The generic kernel gives 16 lanes to a pixel (14 busy), reduces each pixel with
+// four shuffle steps and looks its segment up per item: ~0.11 warp instructions per byte, i.e. issue-bound at ~half of the
+// HBM rate (ncu: profiles/r2_ncu_summary.md).  Here a warp owns SUPER-CHUNKS of 16 pixels = 224 vectors = 7 fully coalesced
+// warp-wide loads (all lanes busy), two super-chunks per iteration (14 independent 16-byte loads per lane in flight); the
+// per-vector partial sums go through shared memory and lanes 0-15 / 16-31 each add the 14 partials of one pixel of
+// super-chunk 0 / 1 (bank = (14 * lane + k) mod 32: conflict-free).  ~0.06 instructions per byte.
+constexpr int kScPix = 16, kScVec = kScPix * 14;   // 224
+struct MtaFastSeg {
+  const uint4* f;
+  float* a;
+  int npix;
+};
+struct MtaPoolFastP {
+  MtaFastSeg seg[kMaxSeg];
+  int sc_begin[kMaxSeg + 1];   // prefix sums of the super-chunks per map
+  int nseg;
+};
+
+__device__ __forceinline__ float sumsq8(const uint4 r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+    a = fmaf(lo, lo, a);
+    b = fmaf(hi, hi, b);
+  }
+  return a + b;
+}
+
+__global__ void __launch_bounds__(256) mta_pool_c112_kernel(const __grid_constant__ MtaPoolFastP P) {
+  __shared__ float s_part[8][2][kScVec];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = gridDim.x * 8;
+  const int total = P.sc_begin[P.nseg];
+  const int u_of_lane = lane >> 4, pl = lane & 15;
+  for (int sc0 = 2 * (blockIdx.x * 8 + warp); sc0 < total; sc0 += 2 * nw) {
+    int si[2] = {0, 0};
+    for (int k = 1; k < P.nseg; ++k) {
+      const int b = P.sc_begin[k];
+      if (sc0 >= b) si[0] = k;
+      if (sc0 + 1 >= b) si[1] = k;
+    }
+    uint4 raw[2][7];
+    int local[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const MtaFastSeg& s = P.seg[si[u]];
+      local[u] = sc0 + u - P.sc_begin[si[u]];
+      const int nvec = (sc0 + u < total) ? s.npix * 14 : 0;
+      const int base = local[u] * kScVec;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int v = base + 32 * j + lane;
+        raw[u][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (v < nvec) raw[u][j] = __ldg(s.f + v);
+      }
+    }
+    __syncwarp();   // (scheduling fence: all 14 loads are issued before the first one is consumed)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) s_part[warp][u][32 * j + lane] = sumsq8(raw[u][j]);
+    __syncwarp();
+    {
+      const float* q = &s_part[warp][u_of_lane][14 * pl];
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 14; ++k) a += q[k];
+      const MtaFastSeg& s = P.seg[u_of_lane ? si[1] : si[0]];
+      const int pix = (u_of_lane ? local[1] : local[0]) * kScPix + pl;
+      if (sc0 + u_of_lane < total && pix < s.npix) s.a[pix] = a * (1.0f / 112.0f);
+    }
+    __syncwarp();
+  }
+}
+
+struct MtaBwdFastSeg {
+  const uint4* f;
+  uint4* g;
+  const float* ga;   // d loss / d a of call 0 for this level; call c at + c * Btot
+  int npix;
+  int level;
+};
+struct MtaBwdFastP {
+  MtaBwdFastSeg seg[MMD_MTA_MAX_LEVELS];
+  int sc_begin[MMD_MTA_MAX_LEVELS + 1];
+  const float* grad_loss;   // [ncalls][n_levels]
+  long long Btot;
+  int n_levels, ncalls;
+  float scale;              // p / C
+};
+
+__global__ void __launch_bounds__(256) mta_bwd_c112_kernel(const __grid_constant__ MtaBwdFastP P) {
+  __shared__ float s_k[8][2][kScPix];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = gridDim.x * 8;
+  const int total = P.sc_begin[P.n_levels];
+  const int u_of_lane = lane >> 4, pl = lane & 15;
+  for (int sc0 = 2 * (blockIdx.x * 8 + warp); sc0 < total; sc0 += 2 * nw) {
+    int si[2] = {0, 0};
+    for (int k = 1; k < P.n_levels; ++k) {
+      const int b = P.sc_begin[k];
+      if (sc0 >= b) si[0] = k;
+      if (sc0 + 1 >= b) si[1] = k;
+    }
+    uint4 raw[2][7];
+    int base[2], nvec[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const MtaBwdFastSeg& s = P.seg[si[u]];
+      nvec[u] = (sc0 + u < total) ? s.npix * 14 : 0;
+      base[u] = (sc0 + u - P.sc_begin[si[u]]) * kScVec;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int v = base[u] + 32 * j + lane;
+        raw[u][j] = make_uint4(0u, 0u, 0u, 0u);
+        if (v < nvec[u]) raw[u][j] = __ldg(s.f + v);
+      }
+    }
+    {   // per-pixel factor: sum over the calls of grad_loss[call][level] * (p / C) * d loss / d a
+      const MtaBwdFastSeg& s = P.seg[u_of_lane ? si[1] : si[0]];
+      const int pix = ((u_of_lane ? base[1] : base[0]) / 14) + pl;
+      float k = 0.f;
+      if (sc0 + u_of_lane < total && pix < s.npix) {
+        for (int c = 0; c < P.ncalls; ++c)
+          k = fmaf(P.grad_loss[c * P.n_levels + s.level], s.ga[(long long)c * P.Btot + pix], k);
+      }
+      s_k[warp][u_of_lane][pl] = k * P.scale;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint4* g = P.seg[si[u]].g;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int vl = 32 * j + lane;                       // vector inside the super-chunk
+        const float k = s_k[warp][u][(vl * 4682) >> 16];    // vl / 14 for vl < 224
+        const float2 k2 = make_float2(k, k);
+        const uint32_t w[4] = {raw[u][j].x, raw[u][j].y, raw[u][j].z, raw[u][j].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+          const float2 r = __fmul2_rn(k2, x);
+          __nv_bfloat162 h = __floats2bfloat162_rn(r.x, r.y);
+          o[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (base[u] + vl < nvec[u]) g[base[u] + vl] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+static int g_mta_fast = -1;   // MMD_NO_MTA_FAST=1 / mmd_set_option("mta_fast", 0): A/B switch back to the generic kernels
+void set_mta_fast(int on) { g_mta_fast = on ? 1 : 0; }
+static bool mta_fast_enabled() {
+  if (g_mta_fast < 0) {
+    const char* e = getenv("MMD_NO_MTA_FAST");
+    g_mta_fast = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_mta_fast == 1;
+}
+
 static int group_lanes(int C, int vec) {
   int nq = C / vec, g = 1;
   while (g < nq && g < 32) g <<= 1;
@@ -511,7 +679,24 @@ extern "C" int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream_) {
   for (int i = 0; i < nseg; ++i) pool_bytes += (double)pp.seg[i].npix * a->C * (a->dtype == MMD_F32 ? 4 : 2);
   {
   ProfScope prof(PK_MTA_POOL, pool_bytes, stream);
-  if (a->layout == MMD_NHWC) {
+  const bool fast = vec8 && a->C == 112 && a->p == 2.0f && mta_fast_enabled();
+  if (fast) {
+    MtaPoolFastP fp;
+    int tot = 0;
+    for (int i = 0; i < nseg; ++i) {
+      fp.seg[i].f = reinterpret_cast<const uint4*>(pp.seg[i].f);
+      fp.seg[i].a = pp.seg[i].a;
+      fp.seg[i].npix = pp.seg[i].npix;
+      fp.sc_begin[i] = tot;
+      tot += (pp.seg[i].npix + kScPix - 1) / kScPix;
+    }
+    for (int i = nseg; i <= kMaxSeg; ++i) fp.sc_begin[i] = tot;
+    for (int i = nseg; i < kMaxSeg; ++i) fp.seg[i] = fp.seg[0];
+    fp.nseg = nseg;
+    int gx = (tot + 15) / 16;            // 8 warps x 2 super-chunks per block and iteration
+    if (gx > 148 * 8) gx = 148 * 8;
+    mta_pool_c112_kernel<<<gx, 256, 0, stream>>>(fp);
+  } else if (a->layout == MMD_NHWC) {
     const int ppi = (32 / pp.group) * MtaPoolP::kU;   // pixels per item
     int items = 0;
     for (int i = 0; i < nseg; ++i) {
@@ -608,7 +793,29 @@ extern "C" int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* co
   double bwd_bytes = 0.0;
   for (int l = 0; l < a->n_levels; ++l) bwd_bytes += 2.0 * bp.seg[l].npix * a->C * (a->dtype == MMD_F32 ? 4 : 2);
   ProfScope prof(PK_MTA_BWD, bwd_bytes, stream);
-  if (a->layout == MMD_NHWC) {
+  if (vec8 && a->C == 112 && mta_fast_enabled()) {
+    MtaBwdFastP fp;
+    int tot = 0;
+    for (int l = 0; l < a->n_levels; ++l) {
+      fp.seg[l].f = reinterpret_cast<const uint4*>(bp.seg[l].f);
+      fp.seg[l].g = reinterpret_cast<uint4*>(bp.seg[l].g);
+      fp.seg[l].ga = bp.seg[l].ga;
+      fp.seg[l].npix = bp.seg[l].npix;
+      fp.seg[l].level = l;
+      fp.sc_begin[l] = tot;
+      tot += (bp.seg[l].npix + kScPix - 1) / kScPix;
+    }
+    for (int l = a->n_levels; l <= MMD_MTA_MAX_LEVELS; ++l) fp.sc_begin[l] = tot;
+    for (int l = a->n_levels; l < MMD_MTA_MAX_LEVELS; ++l) fp.seg[l] = fp.seg[0];
+    fp.grad_loss = grad_loss;
+    fp.Btot = bp.Btot;
+    fp.n_levels = a->n_levels;
+    fp.ncalls = bp.ncalls;
+    fp.scale = a->p / (float)a->C;
+    int gxf = (tot + 15) / 16;
+    if (gxf > 148 * 8) gxf = 148 * 8;
+    mta_bwd_c112_kernel<<<gxf, 256, 0, stream>>>(fp);
+  } else if (a->layout == MMD_NHWC) {
     if (a->dtype == MMD_F32) mta_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(bp);
     else if (vec8) mta_bwd_bf16x8_kernel<<<grid, 256, 0, stream>>>(bp);
     else mta_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(bp);

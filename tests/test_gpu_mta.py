@@ -91,3 +91,35 @@ def test_mta_edge_cases():
         crit([f for f in fs], [f for f in ft])          # CPU tensors: no fallback
     with pytest.raises(TypeError):
         crit([f.to(G.DEV).half() for f in fs], [f.to(G.DEV).half() for f in ft])
+
+
+def test_mta_c112_fast_path_matches_generic_kernels():
+    """bf16 NHWC C=112 p=2 runs on the super-chunk kernels (mta_pool_c112 / mta_bwd_c112: 16 pixels = 7 coalesced warp
+    loads); mmd_set_option("mta_fast", 0) switches back to the generic kernels: same losses, same gradients, including
+    maps whose pixel count is no multiple of the 16-pixel super-chunk (18, 72, 2) and a single-pixel level."""
+    import mm_distillnet_b200 as mmd
+    from mm_distillnet_b200 import _lib
+    gen = torch.Generator().manual_seed(3)
+    sizes = [12, 6, 3, 1]
+    mk = lambda: [(torch.randn(2, 112, s, s, generator=gen) * torch.exp(torch.randn(2, 1, s, s, generator=gen))).to(torch.bfloat16)
+                  .to(G.DEV).contiguous(memory_format=torch.channels_last) for s in sizes]
+    fs0, teachers = mk(), [mk() for _ in range(3)]
+    go = torch.rand(3, len(sizes), generator=gen).to(G.DEV) * 0.01
+    crit = mmd.MTALoss()
+
+    def run():
+        fs = [f.clone().requires_grad_(True) for f in fs0]
+        each = crit.forward_each(fs, teachers)
+        prod = crit(fs, teachers)
+        ((each * go).sum() + 0.01 * prod.sum()).backward()
+        return each.detach().clone(), prod.detach().clone(), [f.grad.clone() for f in fs]
+
+    e1, p1, g1 = run()
+    _lib.set_option("mta_fast", 0)
+    try:
+        e0, p0, g0 = run()
+    finally:
+        _lib.set_option("mta_fast", 1)
+    assert torch.allclose(e1, e0, rtol=0, atol=1e-6) and torch.allclose(p1, p0, rtol=0, atol=1e-6)
+    for a, b in zip(g1, g0):
+        assert H.rel_l2(a.float().cpu(), b.float().cpu()) <= 1e-5       # same arithmetic up to fp32 summation order

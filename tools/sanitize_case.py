@@ -1,0 +1,29 @@
+"""A small end-to-end pass of every product kernel family for compute-sanitizer (memcheck / racecheck):
+bf16 stack forward + backward (tcgen05 / bulk-copy kernels, poolfuse, projections), fp32 stack forward + backward (the
+generic kernels), MTA forward + backward.    compute-sanitizer --tool memcheck python tools/sanitize_case.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import mm_distillnet_b200 as mmd  # noqa: E402
+
+dev = torch.device("cuda", 0)
+CC = [48, 120, 352]
+torch.manual_seed(0)
+for dtype in (torch.bfloat16, torch.float32):
+    stack = mmd.BiFPNStack(*[mmd.BiFPN(112, CC, first_time=(i == 0)) for i in range(2)]).to(dev).train()
+    xs = [torch.randn(1, c, 48 >> i, 48 >> i, device=dev).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+          for i, c in enumerate(CC)]
+    out = stack(tuple(xs))
+    crit = mmd.MTALoss()
+    teachers = [[o.detach().flip(0) * 0.5 for o in out] for _ in range(2)]
+    kd = crit.forward_each(list(out), teachers) if dtype == torch.bfloat16 else torch.stack([crit(list(out), t) for t in teachers])
+    (0.005 * kd.sum() + sum(o.float().mean() for o in out)).backward()
+    stack.eval()
+    with torch.no_grad():
+        stack(tuple(x.detach() for x in xs))
+    torch.cuda.synchronize()
+    print(dtype, "ok", float(kd.sum()))

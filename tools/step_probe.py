@@ -1,9 +1,14 @@
-"""Per-step timing of the persistent small-level chains (MMD_CHAIN_DEBUG=1 makes the library print globaltimer deltas
-for every chain launch).  python tools/chain_probe.py [B]"""
+"""Three eager distillation steps (student + 3 teachers in lockstep, MTA, backward) at batch B: the workload the ncu
+captures of profiles/ are taken on.  With --chain the persistent small-level chains are switched on and the library
+prints %globaltimer deltas for every step of every chain launch (MMD_CHAIN_DEBUG=1).
+    python tools/step_probe.py [B] [--chain]"""
 import os
 import sys
 
-os.environ.setdefault("MMD_CHAIN_DEBUG", "1")
+if "--chain" in sys.argv:
+    sys.argv.remove("--chain")
+    os.environ.setdefault("MMD_CHAIN", "1")
+    os.environ.setdefault("MMD_CHAIN_DEBUG", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
