@@ -306,6 +306,11 @@ struct NodeBwdGroup {
 };
 static_assert(sizeof(NodeFwdGroup) <= 4096 && sizeof(NodeBwdGroup) <= 4096, "kernel parameter space");
 int launch_bnapply_group(const NodeFwdP* p, int n, int C, int dtype, cudaStream_t s);
+// streaming fast paths of the bf16 SAME-mode groups (bifpn_fwd_v4.cu / bifpn_bwd_v4.cu)
+bool bnapply_same_bf16_usable(const NodeFwdP* p, int n);
+int launch_bnapply_same_bf16(const NodeFwdP* p, int n, cudaStream_t s);
+bool slot_same_bf16_usable(const NodeBwdP* p, int n);
+int launch_slot_same_bf16(const NodeBwdP* p, int n, cudaStream_t s);
 int launch_slot_group(const NodeBwdP* p, int n, int C, int dtype, cudaStream_t s);
 
 // kernels' host launchers (defined in bifpn_fwd.cu / bifpn_bwd.cu)

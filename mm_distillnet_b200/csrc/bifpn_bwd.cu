@@ -725,6 +725,7 @@ int launch_slot_group(const NodeBwdP* p, int n, int C, int dtype, cudaStream_t s
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(n >= 1 && n <= kMaxGroupOps, "slot group of %d ops", n);
   if (dtype == MMD_F32) return launch_slot_group_t<float>(p, n, s);
+  if (dtype == MMD_BF16 && !tc_disabled() && slot_same_bf16_usable(p, n)) return launch_slot_same_bf16(p, n, s);
   if (dtype == MMD_BF16) return launch_slot_group_t<__nv_bfloat16>(p, n, s);
   set_error("unsupported dtype %d", dtype);
   return MMD_E_ARG;

@@ -1015,6 +1015,104 @@ static int pick_geom(int H, int W) {
 
 }  // namespace b4
 
+
+// ---- streaming SLOT (bf16, SAME mode): sum G and sum G * xhat per channel for the 5 stack outputs -----------------------
+// Same thread layout as bnapply_same_bf16_kernel (16 positions x 14 channel groups, fixed channel group per thread, four
+// position blocks in flight); per-thread fp32 partials, block reduction through shared memory, 2 * C double atomics per
+// block.  The generic kernel (bifpn_bwd.cu) runs at ~0.2 of the HBM rate (8-byte loads, 64-bit index divisions).
+namespace b4 {
+constexpr int kSlotThreads = 224;
+__global__ void __launch_bounds__(kSlotThreads) slot_same_bf16_kernel(const __grid_constant__ NodeBwdGroup GROUP) {
+  const NodeBwdP& P = GROUP.p[blockIdx.y];
+  __shared__ float s_red[16][NG][16];
+  const long long npos = (long long)P.g.B * P.g.H * P.g.W;
+  const long long nblk = (npos + 15) / 16;
+  long long want = (nblk + 15) / 16;   // >= 16 position blocks per CTA: every CTA ends with 2 * C same-address atomics
+  if (want < 1) want = 1;
+  const long long nctas = want < (long long)gridDim.x ? want : (long long)gridDim.x;
+  if ((long long)blockIdx.x >= nctas) return;
+  pdl_wait();
+  pdl_trigger();
+  const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
+  const float* bn = P.in[0].bn;
+  float2 mu[4], is[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    mu[e] = *reinterpret_cast<const float2*>(bn + 2 * C + 8 * cg + 2 * e);
+    is[e] = *reinterpret_cast<const float2*>(bn + 3 * C + 8 * cg + 2 * e);
+  }
+  const uint4* __restrict__ G = reinterpret_cast<const uint4*>(P.cons[0].du);
+  const uint4* __restrict__ X = reinterpret_cast<const uint4*>(P.in[0].data);
+  float2 s1[4], s2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) s1[e] = s2[e] = make_float2(0.f, 0.f);
+  constexpr int U = 4;
+  for (long long blk = blockIdx.x; blk < nblk; blk += (long long)U * nctas) {
+    uint4 g[U], x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pos = (blk + (long long)u * nctas) * 16 + pl;
+      g[u] = x[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (pos < npos) {
+        g[u] = __ldg(G + pos * NG + cg);
+        x[u] = __ldg(X + pos * NG + cg);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {   // (out-of-range positions carry g = 0: they add nothing)
+      const uint32_t gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w}, xw[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 gg = bf2_to_f2(gw[e]);
+        const float2 xh = mul2(add2(bf2_to_f2(xw[e]), make_float2(-mu[e].x, -mu[e].y)), is[e]);
+        s1[e] = add2(s1[e], gg);
+        s2[e] = fma2(gg, xh, s2[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    s_red[pl][cg][2 * e] = s1[e].x; s_red[pl][cg][2 * e + 1] = s1[e].y;
+    s_red[pl][cg][8 + 2 * e] = s2[e].x; s_red[pl][cg][8 + 2 * e + 1] = s2[e].y;
+  }
+  __syncthreads();
+  {   // thread (cg, k = pl): channel 8 * cg + (k & 7), quantity k >> 3
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) a += s_red[r][cg][pl];
+    const int c = 8 * cg + (pl & 7);
+    atomicAdd(P.in_slot[0] + ((pl >> 3) ? C + c : c), (double)a);
+  }
+}
+}  // namespace b4
+
+bool slot_same_bf16_usable(const NodeBwdP* p, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (p[i].mode[0] != MMD_IN_SAME || p[i].in[0].bn == nullptr || p[i].in_slot[0] == nullptr) return false;
+    if ((((uintptr_t)p[i].in[0].data | (uintptr_t)p[i].cons[0].du) & 15u) != 0) return false;
+  }
+  return true;
+}
+
+int launch_slot_same_bf16(const NodeBwdP* p, int n, cudaStream_t s) {
+  NodeBwdGroup group;
+  double bytes = 0.0;
+  long long maxcta = 1;
+  for (int i = 0; i < kMaxGroupOps; ++i) group.p[i] = p[i < n ? i : 0];
+  for (int i = 0; i < n; ++i) {
+    const long long npos = (long long)p[i].g.B * p[i].g.H * p[i].g.W;
+    bytes += 2.0 * npos * 112 * 2;
+    const long long want = ((npos + 15) / 16 + 15) / 16;
+    if (want > maxcta) maxcta = want;
+  }
+  const long long cap = 4LL * device_sm_count();
+  if (maxcta > cap) maxcta = cap;
+  ProfScope prof(PK_SLOT, bytes, s);
+  MMD_CUDA(launch_pdl(b4::slot_same_bf16_kernel, dim3((unsigned)maxcta, n), dim3(b4::kSlotThreads), 0, s, group));
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
 bool fwgrad_deferral_enabled() {
   static int on = -1;
   if (on < 0) {

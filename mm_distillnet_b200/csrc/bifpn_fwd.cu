@@ -486,6 +486,7 @@ int launch_bnapply_group(const NodeFwdP* p, int n, int C, int dtype, cudaStream_
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(n >= 1 && n <= kMaxGroupOps, "bnapply group of %d ops", n);
   if (dtype == MMD_F32) return launch_bnapply_group_t<float>(p, n, s);
+  if (dtype == MMD_BF16 && !tc_disabled() && bnapply_same_bf16_usable(p, n)) return launch_bnapply_same_bf16(p, n, s);
   if (dtype == MMD_BF16) return launch_bnapply_group_t<__nv_bfloat16>(p, n, s);
   set_error("unsupported dtype %d", dtype);
   return MMD_E_ARG;

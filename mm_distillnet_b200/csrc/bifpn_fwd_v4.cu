@@ -1083,6 +1083,89 @@ __global__ void __launch_bounds__(128) bn_finalize_all_kernel(const __grid_const
 }
 }  // namespace v4
 
+
+// ---- streaming BNAPPLY (bf16, SAME mode): the 5 stack outputs of a training forward -----------------------------------
+// out = scale * x + shift over the flat tensor.  The generic kernel (bifpn_fwd.cu) handles 4 channels per thread with
+// three 64-bit divisions per element and one 8-byte load in flight: ~0.2 of the HBM rate.  Here a block is 16 positions x
+// 14 channel groups (one 16-byte vector per thread, the thread's channel group never changes, so its 8 + 8 coefficients
+// live in registers), four position blocks per iteration in flight.  blockIdx.y = op of the group.
+namespace v4 {
+constexpr int kBnThreads = 224;   // 16 positions x 14 channel groups
+__global__ void __launch_bounds__(kBnThreads) bnapply_same_bf16_kernel(const __grid_constant__ NodeFwdGroup GROUP) {
+  const NodeFwdP& P = GROUP.p[blockIdx.y];
+  __shared__ __align__(16) float s_bn[2 * C];
+  const long long npos = (long long)P.g.B * P.g.H * P.g.W;
+  const long long nblk = (npos + 15) / 16;
+  if ((long long)blockIdx.x >= nblk) return;
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x < C) {
+    float sc1, sh1;
+    bn_coef<C>(P.in[0], P.bnsrc[0], threadIdx.x, sc1, sh1);
+    s_bn[threadIdx.x] = sc1;
+    s_bn[C + threadIdx.x] = sh1;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x % NG, pl = threadIdx.x / NG;
+  float2 sc[4], sh[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    sc[e] = *reinterpret_cast<const float2*>(s_bn + 8 * cg + 2 * e);
+    sh[e] = *reinterpret_cast<const float2*>(s_bn + C + 8 * cg + 2 * e);
+  }
+  const uint4* __restrict__ src = reinterpret_cast<const uint4*>(P.in[0].data);
+  uint4* __restrict__ dst = reinterpret_cast<uint4*>(P.out);
+  constexpr int U = 4;
+  for (long long blk = blockIdx.x; blk < nblk; blk += (long long)U * gridDim.x) {
+    uint4 r[U];
+    long long pos[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pos[u] = (blk + (long long)u * gridDim.x) * 16 + pl;
+      r[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (pos[u] < npos) r[u] = __ldg(src + pos[u] * NG + cg);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pos[u] >= npos) continue;
+      uint4 o;
+      o.x = f2_to_bf2(fma2(bf2_to_f2(r[u].x), sc[0], sh[0]));
+      o.y = f2_to_bf2(fma2(bf2_to_f2(r[u].y), sc[1], sh[1]));
+      o.z = f2_to_bf2(fma2(bf2_to_f2(r[u].z), sc[2], sh[2]));
+      o.w = f2_to_bf2(fma2(bf2_to_f2(r[u].w), sc[3], sh[3]));
+      dst[pos[u] * NG + cg] = o;
+    }
+  }
+}
+}  // namespace v4
+
+bool bnapply_same_bf16_usable(const NodeFwdP* p, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (p[i].mode[0] != MMD_IN_SAME || p[i].pidx[0] != nullptr) return false;
+    if ((((uintptr_t)p[i].in[0].data | (uintptr_t)p[i].out) & 15u) != 0) return false;
+  }
+  return true;
+}
+
+int launch_bnapply_same_bf16(const NodeFwdP* p, int n, cudaStream_t s) {
+  NodeFwdGroup group;
+  double bytes = 0.0;
+  long long maxblk = 1;
+  for (int i = 0; i < kMaxGroupOps; ++i) group.p[i] = p[i < n ? i : 0];
+  for (int i = 0; i < n; ++i) {
+    bytes += node_algo_bytes(p[i].in, 1, p[i].g, 112, 2);
+    const long long nblk = ((long long)p[i].g.B * p[i].g.H * p[i].g.W + 15) / 16;
+    if (nblk > maxblk) maxblk = nblk;
+  }
+  long long grid = (maxblk + 3) / 4;
+  const long long cap = 8LL * device_sm_count();
+  if (grid > cap) grid = cap;
+  ProfScope prof(PK_BNAPPLY, bytes, s);
+  MMD_CUDA(launch_pdl(v4::bnapply_same_bf16_kernel, dim3((unsigned)grid, n), dim3(v4::kBnThreads), 0, s, group));
+  MMD_LAUNCH_CHECK();
+  return 0;
+}
+
 bool bn_deferral_enabled() {
   static int on = -1;
   if (on < 0) {

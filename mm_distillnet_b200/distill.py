@@ -40,7 +40,7 @@ class DistillStep:
     """
 
     def __init__(self, student, teachers, criterion=None, w_kd=0.005, process_group=None, device=None,
-                 batch_networks=True):
+                 batch_networks=True, kd_mode="each"):
         if not isinstance(student, (BiFPN, BiFPNStack)):
             raise TypeError("DistillStep drives mm_distillnet_b200 BiFPN / BiFPNStack modules")
         self.student, self.teachers = student, list(teachers)
@@ -51,6 +51,14 @@ class DistillStep:
         self.device = device if device is not None else next(student.parameters()).device
         self.flat_grad = None
         self.batch_networks = bool(batch_networks)
+        # "each": criterion_kd(features_s, features_t) per teacher, the shipped ModelWithNMSLossAugmented wrapper
+        #         (train_methods.py:351-358) -> losses [n_teachers, n_levels];
+        # "product": ONE call criterion_kd(features_s, [features_t1, features_t2, ...]) against the product of the
+        #         teachers' attention maps, the ModelWithNMSKDListLoss wrapper (train_methods.py:165-262, KD term :256-261;
+        #         MTALoss.forward list-of-lists branch, MTALoss.py:20-34) -> losses [1, n_levels]
+        if kd_mode not in ("each", "product"):
+            raise ValueError("DistillStep: kd_mode must be 'each' or 'product'")
+        self.kd_mode = kd_mode
         # multi-stream fallback (stacks that cannot share launches): the frozen teachers and the student are independent until the MTA loss: each teacher stack runs on its own
         # CUDA stream so the small pyramid levels (P5-P7: fewer CTAs than SMs) of different networks overlap
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.teachers] if self.device.type == "cuda" else []
@@ -80,6 +88,8 @@ class DistillStep:
     def _kd(self, feats_s, feats_t_all):
         """criterion_kd(features_s, features_t) per teacher (train_methods.py:351-358) -> Tensor[n_teachers, n_levels]."""
         teachers = [[f.detach() for f in ft] for ft in feats_t_all]
+        if self.kd_mode == "product":
+            return self.criterion(feats_s, teachers if len(teachers) > 1 else teachers[0]).unsqueeze(0)
         if isinstance(self.criterion, MTALoss) and 1 <= len(teachers) <= 4:
             return self.criterion.forward_each(feats_s, teachers)      # one set of launches for all teachers
         return torch.stack([self.criterion(feats_s, t) for t in teachers])
