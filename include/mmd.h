@@ -209,6 +209,9 @@ int mmd_prof_collect(double* ms, long long* launches, double* algo_bytes);
  *                        slower than separate launches on B200, see profiles/r2_chain_fwd.md.
  *   "mta_fast"   0 / 1   MTA pooling / backward of bf16 NHWC C = 112 p = 2 maps on the super-chunk kernels (7 fully coalesced
  *                        warp loads per 16 pixels) instead of the generic ones.  Default 1 (env MMD_NO_MTA_FAST=1 -> 0).
+ *   "proj_tma"   0 / 1   first-cell projections (forward, bf16) on the warp-specialised tensor-map TMA pipeline
+ *                        (cp.async.bulk.tensor loads / stores, double-buffered TMEM accumulator) instead of
+ *                        proj_fwd_tc_kernel.  Default 1 (env MMD_NO_PROJ_TMA=1 -> 0).
  * Returns 0, or MMD_E_ARG for an unknown name. */
 int mmd_set_option(const char* name, int32_t value);
 

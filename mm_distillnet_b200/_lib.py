@@ -10,8 +10,8 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
-SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_bwd.cu", "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu",
-           "bifpn_run.cu")
+SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_proj_tma.cu", "bifpn_bwd.cu",
+           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1

@@ -132,6 +132,7 @@ extern "C" int mmd_prof_collect(double* ms, long long* launches, double* bytes) 
 namespace mmd {
 void set_chain_fwd(int on);
 void set_mta_fast(int on);
+void set_proj_tma(int on);
 }
 // Runtime switches (each also has an environment default, read once): returns 0, or MMD_E_ARG for an unknown name.
 extern "C" int mmd_set_option(const char* name, int value) {
@@ -141,6 +142,10 @@ extern "C" int mmd_set_option(const char* name, int value) {
   }
   if (name != nullptr && strcmp(name, "mta_fast") == 0) {
     mmd::set_mta_fast(value);
+    return 0;
+  }
+  if (name != nullptr && strcmp(name, "proj_tma") == 0) {
+    mmd::set_proj_tma(value);
     return 0;
   }
   mmd::set_error("mmd_set_option: unknown option '%s'", name ? name : "(null)");

@@ -343,6 +343,10 @@ bool proj_bwd_v4_usable(const NodeBwdP& p);
 int launch_proj_bwd_v4(const NodeBwdP& p, int C, cudaStream_t s);
 int launch_proj_fwd_tc(const NodeFwdP& p, int C, cudaStream_t s);      // bf16, tcgen05 projection Cin -> C
 int launch_proj_fwd_tc_multi(const NodeFwdP* p, int n, int C, cudaStream_t s);   // n networks in one launch
+// warp-specialised tensor-map TMA pipeline for the same op (bifpn_proj_tma.cu); launch_proj_fwd_tc_multi prefers it
+bool proj_fwd_tma_usable(const NodeFwdP* p, int n);
+int launch_proj_fwd_tma(const NodeFwdP* p, int n, int C, cudaStream_t s);
+void set_proj_tma(int on);
 int launch_node_bwd_a_tc(const NodeBwdP& p, int C, cudaStream_t s);     // bf16, tcgen05 dgrad + wgrad
 bool tc_disabled();  // MMD_NO_TC=1: debugging aid, runs the bf16 path on the CUDA-core kernels instead
 int launch_proj_fwd(const NodeFwdP& p, int C, int dtype, cudaStream_t s);

@@ -696,6 +696,7 @@ int launch_proj_fwd_tc_multi(const NodeFwdP* ps, int n, int C, cudaStream_t s) {
   MMD_CHECK_ARG(C == 112, "BiFPN kernels are built for C=112 (EfficientDet-D2), got %d", C);
   MMD_CHECK_ARG(p.Cin % 8 == 0, "bf16 projection needs Cin %% 8 == 0, got %d", p.Cin);
   MMD_CHECK_ARG(n >= 1 && n <= kMaxBatchNets, "proj_fwd: %d networks in one launch", n);
+  if (proj_fwd_tma_usable(ps, n)) return launch_proj_fwd_tma(ps, n, C, s);
   constexpr int CC = 112;
   const int Kp = (p.Cin + 15) / 16 * 16, KG = Kp / 8;
   const size_t smem = (size_t)KG * kTileP * 16 + ((KG * CC * 16 + 127) / 128) * 128 + kTileP * (CC + 8) * 2 + CC * 4 + 32;
