@@ -865,6 +865,99 @@ __device__ __forceinline__ void pool_pair_final(const bf16* __restrict__ src, co
   }
 }
 
+// ---- what a thread does with the window maxima of its output pair (shared by poolfuse_kernel and poolfuse_tiled_kernel) ----
+// frozen network: packed bf16 maxima -> w_a * max [+ second input] -> operand
+__device__ __forceinline__ void emit_pair_final(const uint32_t (&bA)[4], const uint32_t (&bB)[4], const bool pA, const bool pB,
+                                                const bool second, const long long oo0, const int cg, const float wa,
+                                                const float* s_c, const bf16* __restrict__ same, bf16* __restrict__ out) {
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    if (o == 1 && !second) break;
+    const uint32_t* best = o ? bB : bA;
+    const bool has_pad = o ? pB : pA;
+    const long long oo = oo0 + (long long)o * C;
+    uint4 sm = make_uint4(0u, 0u, 0u, 0u);
+    if (same != nullptr) sm = __ldg(reinterpret_cast<const uint4*>(same + oo));
+    const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t m = has_pad ? bfmax2(best[e], 0u) : best[e];   // the zero padding takes part in the maximum
+      float2 u = mul2(bf2_to_f2(m), make_float2(wa, wa));
+      if (same != nullptr) {
+        const float2 f = bf2_to_f2(sw[e]);
+        u.x += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+        u.y += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
+      }
+      pk[e] = f2_to_bf2(u);
+    }
+    *reinterpret_cast<uint4*>(out + oo) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// training network: tagged fp32 keys -> value, window index (9 = padding), raw value at the arg-max; operand, arg-max bytes and
+// raw values go to HBM
+__device__ __forceinline__ void emit_pair_train(const float (&bestA)[8], const float (&bestB)[8], const bool padA, const bool padB,
+                                                const bool pad_first, const bool second, const long long oo0, const int cg,
+                                                const float wa, const float (&sc)[8], const float (&sh)[8], const uint32_t (&sgn)[8],
+                                                const float* s_c, const bf16* __restrict__ same, bf16* __restrict__ out,
+                                                unsigned char* __restrict__ pidx, bf16* __restrict__ praw) {
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    if (o == 1 && !second) break;
+    const float* best = o ? bestB : bestA;
+    const bool has_pad = o ? padB : padA;
+    float u[8];
+    uint32_t idx[8], rawb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t bits = __float_as_uint(best[e]);
+      const uint32_t t = 31u - (bits & 31u);
+      const uint32_t wy = (t * 52u) >> 8;            // t / 5 for t < 32
+      idx[e] = wy * 3u + (t - wy * 5u) - (o ? 2u : 0u);
+      rawb[e] = (bits ^ sgn[e]) & 0xffff0000u;
+      float val = fmaf(__uint_as_float(rawb[e]), sc[e], sh[e]);
+      if (has_pad && (pad_first ? (0.f >= val) : (0.f > val))) {
+        val = 0.f;
+        idx[e] = 9u;
+        rawb[e] = 0u;
+      }
+      u[e] = wa * val;
+    }
+    const long long oo = oo0 + (long long)o * C;
+    if (same != nullptr) {
+      const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + oo));
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = bf2_to_f2(w[e]);
+        u[2 * e] += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
+        u[2 * e + 1] += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
+      }
+    }
+    uint4 pk;
+    pk.x = f2_to_bf2(make_float2(u[0], u[1]));
+    pk.y = f2_to_bf2(make_float2(u[2], u[3]));
+    pk.z = f2_to_bf2(make_float2(u[4], u[5]));
+    pk.w = f2_to_bf2(make_float2(u[6], u[7]));
+    *reinterpret_cast<uint4*>(out + oo) = pk;
+    if (pidx != nullptr) {
+      uint2 ip;
+      ip.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
+      ip.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+      *reinterpret_cast<uint2*>(pidx + oo) = ip;
+    }
+    if (praw != nullptr) {
+      uint4 rp;
+      rp.x = (rawb[0] >> 16) | rawb[1];
+      rp.y = (rawb[2] >> 16) | rawb[3];
+      rp.z = (rawb[4] >> 16) | rawb[5];
+      rp.w = (rawb[6] >> 16) | rawb[7];
+      *reinterpret_cast<uint4*>(praw + oo) = rp;
+    }
+  }
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
   int net = 0;
@@ -926,29 +1019,7 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
       bool pA, pB;
       if (!border) pool_pair_final<false>(src, SH, SWd, img, fy0, fx0, cg, bA, bB, pA, pB);
       else pool_pair_final<true>(src, SH, SWd, img, fy0, fx0, cg, bA, bB, pA, pB);
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        if (o == 1 && !second) break;
-        const uint32_t* best = o ? bB : bA;
-        const bool has_pad = o ? pB : pA;
-        const long long oo = (((long long)b * H + y) * W + x0 + o) * C + 8 * cg;
-        uint4 sm = make_uint4(0u, 0u, 0u, 0u);
-        if (same != nullptr) sm = __ldg(reinterpret_cast<const uint4*>(same + oo));
-        const uint32_t sw[4] = {sm.x, sm.y, sm.z, sm.w};
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t m = has_pad ? bfmax2(best[e], 0u) : best[e];   // the zero padding takes part in the maximum
-          float2 u = mul2(bf2_to_f2(m), make_float2(wa, wa));
-          if (same != nullptr) {
-            const float2 f = bf2_to_f2(sw[e]);
-            u.x += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
-            u.y += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
-          }
-          pk[e] = f2_to_bf2(u);
-        }
-        *reinterpret_cast<uint4*>(out + oo) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
+      emit_pair_final(bA, bB, pA, pB, second, (((long long)b * H + y) * W + x0) * C + 8 * cg, cg, wa, s_c, same, out);
       continue;
     }
     float bestA[8], bestB[8];
@@ -960,60 +1031,186 @@ __global__ void __launch_bounds__(kPoolThreads, MINB) poolfuse_kernel(const __gr
       pool_pair<true, true>(src, SH, SWd, img, fy0, fx0, cg, sgn, bestA, bestB, padA, padB);
     }
     const bool pad_first = (fy0 < 0) || (fx0 < 0);   // left / top padding precedes the real elements in scan order
+    emit_pair_train(bestA, bestB, padA, padB, pad_first, second, (((long long)b * H + y) * W + x0) * C + 8 * cg, cg, wa, sc, sh, sgn,
+                    s_c, same, out, pidx, praw);
+  }
+}
+
+// ---- pooling pre-pass, shared-memory tiled (large levels: P3 -> P4, P4 -> P5) -------------------------------------------
+// poolfuse_kernel reads every source element ~1.9 times through L1 / L2 (3 x 5 window loads per output pair, rows shared
+// with the pair below) and is bound by the latency of those loads (ncu: 12.9 warps stalled on the long scoreboard per issue,
+// DRAM traffic 1.27 x the algorithmic bytes).  Here a CTA walks a strip of kPtRows output rows x kPtCols output columns of one
+// image top to bottom and keeps the source rows it needs in a RING of shared-memory row slots filled by bulk asynchronous
+// copies (one per source row, mbarrier completion) kPtSlots - 3 source rows ahead of the compute: every source element is
+// read from HBM once per strip (+ one halo row per strip and one halo column) and the window scan reads shared memory.
+// Work item = (image, row strip, column strip); thread = (output pair, channel group) as in poolfuse_kernel, whose scan
+// (tagged keys for the training network, packed bf16 maxima for frozen ones) and emit code it shares.
+// Even source sizes only (no top / left padding): the D2 pyramid.
+constexpr int kPtCols = 24;                       // output columns per strip  -> 49 source columns per row slot
+constexpr int kPtRows = 8;                        // output rows per strip     -> 17 source rows
+constexpr int kPtSlots = 9;                       // ring slots (source rows)
+constexpr int kPtSlotBytes = up128((2 * kPtCols + 1) * POS);   // 11 008
+constexpr int kPtThreads = (kPtCols / 2) * NG;    // 168: 12 output pairs x 14 channel groups
+constexpr int kPtSmem = kPtSlots * kPtSlotBytes + 4 * C * 4 + kPtSlots * 8 + 16;
+
+__global__ void __launch_bounds__(kPtThreads, 2) poolfuse_tiled_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
+  int net = 0;
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      if (o == 1 && !second) break;
-      const float* best = o ? bestB : bestA;
-      const bool has_pad = o ? padB : padA;
-      float u[8];
-      uint32_t idx[8], rawb[8];
+  for (int k = 1; k < kMaxBatchNets; ++k)
+    if ((int)blockIdx.x >= BATCH.cta_begin[k]) net = k;
+  const NodeFwdP& P = BATCH.p[net];
+  const int cta = (int)blockIdx.x - BATCH.cta_begin[net], nctas = BATCH.cta_begin[net + 1] - BATCH.cta_begin[net];
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* s_c = reinterpret_cast<float*>(smem + kPtSlots * kPtSlotBytes);   // scale | shift | w_b*scale_b | w_b*shift_b
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_c + 4 * C);                // [kPtSlots] slot filled
+  const int tid = threadIdx.x, cg = tid % NG, pl = tid / NG;
+  const int H = P.g.H, W = P.g.W, SH = P.in[0].H, SWd = P.in[0].W;
+  const bf16* __restrict__ src = reinterpret_cast<const bf16*>(P.in[0].data);
+  const bf16* __restrict__ same = (P.n_in >= 2) ? reinterpret_cast<const bf16*>(P.in[1].data) : nullptr;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(P.out);
+  bf16* __restrict__ praw = reinterpret_cast<bf16*>(P.save_d);
+  unsigned char* __restrict__ pidx = P.pidx[0];
+  if (tid == 0) {
+    for (int i = 0; i < kPtSlots; ++i) tc::mbar_init(bar + i, 1);
+    tc::fence_mbar_init();
+  }
+  pdl_wait();
+  pdl_trigger();
+  const float wa = in_weight(P, 0);
+  if (tid < C) {
+    const float wb = (P.n_in >= 2) ? in_weight(P, 1) : 0.f;
+    float ps0, ph0, ps1 = 1.f, ph1 = 0.f;
+    bn_coef<C>(P.in[0], P.bnsrc[0], tid, ps0, ph0);
+    if (P.n_in >= 2) bn_coef<C>(P.in[1], P.bnsrc[1], tid, ps1, ph1);
+    s_c[tid] = ps0;
+    s_c[C + tid] = ph0;
+    s_c[2 * C + tid] = ps1 * wb;
+    s_c[3 * C + tid] = ph1 * wb;
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+  uint32_t sgn[8];
+  bool anyneg = false;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t bits = __float_as_uint(best[e]);
-        const uint32_t t = 31u - (bits & 31u);
-        const uint32_t wy = (t * 52u) >> 8;            // t / 5 for t < 32
-        idx[e] = wy * 3u + (t - wy * 5u) - (o ? 2u : 0u);
-        rawb[e] = (bits ^ sgn[e]) & 0xffff0000u;
-        float val = fmaf(__uint_as_float(rawb[e]), sc[e], sh[e]);
-        if (has_pad && (pad_first ? (0.f >= val) : (0.f > val))) {
-          val = 0.f;
-          idx[e] = 9u;
-          rawb[e] = 0u;
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = s_c[8 * cg + e];
+    sh[e] = s_c[C + 8 * cg + e];
+    sgn[e] = (sc[e] < 0.f) ? 0x80000000u : 0u;
+    anyneg = anyneg || (sc[e] < 0.f);
+  }
+  const bool final_in = (P.in[0].bn == nullptr) && (pidx == nullptr) && (praw == nullptr);
+
+  const int strips_y = (H + kPtRows - 1) / kPtRows, strips_x = W / kPtCols;
+  const int nitems = P.g.B * strips_y * strips_x;
+  uint32_t phases = 0u;   // bit i: parity the next wait on slot i expects
+  for (int item = cta; item < nitems; item += nctas) {
+    const int b = item / (strips_y * strips_x);
+    const int rem = item - b * (strips_y * strips_x);
+    const int y0 = (rem / strips_x) * kPtRows, xs0 = (rem % strips_x) * kPtCols;
+    const int ny = min(kPtRows, H - y0);
+    const int sy0 = 2 * y0, sx0 = 2 * xs0;
+    const int nsrc = min(2 * ny + 1, SH - sy0);                 // source rows of this strip that exist
+    const int ncol = min(2 * kPtCols + 1, SWd - sx0);           // source columns that exist (49, or 48 at the right border)
+    const bf16* src0 = src + (((long long)b * SH + sy0) * SWd + sx0) * C;
+    auto issue_row = [&](int r) {   // source row r of the strip -> slot r % kPtSlots   (thread 0)
+      const int sl = r % kPtSlots;
+      tc::mbar_expect_tx(bar + sl, (uint32_t)ncol * POS);
+      tc::bulk_g2s(smem + sl * kPtSlotBytes, src0 + (long long)r * SWd * C, (uint32_t)ncol * POS, bar + sl);
+    };
+    if (tid == 0)
+      for (int r = 0; r < min(nsrc, kPtSlots); ++r) issue_row(r);
+    int waited = 0;   // source rows [0, waited) of this strip have landed and been observed by this thread
+    for (int yy = 0; yy < ny; ++yy) {
+      const int y = y0 + yy;
+      const int need = min(2 * yy + 3, nsrc);
+      for (; waited < need; ++waited) {
+        const int sl = waited % kPtSlots;
+        tc::mbar_wait(bar + sl, (phases >> sl) & 1u);
+        phases ^= (1u << sl);
+      }
+      const int x0 = xs0 + 2 * pl;
+      const long long oo0 = (((long long)b * H + y) * W + x0) * C + 8 * cg;
+      // the three window rows of this output row (a row beyond the image is the zero padding: any readable slot will do)
+      const unsigned char* rows[3];
+      bool rok[3];
+#pragma unroll
+      for (int wy = 0; wy < 3; ++wy) {
+        const int r = 2 * yy + wy;
+        rok[wy] = r < nsrc;
+        rows[wy] = smem + ((rok[wy] ? r : 2 * yy) % kPtSlots) * kPtSlotBytes + (4 * pl) * POS + cg * 16;
+      }
+      const int cols_ok = ncol - 4 * pl;   // valid source columns from this thread's first one (>= 5 unless at the right border)
+      const bool border = !rok[2] || cols_ok < 5;
+      if (final_in) {
+        uint32_t bA[4], bB[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bA[e] = bB[e] = 0xff80ff80u;   // (-inf, -inf)
+        bool pA = false, pB = false;
+#pragma unroll
+        for (int wy = 0; wy < 3; ++wy) {
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) {
+            uint4 r = *reinterpret_cast<const uint4*>(rows[wy] + (cc < cols_ok ? cc : 0) * POS);
+            if (border && !(rok[wy] && cc < cols_ok)) {
+              r = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+              if (cc <= 2) pA = true;
+              if (cc >= 2) pB = true;
+            }
+            if (cc <= 2) {
+              bA[0] = bfmax2(bA[0], r.x); bA[1] = bfmax2(bA[1], r.y); bA[2] = bfmax2(bA[2], r.z); bA[3] = bfmax2(bA[3], r.w);
+            }
+            if (cc >= 2) {
+              bB[0] = bfmax2(bB[0], r.x); bB[1] = bfmax2(bB[1], r.y); bB[2] = bfmax2(bB[2], r.z); bB[3] = bfmax2(bB[3], r.w);
+            }
+          }
         }
-        u[e] = wa * val;
-      }
-      const long long oo = (((long long)b * H + y) * W + x0 + o) * C + 8 * cg;
-      if (same != nullptr) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(same + oo));
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        emit_pair_final(bA, bB, pA, pB, true, oo0, cg, wa, s_c, same, out);
+      } else {
+        float bestA[8], bestB[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = bf2_to_f2(w[e]);
-          u[2 * e] += fmaf(f.x, s_c[2 * C + 8 * cg + 2 * e], s_c[3 * C + 8 * cg + 2 * e]);
-          u[2 * e + 1] += fmaf(f.y, s_c[2 * C + 8 * cg + 2 * e + 1], s_c[3 * C + 8 * cg + 2 * e + 1]);
+        for (int e = 0; e < 8; ++e) bestA[e] = bestB[e] = -INFINITY;
+        bool padA = false, padB = false;
+#pragma unroll
+        for (int wy = 0; wy < 3; ++wy) {
+#pragma unroll
+          for (int cc = 0; cc < 5; ++cc) {
+            const uint4 r = *reinterpret_cast<const uint4*>(rows[wy] + (cc < cols_ok ? cc : 0) * POS);
+            float key[8];
+            if (anyneg) pool_key8<true>(r, 31u - (uint32_t)(wy * 5 + cc), sgn, key);
+            else pool_key8<false>(r, 31u - (uint32_t)(wy * 5 + cc), sgn, key);
+            if (border && !(rok[wy] && cc < cols_ok)) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) key[e] = -INFINITY;
+              if (cc <= 2) padA = true;
+              if (cc >= 2) padB = true;
+            }
+            if (cc <= 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bestA[e] = fmaxf(bestA[e], key[e]);
+            }
+            if (cc >= 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bestB[e] = fmaxf(bestB[e], key[e]);
+            }
+          }
         }
+        emit_pair_train(bestA, bestB, padA, padB, false, true, oo0, cg, wa, sc, sh, sgn, s_c, same, out, pidx, praw);
       }
-      uint4 pk;
-      pk.x = f2_to_bf2(make_float2(u[0], u[1]));
-      pk.y = f2_to_bf2(make_float2(u[2], u[3]));
-      pk.z = f2_to_bf2(make_float2(u[4], u[5]));
-      pk.w = f2_to_bf2(make_float2(u[6], u[7]));
-      *reinterpret_cast<uint4*>(out + oo) = pk;
-      if (pidx != nullptr) {
-        uint2 ip;
-        ip.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-        ip.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
-        *reinterpret_cast<uint2*>(pidx + oo) = ip;
-      }
-      if (praw != nullptr) {
-        uint4 rp;
-        rp.x = (rawb[0] >> 16) | rawb[1];
-        rp.y = (rawb[2] >> 16) | rawb[3];
-        rp.z = (rawb[4] >> 16) | rawb[5];
-        rp.w = (rawb[6] >> 16) | rawb[7];
-        *reinterpret_cast<uint4*>(praw + oo) = rp;
+      // rows 2yy and 2yy+1 are dead: their slots take the rows kPtSlots further down (generic reads -> async-proxy writes)
+      tc::fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        for (int r = 2 * yy + kPtSlots; r < min(nsrc, 2 * yy + 2 + kPtSlots); ++r) issue_row(r);
       }
     }
+    // drain: rows of this strip that were loaded but never needed (none: need == nsrc at the last output row), and make sure
+    // every thread has observed every landed row before the next strip re-arms the barriers
+    for (; waited < nsrc; ++waited) {
+      const int sl = waited % kPtSlots;
+      tc::mbar_wait(bar + sl, (phases >> sl) & 1u);
+      phases ^= (1u << sl);
+    }
+    __syncthreads();
   }
 }
 
@@ -1468,6 +1665,22 @@ int launch_poolfuse(const NodeFwdP* p, int n, int C, cudaStream_t s) {
     for (int k = 0; k < p[i].n_in; ++k) bytes += (double)p[i].g.B * p[i].in[k].H * p[i].in[k].W * C * 2.0;
   }
   for (int i = n; i < kMaxBatchNets; ++i) batch.p[i] = p[0];
+  // large levels (P3 -> P4, P4 -> P5): the shared-memory tiled kernel
+  static const int no_tiled = getenv("MMD_NO_POOL_TILED") ? 1 : 0;
+  bool tiled = !no_tiled && p[0].g.W % v4::kPtCols == 0 && p[0].in[0].H == 2 * p[0].g.H && p[0].in[0].W == 2 * p[0].g.W;
+  for (int i = 0; i < n && tiled; ++i)
+    tiled = (((uintptr_t)p[i].in[0].data | (uintptr_t)p[i].out | (uintptr_t)p[i].in[1].data | (uintptr_t)p[i].pidx[0] |
+              (uintptr_t)p[i].save_d) & 15u) == 0;
+  if (tiled) {
+    const int items = p[0].g.B * ((p[0].g.H + v4::kPtRows - 1) / v4::kPtRows) * (p[0].g.W / v4::kPtCols);
+    static const float tiled_train_w = env_float("MMD_POOL_TILED_TRAIN_SHARE", 2.0f);   // measured: 1.0 -> +0.3 ms, 1.5 .. 2.5 flat
+    batch_shares(batch, n, 2 * device_sm_count(), items, tiled_train_w);
+    MMD_SMEM(v4::poolfuse_tiled_kernel, v4::kPtSmem);
+    ProfScope prof(PK_POOLFUSE, bytes, s);
+    MMD_CUDA(launch_pdl(v4::poolfuse_tiled_kernel, dim3(batch.cta_begin[n]), dim3(v4::kPtThreads), v4::kPtSmem, s, batch));
+    MMD_LAUNCH_CHECK();
+    return 0;
+  }
   const int npairs = p[0].g.B * p[0].g.H * ((p[0].g.W + 1) / 2);
   const int gx = (npairs + v4::kPoolLanes - 1) / v4::kPoolLanes;
   // ~2 resident CTAs per SM and 2 waves over all networks; a training network (tagged arg-max search, two extra
