@@ -79,7 +79,13 @@ struct CfgA {
   static constexpr int offBar = offCoef + 3 * C * 4;
   static constexpr int kBytes = offBar + 64;
   static constexpr int kLoadThreads = NG * TW;
-  static constexpr int RC = (TH % 4 == 0) ? 4 : 2;         // rows per register chunk of the load phase
+  // rows per register chunk of the load phase.  Large levels (16-wide tiles, several tiles per CTA, 2 CTAs / SM at <= 128
+  // registers): 4.  Small levels (P5-P7: ONE tile per CTA, fewer CTAs than SMs): the whole tile at once — their time is the
+  // latency of the gather's dependent load groups (ncu: 7 - 17 warps stalled on the long scoreboard per issue), which chunking
+  // multiplies; the kernel is then compiled for one CTA per SM so that the TH x 4 gather accumulators fit without spills.
+  static constexpr bool kSmall = TW < 16;
+  static constexpr int RC = kSmall ? TH : ((TH % 4 == 0) ? 4 : 2);
+  static constexpr int kMinCtas = kSmall ? 1 : 2;
   static_assert(NP <= 128 && kLoadThreads <= kThreads && TH % RC == 0, "tile shape");
   static_assert(2 * (kBytes + 1024) <= 233472, "two CTAs per SM");
 };
@@ -157,7 +163,7 @@ __device__ __forceinline__ void gather_rows(const NodeBwdP& P, const float (&cw)
 }
 
 template <int TW, int TH>
-__global__ void __launch_bounds__(kThreads, 2) node_bwd_a4_kernel(const __grid_constant__ NodeBwdP P, int packed_off_bwd) {
+__global__ void __launch_bounds__(kThreads, CfgA<TW, TH>::kMinCtas) node_bwd_a4_kernel(const __grid_constant__ NodeBwdP P, int packed_off_bwd) {
   using S = CfgA<TW, TH>;
   constexpr int RC = S::RC;
   constexpr uint32_t kTmemCols = 256;   // [0,128): dL/dd accumulator, [128,256): [dW | db] accumulator
@@ -963,7 +969,8 @@ static int launch_geom(const NodeBwdP& p, cudaStream_t s) {
   const int ntiles = p.g.B * (p.g.H / TH) * (p.g.W / TW);
   const double bytes = node_algo_bytes(p.in, p.n_in, p.g, C, 2);
   {
-    const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
+    const int cap = SA::kMinCtas * sm_count();   // resident CTAs (small levels: one per SM, whole-tile gather chunks)
+    const int grid = ntiles < cap ? ntiles : cap;
     ProfScope prof((TW == 16 && TH == 8) ? PK_NODE_BWD_A_16x8 : PK_NODE_BWD_A, bytes, s);
     MMD_CUDA(launch_pdl(node_bwd_a4_kernel<TW, TH>, dim3(grid), dim3(kThreads), SA::kBytes, s, p,
                         packed_layout(MMD_OP_NODE_FWD, C, C).offBwd));
