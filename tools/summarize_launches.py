@@ -17,8 +17,8 @@ import sys
 KINDS = [("node_fwd<16,8>", r"node_fwd_v4_kernel<\(?(int\))?16, \(?(int\))?8[,>]"), ("node_bwd_a<16,8>", r"node_bwd_a4_kernel<\(?(int\))?16, \(?(int\))?8[,>]"),
          ("node_bwd_b<16,8>", r"node_bwd_b4_kernel<\(?(int\))?16, \(?(int\))?8"), ("node_fwd", r"node_fwd"), ("poolfuse", r"poolfuse"), ("proj_fwd", r"proj_fwd"), ("bnapply", r"bnapply"),
          ("node_bwd_a", r"node_bwd_a"), ("node_bwd_b", r"node_bwd_b"), ("proj_bwd", r"proj_bwd"), ("pull", r"pull_kernel"),
-         ("slot", r"slot_kernel"), ("mta_pool", r"mta_pool"), ("mta_level", r"mta_level"), ("mta_bwd", r"mta_bwd"),
-         ("mta_finish", r"mta_finish"), ("prep", r"prep_kernel")]
+         ("slot", r"slot_(same|group_|kernel)"), ("mta_pool", r"mta_pool"), ("mta_level", r"mta_level"), ("mta_bwd", r"mta_bwd"),
+         ("mta_finish", r"mta_finish"), ("prep", r"prep_kernel"), ("bn_finalize", r"bn_finalize"), ("fwgrad", r"fwgrad")]
 
 
 def to_us(v, unit):
