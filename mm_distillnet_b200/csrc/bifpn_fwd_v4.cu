@@ -55,7 +55,13 @@ struct Cfg {
   static constexpr int kABytes = NG * kAStride;                // 28 896
   static constexpr int kStage = 128 * POS;                     // dense output staging tile (rows >= NP unused)
   static constexpr int kR0 = up128(cmax(NH * POS, kStage));
-  static constexpr int kR1 = up128(cmax(NH * POS, kABytes));
+  // region 1: raw input 1 (a full halo tile, or the (TH/2+2) x (TW/2+2) source rectangle of a nearest-x2 input) -> UMMA A
+  // operand.  Nodes with a nearest-x2 input also stage their OUTPUT tile here, behind the next tile's input-1 rectangle
+  // (the A operand is dead once the MMA has completed): region 0 is then free right after phase 2 and the next tile's
+  // input 0 is requested a whole MMA + epilogue + store earlier (ncu source view: 18 % of the forward kernel's stall
+  // samples sat in the mbarrier wait for the input tiles).
+  static constexpr int kUp2Bytes = UH * UW * POS;
+  static constexpr int kR1 = up128(cmax(cmax(NH * POS, kABytes), kUp2Bytes + kStage));
   static constexpr int kWBytes = C * C * 2;
   static constexpr int kPackBytes = kWBytes + C * 4 + 9 * C * 4;   // 29 568
   static constexpr int offR0 = kFront, offR1 = offR0 + kR0, offPack = offR1 + kR1, offCoef = offPack + kPackBytes;
@@ -479,8 +485,13 @@ __device__ __forceinline__ void node_fwd_body(const NodeFwdP& P, const NodeFwdP&
                         : nullptr;
       phase2<TW, TH>(r0, r1, s_k, tid, dsave, W);
     }
-    tc::fence_async_smem();   // the A operand was written through the generic proxy
+    tc::fence_async_smem();   // the A operand was written through the generic proxy (and region 0 has been read)
     __syncthreads();
+    const bool early0 = !PRE && (m1 == M1_UP2);   // output staged in region 1: region 0 is free from here on
+    if (early0 && warp == 1 && next < ntiles) {
+      const TilePos tn = tile_pos(next, tdiv, TW, TH);
+      issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
+    }
     // ---- (4) pointwise 1x1 on the tensor cores
     if (tid == 0) {
       tc::fence_after_sync();
@@ -501,8 +512,10 @@ __device__ __forceinline__ void node_fwd_body(const NodeFwdP& P, const NodeFwdP&
       issue_input<TW, TH>(r1, in1, m1 == M1_UP2, tn, H, W, lane, bar_in1);
     }
 
-    // ---- (5) epilogue: TMEM -> +bias -> dense bf16 staging tile (region 0)
-    bf16* s_y = reinterpret_cast<bf16*>(r0);
+    // ---- (5) epilogue: TMEM -> +bias -> dense bf16 staging tile (region 0; region 1 behind the input-1 rectangle for
+    //      nodes with a nearest-x2 input)
+    unsigned char* stg = early0 ? (r1 + S::kUp2Bytes) : r0;
+    bf16* s_y = reinterpret_cast<bf16*>(stg);
     {
       const int row = 32 * (warp & 3) + lane;
       const int col0 = (warp >> 2) * (C / 2);
@@ -530,7 +543,7 @@ __device__ __forceinline__ void node_fwd_body(const NodeFwdP& P, const NodeFwdP&
     // ---- (6) output tile: one bulk copy per tile row; BatchNorm statistics from the staging tile
     if (warp == 1) {
       if (lane < TH)
-        bulk_s2g(out + (((long long)t.b * H + t.ty0 + lane) * W + t.tx0) * C, r0 + lane * (TW * POS), TW * POS);
+        bulk_s2g(out + (((long long)t.b * H + t.ty0 + lane) * W + t.tx0) * C, stg + lane * (TW * POS), TW * POS);
       bulk_commit();
     }
     if (train && ss < 4) {
@@ -551,7 +564,7 @@ __device__ __forceinline__ void node_fwd_body(const NodeFwdP& P, const NodeFwdP&
     if (warp == 1) {
       bulk_wait_read0();      // the bulk stores have read the staging tile
       __syncwarp();
-      if (next < ntiles) {
+      if (!early0 && next < ntiles) {
         const TilePos tn = tile_pos(next, tdiv, TW, TH);
         issue_input<TW, TH>(r0, in0, false, tn, H, W, lane, bar_in0);
       }
