@@ -223,6 +223,38 @@ def algo_bytes_per_step(B, esize, n_teachers=N_TEACHERS):
     return 3 * fwd + n_teachers * fwd + (1 + n_teachers) * pyr + 2 * pyr
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Best effort: run this process on the CPUs of the NUMA node the GPU hangs off BEFORE the pinned staging buffers are
+    allocated and first touched (first-touch places their pages on that node), so that the per-step host->device copies
+    of N ranks do not all cross the same socket.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]               # sysfs uses a 4-digit domain, NVML prints 8
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa_node=-1 (single node / not exposed)"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return "numa_node=%d has no CPU this process may use" % node
+        os.sched_setaffinity(0, allowed)
+        return "bound to NUMA node %d (%d CPUs)" % (node, len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s: %s)" % (type(e).__name__, str(e)[:80])
+
+
 def measure(B, args, rank, world, dev, dtype, min_timed_s):
     """Everything measured at one per-GPU batch size: resident (device-timed) step, end-to-end step, per-kernel
     instrumented pass.  Timed regions are blocks of EXACTLY args.steps steps bracketed by barrier + synchronize; blocks are
@@ -435,6 +467,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     B = args.batch
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     main_r = measure(B, args, rank, world, dev, dtype, args.min_seconds)
     cfg2 = None
     if B != 16 and not args.no_cfg2:   # BASELINE configs[1]: the microbench batch, same run, shorter timed region
@@ -475,7 +508,7 @@ def run_ours(args, rank, world, local_rank):
         "roofline": r["roof"], "cpu_baseline": cpu,
         "e2e": {"value": B * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d"],
                 "d2h_bytes_per_step": N_TEACHERS * 5 * 4, "ms_per_step": ms_e2e / steps,
-                "h2d_feed_GBps_per_rank": r["h2d_gbs"],
+                "h2d_feed_GBps_per_rank": r["h2d_gbs"], "host_numa": numa,
                 "h2d_ms_per_step_alone": (r["h2d"] / (r["h2d_gbs"] * 1e9) * 1e3) if r["h2d_gbs"] else None,
                 "bound": ("host feed: the H2D copy of a step alone takes longer than the resident step"
                           if r["h2d_gbs"] and r["h2d"] / (r["h2d_gbs"] * 1e9) * 1e3 > ms / steps else "device step")},
