@@ -349,3 +349,30 @@ def test_patch_reference_on_the_real_modules():
             det.YetAnotherEfficientDet._mmd_patched = False
     finally:
         sys.path.remove(REF)
+
+
+def test_set_option_switches_exist_and_reject_unknown_names():
+    """mmd_set_option (include/mmd.h): the documented A/B switches are accepted without a GPU (they only set flags), an
+    unknown name is an argument error with a message."""
+    for name, default in (("chain_fwd", 0), ("mta_fast", 1), ("proj_tma", 1)):
+        _lib.set_option(name, 1 - default)
+        _lib.set_option(name, default)
+    with pytest.raises(RuntimeError, match="unknown option"):
+        _lib.set_option("definitely_not_an_option", 1)
+    hdr = open(os.path.join(ROOT, "include", "mmd.h")).read()
+    for name in ("chain_fwd", "mta_fast", "proj_tma"):
+        assert '"%s"' % name in hdr, "include/mmd.h does not document option %s" % name
+
+
+def test_plan_records_pool_tags_for_the_argmax_hook():
+    """The parity tests force the oracle's max-pool arg-max to the CUDA forward's own choice (bifpn.debug_pool_argmax):
+    every op that pools carries a (cell, name) tag and arg-max storage in a training plan with gradients."""
+    cells = [mmd.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(2)]
+    shapes = [(2, 48, 32, 32), (2, 120, 16, 16), (2, 352, 8, 8)]
+    for dt in (torch.float32, torch.bfloat16):
+        plan = bifpn._Plan(cells, "cells", shapes, dt, True, True, [True] * 3)
+        tags = sorted(op.tag for op in plan.ops if op.tag is not None)
+        assert tags == sorted([(0, "p6_in"), (0, "p7_in")] + [(c, n) for c in range(2) for n in ("p3_out", "p4_out", "p5_out", "p6_out")])
+        assert all(any(r is not None for r in op.pidx) for op in plan.ops if op.tag is not None)
+    with pytest.raises(RuntimeError):
+        bifpn.debug_pool_argmax(torch.zeros(1, requires_grad=True) * 2)     # not an output of a BiFPN forward
