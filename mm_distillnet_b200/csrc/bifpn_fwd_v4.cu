@@ -1078,7 +1078,9 @@ constexpr int kPtCols = 24;                       // output columns per strip  -
 constexpr int kPtRows = 8;                        // output rows per strip     -> 17 source rows
 constexpr int kPtSlots = 9;                       // ring slots (source rows)
 constexpr int kPtSlotBytes = up128((2 * kPtCols + 1) * POS);   // 11 008
-constexpr int kPtThreads = (kPtCols / 2) * NG;    // 168: 12 output pairs x 14 channel groups
+constexpr int kPtRowThreads = (kPtCols / 2) * NG; // 168: 12 output pairs x 14 channel groups = one output row of the strip
+constexpr int kPtRowsPerStep = 2;                 // output rows computed concurrently (2 x 168 threads: more warps per SM)
+constexpr int kPtThreads = kPtRowsPerStep * kPtRowThreads;
 constexpr int kPtSmem = kPtSlots * kPtSlotBytes + 4 * C * 4 + kPtSlots * 8 + 16;
 
 __global__ void __launch_bounds__(kPtThreads, 2) poolfuse_tiled_kernel(const __grid_constant__ NodeFwdBatch BATCH) {
@@ -1091,7 +1093,8 @@ __global__ void __launch_bounds__(kPtThreads, 2) poolfuse_tiled_kernel(const __g
   extern __shared__ __align__(128) unsigned char smem[];
   float* s_c = reinterpret_cast<float*>(smem + kPtSlots * kPtSlotBytes);   // scale | shift | w_b*scale_b | w_b*shift_b
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_c + 4 * C);                // [kPtSlots] slot filled
-  const int tid = threadIdx.x, cg = tid % NG, pl = tid / NG;
+  const int tid = threadIdx.x, rg = tid / kPtRowThreads, tl = tid - rg * kPtRowThreads;   // row group, thread inside it
+  const int cg = tl % NG, pl = tl / NG;
   const int H = P.g.H, W = P.g.W, SH = P.in[0].H, SWd = P.in[0].W;
   const bf16* __restrict__ src = reinterpret_cast<const bf16*>(P.in[0].data);
   const bf16* __restrict__ same = (P.n_in >= 2) ? reinterpret_cast<const bf16*>(P.in[1].data) : nullptr;
@@ -1148,14 +1151,16 @@ __global__ void __launch_bounds__(kPtThreads, 2) poolfuse_tiled_kernel(const __g
     if (tid == 0)
       for (int r = 0; r < min(nsrc, kPtSlots); ++r) issue_row(r);
     int waited = 0;   // source rows [0, waited) of this strip have landed and been observed by this thread
-    for (int yy = 0; yy < ny; ++yy) {
-      const int y = y0 + yy;
-      const int need = min(2 * yy + 3, nsrc);
+    for (int ys = 0; ys < ny; ys += kPtRowsPerStep) {
+      const int yy = ys + rg;                      // this row group's output row of the step
+      const int need = min(2 * (ys + kPtRowsPerStep - 1) + 3, nsrc);
       for (; waited < need; ++waited) {
         const int sl = waited % kPtSlots;
         tc::mbar_wait(bar + sl, (phases >> sl) & 1u);
         phases ^= (1u << sl);
       }
+      if (yy < ny) {
+      const int y = y0 + yy;
       const int x0 = xs0 + 2 * pl;
       const long long oo0 = (((long long)b * H + y) * W + x0) * C + 8 * cg;
       // the three window rows of this output row (a row beyond the image is the zero padding: any readable slot will do)
@@ -1224,11 +1229,13 @@ __global__ void __launch_bounds__(kPtThreads, 2) poolfuse_tiled_kernel(const __g
         }
         emit_pair_train(bestA, bestB, padA, padB, false, true, oo0, cg, wa, sc, sh, sgn, s_c, same, out, pidx, praw);
       }
-      // rows 2yy and 2yy+1 are dead: their slots take the rows kPtSlots further down (generic reads -> async-proxy writes)
+      }
+      // the first 2 * kPtRowsPerStep source rows of the step are dead: their slots take the rows kPtSlots further down
+      // (generic reads -> async-proxy writes)
       tc::fence_async_smem();
       __syncthreads();
       if (tid == 0) {
-        for (int r = 2 * yy + kPtSlots; r < min(nsrc, 2 * yy + 2 + kPtSlots); ++r) issue_row(r);
+        for (int r = 2 * ys + kPtSlots; r < min(nsrc, 2 * ys + 2 * kPtRowsPerStep + kPtSlots); ++r) issue_row(r);
       }
     }
     // drain: rows of this strip that were loaded but never needed (none: need == nsrc at the last output row), and make sure
