@@ -376,3 +376,22 @@ def test_plan_records_pool_tags_for_the_argmax_hook():
         assert all(any(r is not None for r in op.pidx) for op in plan.ops if op.tag is not None)
     with pytest.raises(RuntimeError):
         bifpn.debug_pool_argmax(torch.zeros(1, requires_grad=True) * 2)     # not an output of a BiFPN forward
+
+
+def test_product_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under mm_distillnet_b200/ (Python or CUDA) may import, open or mention
+    oracle/ or /root/reference at run time; bench.py may use oracle/ only in its CPU legs (cpu_step / time_cpu /
+    run_reference)."""
+    pkg = os.path.join(ROOT, "mm_distillnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            txt = open(os.path.join(dirpath, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
+            assert "mmd_oracle" not in txt and "/root/reference" not in txt, fn
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    assert len(uses) == 2                                     # cpu_state() and cpu_step() only
+    gpu_arm = bench[bench.index("def measure("):bench.index("def main(")]
+    assert "oracle" not in gpu_arm.replace("oracle port", "")  # the CUDA arm only NAMES the port in its cpu_baseline text
