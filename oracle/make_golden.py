@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from oracle import mmd_oracle as O  # noqa: E402
-from src.YetAnotherEfficientDet import BiFPN  # noqa: E402  (reference)
+from src.YetAnotherEfficientDet import BiFPN, Classifier, Regressor  # noqa: E402  (reference)
 from src.loss.MTALoss import MTALoss  # noqa: E402  (reference)
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -81,6 +81,36 @@ def run_stack_case(name, C, conv_channels, n_cells, first, B, s3, seed, save_par
     print(name, "->", len(out), "arrays")
 
 
+def run_head_case(name, kind, C, num_anchors, num_classes, num_layers, B, s3, seed):
+    """Reference Regressor / Classifier: eval forward, train forward + backward (both outputs carry a gradient)."""
+    out_ch = num_anchors * (4 if kind == "reg" else num_classes)
+    params = O.synth_head_params(C, out_ch, num_layers, seed)
+    head = Regressor(C, num_anchors, num_layers) if kind == "reg" else Classifier(C, num_anchors, num_classes, num_layers)
+    missing, unexpected = head.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+    assert not missing and not unexpected
+    out = {}
+    head.eval()
+    with torch.no_grad():
+        y, a = head(tuple(pyramid_inputs(B, C, s3, seed + 50)))
+    out["eval_out"], out["eval_align"] = y.numpy(), a.numpy()
+    head.train()
+    xs = [x.requires_grad_(True) for x in pyramid_inputs(B, C, s3, seed + 50)]
+    y, a = head(tuple(xs))
+    gy = O.synth(tuple(y.shape), seed + 70, 1.0, 0.0)
+    ga = O.synth(tuple(a.shape), seed + 71, 1.0, 0.0)
+    ((y * gy).sum() + (a * ga).sum()).backward()
+    out["train_out"], out["train_align"] = y.detach().numpy(), a.detach().numpy()
+    for i, x in enumerate(xs):
+        out["grad_in%d" % i] = x.grad.numpy()
+    for k, v in head.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            out["buf_" + k] = v.numpy()
+    for k, v in head.named_parameters():
+        out["pgrad_" + k] = v.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "->", len(out), "arrays")
+
+
 def structured_features(B, C, sizes, seed):
     """Features whose channel-pooled attention is far from uniform (SURVEY.md 8d 'structured' set)."""
     fs = []
@@ -131,6 +161,9 @@ def main():
     # D2 channel counts (what the CUDA kernels are built for), tiny spatial size; full parameter gradients as well
     run_stack_case("stack2_c112", 112, [48, 120, 352], 2, True, B=2, s3=16, seed=5, save_param_grads=True)
     run_stack_case("cell_c112", 112, [48, 120, 352], 1, False, B=2, s3=16, seed=6, save_param_grads=True)
+    # detection heads: D2 configuration (112 channels, 9 anchors, 3 layers; 20 classes), tiny pyramid
+    run_head_case("reg_c112", "reg", 112, 9, 20, 3, B=2, s3=16, seed=9)
+    run_head_case("cls_c112", "cls", 112, 9, 20, 3, B=2, s3=16, seed=10)
     run_mta_case("mta_c112", B=2, C=112, sizes=[12, 6, 3], seed=7)
     run_mta_case("mta_c16", B=3, C=16, sizes=[16, 8, 4, 2, 1], seed=8)
 

@@ -113,9 +113,10 @@ def batch_norm(x, p, prefix, training, stats_out=None):
     return (x - mean[None, :, None, None]) * (inv * w)[None, :, None, None] + b[None, :, None, None]
 
 
-def separable_block(x, p, prefix, training, stats_out=None):
+def separable_block(x, p, prefix, training, stats_out=None, norm=True):
     """SeparableConvBlock.forward: depthwise 3x3 (no bias, SAME pad = 1,1,1,1) -> pointwise 1x1
-    (+bias) -> BatchNorm; no activation inside BiFPN.  src/YetAnotherEfficientDet.py:154-192,
+    (+bias) -> BatchNorm (norm=True; no activation inside BiFPN; the detection heads build their blocks
+    with norm=False and normalise per pyramid level themselves).  src/YetAnotherEfficientDet.py:154-192,
     padding src/YetAnotherEfficientNet.py:51-65."""
     c = x.shape[1]
     h, w = x.shape[-2:]
@@ -124,6 +125,8 @@ def separable_block(x, p, prefix, training, stats_out=None):
     x = F.pad(x, [left, right, top, bottom])
     x = F.conv2d(x, p[prefix + ".depthwise_conv.conv.weight"], None, groups=c)
     x = F.conv2d(x, p[prefix + ".pointwise_conv.conv.weight"], p[prefix + ".pointwise_conv.conv.bias"])
+    if not norm:
+        return x
     return batch_norm(x, p, prefix + ".bn", training, stats_out)
 
 
@@ -206,6 +209,78 @@ def bifpn_stack(inputs, p, n_cells, prefix="", first_cell_first_time=True, train
                            training=training, attention=attention, stats_out=stats_out,
                            pool_hints=None if pool_hints is None else pool_hints[i])
     return feats
+
+
+# ----------------------------------------------------------------------------------------------
+# detection heads
+# ----------------------------------------------------------------------------------------------
+def head_tower(feat, p, prefix, level, num_layers, training, stats_out=None):
+    """The shared-weight tower of Regressor / Classifier for one pyramid level: num_layers x
+    [SeparableConvBlock(norm=False) -> the level's own BatchNorm -> swish].
+    src/YetAnotherEfficientDet.py:466-470 (Regressor), :511-515 (Classifier)."""
+    for i in range(num_layers):
+        feat = separable_block(feat, p, prefix + "conv_list.%d" % i, training, norm=False)
+        feat = batch_norm(feat, p, prefix + "bn_list.%d.%d" % (level, i), training, stats_out)
+        feat = swish(feat)
+    return feat
+
+
+def regressor(inputs, p, prefix="", num_layers=3, training=False, stats_out=None):
+    """Regressor.forward: per level tower -> header (dw3x3 -> pw 112 -> num_anchors*4) -> NHWC -> [B, H*W*A, 4];
+    levels concatenated; second output = the last level's tower output.  src/YetAnotherEfficientDet.py:463-488."""
+    feats, before_head = [], None
+    for level, feat in enumerate(inputs):
+        feat = head_tower(feat, p, prefix, level, num_layers, training, stats_out)
+        before_head = feat
+        feat = separable_block(feat, p, prefix + "header", training, norm=False)
+        feat = feat.permute(0, 2, 3, 1).contiguous().view(feat.shape[0], -1, 4)
+        feats.append(feat)
+    return torch.cat(feats, dim=1), before_head
+
+
+def classifier(inputs, p, num_anchors, num_classes, prefix="", num_layers=3, training=False, stats_out=None):
+    """Classifier.forward: as the regressor with num_anchors*num_classes header channels viewed as
+    [B, H*W*A, num_classes], concatenated over the levels, then sigmoid.  src/YetAnotherEfficientDet.py:508-532."""
+    feats, before_head = [], None
+    for level, feat in enumerate(inputs):
+        feat = head_tower(feat, p, prefix, level, num_layers, training, stats_out)
+        before_head = feat
+        feat = separable_block(feat, p, prefix + "header", training, norm=False)
+        feat = feat.permute(0, 2, 3, 1).contiguous()
+        feat = feat.view(feat.shape[0], feat.shape[1], feat.shape[2], num_anchors, num_classes)
+        feats.append(feat.contiguous().view(feat.shape[0], -1, num_classes))
+    return torch.cat(feats, dim=1).sigmoid(), before_head
+
+
+def synth_head_params(num_channels, out_channels, num_layers, seed, prefix="", n_levels=5, dtype=torch.float32):
+    """Parameter / buffer dict of a Regressor (out_channels = num_anchors*4) or Classifier (num_anchors*num_classes)
+    with the reference's state_dict names, filled from `synth`."""
+    C = num_channels
+    p = {}
+    k = [seed * 1000 + 500]
+
+    def nxt():
+        k[0] += 1
+        return k[0]
+
+    for i in range(num_layers):
+        pre = prefix + "conv_list.%d" % i
+        p[pre + ".depthwise_conv.conv.weight"] = synth((C, 1, 3, 3), nxt(), 0.4, 0.0, dtype)
+        p[pre + ".pointwise_conv.conv.weight"] = synth((C, C, 1, 1), nxt(), 1.5 / math.sqrt(C), 0.0, dtype)
+        p[pre + ".pointwise_conv.conv.bias"] = synth((C,), nxt(), 0.1, 0.0, dtype)
+    for lvl in range(n_levels):
+        for i in range(num_layers):
+            pre = prefix + "bn_list.%d.%d" % (lvl, i)
+            p[pre + ".weight"] = synth((C,), nxt(), 0.5, 1.0, dtype)
+            p[pre + ".bias"] = synth((C,), nxt(), 0.2, 0.0, dtype)
+            p[pre + ".running_mean"] = synth((C,), nxt(), 0.3, 0.0, dtype)
+            p[pre + ".running_var"] = synth((C,), nxt(), 0.5, 1.2, dtype)
+            p[pre + ".num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
+    pre = prefix + "header"
+    p[pre + ".depthwise_conv.conv.weight"] = synth((C, 1, 3, 3), nxt(), 0.4, 0.0, dtype)
+    p[pre + ".pointwise_conv.conv.weight"] = synth((out_channels, C, 1, 1), nxt(), 1.5 / math.sqrt(C), 0.0, dtype)
+    p[pre + ".pointwise_conv.conv.bias"] = synth((out_channels,), nxt(), 0.5, -0.5, dtype)
+    return p
 
 
 # ----------------------------------------------------------------------------------------------

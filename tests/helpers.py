@@ -18,6 +18,8 @@ STACK_CASES = {
     "stack2_c112": (112, [48, 120, 352], 2, True, 2, 16, 5),
     "cell_c112": (112, [48, 120, 352], 1, False, 2, 16, 6),
 }
+# name -> (kind, C, num_anchors, num_classes, num_layers, B, s3, seed)   (must mirror oracle/make_golden.py main())
+HEAD_CASES = {"reg_c112": ("reg", 112, 9, 20, 3, 2, 16, 9), "cls_c112": ("cls", 112, 9, 20, 3, 2, 16, 10)}
 MTA_CASES = {"mta_c112": (2, 112, [12, 6, 3], 7), "mta_c16": (3, 16, [16, 8, 4, 2, 1], 8)}
 
 
@@ -39,6 +41,17 @@ def stack_case_inputs(name, dtype=torch.float32):
     params = O.synth_stack_params(C, cc, n_cells, seed, first_cell_first_time=first, dtype=dtype)
     xs = backbone_inputs(B, cc, s3, seed + 50, dtype) if first else pyramid_inputs(B, C, s3, seed + 50, dtype)
     return params, xs
+
+
+def head_case_inputs(name, dtype=torch.float32):
+    kind, C, A, K, L, B, s3, seed = HEAD_CASES[name]
+    params = O.synth_head_params(C, A * (4 if kind == "reg" else K), L, seed, dtype=dtype)
+    return params, pyramid_inputs(B, C, s3, seed + 50, dtype)
+
+
+def head_case_gouts(name, y, a):
+    seed = HEAD_CASES[name][7]
+    return O.synth(tuple(y.shape), seed + 70, 1.0, 0.0), O.synth(tuple(a.shape), seed + 71, 1.0, 0.0)
 
 
 def stack_case_gouts(name, outs):

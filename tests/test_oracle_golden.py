@@ -56,6 +56,40 @@ def test_stack_matches_reference(name):
             assert abs(v.grad.double().norm().item() - nrm) <= tol * max(nrm, 1e-6), k
 
 
+@pytest.mark.parametrize("name", sorted(H.HEAD_CASES))
+def test_heads_match_reference(name):
+    """Regressor / Classifier restatement against outputs of the unmodified reference modules."""
+    kind, C, A, K, L, B, s3, seed = H.HEAD_CASES[name]
+    g = H.golden(name)
+    params, xs = H.head_case_inputs(name)
+    run = (lambda x, p, tr, st=None: O.regressor(x, p, num_layers=L, training=tr, stats_out=st)) if kind == "reg" else \
+        (lambda x, p, tr, st=None: O.classifier(x, p, A, K, num_layers=L, training=tr, stats_out=st))
+    with torch.no_grad():
+        y, a = run(tuple(xs), params, False)
+    assert tuple(y.shape) == g["eval_out"].shape and tuple(a.shape) == g["eval_align"].shape
+    assert H.max_rel(y, g["eval_out"]) < TOL and H.max_rel(a, g["eval_align"]) < TOL
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in params.items()}
+    xs = [x.requires_grad_(True) for x in xs]
+    stats = {}
+    y, a = run(tuple(xs), leaf, True, stats)
+    gy, ga = H.head_case_gouts(name, y, a)
+    ((y * gy).sum() + (a * ga).sum()).backward()
+    assert H.max_rel(y.detach(), g["train_out"]) < 1e-4 and H.max_rel(a.detach(), g["train_align"]) < 1e-4
+    for i, x in enumerate(xs):
+        assert H.rel_l2(x.grad, g["grad_in%d" % i]) < 2e-4, (name, i)
+    for k, v in stats.items():
+        if "num_batches" in k:
+            assert int(v) == int(g["buf_" + k])
+        else:
+            assert H.max_rel(v, g["buf_" + k]) < TOL, k
+    for k, v in leaf.items():
+        if torch.is_tensor(v) and v.requires_grad:
+            ref = g["pgrad_" + k]
+            if k.startswith("conv_list") and k.endswith("conv.bias"):
+                continue   # bias feeding a train-mode BatchNorm: zero gradient up to rounding
+            assert H.rel_l2(v.grad, ref) < 5e-4 or np.abs(ref).max() < 1e-6, k
+
+
 @pytest.mark.parametrize("name", sorted(H.MTA_CASES))
 def test_mta_matches_reference(name):
     B, C, sizes, seed = H.MTA_CASES[name]
