@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 105
+#define MMD_VERSION 106
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -115,9 +115,21 @@ enum {
   MMD_OP_PROJ_BWD = 5,  /* backward of PROJ_FWD                                                                                      */
   MMD_OP_PULL = 6,      /* dx = gathered gradient of `out` from its consumers (stack inputs, P6/P7 synthesis)                        */
   MMD_OP_SLOT = 7,      /* slot = (sum G, sum G*xhat) for a deferred tensor consumed by a BNAPPLY op                                 */
-  MMD_OP_POOLFUSE = 8   /* bf16 plans: out = w_a * pool3x3s2(bn(in[0])) [+ w_b * bn(in[1])], final values; the pre-pass that turns a  */
+  MMD_OP_POOLFUSE = 8,  /* bf16 plans: out = w_a * pool3x3s2(bn(in[0])) [+ w_b * bn(in[1])], final values; the pre-pass that turns a  */
                         /* node's pooled input (and its second same-resolution input) into ONE same-resolution operand, so that   */
                         /* every NODE_FWD stages at most two inputs.  pidx[0]: arg-max bytes, save_d: raw value at the arg-max    */
+  /* detection heads (Regressor / Classifier, src/YetAnotherEfficientDet.py:445-532): the towers are NODE ops (one input,      */
+  /* unweighted), the headers NODE ops with train = 0 on zero-padded weights; these small ops do the rest                     */
+  MMD_OP_ACT_FWD = 9,     /* out = swish(in[0])   (in[0] final values): the `alignment` output, :472/:487                      */
+  MMD_OP_ACT_BWD = 10,    /* dx  = cons[0].du * swish'(in[0])                                                                  */
+  MMD_OP_HEAD_GATHER = 11,/* out[b][head_off + p][k] = act(in[k / C][b][p][k % C]), k < head_K: the header output of one level */
+                          /* (n_in = ceil(head_K / C) NHWC tensors padded to C channels) placed into the [B][head_tot][head_K] */
+                          /* result, i.e. permute(0,2,3,1) + view + cat(dim=1) (:475-482, :520-530); head_act = 1: sigmoid     */
+  MMD_OP_HEAD_SCATTER = 12,/* inverse: in[j] of the forward op = dst j here (`du`, `dd`); cons[0].du = dL/d(result),           */
+                          /* out.data = the result itself (sigmoid' = y(1-y)); padding channels are written as zero           */
+  MMD_OP_COPY = 13        /* copy_dst[0..copy_n) = copy_src[0..copy_n) (fp32): refresh a zero-padded staging copy of a header's */
+                          /* pointwise weight / bias.  Executed by mmd_bifpn_prep (before the packed blocks are rebuilt),      */
+                          /* ignored by mmd_bifpn_run                                                                          */
 };
 
 typedef struct {
@@ -167,6 +179,12 @@ typedef struct {
   /* NODE_BWD of a bf16 node whose forward ran as POOLFUSE + NODE_FWD: what the pre-pass left behind                       */
   MmdRef aux;             /* the pre-weighted operand (pooled input [+ second same-resolution input]), final values         */
   MmdRef praw;            /* raw value of the pooled input at each arg-max (0 where the padding won)                         */
+  /* detection heads */
+  int32_t head_K, head_tot, head_off, head_act;  /* HEAD_GATHER / HEAD_SCATTER: valid channels, positions per sample of the  */
+                                                 /* concatenated result, first position of this level, 1 = sigmoid           */
+  const float* copy_src;  /* COPY */
+  float* copy_dst;
+  int64_t copy_n;
 } MmdOp;
 
 /* Packed parameter block of one NODE / PROJ op (bf16 storage only; every section starts 128-byte aligned):
@@ -180,7 +198,9 @@ size_t mmd_packed_bytes(int32_t kind, int32_t Cin, int32_t C);
 
 /* (Re)build the packed blocks of every NODE_FWD / PROJ_FWD op in `ops` whose `packed` reference is non-NULL, from the
  * current fp32 parameters (and, in eval mode, the running statistics).  One or two launches for a whole stack.  Call it
- * whenever the parameters may have changed since the last call (every training step; once for frozen teachers). */
+ * whenever the parameters may have changed since the last call (every training step; once for frozen teachers).
+ * COPY ops of the list run first, for both dtypes.  An op with train = 0 that saves its depthwise output (save_d) is a
+ * header that will be differentiated: its backward operand is packed as well. */
 int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* bases, int32_t n_bases, int32_t C, int32_t dtype,
                    mmd_stream_t stream);
 

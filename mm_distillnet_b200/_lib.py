@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
 SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_proj_tma.cu", "bifpn_bwd.cu",
-           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "bifpn_run.cu")
+           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "heads.cu", "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1
@@ -21,6 +21,7 @@ STATS_REPLICAS = 1   # MMD_STATS_REPLICAS
 IN_SAME, IN_UP2, IN_POOL = 0, 1, 2
 CONS_SAME, CONS_UP2, CONS_POOL = 0, 1, 2
 OP_NODE_FWD, OP_PROJ_FWD, OP_BNAPPLY, OP_NODE_BWD, OP_PROJ_BWD, OP_PULL, OP_SLOT, OP_POOLFUSE = 1, 2, 3, 4, 5, 6, 7, 8
+OP_ACT_FWD, OP_ACT_BWD, OP_HEAD_GATHER, OP_HEAD_SCATTER, OP_COPY = 9, 10, 11, 12, 13
 
 
 class MtaArgs(C.Structure):
@@ -65,6 +66,8 @@ class Op(C.Structure):
         ("g_dw", Ref), ("g_pw", Ref), ("g_pb", Ref), ("g_bn_w", Ref), ("g_bn_b", Ref), ("g_fw", Ref),
         ("fw_n", C.c_int32), ("fw_idx", C.c_int32 * 3),
         ("aux", Ref), ("praw", Ref),
+        ("head_K", C.c_int32), ("head_tot", C.c_int32), ("head_off", C.c_int32), ("head_act", C.c_int32),
+        ("copy_src", C.c_void_p), ("copy_dst", C.c_void_p), ("copy_n", C.c_int64),
     ]
 
 

@@ -55,26 +55,32 @@ class _Stateless(_ParamOnly):
 
 
 class SeparableConvBlock(nn.Module):
-    """depthwise 3x3 (no bias) -> pointwise 1x1 (+bias) -> BatchNorm(momentum .01, eps 1e-3).
-    Signature of src/YetAnotherEfficientDet.py:154-192.  Only the configuration BiFPN uses is supported by the
-    kernels (out_channels == in_channels, norm=True, activation=False)."""
+    """depthwise 3x3 (no bias) -> pointwise 1x1 (+bias) [-> BatchNorm(momentum .01, eps 1e-3)] [-> swish].
+    Signature and state_dict of src/YetAnotherEfficientDet.py:154-192.  Called on its own, the block runs the
+    configuration BiFPN uses (out_channels == in_channels, norm=True, activation=False); the other configurations
+    (norm=False towers and headers of the detection heads) are parameter holders driven by Regressor / Classifier
+    (mm_distillnet_b200/heads.py), as in the reference, where nothing else instantiates them."""
 
     def __init__(self, in_channels, out_channels=None, norm=True, activation=False, onnx_export=False):
         super(SeparableConvBlock, self).__init__()
         if out_channels is None:
             out_channels = in_channels
-        if out_channels != in_channels or not norm or activation:
-            raise NotImplementedError("mm_distillnet_b200.SeparableConvBlock implements the BiFPN configuration only "
-                                      "(out_channels == in_channels, norm=True, activation=False)")
         self.depthwise_conv = Conv2dStaticSamePadding(in_channels, in_channels, kernel_size=3, stride=1,
                                                       groups=in_channels, bias=False)
         self.pointwise_conv = Conv2dStaticSamePadding(in_channels, out_channels, kernel_size=1, stride=1)
         self.norm = norm
-        self.bn = nn.BatchNorm2d(num_features=out_channels, momentum=BN_MOMENTUM, eps=BN_EPS)
+        if self.norm:
+            self.bn = nn.BatchNorm2d(num_features=out_channels, momentum=BN_MOMENTUM, eps=BN_EPS)
         self.activation = activation
+        if self.activation:
+            self.swish = _Stateless()
         self._runner = _Runner()
 
     def forward(self, x):
+        if not self.norm or self.activation or self.pointwise_conv.conv.out_channels != self.pointwise_conv.conv.in_channels:
+            raise NotImplementedError("mm_distillnet_b200.SeparableConvBlock runs on its own in the BiFPN configuration only "
+                                      "(out_channels == in_channels, norm=True, activation=False); the norm=False blocks "
+                                      "of the detection heads are driven by mm_distillnet_b200.Regressor / Classifier")
         return self._runner.run([self], (x,), self.training, kind="sep")[0]
 
 
@@ -156,6 +162,32 @@ class BiFPNStack(nn.Sequential):
 # ------------------------------------------------------------------------------------------------------------
 # graph -> op list
 # ------------------------------------------------------------------------------------------------------------
+class _Holder:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class _SepView:
+    """(separable conv, BatchNorm) pair seen as one SeparableConvBlock: the heads share one conv across the pyramid levels
+    and keep one BatchNorm per level (src/YetAnotherEfficientDet.py:455-459); `conv` overrides the pointwise parameters
+    (zero-padded header halves)."""
+
+    def __init__(self, sep, bn, conv=None):
+        self.depthwise_conv = sep.depthwise_conv
+        self.pointwise_conv = sep.pointwise_conv if conv is None else _Holder(conv=conv)
+        self.bn = bn
+
+
+class _IdentityBN:
+    """gamma 1, beta 0, running mean 0, running var 1, eps 0: what a header without BatchNorm hands the kernels."""
+
+    def __init__(self, const, Cc):
+        self.weight, self.bias = const[0:Cc], const[Cc:2 * Cc]
+        self.running_mean, self.running_var = const[Cc:2 * Cc], const[3 * Cc:4 * Cc]
+        self.num_batches_tracked = None
+        self.eps, self.momentum = 0.0, 0.0
+
+
 class _Arena:
     def __init__(self):
         self.size = 0
@@ -179,7 +211,8 @@ class _Tn:
 
 class _OpN:
     __slots__ = ("kind", "ins", "modes", "conv", "bn", "dw", "fw", "fw_eps", "swish", "out", "save_d", "pidx",
-                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed", "aux", "praw", "tag")
+                 "stats", "counter", "du", "slots", "glike", "bwd_counter", "cin", "gref", "packed", "aux", "praw", "tag",
+                 "train", "gover", "head", "copy", "gpad", "dxref")
 
     def __init__(self, kind):
         self.kind = kind
@@ -199,6 +232,12 @@ class _OpN:
         self.aux = None        # bf16 plans, nodes with a pooled input: (base, off) of the POOLFUSE pre-pass output
         self.praw = None       # ... and of the raw value at each pooling arg-max (kept for the backward)
         self.tag = None        # (cell index, name) of the 3x3-s2 max-pool this op performs (debug_pool_argmax)
+        self.train = None      # per-op override of the plan's mode (head headers: always 0, there is no BatchNorm)
+        self.gover = None      # header halves: {"pw": ref, "pb": ref} rows of the zero-padded parameter gradients
+        self.head = None       # HEAD_GATHER: (K, tot, off, act)
+        self.copy = None       # COPY: (source tensor, destination pointer, floats)
+        self.gpad = []         # HEAD_GATHER: (base, off) of the padded gradient of each input
+        self.dxref = None      # ACT_FWD: (base, off) of the gradient its backward writes
 
 
 # fixed base indices
@@ -262,36 +301,47 @@ class _Plan:
         self.mods = list(mods)
         self.state_tensors = [t for m in mods for t in list(m.parameters()) + list(m.buffers())]
         self.grad_off = {}
+        self.copies = []     # head plans: zero-padded staging copies of the header parameters (COPY ops)
+        grad_pad = {}
+        if kind == "head":   # the header's 1x1 conv runs on C-row operands: its gradients are written C rows at a time
+            hc = mods[0].header.pointwise_conv.conv
+            rows = (hc.out_channels + hc.in_channels - 1) // hc.in_channels * hc.in_channels
+            grad_pad = {id(hc.weight): rows * hc.in_channels, id(hc.bias): rows}
         if self.need_grad:   # parameter gradients: ONE flat fp32 buffer in parameter order at the head of the zero arena
             off = 0
             for p in self.params:   # every gradient starts 16-byte aligned (the kernels use 16-byte vector reductions)
                 off = (off + 15) // 16 * 16
                 self.grad_off[id(p)] = (off, p.numel(), tuple(p.shape))
-                off += p.numel() * 4
+                off += max(p.numel(), grad_pad.get(id(p), 0)) * 4
             self.grad_floats = off // 4
             self.zero_arena.alloc(off)
         ext = [_Tn(s[2], s[3], s[1], B_EXT + i, 0) for i, s in enumerate(in_shapes)]
         self.ext = ext
-        self.n_out = 5 if kind == "cells" else 1
+        self.n_out = {"cells": 5, "sep": 1, "head": 2}[kind]
         self.B_OUT = B_EXT + self.n_in
         self.B_GOUT = self.B_OUT + self.n_out
         self.B_GIN = self.B_GOUT + self.n_out
-        self.n_bases = self.B_GIN + self.n_in
-        if kind == "sep":
-            self.Cc = in_shapes[0][1]
-            outs = [self._node(mods[0], [(ext[0], _lib.IN_SAME)], None, 0.0, swish=0)]
+        self.B_CONST = self.B_GIN + self.n_in     # head plans: identity-BatchNorm constants
+        self.n_bases = self.B_CONST + 1
+        self.const = None
+        if kind == "head":
+            self._head(mods[0], ext)
         else:
-            outs = self._cells(mods, ext)
-        self.out_shapes = [(self.B, self.Cc, t.H, t.W) for t in outs]
-        self._finish_outputs(outs)
+            if kind == "sep":
+                self.Cc = in_shapes[0][1]
+                outs = [self._node(mods[0], [(ext[0], _lib.IN_SAME)], None, 0.0, swish=0)]
+            else:
+                outs = self._cells(mods, ext)
+            self.out_shapes = [(self.B, self.Cc, t.H, t.W) for t in outs]
+            self._finish_outputs(outs)
         self.fwd_ops = self._emit_fwd()
         self.bwd_ops = self._emit_bwd() if self.need_grad else None
 
     # ---- graph construction --------------------------------------------------------------------------------
-    def _new_raw(self, H, W, bn_mod):
+    def _new_raw(self, H, W, bn_mod, train=None):
         n = self.B * H * W * self.Cc * self.esize
         t = _Tn(H, W, self.Cc, B_FWD, self.fwd_arena.alloc(n), producer=None, bn_mod=bn_mod)
-        if self.train:
+        if self.train if train is None else train:
             t.bn = (B_FWD, self.fwd_arena.alloc(4 * self.Cc * 4))
         return t
 
@@ -303,17 +353,21 @@ class _Plan:
 
     def _train_storage(self, op):
         self._packed_storage(op)
-        if self.train:
+        if self.train if op.train is None else op.train:
             op.stats = (B_PERSIST, self.persist.alloc(_lib.STATS_REPLICAS * 2 * self.Cc * 8))
             op.counter = (B_PERSIST, self.persist.alloc(4))
             op.bwd_counter = (B_PERSIST, self.persist.alloc(4))
-        elif self.dtype == torch.bfloat16:
-            # eval plans too: the persistent small-level chain keeps its grid-barrier words in the first node's counter
-            op.counter = (B_PERSIST, self.persist.alloc(4))
+        else:
+            if self.dtype == torch.bfloat16:
+                # eval plans too: the persistent small-level chain keeps its grid-barrier words in the first node's counter
+                op.counter = (B_PERSIST, self.persist.alloc(4))
+            if self.need_grad:   # a header (no BatchNorm) inside a training plan
+                op.bwd_counter = (B_PERSIST, self.persist.alloc(4))
 
-    def _node(self, sep, ins, fw, fw_eps, swish=1, tag=None):
+    def _node(self, sep, ins, fw, fw_eps, swish=1, tag=None, train=None):
         op = _OpN(_lib.OP_NODE_FWD)
         op.tag = tag
+        op.train = train
         op.ins = [t for t, _ in ins]
         op.modes = [m for _, m in ins]
         op.conv, op.bn, op.dw = sep.pointwise_conv.conv, sep.bn, sep.depthwise_conv.conv
@@ -330,7 +384,7 @@ class _Plan:
                 raise ValueError("BiFPN: pooled input %dx%d does not match level %dx%d" % (t.H, t.W, H, W))
             if m == _lib.IN_SAME and (t.H != H or t.W != W):
                 raise ValueError("BiFPN: input %dx%d does not match level %dx%d" % (t.H, t.W, H, W))
-        op.out = self._new_raw(H, W, sep.bn)
+        op.out = self._new_raw(H, W, sep.bn, train)
         op.out.producer = op
         self._train_storage(op)
         if self.dtype == torch.bfloat16 and _lib.IN_POOL in op.modes:
@@ -430,6 +484,74 @@ class _Plan:
             p4_in2, p5_in2 = p4_in, p5_in
         return [p3_in, p4_in, p5_in, p6_in, p7_in]
 
+    def _head(self, mod, ext):
+        """Regressor / Classifier (src/YetAnotherEfficientDet.py:463-487, :508-533).  Per level: num_layers tower layers
+        (shared separable conv, per-level BatchNorm, swish) as one-input nodes whose BatchNorm + swish is applied by the
+        NEXT op on load; the header (no BatchNorm) as train=0 node ops on the header weights zero-padded to a multiple of
+        C output rows (identity BatchNorm constants, so the eval-mode fold is a no-op); HEAD_GATHER places the valid
+        channels into the concatenated [B, sum HW * anchors, k] result (sigmoid for the classifier); the `alignment`
+        output is swish(bn(last tower layer)) of the LAST level."""
+        Cc = self.Cc = mod.in_channels
+        S = _lib.IN_SAME
+        dev = self.params[0].device
+        for t in ext:
+            if t.C != Cc:
+                raise ValueError("%s: input has %d channels, expected %d" % (type(mod).__name__, t.C, Cc))
+        if len(ext) != len(mod.bn_list):
+            raise ValueError("%s takes %d pyramid levels, got %d" % (type(mod).__name__, len(mod.bn_list), len(ext)))
+        hc = mod.header.pointwise_conv.conv
+        K = hc.out_channels
+        n_half = (K + Cc - 1) // Cc
+        rows = n_half * Cc
+        one, zero = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
+        self.const = torch.cat([one, zero, zero, one]).contiguous()     # scale | shift | mean | invstd of "no BatchNorm"
+        ident = _IdentityBN(self.const, Cc)
+        self.padw = torch.zeros(rows * Cc + rows, dtype=torch.float32, device=dev)
+        for src, off, n in ((hc.weight, 0, K * Cc), (hc.bias, rows * Cc, K)):
+            cp = _OpN(_lib.OP_COPY)
+            cp.copy = (src, self.padw.data_ptr() + 4 * off, n)
+            self.ops.append(cp)
+            self.copies.append(cp)
+        tot = sum(t.H * t.W for t in ext)
+        res = _Tn(1, tot, K, self.B_OUT, 0)
+        pos = 0
+        for lvl, x in enumerate(ext):
+            t = x
+            for i in range(mod.num_layers):                                            # :467-470 / :511-514
+                t = self._node(_SepView(mod.conv_list[i], mod.bn_list[lvl][i]), [(t, S)], None, 0.0, swish=0 if i == 0 else 1)
+            ga = _OpN(_lib.OP_HEAD_GATHER)
+            for j in range(n_half):                                                    # :473 / :517
+                conv = _Holder(weight=self.padw[j * Cc * Cc:(j + 1) * Cc * Cc], bias=self.padw[rows * Cc + j * Cc: rows * Cc + (j + 1) * Cc])
+                h = self._node(_SepView(mod.header, ident, conv), [(t, S)], None, 0.0, swish=1 if mod.num_layers > 0 else 0, train=False)
+                hop = self.ops[-1]
+                if self.need_grad:
+                    goff = self.grad_off[id(hc.weight)][0], self.grad_off[id(hc.bias)][0]
+                    hop.gover = {"pw": (B_ZERO, goff[0] + 4 * j * Cc * Cc), "pb": (B_ZERO, goff[1] + 4 * j * Cc)}
+                    ga.gpad.append((B_BWD, self.bwd_arena.alloc(self.B * x.H * x.W * Cc * self.esize)))
+                    ga.slots[j] = (B_ZERO, self.zero_arena.alloc(2 * Cc * 8))        # stays zero: no statistics flow back
+                ga.ins.append(h)
+                ga.modes.append(S)
+                h.consumers.append((ga, j))
+            ga.head = (K, tot, pos, 1 if mod.sigmoid_output else 0)
+            ga.out = res
+            self.ops.append(ga)
+            pos += x.H * x.W
+        # alignment[-1] (:472/:487, :515/:533): the activated last tower layer of the last level
+        if mod.num_layers == 0:
+            raise NotImplementedError("detection heads with num_layers == 0")
+        v = self._bnapply(t, S) if self.train else t
+        if self.train and self.need_grad:
+            self.ops[-1].glike = (B_BWD, self.bwd_arena.alloc(self.B * t.H * t.W * Cc * self.esize))
+        act = _OpN(_lib.OP_ACT_FWD)
+        act.ins, act.modes = [v], [S]
+        act.out = _Tn(t.H, t.W, Cc, self.B_OUT + 1, 0)
+        if self.train and self.need_grad:
+            act.dxref = self.ops[-1].glike
+        self.ops.append(act)
+        A = mod.num_anchors
+        self.out_shapes = [(self.B, tot * A, K // A), (self.B, Cc, t.H, t.W)]
+        self.out_ops = []
+
     def _finish_outputs(self, outs):
         """Train: the raw outputs are normalised into the user-visible tensors.  Eval: the producing kernels write
         the user-visible tensors directly (BatchNorm is folded into the 1x1 conv)."""
@@ -484,8 +606,14 @@ class _Plan:
         for op in self.ops:
             o = _new_op()
             o.kind = op.kind
-            o.train = 1 if self.train else 0
+            if op.kind == _lib.OP_COPY:
+                o.copy_src, o.copy_dst, o.copy_n = op.copy[0].data_ptr(), op.copy[1], op.copy[2]
+                out.append(o)
+                continue
+            o.train = 1 if (self.train if op.train is None else op.train) else 0
             self._fill_common(o, op)
+            if op.head is not None:
+                o.head_K, o.head_tot, o.head_off, o.head_act = op.head
             o.stats, o.counter = _ref(op.stats), _ref(op.counter)
             if op.aux is not None:
                 out.append(self._split_pooled(o, op))
@@ -545,6 +673,9 @@ class _Plan:
                     raise RuntimeError("internal: BNAPPLY consumer without a gradient tensor")
                 c.du = _lib.Tensor(_ref(cop.glike), _ref(None), cop.out.H, cop.out.W, self.Cc, 0)
                 c.fw = None
+            elif cop.kind == _lib.OP_HEAD_GATHER:   # the zero-padded gradient HEAD_SCATTER wrote for this half
+                c.du = _lib.Tensor(_ref(cop.gpad[idx]), _ref(None), t.H, t.W, self.Cc, 0)
+                c.fw = None
             else:
                 raise RuntimeError("internal: unexpected consumer kind")
             c.mode = {_lib.IN_SAME: _lib.CONS_SAME, _lib.IN_UP2: _lib.CONS_UP2, _lib.IN_POOL: _lib.CONS_POOL}[mode]
@@ -560,6 +691,7 @@ class _Plan:
 
     def _emit_bwd(self):
         max_n = max(self.B * op.out.H * op.out.W * self.Cc for op in self.ops if op.kind == _lib.OP_NODE_FWD)
+        gout0 = (self.B_GOUT, 0)
         dd = (B_BWD, self.bwd_arena.alloc(max_n * self.esize))
         out = []
         ext_written = set()
@@ -579,7 +711,25 @@ class _Plan:
                 o.cons[i] = c
 
         for op in reversed(self.ops):
-            if op.kind == _lib.OP_BNAPPLY:
+            if op.kind == _lib.OP_ACT_FWD:          # g(bn(x)) = g(alignment) * swish'(bn(x))
+                o = new(_lib.OP_ACT_BWD, op)
+                o.n_cons = 1
+                c = _new_cons()
+                c.du = _lib.Tensor(_ref((self.B_GOUT + 1, 0)), _ref(None), op.out.H, op.out.W, self.Cc, 0)
+                o.cons[0] = c
+                o.dx = _ref(op.dxref)
+                out.append(o)
+            elif op.kind == _lib.OP_HEAD_GATHER:
+                o = new(_lib.OP_HEAD_SCATTER, op)
+                o.head_K, o.head_tot, o.head_off, o.head_act = op.head
+                o.n_cons = 1
+                c = _new_cons()
+                c.du = _lib.Tensor(_ref(gout0), _ref(None), 1, op.head[1], op.head[0], 0)
+                o.cons[0] = c
+                o.du = _ref(op.gpad[0])
+                o.dd = _ref(op.gpad[1] if len(op.gpad) > 1 else None)
+                out.append(o)
+            elif op.kind == _lib.OP_BNAPPLY:
                 src = op.ins[0]
                 if op.glike is None:   # internal materialisation (P6 / P7 synthesis): gather its gradient first
                     n = self.B * op.out.H * op.out.W * self.Cc
@@ -602,6 +752,11 @@ class _Plan:
                 o.du = _ref((op.du.base, op.du.off))
                 o.dd = _ref(dd)
                 o.g_dw = _ref(self._galloc(op.dw.weight))
+                if op.gover is not None:   # a header half: no BatchNorm (identity constants), zero-padded weight rows
+                    o.out = _lib.Tensor(_ref((op.out.base, op.out.off)), _ref((self.B_CONST, 0)), op.out.H, op.out.W, self.Cc, 0)
+                    o.g_pw, o.g_pb = _ref(op.gover["pw"]), _ref(op.gover["pb"])
+                    out.append(o)
+                    continue
                 o.g_pw = _ref(self._galloc(op.conv.weight))
                 o.g_pb = _ref(self._galloc(op.conv.bias))
                 o.g_bn_w = _ref(self._galloc(op.bn.weight))
@@ -884,7 +1039,7 @@ class _Runner:
         """(Re)build the packed parameter blocks when the parameters may have changed: every training forward (the
         optimiser updates the weights between steps); for eval plans (frozen teachers) only when a parameter / buffer
         version or the global running-statistics epoch moved."""
-        if plan.dtype != torch.bfloat16:
+        if plan.dtype != torch.bfloat16 and not plan.copies:
             return
         if plan.train:
             for m in plan.mods:   # this forward updates running statistics through raw pointers
@@ -897,7 +1052,8 @@ class _Runner:
         arr = (C.c_void_p * len(bases))(*bases)
         with torch.cuda.device(plan.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rc = _lib.lib().mmd_bifpn_prep(plan.fwd_ops, len(plan.fwd_ops), arr, len(bases), plan.Cc, _lib.MMD_BF16, stream)
+            rc = _lib.lib().mmd_bifpn_prep(plan.fwd_ops, len(plan.fwd_ops), arr, len(bases), plan.Cc,
+                                           _lib.MMD_F32 if plan.dtype == torch.float32 else _lib.MMD_BF16, stream)
         _lib.check(rc, "mmd_bifpn_prep")
 
     def _forward_prepare(self, plan, inputs):
@@ -905,7 +1061,8 @@ class _Runner:
         dev = plan.device
         xs = [x.detach().contiguous(memory_format=torch.channels_last) for x in inputs]
         arena = _Lease(plan.pool_fwd, plan.fwd_arena.size, dev)
-        outs = [torch.empty(s, dtype=plan.dtype, device=dev, memory_format=torch.channels_last) for s in plan.out_shapes]
+        outs = [torch.empty(s, dtype=plan.dtype, device=dev, memory_format=torch.channels_last) if len(s) == 4 else
+                torch.empty(s, dtype=plan.dtype, device=dev) for s in plan.out_shapes]
         bases = [0] * plan.n_bases
         bases[B_FWD] = arena.data_ptr()
         bases[B_PERSIST] = self._persist_ws(plan).data_ptr()
@@ -913,6 +1070,8 @@ class _Runner:
             bases[B_EXT + i] = x.data_ptr()
         for k, o in enumerate(outs):
             bases[plan.B_OUT + k] = o.data_ptr()
+        if plan.const is not None:
+            bases[plan.B_CONST] = plan.const.data_ptr()
         self._prep(plan, bases)
         return bases, outs, (xs, arena, outs)
 
@@ -928,7 +1087,8 @@ class _Runner:
         for g, o in zip(gouts, outs):
             if g is None:
                 g = torch.zeros_like(o)
-            gs.append(g.detach().to(plan.dtype).contiguous(memory_format=torch.channels_last))
+            g = g.detach().to(plan.dtype)
+            gs.append(g.contiguous(memory_format=torch.channels_last) if g.dim() == 4 else g.contiguous())
         bwd = _Lease(plan.pool_bwd, plan.bwd_arena.size, dev)
         zero = torch.zeros(max(plan.zero_arena.size, _ALIGN) // 4, dtype=torch.float32, device=dev)
         gin = [torch.empty_like(x) if need else None for x, need in zip(xs, plan.in_need_grad)]
@@ -944,6 +1104,8 @@ class _Runner:
         for k, (o, g) in enumerate(zip(outs, gs)):
             bases[plan.B_OUT + k] = o.data_ptr()
             bases[plan.B_GOUT + k] = g.data_ptr()
+        if plan.const is not None:
+            bases[plan.B_CONST] = plan.const.data_ptr()
         self._call(plan, plan.bwd_ops, bases)
         bwd.release()
         return gin, zero

@@ -356,5 +356,11 @@ int launch_node_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
 int launch_proj_bwd(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
 int launch_pull(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
 int launch_slot(const NodeBwdP& p, int C, int dtype, cudaStream_t s);
+// detection-head glue (heads.cu)
+int launch_act_fwd(const void* x, void* y, long long n, int dtype, cudaStream_t s);
+int launch_act_bwd(const void* x, const void* g, void* dx, long long n, int dtype, cudaStream_t s);
+int launch_head_move(int scatter, const void* const* in, void* const* dst, void* out, const void* gout, int B, int HW, int C, int K,
+                     int tot, int off, int act, int dtype, cudaStream_t s);
+int launch_copy_f32(const float* src, float* dst, long long n, cudaStream_t s);
 
 }  // namespace mmd

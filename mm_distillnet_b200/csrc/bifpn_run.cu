@@ -503,6 +503,30 @@ static int run_one(const MmdOp& op, int i, const Bases& B, int batch, int C, int
       }
       break;
     }
+    case MMD_OP_COPY:   // executed by mmd_bifpn_prep
+      break;
+    case MMD_OP_ACT_FWD:
+    case MMD_OP_ACT_BWD: {
+      const long long n = (long long)batch * op.in[0].H * op.in[0].W * C;
+      MMD_CHECK_ARG(op.n_in == 1 && op.in[0].C == C && op.in[0].bn.base < 0, "act op %d: one final C-channel input expected", i);
+      if (op.kind == MMD_OP_ACT_FWD)
+        rc = launch_act_fwd(B.get<void>(op.in[0].data), B.get<void>(op.out.data), n, dtype, stream);
+      else
+        rc = launch_act_bwd(B.get<void>(op.in[0].data), op.n_cons == 1 ? B.get<void>(op.cons[0].du.data) : nullptr,
+                            B.get<void>(op.dx), n, dtype, stream);
+      break;
+    }
+    case MMD_OP_HEAD_GATHER:
+    case MMD_OP_HEAD_SCATTER: {
+      const bool scatter = op.kind == MMD_OP_HEAD_SCATTER;
+      MMD_CHECK_ARG(op.n_in >= 1 && op.n_in <= 2 && op.n_in == (op.head_K + C - 1) / C, "head op %d: n_in=%d for K=%d", i, op.n_in, op.head_K);
+      const void* in[2] = {B.get<void>(op.in[0].data), op.n_in > 1 ? B.get<void>(op.in[1].data) : nullptr};
+      void* dst[2] = {B.get<void>(op.du), B.get<void>(op.dd)};
+      rc = launch_head_move(scatter ? 1 : 0, in, dst, B.get<void>(op.out.data),
+                            scatter && op.n_cons == 1 ? B.get<void>(op.cons[0].du.data) : nullptr, batch,
+                            op.in[0].H * op.in[0].W, C, op.head_K, op.head_tot, op.head_off, op.head_act, dtype, stream);
+      break;
+    }
     default:
       set_error("mmd_bifpn_run: op %d has unknown kind %d", i, op.kind);
       return MMD_E_ARG;

@@ -91,7 +91,9 @@ enum ProfKind {
   // list and are timed as such; the kinds above then hold the remaining tile shapes
   PK_NODE_FWD_16x8, PK_NODE_BWD_A_16x8, PK_NODE_BWD_B_16x8,
   // persistent small-level chains (several P5-P7 nodes per launch)
-  PK_CHAIN_FWD, PK_CHAIN_BWD, PK_COUNT
+  PK_CHAIN_FWD, PK_CHAIN_BWD,
+  // element-wise glue of the detection heads (heads.cu)
+  PK_HEAD, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

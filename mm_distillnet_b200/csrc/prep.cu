@@ -14,7 +14,7 @@ namespace mmd {
 struct PrepDesc {
   const float *pw_w, *pw_b, *bn_w, *bn_b, *bn_rm, *bn_rv, *dw_w;
   unsigned char* dst;
-  int Cin, Kp, train, node, NC, nchunks;
+  int Cin, Kp, train, node, NC, nchunks, bwd;
   int offBias, offTaps, offBwd;
   float eps;
 };
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepA
     reinterpret_cast<float*>(D.dst + D.offBias)[c] = bia;
   }
   if (!D.node) {
-    if (!D.train) return;
+    if (!D.bwd) return;
     // projection backward operand: chunk (ch, og, i) holds W[8*og + j][ch*NC + i], j = 0..7 (zero beyond Cin)
     for (int item = tid; item < D.nchunks * (C / 8) * D.NC; item += nthr) {
       const int i = item % D.NC, og = (item / D.NC) % (C / 8), ch = item / (D.NC * (C / 8));
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ PrepA
     const int tap = idx / C, c = idx - tap * C;
     taps[idx] = D.dw_w[c * 9 + tap];
   }
-  if (!D.train) return;
+  if (!D.bwd) return;
   // backward B operand: chunk (og, i) holds W[8*og + j][i], j = 0..7
   for (int item = tid; item < (C / 8) * C; item += nthr) {
     const int og = item / C, i = item - og * C;
@@ -110,6 +110,11 @@ extern "C" int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* base
   cudaStream_t stream = (cudaStream_t)stream_;
   MMD_CHECK_ARG(ops != nullptr && n_ops >= 0 && bases != nullptr, "mmd_bifpn_prep: null arguments");
   MMD_CHECK_ARG(C == 112, "mmd_bifpn_prep: kernels are built for C=112 (EfficientDet-D2), got %d", C);
+  for (int i = 0; i < n_ops; ++i)     // staging copies of zero-padded header parameters: before anything reads them
+    if (ops[i].kind == MMD_OP_COPY) {
+      const int rc = launch_copy_f32(ops[i].copy_src, ops[i].copy_dst, (long long)ops[i].copy_n, stream);
+      if (rc) return rc;
+    }
   if (dtype != MMD_BF16) return 0;   // the fp32 parity kernels read the fp32 parameters directly
   Bases B{bases, n_bases};
   PrepArgs args;
@@ -137,6 +142,7 @@ extern "C" int mmd_bifpn_prep(const MmdOp* ops, int32_t n_ops, void* const* base
     D.bn_rm = op.bn_rm; D.bn_rv = op.bn_rv; D.dw_w = op.dw_w;
     D.dst = dst;
     D.Cin = Cin; D.Kp = L.Kp; D.train = op.train; D.node = node ? 1 : 0;
+    D.bwd = (op.train || op.save_d.base >= 0) ? 1 : 0;
     D.offBias = L.offBias; D.offTaps = L.offTaps; D.offBwd = L.offBwd;
     D.eps = op.bn_eps;
     const ProjChunks pc = proj_chunks(Cin);

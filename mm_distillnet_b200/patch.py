@@ -7,6 +7,8 @@ module-global name, so `patch_reference()` rebinds those names before any model 
 Rebinds:
     src.YetAnotherEfficientDet.BiFPN                     -> mm_distillnet_b200.BiFPN   (looked up at :639-644)
     src.loss.MTALoss.MTALoss, src.utils.utils.MTALoss    -> mm_distillnet_b200.MTALoss (utils.py:50, :1603-1604)
+    src.YetAnotherEfficientDet.Regressor / Classifier    -> mm_distillnet_b200.Regressor / Classifier   (heads=True only;
+                                                            looked up at :646-652; at most 224 header channels)
 and wraps YetAnotherEfficientDet.__init__ so `self.bifpn` (an nn.Sequential of cells) becomes a `BiFPNStack` with
 identical children and state_dict keys, which runs all cells as one fused op list.
 """
@@ -29,12 +31,16 @@ def fuse_bifpn_stacks(model):
     return model
 
 
-def patch_reference(det_module=None, loss_module=None, utils_module=None):
-    """Rebind the reference's globals.  Modules default to the already-imported `src.*` modules."""
+def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=False):
+    """Rebind the reference's globals.  Modules default to the already-imported `src.*` modules.  `heads=True` also
+    rebinds the detection heads (their header is limited to 224 output channels, e.g. 9 anchors x 24 classes)."""
     import importlib
     det = det_module or importlib.import_module("src.YetAnotherEfficientDet")
     loss = loss_module or importlib.import_module("src.loss.MTALoss")
     det.BiFPN = BiFPN
+    if heads:
+        from .heads import Classifier, Regressor
+        det.Regressor, det.Classifier = Regressor, Classifier
     loss.MTALoss = MTALoss
     utils = utils_module or sys.modules.get("src.utils.utils")
     if utils is not None and hasattr(utils, "MTALoss"):

@@ -135,8 +135,8 @@ def test_shape_validation_and_errors():
         cells[0](tuple(torch.randn(1, c, 16 >> i, 16 >> i) for i, c in enumerate([48, 120, 352])))
     with pytest.raises(RuntimeError):
         mmd.MTALoss()([torch.randn(1, 112, 4, 4)], [torch.randn(1, 112, 4, 4)])
-    with pytest.raises(NotImplementedError):
-        mmd.SeparableConvBlock(112, 36, norm=False)
+    with pytest.raises(NotImplementedError):   # a norm=False block is a parameter holder of the heads, not runnable alone
+        mmd.SeparableConvBlock(112, 36, norm=False)(torch.randn(1, 112, 4, 4))
     crit = mmd.MTALoss(T="9", p="2")     # config passes strings (src/utils/utils.py:1603-1604)
     assert crit.T == 9.0 and crit.p == 2.0
 
@@ -322,6 +322,7 @@ def test_patch_reference_on_the_real_modules():
         det = importlib.import_module("src.YetAnotherEfficientDet")
         loss = importlib.import_module("src.loss.MTALoss")
         orig_bifpn, orig_mta, orig_init = det.BiFPN, loss.MTALoss, det.YetAnotherEfficientDet.__init__
+        orig_heads = det.Regressor, det.Classifier
         torch.manual_seed(0)
         ref_model = det.YetAnotherEfficientDet(num_classes=20, compound_coef=2)
         ref_sd = ref_model.state_dict()
@@ -343,8 +344,22 @@ def test_patch_reference_on_the_real_modules():
                 det.YetAnotherEfficientDet(num_classes=20, compound_coef=0)
             crit = loss.MTALoss(T="9", p="2")
             assert isinstance(crit, mmd.MTALoss)
+            assert det.Regressor is orig_heads[0]      # the heads are rebound on request only
+            # heads=True: the detection heads become ours too, with the same keys, shapes and initial weights
+            mmd.patch_reference(heads=True)
+            assert det.Regressor is mmd.Regressor and det.Classifier is mmd.Classifier
+            torch.manual_seed(0)
+            ours = det.YetAnotherEfficientDet(num_classes=20, compound_coef=2)
+            assert isinstance(ours.regressor, mmd.Regressor) and isinstance(ours.classifier, mmd.Classifier)
+            sd = ours.state_dict()
+            assert list(sd.keys()) == list(ref_sd.keys())
+            assert all(torch.equal(sd[k], ref_sd[k]) for k in sd if k.startswith(("bifpn.", "regressor.", "classifier.")))
+            ours.load_state_dict(ref_sd, strict=True)
+            with pytest.raises(NotImplementedError):   # 9 x 90 = 810 header channels: more than two C-row halves
+                det.YetAnotherEfficientDet(num_classes=90, compound_coef=2)
         finally:
             det.BiFPN, loss.MTALoss = orig_bifpn, orig_mta
+            det.Regressor, det.Classifier = orig_heads
             det.YetAnotherEfficientDet.__init__ = orig_init
             det.YetAnotherEfficientDet._mmd_patched = False
     finally:
@@ -395,3 +410,40 @@ def test_product_never_touches_the_oracle_or_the_reference_tree():
     assert len(uses) == 2                                     # cpu_state() and cpu_step() only
     gpu_arm = bench[bench.index("def measure("):bench.index("def main(")]
     assert "oracle" not in gpu_arm.replace("oracle port", "")  # the CUDA arm only NAMES the port in its cpu_baseline text
+
+
+def test_head_modules_mirror_reference_state_dict_and_plan():
+    """Regressor / Classifier: the reference's state_dict names and shapes, and the op list a head plan is
+    made of — towers and header halves as NODE ops, one HEAD_GATHER per level, COPY ops for the zero-padded header."""
+    import collections
+    from oracle import mmd_oracle as O
+    from mm_distillnet_b200 import bifpn as bf
+    for cls, args, kout in ((mmd.Regressor, (112, 9, 3), 36), (mmd.Classifier, (112, 9, 20, 3), 180)):
+        m = cls(*args)
+        ref = O.synth_head_params(112, kout, 3, 1)       # names recorded from the reference modules (make_golden.py)
+        sd = m.state_dict()
+        assert set(sd) == set(ref) and all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in ref)
+        m.load_state_dict(ref, strict=True)
+        halves = (kout + 111) // 112
+        shapes = [(2, 112, s, s) for s in (16, 8, 4, 2, 1)]
+        for dt in (torch.float32, torch.bfloat16):
+            pl = bf._Plan([m], "head", shapes, dt, True, True, [True] * 5)
+            kf = collections.Counter(o.kind for o in pl.fwd_ops)
+            kb = collections.Counter(o.kind for o in pl.bwd_ops)
+            assert kf == {_lib.OP_COPY: 2, _lib.OP_NODE_FWD: 5 * (3 + halves), _lib.OP_HEAD_GATHER: 5, _lib.OP_BNAPPLY: 1,
+                          _lib.OP_ACT_FWD: 1}
+            assert kb == {_lib.OP_ACT_BWD: 1, _lib.OP_SLOT: 1, _lib.OP_HEAD_SCATTER: 5, _lib.OP_NODE_BWD: 5 * (3 + halves),
+                          _lib.OP_PULL: 5}
+            assert pl.out_shapes == [(2, 341 * 9, kout // 9), (2, 112, 1, 1)]
+            hdr = [o for o in pl.fwd_ops if o.kind == _lib.OP_NODE_FWD and o.train == 0]
+            assert len(hdr) == 5 * halves and all(o.save_d.base >= 0 and o.out.bn.base == -1 for o in hdr)
+            ev = bf._Plan([m], "head", shapes, dt, False, False, [False] * 5)
+            assert ev.bwd_ops is None and all(o.train == 0 for o in ev.fwd_ops)
+    with pytest.raises(NotImplementedError):
+        mmd.Regressor(64, 9, 3)
+    with pytest.raises(NotImplementedError):
+        mmd.Classifier(112, 9, 90, 3)
+    blk = mmd.SeparableConvBlock(112, 36, norm=False)
+    assert "bn.weight" not in blk.state_dict()
+    with pytest.raises(NotImplementedError):
+        blk(torch.zeros(1, 112, 4, 4))

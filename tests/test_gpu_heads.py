@@ -1,0 +1,302 @@
+"""GPU parity of the detection heads (Regressor / Classifier, src/YetAnotherEfficientDet.py:445-533)
+through the public modules -> C ABI, against (a) the stored outputs of the unmodified reference modules
+(tests/golden/reg_c112.npz, cls_c112.npz) and (b) the CPU oracle on a larger seeded pyramid.
+
+Bounds: fp32 storage — forward <= 2e-5 max-rel, every gradient tensor <= 1e-4 rel-L2 (north_star), on every case.  bf16
+storage (fp32 arithmetic, bf16 tensors between kernels) — forward <= 2e-2 of the tensor's range, input gradients <= 3e-2,
+parameter gradients <= 4e-2 rel-L2 per tensor and never worse than eager PyTorch in bf16, on a well-conditioned case
+(test_heads_bf16_vs_oracle); on the tiny golden fixture the train-mode bf16 numbers are bounded against that PyTorch run."""
+import numpy as np
+import pytest
+import torch
+
+import mm_distillnet_b200 as mmd
+from oracle import mmd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF16_E2E_TOL = (5e-2, 8e-2)   # bf16 neck+heads chain (~20 bf16 tensors deep): forward max-rel (measured 1.7-2.9e-2), gradient rel-L2 (2.5-4.7e-2)
+
+
+def _build(kind, C, A, K, L, params):
+    m = mmd.Regressor(C, A, L) if kind == "reg" else mmd.Classifier(C, A, K, L)
+    m.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+    return m.to(DEV)
+
+
+def _oracle(kind, xs, p, A, K, L, training, stats=None):
+    if kind == "reg":
+        return O.regressor(tuple(xs), p, num_layers=L, training=training, stats_out=stats)
+    return O.classifier(tuple(xs), p, A, K, num_layers=L, training=training, stats_out=stats)
+
+
+def _run_case(kind, C, A, K, L, params, xs, gouts_fn, dtype):
+    """-> dict of CUDA tensors moved to the CPU: eval_out/align, train_out/align, grads, parameter grads, buffers."""
+    r = {}
+    m = _build(kind, C, A, K, L, params)
+    m.eval()
+    with torch.no_grad():
+        y, a = m([x.to(DEV).to(dtype) for x in xs])
+    r["eval_out"], r["eval_align"] = y.float().cpu(), a.float().cpu()
+    m.train()
+    xd = [x.to(DEV).to(dtype).requires_grad_(True) for x in xs]
+    y, a = m(xd)
+    gy, ga = gouts_fn(y, a)
+    ((y.float() * gy.to(DEV)).sum() + (a.float() * ga.to(DEV)).sum()).backward()
+    r["train_out"], r["train_align"] = y.detach().float().cpu(), a.detach().float().cpu()
+    for i, x in enumerate(xd):
+        r["grad_in%d" % i] = x.grad.float().cpu()
+    for k, p in m.named_parameters():
+        r["pgrad_" + k] = p.grad.float().cpu()
+    for k, v in m.state_dict().items():
+        if "running_" in k or "num_batches" in k:
+            r["buf_" + k] = v.cpu()
+    return r
+
+
+def rand_case(C, kout, L, B, s3, seed):
+    """Gaussian parameters / inputs from a seeded generator, at the scales of the synth case.  The closed-form `synth`
+    weights are sums of two sinusoids: a 112-term dot product of two such patterns cancels to ~1/10 of a random one's
+    size, which multiplies every bf16 rounding error by ~10 (same for eager PyTorch in bf16) — fine for the fp32 cases,
+    useless as a bf16 yardstick."""
+    gen = torch.Generator().manual_seed(seed)
+    p = O.synth_head_params(C, kout, L, seed)
+    for k, v in p.items():
+        if not v.is_floating_point():
+            continue
+        r = torch.randn(v.shape, generator=gen)
+        if k.endswith("depthwise_conv.conv.weight"):
+            p[k] = 0.35 * r
+        elif k.endswith("pointwise_conv.conv.weight"):
+            p[k] = r * (1.2 / C ** 0.5)
+        elif k.endswith("conv.bias"):
+            p[k] = 0.1 * r - (0.5 if k.startswith("header") else 0.0)
+        elif k.endswith("running_var"):
+            p[k] = 1.0 + 0.3 * r.abs()
+        elif k.endswith(".weight"):
+            p[k] = 1.0 + 0.2 * r
+        else:
+            p[k] = 0.2 * r
+    sizes = [s3, s3 // 2, s3 // 4, s3 // 8, max(s3 // 16, 1)]
+    xs = [torch.randn(B, C, s, s, generator=gen) for s in sizes]
+    return p, xs
+
+
+def quad_gouts(seed):
+    """dL/d(outputs) of L = 1/2 |y - t|^2 + 1/2 |a - t_a|^2 with fixed pseudo-random targets: a gradient that is correlated
+    with the activations, as a training loss's is (the oscillating `synth` upstream gradients of the fp32 cases make every
+    per-channel sum cancel to ~1e-2 of its terms, which measures bf16 rounding noise, not the kernels)."""
+    def fn(y, a):
+        ty, ta = O.synth(tuple(y.shape), seed + 70, 0.5, 0.0), O.synth(tuple(a.shape), seed + 71, 0.5, 0.0)
+        dt = torch.float64 if y.dtype == torch.float64 else torch.float32
+        return (y.detach().cpu().to(dt) - ty.to(dt)), (a.detach().cpu().to(dt) - ta.to(dt))
+    return fn
+
+
+def torch_bf16(kind, C, A, K, L, params, xs, gouts_fn):
+    """The oracle's own torch code run with bf16 tensors on the GPU (= eager PyTorch under .bfloat16()): the calibration
+    the bf16 bounds are stated against."""
+    p = {k: (v.to(DEV).bfloat16() if v.is_floating_point() else v.to(DEV)) for k, v in params.items()}
+    r = {}
+    with torch.no_grad():
+        y, a = _oracle(kind, [x.to(DEV).bfloat16() for x in xs], p, A, K, L, False)
+    r["eval_out"], r["eval_align"] = y.float().cpu(), a.float().cpu()
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in p.items()}
+    xd = [x.to(DEV).bfloat16().requires_grad_(True) for x in xs]
+    y, a = _oracle(kind, xd, leaf, A, K, L, True, {})
+    gy, ga = gouts_fn(y, a)
+    ((y.float() * gy.to(DEV)).sum() + (a.float() * ga.to(DEV)).sum()).backward()
+    r["train_out"], r["train_align"] = y.detach().float().cpu(), a.detach().float().cpu()
+    for i, x in enumerate(xd):
+        r["grad_in%d" % i] = x.grad.float().cpu()
+    for k, v in leaf.items():
+        if torch.is_tensor(v) and v.requires_grad:
+            r["pgrad_" + k] = v.grad.float().cpu()
+    return r
+
+
+def head_metrics(r, g):
+    """Worst error per class of quantity: fwd (max-rel of the four outputs), grad_in, pgrad (element-wise rel-L2 per
+    parameter tensor), buf (running statistics)."""
+    m = {"fwd": 0.0, "grad_in": 0.0, "pgrad": 0.0, "buf": 0.0}
+    for k in ("eval_out", "eval_align", "train_out", "train_align"):
+        assert tuple(r[k].shape) == tuple(np.shape(g[k])), k
+        m[k] = H.max_rel(r[k], g[k])
+        m["fwd"] = max(m["fwd"], m[k])
+    for k in sorted(r):
+        ref = torch.as_tensor(np.asarray(g[k])) if k in g else None
+        if k.startswith("grad_in"):
+            m[k] = H.rel_l2(r[k], ref)
+            m["grad_in"] = max(m["grad_in"], m[k])
+        elif k.startswith("pgrad_"):
+            if k.startswith("pgrad_conv_list") and k.endswith("conv.bias"):
+                continue   # bias feeding a train-mode BatchNorm: zero gradient up to rounding
+            assert tuple(ref.shape) == tuple(r[k].shape), k
+            if ref.abs().max() > 1e-6:
+                m[k] = H.rel_l2(r[k], ref)
+                m["pgrad"] = max(m["pgrad"], m[k])
+        elif k.startswith("buf_"):
+            if "num_batches" in k:
+                assert int(r[k]) == int(ref), k
+            else:
+                m["buf"] = max(m["buf"], H.max_rel(r[k], ref))
+    return m
+
+
+def _compare(r, g, fwd_tol, grad_tol, buf_tol, fwd_metric=None):
+    m = head_metrics(r, g)
+    assert m["fwd"] < fwd_tol, {k: v for k, v in m.items() if k.startswith(("eval", "train"))}
+    assert m["grad_in"] < grad_tol, {k: v for k, v in m.items() if k.startswith("grad_in")}
+    assert m["pgrad"] < grad_tol, {k: v for k, v in m.items() if k.startswith("pgrad") and v >= grad_tol}
+    assert m["buf"] < buf_tol, m["buf"]
+    return m
+
+
+@pytest.mark.parametrize("name", sorted(H.HEAD_CASES))
+def test_heads_golden_fp32(name):
+    """fp32 storage against the stored reference outputs: every output, input gradient, parameter gradient (element-wise)
+    and BatchNorm buffer."""
+    kind, C, A, K, L, B, s3, seed = H.HEAD_CASES[name]
+    params, xs = H.head_case_inputs(name)
+    r = _run_case(kind, C, A, K, L, params, xs, lambda y, a: H.head_case_gouts(name, y, a), torch.float32)
+    _compare(r, H.golden(name), 2e-5, 1e-4, 2e-5, H.max_rel)
+
+
+@pytest.mark.parametrize("name", sorted(H.HEAD_CASES))
+def test_heads_golden_bf16(name):
+    """bf16 storage against the same reference outputs.  Eval mode (running statistics) and the running-stat update are
+    held to absolute caps.  The fixture's train-mode BatchNorms normalise over 2 (P7, 1x1) to 512 values with the
+    cancellation-heavy `synth` weights — ill-conditioned in bf16 for ANY implementation (eager PyTorch in bf16: forward
+    3-8e-2, gradients 0.12-0.85) — so the train-mode quantities are bounded relative to that run; the absolute bf16
+    gradient caps live in test_heads_bf16_vs_oracle."""
+    kind, C, A, K, L, B, s3, seed = H.HEAD_CASES[name]
+    params, xs = H.head_case_inputs(name)
+    g = H.golden(name)
+    gf = lambda y, a: H.head_case_gouts(name, y, a)   # noqa: E731
+    m = head_metrics(_run_case(kind, C, A, K, L, params, xs, gf, torch.bfloat16), g)
+    ref = head_metrics(torch_bf16(kind, C, A, K, L, params, xs, gf), g)
+    assert m["eval_out"] < 1e-2 and m["eval_align"] < 1e-2, m        # measured 3.6-3.9e-3 / 3.8-4.3e-3
+    assert m["buf"] < 1e-3, m["buf"]                                  # measured <= 9.5e-5
+    for k in ("train_out", "train_align", "grad_in", "pgrad"):
+        assert m[k] < 1.5 * ref[k], (k, m[k], ref[k])                # measured 0.36-1.23x
+
+
+@pytest.mark.parametrize("kind,K", [("reg", 20), ("cls", 20), ("cls", 3)])
+def test_heads_vs_oracle(kind, K):
+    """fp32 storage on a larger pyramid (64x64 .. 4x4: the big-level tile shapes) against the fp64 CPU oracle; classifier
+    widths that need two (180) and one (27) header halves."""
+    C, A, L, B, s3, seed = 112, 9, 3, 2, 64, 31
+    kout = A * (4 if kind == "reg" else K)
+    params = O.synth_head_params(C, kout, L, seed)
+    xs = H.pyramid_inputs(B, C, s3, seed + 50)
+
+    def gouts(y, a):
+        return O.synth(tuple(y.shape), seed + 70, 1.0, 0.0), O.synth(tuple(a.shape), seed + 71, 1.0, 0.0)
+
+    r = _run_case(kind, C, A, K, L, params, xs, gouts, torch.float32)
+    _compare(r, oracle_reference(kind, C, A, K, L, params, xs, gouts), 2e-5, 1e-4, 2e-5)   # measured 2e-6 / 7e-6 / 3.6e-5
+
+
+@pytest.mark.parametrize("kind,K,s3,B", [("reg", 20, 64, 2), ("cls", 20, 64, 2), ("cls", 3, 64, 2), ("cls", 20, 96, 4)])
+def test_heads_bf16_vs_oracle(kind, K, s3, B):
+    """bf16 storage, Gaussian parameters and inputs (rand_case), quadratic loss: every output, input gradient and parameter
+    gradient against the fp64 oracle, with absolute caps and never worse than eager PyTorch in bf16 on the same case."""
+    C, A, L, seed = 112, 9, 3, 77
+    params, xs = rand_case(C, A * (4 if kind == "reg" else K), L, B, s3, seed)
+    gf = quad_gouts(seed)
+    g = oracle_reference(kind, C, A, K, L, params, xs, gf)
+    m = head_metrics(_run_case(kind, C, A, K, L, params, xs, gf, torch.bfloat16), g)
+    ref = head_metrics(torch_bf16(kind, C, A, K, L, params, xs, gf), g)
+    assert m["fwd"] < 2e-2 and m["buf"] < 1e-3, m            # measured <= 1.0e-2 / 4.5e-5   (PyTorch bf16: 1.5-1.8e-2)
+    assert m["grad_in"] < 3e-2, m["grad_in"]                 # measured <= 1.4e-2            (PyTorch bf16: 2.4-2.6e-2)
+    assert m["pgrad"] < 4e-2, m["pgrad"]                     # measured <= 1.5e-2            (PyTorch bf16: 5.3-13e-2)
+    for k in ("fwd", "grad_in", "pgrad"):
+        assert m[k] <= ref[k], (k, m[k], ref[k])
+    # fp32 storage on the same case: the north_star bar
+    _compare(_run_case(kind, C, A, K, L, params, xs, gf, torch.float32), g, 2e-5, 1e-4, 2e-5)
+
+
+def oracle_reference(kind, C, A, K, L, params, xs, gouts):
+    """fp64 run of the CPU oracle: the same dict of quantities _run_case returns."""
+    g = {}
+    with torch.no_grad():
+        y, a = _oracle(kind, [x.double() for x in xs], {k: (v.double() if v.is_floating_point() else v) for k, v in params.items()}, A, K, L, False)
+    g["eval_out"], g["eval_align"] = y.float().numpy(), a.float().numpy()
+    leaf = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+                (v.double() if v.is_floating_point() else v)) for k, v in params.items()}
+    xd = [x.double().requires_grad_(True) for x in xs]
+    stats = {}
+    y, a = _oracle(kind, xd, leaf, A, K, L, True, stats)
+    gy, ga = gouts(y, a)
+    ((y * gy).sum() + (a * ga).sum()).backward()
+    g["train_out"], g["train_align"] = y.detach().float().numpy(), a.detach().float().numpy()
+    for i, x in enumerate(xd):
+        g["grad_in%d" % i] = x.grad.float().numpy()
+    for k, v in leaf.items():
+        if torch.is_tensor(v) and v.requires_grad:
+            g["pgrad_" + k] = v.grad.float().numpy()
+    for k, v in stats.items():
+        g["buf_" + k] = v.float().numpy() if v.is_floating_point() else v.numpy()
+    return g
+
+
+def test_heads_state_dict_and_errors():
+    m = mmd.Classifier(112, 9, 20, 3)
+    assert len(m.state_dict()) == 87 and "bn_list.4.2.running_var" in m.state_dict()
+    with pytest.raises(NotImplementedError):
+        mmd.Regressor(64, 9, 3)                       # D0 width: loud at construction
+    with pytest.raises(NotImplementedError):
+        mmd.Classifier(112, 9, 90, 3)                 # 810 header channels
+    with pytest.raises(RuntimeError):
+        m([torch.zeros(1, 112, 8 >> i or 1, 8 >> i or 1) for i in range(5)])   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_neck_and_heads_end_to_end(dtype):
+    """features = bifpn(p3, p4, p5); regression = regressor(features); classification = classifier(features)
+    (YetAnotherEfficientDet.forward, src/YetAnotherEfficientDet.py:667-672) on our modules, gradients flowing from both
+    heads back through the 2-cell BiFPN stack into the backbone features — against the fp64 oracle following the CUDA
+    forward's own max-pool arg-max (tests/test_gpu_bifpn.py docstring)."""
+    from mm_distillnet_b200.bifpn import debug_pool_argmax
+    C, cc, A, K, L, B, s3, seed, n_cells = 112, [48, 120, 352], 9, 3, 3, 2, 64, 5, 2
+    gen = torch.Generator().manual_seed(seed)
+    stack = mmd.BiFPNStack(*[mmd.BiFPN(C, cc, first_time=(i == 0)) for i in range(n_cells)])
+    hp_r, _ = rand_case(C, A * 4, L, B, s3, seed + 1)
+    hp_c, _ = rand_case(C, A * K, L, B, s3, seed + 2)
+    reg, cls = _build("reg", C, A, K, L, hp_r), _build("cls", C, A, K, L, hp_c)
+    sp = {k: v.clone() for k, v in stack.state_dict().items()}
+    stack = stack.to(DEV).train()
+    xs = [torch.randn(B, c, s3 >> i, s3 >> i, generator=gen).to(dtype).float() for i, c in enumerate(cc)]
+    xd = [x.to(DEV).to(dtype).requires_grad_(True) for x in xs]
+    feats = stack(tuple(xd))
+    hints = debug_pool_argmax(feats[0])
+    ry, _ = reg(feats)
+    cy, ca = cls(feats)
+    # oracle, fp64
+    leaf = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else
+                (v.double() if v.is_floating_point() else v)) for k, v in sp.items()}
+    lr = {k: (v.double() if v.is_floating_point() else v) for k, v in hp_r.items()}
+    lc = {k: (v.double() if v.is_floating_point() else v) for k, v in hp_c.items()}
+    xo = [x.double().requires_grad_(True) for x in xs]
+    fo = O.bifpn_stack(tuple(xo), leaf, n_cells, first_cell_first_time=True, training=True, pool_hints=hints)
+    ro, _ = O.regressor(tuple(fo), lr, num_layers=L, training=True)
+    co, cao = O.classifier(tuple(fo), lc, A, K, num_layers=L, training=True)
+    tr, tc = O.synth(tuple(ro.shape), 1, 0.5, 0.0).double(), O.synth(tuple(co.shape), 2, 0.5, 0.5).double()
+    (0.5 * (ro - tr).pow(2).sum() + 0.5 * (co - tc).pow(2).sum() + 0.5 * cao.pow(2).sum()).backward()
+    (0.5 * (ry.float() - tr.float().to(DEV)).pow(2).sum() + 0.5 * (cy.float() - tc.float().to(DEV)).pow(2).sum()
+     + 0.5 * ca.float().pow(2).sum()).backward()
+    m = {"reg": H.max_rel(ry.detach().float().cpu(), ro.detach()), "cls": H.max_rel(cy.detach().float().cpu(), co.detach()),
+         "align": H.max_rel(ca.detach().float().cpu(), cao.detach())}
+    for i, (a, b) in enumerate(zip(xd, xo)):
+        m["grad_in%d" % i] = H.rel_l2(a.grad.float().cpu(), b.grad)
+    m["pgrad_bifpn"] = 0.0
+    for k, p in stack.named_parameters():
+        r = leaf[k].grad
+        if k.endswith("conv.bias") or k[-3:-1] == "_w" or r.abs().max() == 0:
+            continue
+        m["pgrad_bifpn"] = max(m["pgrad_bifpn"], H.rel_l2(p.grad.float().cpu(), r))
+    print("neck+heads", dtype, {k: round(v, 6) for k, v in m.items()})
+    fwd_tol, grad_tol = (2e-5, 1e-4) if dtype == torch.float32 else BF16_E2E_TOL
+    bad = {k: v for k, v in m.items() if not v < (fwd_tol if k in ("reg", "cls", "align") else grad_tol)}
+    assert not bad, (bad, m)
