@@ -18,11 +18,18 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
+import types  # noqa: E402
+sys.modules.setdefault("cv2", types.ModuleType("cv2"))   # the reference's loss file imports cv2 without using it; not installed here
+
 from oracle import mmd_oracle as O  # noqa: E402
 from src.YetAnotherEfficientDet import BiFPN, Classifier, Regressor  # noqa: E402  (reference)
 from src.loss.MTALoss import MTALoss  # noqa: E402  (reference)
+from src.loss.YetAnotherFocalLoss import YetAnotherFocalLoss  # noqa: E402  (reference)
+from src.YetAnotherEfficientDet import Anchors  # noqa: E402  (reference)
 
 OUT = os.path.join(ROOT, "tests", "golden")
+# name -> (annotation kind, B, image size, classes, seed)   (mirrored by tests/helpers.py FOCAL_CASES)
+FOCAL_CASES = {"focal_mixed": ("mixed", 4, 128, 20, 21), "focal_dense": ("dense", 2, 128, 20, 22), "focal_none": ("none", 2, 128, 20, 23)}
 LEVEL_NAMES = ("p3", "p4", "p5", "p6", "p7")
 
 
@@ -149,6 +156,24 @@ def run_mta_case(name, B, C, sizes, seed):
     print(name, "->", len(out), "arrays")
 
 
+def run_focal_case(name, kind, B, size, K, seed):
+    """Reference YetAnotherFocalLoss on the reference's own Anchors for a size x size image: losses and the gradients of
+    1.3 * regression_loss + 0.7 * classification_loss w.r.t. the classification scores and box deltas."""
+    anchors = Anchors(anchor_scale=4.)(torch.zeros(1, 3, size, size), torch.float32)
+    N = anchors.shape[1]
+    c, r = O.synth_detections(B, N, K, seed)
+    ann = O.synth_annotations(kind, B, size, K)
+    c.requires_grad_(True)
+    r.requires_grad_(True)
+    rl, cl = YetAnotherFocalLoss()((c, r, anchors), ann)
+    out = {"anchors": anchors.numpy(), "reg_loss": rl.detach().numpy(), "cls_loss": cl.detach().numpy()}
+    if rl.requires_grad or cl.requires_grad:
+        (1.3 * rl + 0.7 * cl).sum().backward()
+        out["grad_cls"], out["grad_reg"] = c.grad.numpy(), r.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N=%d" % N, "reg %.6f cls %.4f" % (float(rl), float(cl)), "annots", [len(a) for a in ann])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(4)
@@ -161,6 +186,9 @@ def main():
     # D2 channel counts (what the CUDA kernels are built for), tiny spatial size; full parameter gradients as well
     run_stack_case("stack2_c112", 112, [48, 120, 352], 2, True, B=2, s3=16, seed=5, save_param_grads=True)
     run_stack_case("cell_c112", 112, [48, 120, 352], 1, False, B=2, s3=16, seed=6, save_param_grads=True)
+    # detection loss: the reference's own anchors for a 128x128 image (3 069 boxes), 20 classes
+    for name, (kind, B, size, K, seed) in FOCAL_CASES.items():
+        run_focal_case(name, kind, B, size, K, seed)
     # detection heads: D2 configuration (112 channels, 9 anchors, 3 layers; 20 classes), tiny pyramid
     run_head_case("reg_c112", "reg", 112, 9, 20, 3, B=2, s3=16, seed=9)
     run_head_case("cls_c112", "cls", 112, 9, 20, 3, B=2, s3=16, seed=10)

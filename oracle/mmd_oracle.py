@@ -339,6 +339,108 @@ def mta_grad_closed_form(f_s, a_t_normalised, grad_out, T=9.0):
 
 
 # ----------------------------------------------------------------------------------------------
+# detection loss
+# ----------------------------------------------------------------------------------------------
+def box_iou_anchor_gt(anchors, gt):
+    """IoU of anchors [N,4] given as (y1, x1, y2, x2) against ground-truth boxes [M,4] given as (x1, y1, x2, y2):
+    intersection / max(area_a + area_b - intersection, 1e-8).  src/loss/YetAnotherFocalLoss.py:6-20 (same operation order,
+    so an fp32 run takes the same side of the 0.4 / 0.5 thresholds as the reference)."""
+    area_b = (gt[:, 2] - gt[:, 0]) * (gt[:, 3] - gt[:, 1])
+    iw = (torch.minimum(anchors[:, 3:4], gt[:, 2]) - torch.maximum(anchors[:, 1:2], gt[:, 0])).clamp(min=0)
+    ih = (torch.minimum(anchors[:, 2:3], gt[:, 3]) - torch.maximum(anchors[:, 0:1], gt[:, 1])).clamp(min=0)
+    inter = iw * ih
+    union = (((anchors[:, 2] - anchors[:, 0]) * (anchors[:, 3] - anchors[:, 1])).unsqueeze(1) + area_b - inter).clamp(min=1e-8)
+    return inter / union
+
+
+def focal_loss(classifications, regressions, anchors, annotations, alpha=0.25, gamma=2.0, assign=None):
+    """YetAnotherFocalLoss.forward (src/loss/YetAnotherFocalLoss.py:27-190) -> (regression_loss [1], classification_loss [1]).
+    classifications [B,N,K] (sigmoid scores), regressions [B,N,4] (dy, dx, dh, dw), anchors [1,N,4] (y1,x1,y2,x2),
+    annotations: list of B arrays [M_b,5] (x1, y1, x2, y2, class).  Per sample: anchors with max-IoU < 0.4 are negatives,
+    >= 0.5 positives of the arg-max box's class, in between ignored; focal BCE summed and divided by max(#positives, 1);
+    smooth-L1 (beta 1/9) on the positives' box deltas, mean over #positives*4; both averaged over the samples.  A sample
+    without boxes contributes the all-negative classification sum (undivided) and a zero regression term; if NO sample has a
+    box the reference skips every sample and returns zeros.
+    `assign` (test-only): [B,N] int tensor from the other implementation (-2 ignore, -1 negative, m >= 0 positive of box m
+    of the sample's valid boxes) used instead of this function's own IoU thresholds."""
+    B = classifications.shape[0]
+    dt = classifications.dtype
+    a = anchors[0].to(dt)
+    if max((len(x) for x in annotations), default=0) == 0:
+        z = torch.zeros(1, dtype=dt)
+        return z, z.clone()
+    aw, ah = a[:, 3] - a[:, 1], a[:, 2] - a[:, 0]
+    acx, acy = a[:, 1] + 0.5 * aw, a[:, 0] + 0.5 * ah
+    cls_terms, reg_terms = [], []
+    for b in range(B):
+        c = classifications[b].clamp(1e-4, 1.0 - 1e-4)
+        gt = torch.as_tensor(annotations[b], dtype=dt).reshape(-1, 5)
+        gt = gt[gt[:, 4] != -1]
+        neg_term = (1.0 - alpha) * c.pow(gamma) * (-torch.log(1.0 - c))
+        if gt.shape[0] == 0:
+            cls_terms.append(neg_term.sum())
+            reg_terms.append(torch.zeros((), dtype=dt))
+            continue
+        if assign is None:
+            iou_max, iou_arg = box_iou_anchor_gt(a, gt[:, :4]).max(dim=1)
+            pos, neg = iou_max >= 0.5, iou_max < 0.4
+        else:
+            pos, neg, iou_arg = assign[b] >= 0, assign[b] == -1, assign[b].clamp(min=0).long()
+        box = gt[iou_arg]
+        onehot = torch.zeros_like(c, dtype=torch.bool)
+        onehot[pos, box[pos, 4].long()] = True
+        pos_term = alpha * (1.0 - c).pow(gamma) * (-torch.log(c))
+        term = torch.where(onehot, pos_term, neg_term) * (pos | neg).unsqueeze(1).to(dt)
+        npos = pos.sum()
+        cls_terms.append(term.sum() / npos.to(dt).clamp(min=1.0))
+        if int(npos) == 0:
+            reg_terms.append(torch.zeros((), dtype=dt))
+            continue
+        box = box[pos]
+        gw, gh = box[:, 2] - box[:, 0], box[:, 3] - box[:, 1]
+        gcx, gcy = box[:, 0] + 0.5 * gw, box[:, 1] + 0.5 * gh
+        gw, gh = gw.clamp(min=1), gh.clamp(min=1)
+        tgt = torch.stack(((gcy - acy[pos]) / ah[pos], (gcx - acx[pos]) / aw[pos],
+                           torch.log(gh / ah[pos]), torch.log(gw / aw[pos])), dim=1)
+        d = (tgt - regressions[b][pos]).abs()
+        reg_terms.append(torch.where(d <= 1.0 / 9.0, 0.5 * 9.0 * d * d, d - 0.5 / 9.0).mean())
+    return torch.stack(reg_terms).mean(dim=0, keepdim=True), torch.stack(cls_terms).mean(dim=0, keepdim=True)
+
+
+def synth_detections(B, N, K, seed, dtype=torch.float32):
+    """Classification scores in (0, 1) with a few exact 0 / 1 / sub-clamp entries, and box deltas."""
+    c = 0.5 + 0.5 * synth((B, N, K), seed, 1.0, 0.0, dtype)
+    c = c.clamp(0.0, 1.0)
+    flat = c.view(-1)
+    flat[0], flat[1], flat[2], flat[3] = 0.0, 1.0, 5e-5, 1.0 - 5e-5
+    r = synth((B, N, 4), seed + 1, 0.8, 0.0, dtype)
+    return c, r
+
+
+def synth_annotations(kind, B, size, K):
+    """Deterministic pseudo-label sets for a `size` x `size` image: list of B float32 arrays [M_b, 5] (x1, y1, x2, y2, class).
+    "mixed": 3 boxes / none / 1 box / 2 boxes ... (a sample without boxes in a batch that has some);
+    "dense": 6 overlapping boxes per sample (arg-max competition between boxes); "none": no box in any sample."""
+    import numpy as np
+    out = []
+    for b in range(B):
+        if kind == "none" or (kind == "mixed" and b % 4 == 1):
+            out.append(np.zeros((0, 5), dtype=np.float32))
+            continue
+        m = 6 if kind == "dense" else (3, 0, 1, 2)[b % 4]
+        rows = []
+        for j in range(m):
+            t = 0.37 * (b + 1) + 0.91 * j
+            cx, cy = size * (0.5 + 0.3 * math.sin(t)), size * (0.5 + 0.3 * math.cos(1.7 * t))
+            w, h = size * (0.2 + 0.15 * math.sin(2.3 * t + 1.0) ** 2), size * (0.25 + 0.2 * math.cos(1.1 * t) ** 2)
+            if kind == "dense":
+                cx, cy = size * (0.45 + 0.04 * j), size * (0.5 + 0.03 * j)
+            rows.append([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, float((3 * b + 5 * j + 1) % K)])
+        out.append(np.asarray(rows, dtype=np.float32))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic, RNG-free data so fixtures never depend on a torch/numpy RNG stream
 # ----------------------------------------------------------------------------------------------
 def synth(shape, seed, scale=1.0, offset=0.0, dtype=torch.float32):

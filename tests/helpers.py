@@ -20,6 +20,8 @@ STACK_CASES = {
 }
 # name -> (kind, C, num_anchors, num_classes, num_layers, B, s3, seed)   (must mirror oracle/make_golden.py main())
 HEAD_CASES = {"reg_c112": ("reg", 112, 9, 20, 3, 2, 16, 9), "cls_c112": ("cls", 112, 9, 20, 3, 2, 16, 10)}
+# name -> (annotation kind, B, image size, classes, seed)   (must mirror oracle/make_golden.py FOCAL_CASES)
+FOCAL_CASES = {"focal_mixed": ("mixed", 4, 128, 20, 21), "focal_dense": ("dense", 2, 128, 20, 22), "focal_none": ("none", 2, 128, 20, 23)}
 MTA_CASES = {"mta_c112": (2, 112, [12, 6, 3], 7), "mta_c16": (3, 16, [16, 8, 4, 2, 1], 8)}
 
 
@@ -41,6 +43,14 @@ def stack_case_inputs(name, dtype=torch.float32):
     params = O.synth_stack_params(C, cc, n_cells, seed, first_cell_first_time=first, dtype=dtype)
     xs = backbone_inputs(B, cc, s3, seed + 50, dtype) if first else pyramid_inputs(B, C, s3, seed + 50, dtype)
     return params, xs
+
+
+def focal_case_inputs(name, dtype=torch.float32):
+    """-> classification [B,N,K], regression [B,N,4], anchors [1,N,4] (the reference's, stored in the fixture), annotations."""
+    kind, B, size, K, seed = FOCAL_CASES[name]
+    anchors = torch.from_numpy(golden(name)["anchors"])
+    c, r = O.synth_detections(B, anchors.shape[1], K, seed, dtype)
+    return c, r, anchors, O.synth_annotations(kind, B, size, K)
 
 
 def head_case_inputs(name, dtype=torch.float32):

@@ -56,6 +56,42 @@ def test_stack_matches_reference(name):
             assert abs(v.grad.double().norm().item() - nrm) <= tol * max(nrm, 1e-6), k
 
 
+@pytest.mark.parametrize("name", sorted(H.FOCAL_CASES))
+def test_focal_loss_matches_reference(name):
+    """YetAnotherFocalLoss restatement against the reference's losses and gradients on its own anchors."""
+    g = H.golden(name)
+    c, r, anchors, ann = H.focal_case_inputs(name)
+    c.requires_grad_(True)
+    r.requires_grad_(True)
+    rl, cl = O.focal_loss(c, r, anchors, ann)
+    assert rl.shape == (1,) and cl.shape == (1,)
+    assert abs(float(rl) - float(g["reg_loss"])) <= 1e-6 * max(1.0, abs(float(g["reg_loss"])))
+    assert abs(float(cl) - float(g["cls_loss"])) <= 1e-6 * max(1.0, abs(float(g["cls_loss"])))
+    if "grad_cls" in g:
+        (1.3 * rl + 0.7 * cl).sum().backward()
+        assert H.rel_l2(c.grad, g["grad_cls"]) < 1e-6 and H.rel_l2(r.grad, g["grad_reg"]) < 1e-6
+    else:
+        assert not rl.requires_grad and float(rl) == 0.0 and float(cl) == 0.0   # no box anywhere: the reference returns zeros
+
+
+def test_focal_loss_forced_assignment_is_the_own_assignment():
+    """The test-only `assign` argument (anchor states handed over by the CUDA implementation) reproduces the oracle's own
+    thresholds when it is given the oracle's own states."""
+    c, r, anchors, ann = H.focal_case_inputs("focal_dense")
+    states = []
+    for b in range(c.shape[0]):
+        gt = torch.as_tensor(ann[b])
+        iou_max, iou_arg = O.box_iou_anchor_gt(anchors[0], gt[:, :4]).max(dim=1)
+        st = torch.full_like(iou_arg, -2)
+        st[iou_max < 0.4] = -1
+        st[iou_max >= 0.5] = iou_arg[iou_max >= 0.5]
+        states.append(st)
+    a = O.focal_loss(c, r, anchors, ann)
+    b = O.focal_loss(c, r, anchors, ann, assign=torch.stack(states))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert int((torch.stack(states) >= 0).sum()) > 20      # the case has positives of several boxes
+
+
 @pytest.mark.parametrize("name", sorted(H.HEAD_CASES))
 def test_heads_match_reference(name):
     """Regressor / Classifier restatement against outputs of the unmodified reference modules."""
