@@ -6,6 +6,7 @@
  *
  *   mmd_mta_fwd / mmd_mta_bwd      replace  MTALoss.forward / .mtaloss / .at and their autograd
  *                                           (src/loss/MTALoss.py:15-34, :36-74, :76-77)
+ *   mmd_focal_fwd / mmd_focal_bwd  replace  YetAnotherFocalLoss.forward and its autograd (src/loss/YetAnotherFocalLoss.py:27-190)
  *   mmd_bifpn_run                  replaces nn.Sequential(*[BiFPN(...)]) forward and its autograd
  *                                           (src/YetAnotherEfficientDet.py:639-644, :668; one cell :320-392;
  *                                            SeparableConvBlock.forward :182-192; same-pad conv / pool
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 106
+#define MMD_VERSION 107
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -80,6 +81,37 @@ typedef struct {
 int mmd_mta_fwd(const MmdMtaArgs* a, mmd_stream_t stream);
 /* grad_fs[l] = grad_loss[l] * (p/C) * fs[l]^(p-1) * ga_ws  (same dtype/layout as fs); needs ga_ws from the fwd */
 int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* const* grad_fs, mmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Detection loss (src/loss/YetAnotherFocalLoss.py:27-190), every sample of the batch in one launch.
+ *   per sample b: IoU of every anchor against the sample's boxes (calc_iou :6-20, same operation order in fp32, so the
+ *   0.4 / 0.5 decisions are the reference's); max-IoU < 0.4 negative, >= 0.5 positive of the arg-max box's class (first
+ *   maximum wins), otherwise ignored; classification scores clamped to [1e-4, 1 - 1e-4]; focal BCE (alpha 0.25, gamma 2)
+ *   summed / max(#positives, 1); smooth-L1 (beta 1/9) of the positives' (dy, dx, dh, dw) against the EfficientDet box
+ *   encoding, mean over #positives * 4; loss[0] = mean_b regression, loss[1] = mean_b classification.
+ *   A sample whose rows are all padding is the reference's "no annotation" branch (all anchors negative, undivided sum).
+ *   The caller handles M == 0 (no box in any sample: the reference returns zeros without touching the predictions).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define MMD_FOCAL_MAX_BOXES 2048
+typedef struct {
+  int32_t B, N, K, M;      /* samples, anchors, classes, (padded) boxes per sample: 1 <= M <= MMD_FOCAL_MAX_BOXES       */
+  int32_t dtype, pad_;     /* MMD_F32 / MMD_BF16: element type of cls / reg and of their gradients                      */
+  float alpha, gamma;      /* 0.25, 2.0 in the reference (:44-45); gamma must be 2                                       */
+  const void* cls;         /* [B][N][K] sigmoid scores                                                                   */
+  const void* reg;         /* [B][N][4] predicted (dy, dx, dh, dw)                                                       */
+  const float* anchors;    /* [N][4] (y1, x1, y2, x2), fp32                                                              */
+  const float* boxes;      /* [B][M][5] (x1, y1, x2, y2, class), fp32; class == -1 marks a padding row                   */
+  double* acc;             /* workspace [B][4]: classification sum, regression sum, #positives, unused.  Zero on entry   */
+                           /* of mmd_focal_fwd; read again by mmd_focal_bwd                                              */
+  int32_t* assign;         /* optional out [B][N]: -2 ignored, -1 negative, m >= 0 positive of the sample's m-th valid box */
+  float* loss;             /* out [2]: regression_loss, classification_loss                                              */
+} MmdFocalArgs;
+
+int mmd_focal_fwd(const MmdFocalArgs* a, mmd_stream_t stream);
+/* grad_cls [B][N][K], grad_reg [B][N][4] (dtype of the inputs; every element is written) from the upstream gradients of
+ * loss[0] / loss[1] (device scalars; NULL = 0).  Needs `acc` as mmd_focal_fwd left it. */
+int mmd_focal_bwd(const MmdFocalArgs* a, const float* grad_reg_loss, const float* grad_cls_loss, void* grad_cls, void* grad_reg,
+                  mmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BiFPN stack.  The host describes the whole multi-cell forward (or backward) as a flat list of ops over
@@ -238,6 +270,7 @@ int mmd_set_option(const char* name, int32_t value);
 /* sizeof(MmdOp) / sizeof(MmdMtaArgs) as compiled, so a binding can verify its struct mirror */
 size_t mmd_sizeof_op(void);
 size_t mmd_sizeof_mta_args(void);
+size_t mmd_sizeof_focal_args(void);
 
 #ifdef __cplusplus
 }

@@ -5,15 +5,17 @@ Public API mirrors the reference (robot-learning-freiburg/MM-DistillNet):
     BiFPN, SeparableConvBlock      src/YetAnotherEfficientDet.py:154-442
     BiFPNStack                     the nn.Sequential of cells built at src/YetAnotherEfficientDet.py:639-644
     Regressor, Classifier          src/YetAnotherEfficientDet.py:445-533 (detection heads on the same kernels)
+    YetAnotherFocalLoss            src/loss/YetAnotherFocalLoss.py:23-190 (detection loss, one launch per direction)
     MTALoss                        src/loss/MTALoss.py:9-77
     patch_reference()              rebinds the reference's module globals to these classes (drop-in seam)
 """
 from .bifpn import BiFPN, BiFPNStack, SeparableConvBlock  # noqa: F401
 from .heads import Classifier, Regressor  # noqa: F401
+from .focal import YetAnotherFocalLoss  # noqa: F401
 from .mta import MTALoss  # noqa: F401
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
 from .distill import DistillStep  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
-__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
+__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
            "launch_count"]

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
 SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_proj_tma.cu", "bifpn_bwd.cu",
-           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "heads.cu", "bifpn_run.cu")
+           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "heads.cu", "focal.cu", "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1
@@ -34,6 +34,15 @@ class MtaArgs(C.Structure):
         ("ft", (C.c_void_p * MTA_MAX_LEVELS) * MTA_MAX_TEACHERS),
         ("att_ws", C.c_void_p), ("ga_ws", C.c_void_p), ("loss_b", C.c_void_p), ("loss", C.c_void_p),
     ]
+
+
+class FocalArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("M", C.c_int32), ("dtype", C.c_int32), ("pad_", C.c_int32),
+                ("alpha", C.c_float), ("gamma", C.c_float), ("cls", C.c_void_p), ("reg", C.c_void_p), ("anchors", C.c_void_p),
+                ("boxes", C.c_void_p), ("acc", C.c_void_p), ("assign", C.c_void_p), ("loss", C.c_void_p)]
+
+
+FOCAL_MAX_BOXES = 2048
 
 
 class Ref(C.Structure):
@@ -173,6 +182,11 @@ def lib():
     L.mmd_mta_fwd.argtypes = [C.POINTER(MtaArgs), C.c_void_p]
     L.mmd_mta_bwd.restype = C.c_int
     L.mmd_mta_bwd.argtypes = [C.POINTER(MtaArgs), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.mmd_focal_fwd.restype = C.c_int
+    L.mmd_focal_fwd.argtypes = [C.POINTER(FocalArgs), C.c_void_p]
+    L.mmd_focal_bwd.restype = C.c_int
+    L.mmd_focal_bwd.argtypes = [C.POINTER(FocalArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mmd_sizeof_focal_args.restype = C.c_size_t
     L.mmd_bifpn_run.restype = C.c_int
     L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -192,6 +206,8 @@ def lib():
     L.mmd_prof_kind_name.argtypes = [C.c_int]
     L.mmd_prof_collect.restype = C.c_int
     L.mmd_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+    if L.mmd_sizeof_focal_args() != C.sizeof(FocalArgs):
+        raise RuntimeError("libmmd_b200.so / _lib.py struct mismatch: MmdFocalArgs %d vs %d" % (L.mmd_sizeof_focal_args(), C.sizeof(FocalArgs)))
     if L.mmd_sizeof_op() != C.sizeof(Op) or L.mmd_sizeof_mta_args() != C.sizeof(MtaArgs):
         raise RuntimeError("libmmd_b200.so struct layout mismatch: Op %d vs %d, MtaArgs %d vs %d" % (
             L.mmd_sizeof_op(), C.sizeof(Op), L.mmd_sizeof_mta_args(), C.sizeof(MtaArgs)))
@@ -228,7 +244,8 @@ def prof_collect():
             for i in range(n) if cnt[i] > 0}
 
 
-EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_set_option", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_bifpn_run", "mmd_bifpn_run_multi",
+EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_set_option", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_focal_fwd",
+           "mmd_focal_bwd", "mmd_sizeof_focal_args", "mmd_bifpn_run", "mmd_bifpn_run_multi",
            "mmd_bifpn_prep", "mmd_packed_bytes",
            "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
            "mmd_prof_collect")

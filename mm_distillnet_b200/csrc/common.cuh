@@ -93,7 +93,9 @@ enum ProfKind {
   // persistent small-level chains (several P5-P7 nodes per launch)
   PK_CHAIN_FWD, PK_CHAIN_BWD,
   // element-wise glue of the detection heads (heads.cu)
-  PK_HEAD, PK_COUNT
+  PK_HEAD,
+  // detection loss (focal.cu)
+  PK_FOCAL, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

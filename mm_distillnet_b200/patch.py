@@ -31,9 +31,11 @@ def fuse_bifpn_stacks(model):
     return model
 
 
-def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=False):
+def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=False, detection_loss=False):
     """Rebind the reference's globals.  Modules default to the already-imported `src.*` modules.  `heads=True` also
-    rebinds the detection heads (their header is limited to 224 output channels, e.g. 9 anchors x 24 classes)."""
+    rebinds the detection heads (their header is limited to 224 output channels, e.g. 9 anchors x 24 classes);
+    `detection_loss=True` rebinds YetAnotherFocalLoss in src.loss.YetAnotherFocalLoss and src.utils.utils (bound by
+    `from ... import` at utils.py:53, instantiated at :1581-1582)."""
     import importlib
     det = det_module or importlib.import_module("src.YetAnotherEfficientDet")
     loss = loss_module or importlib.import_module("src.loss.MTALoss")
@@ -45,6 +47,13 @@ def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=
     utils = utils_module or sys.modules.get("src.utils.utils")
     if utils is not None and hasattr(utils, "MTALoss"):
         utils.MTALoss = MTALoss
+    if detection_loss:
+        from .focal import YetAnotherFocalLoss
+        fl = sys.modules.get("src.loss.YetAnotherFocalLoss")
+        if fl is not None:
+            fl.YetAnotherFocalLoss = YetAnotherFocalLoss
+        if utils is not None and hasattr(utils, "YetAnotherFocalLoss"):
+            utils.YetAnotherFocalLoss = YetAnotherFocalLoss
     cls = det.YetAnotherEfficientDet
     if not getattr(cls, "_mmd_patched", False):
         orig_init = cls.__init__

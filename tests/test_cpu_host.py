@@ -447,3 +447,32 @@ def test_head_modules_mirror_reference_state_dict_and_plan():
     assert "bn.weight" not in blk.state_dict()
     with pytest.raises(NotImplementedError):
         blk(torch.zeros(1, 112, 4, 4))
+
+
+def test_focal_loss_host_side():
+    """YetAnotherFocalLoss: label padding as the reference's annot_padded (:35-39), the mirrored argument
+    struct, no CPU fallback, and the opt-in rebinding of the reference's names."""
+    import types
+    import numpy as np
+    from mm_distillnet_b200 import focal
+    ann = [np.array([[1, 2, 3, 4, 5], [6, 7, 8, 9, 0]], dtype=np.float64), np.zeros((0, 5)), np.array([[1, 1, 2, 2, 3]])]
+    p = focal.pad_annotations(ann)
+    assert p.shape == (3, 2, 5) and p.dtype == np.float32
+    assert (p[1] == -1).all() and (p[2, 1] == -1).all() and p[0, 1, 4] == 0 and p[2, 0, 4] == 3
+    assert focal.pad_annotations([np.zeros((0, 5))] * 2).shape == (2, 0, 5)
+    assert _lib.lib().mmd_sizeof_focal_args() == ctypes.sizeof(_lib.FocalArgs)
+    hdr = open(os.path.join(ROOT, "include", "mmd.h")).read()
+    assert int(re.search(r"#define\s+MMD_FOCAL_MAX_BOXES\s+(\d+)", hdr).group(1)) == _lib.FOCAL_MAX_BOXES
+    crit = mmd.YetAnotherFocalLoss()
+    with pytest.raises(RuntimeError):
+        crit((torch.rand(1, 8, 3), torch.rand(1, 8, 4), torch.rand(1, 8, 4)), [np.zeros((0, 5))])
+    det, loss, utils = types.ModuleType("det"), types.ModuleType("loss"), types.ModuleType("utils")
+
+    class _Det:
+        def __init__(self):
+            pass
+    det.YetAnotherEfficientDet, det.BiFPN = _Det, object
+    loss.MTALoss = object
+    utils.MTALoss, utils.YetAnotherFocalLoss = object, object
+    mmd.patch_reference(det, loss, utils, detection_loss=True)
+    assert utils.YetAnotherFocalLoss is mmd.YetAnotherFocalLoss and utils.MTALoss is mmd.MTALoss
