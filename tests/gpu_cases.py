@@ -87,7 +87,7 @@ def param_class(k):
 
 
 def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channels_last=False, ref64=True,
-                      fw_mode="ones", force_argmax=None):
+                      fw_mode="ones", force_argmax=None, attention=True):
     """CUDA stack vs the oracle (fp64 and fp32) on D2-shaped random data.  Returns metrics for ours and, for
     calibration, for the fp32 oracle against the fp64 oracle.
     force_argmax (default on): every oracle run takes its max-pool arg-max from the window indices the CUDA forward itself
@@ -101,7 +101,7 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
     from mm_distillnet_b200.bifpn import debug_pool_argmax
     C, cc = 112, [48, 120, 352]
     gen = torch.Generator().manual_seed(seed)
-    cells = [mmd.BiFPN(C, cc, first_time=(i == 0 and first)) for i in range(n_cells)]
+    cells = [mmd.BiFPN(C, cc, first_time=(i == 0 and first), attention=attention) for i in range(n_cells)]
     stack = mmd.BiFPNStack(*cells)
     with torch.no_grad():
         for k, p in stack.named_parameters():
@@ -142,10 +142,11 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
                 for k, v in p.items()}
         xin = [x.detach().clone().to(dt).requires_grad_(training) for x in xs]
         if training:
-            out = O.bifpn_stack(tuple(xin), leaf, n_cells, first_cell_first_time=first, training=True, pool_hints=hints)
+            out = O.bifpn_stack(tuple(xin), leaf, n_cells, first_cell_first_time=first, training=True, pool_hints=hints,
+                                attention=attention)
         else:
             with torch.no_grad():
-                out = O.bifpn_stack(tuple(xin), leaf, n_cells, first_cell_first_time=first, training=False)
+                out = O.bifpn_stack(tuple(xin), leaf, n_cells, first_cell_first_time=first, training=False, attention=attention)
         return out, xin, leaf
 
     gout_seed = torch.Generator().manual_seed(seed + 1)
@@ -169,7 +170,7 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
             if not (torch.is_tensor(v) and v.requires_grad) or k.endswith("conv.bias"):
                 continue
             r = leaf_ref[k].grad
-            if r.abs().max().item() == 0.0:
+            if r is None or r.abs().max().item() == 0.0:
                 continue
             cls = param_class(k)
             m["torchbf16_pgrad_" + cls] = max(m.get("torchbf16_pgrad_" + cls, 0.0), H.rel_l2(v.grad.float(), r))
@@ -198,6 +199,10 @@ def random_stack_case(n_cells, first, B, s3, dtype=torch.float32, seed=0, channe
             continue
         cls = param_class(k)
         r = leaf_ref[k].grad
+        if r is None:   # attention=False: the fusion weights exist (state_dict contract) but take no part in _forward (:394-442)
+            assert cls == "fw" and not attention
+            m["zero_grad_abs"] = max(m.get("zero_grad_abs", 0.0), 0.0 if p.grad is None else p.grad.abs().max().item())
+            continue
         if r.abs().max().item() == 0.0:
             # exactly-zero true gradient (e.g. both fusion weights of a node clamped by the ReLU -> constant node):
             # nothing to be relative to; require it to stay at rounding-noise level instead
