@@ -27,3 +27,22 @@ for dtype in (torch.bfloat16, torch.float32):
         stack(tuple(x.detach() for x in xs))
     torch.cuda.synchronize()
     print(dtype, "ok", float(kd.sum()))
+
+# detection heads (node kernels with one input, header halves, gather / scatter / act glue) and the detection loss
+import numpy as np  # noqa: E402
+for dtype in (torch.bfloat16, torch.float32):
+    reg, cls = mmd.Regressor(112, 9, 3).to(dev).train(), mmd.Classifier(112, 9, 20, 3).to(dev).train()
+    feats = [torch.randn(1, 112, max(48 >> i, 1), max(48 >> i, 1), device=dev).to(dtype).requires_grad_(True) for i in range(5)]
+    r, ar = reg(feats)
+    c, ac = cls(feats)
+    N = r.shape[1]
+    xy = torch.rand(N, 2, device=dev) * 300
+    anchors = torch.cat([xy, xy + 20 + torch.rand(N, 2, device=dev) * 100], dim=1).unsqueeze(0)
+    ann = [np.array([[20, 30, 200, 180, 3], [100, 90, 260, 300, 7]], dtype=np.float32)]
+    lr, lc = mmd.YetAnotherFocalLoss()((c, r, anchors), ann)
+    (lr + lc + ar.float().mean() + ac.float().mean()).sum().backward()
+    reg.eval()
+    with torch.no_grad():
+        reg([f.detach() for f in feats])
+    torch.cuda.synchronize()
+    print(dtype, "heads + focal ok", float(lr), float(lc))
