@@ -156,6 +156,61 @@ def run_mta_case(name, B, C, sizes, seed):
     print(name, "->", len(out), "arrays")
 
 
+PSEUDO_VALID_IDS = [2, 4, 6, 7, 9, 11, 14, 16, 19]    # prediction ids of the classes kept (mirrored by tests/helpers.py)
+PSEUDO_CASES = {"pseudo_a": (4, 128, 20, 100, 3)}       # name -> (B, image size, classes, seed, teachers)
+
+
+def reference_pseudo_label_functions():
+    """EfficientDet_post_processing / logits_to_ground_truth / ClipBoxes exactly as written in the reference, compiled from
+    their lines of src/utils/utils.py (:123-324) — the module itself does not import here (librosa, tensorboardX,
+    hpbandster, ... are not installed) and none of its other 2 300 lines is on this path."""
+    import torch.nn as nn
+    from torchvision.ops import nms
+    from torchvision.ops.boxes import batched_nms
+    from src.YetAnotherEfficientDet import YetAnotherEfficientDetBBoxTransform
+    txt = open("/root/reference/src/utils/utils.py").read()
+    sl = txt[txt.index("class ClipBoxes"):txt.index("def filter_model_dict")]
+    ns = {"torch": torch, "nn": nn, "np": np, "batched_nms": batched_nms, "nms": nms,
+          "YetAnotherEfficientDetBBoxTransform": YetAnotherEfficientDetBBoxTransform, "EfficientDetBBoxTransform": None}
+    exec(compile(sl, "/root/reference/src/utils/utils.py[123:324]", "exec"), ns)
+    return ns, nms
+
+
+def run_pseudo_case(name, B, size, K, seed, n_teachers):
+    """Reference pseudo-label generation: logits_to_ground_truth(include_scores=True) per teacher (train_methods.py:343-349)
+    and the cross-teacher integration (:360-411, restated here line by line around torchvision's nms, as it is inline
+    code of a forward method)."""
+    import configparser
+    ns, nms = reference_pseudo_label_functions()
+    cfg = configparser.ConfigParser()
+    cfg.read_dict({"s": {"conf_threshold": "0.3", "nms_threshold": "0.5", "image_size": str(size),
+                         "student": "YetAnotherEfficientDet", "ignore_labels": "4"}})
+    vcd = {"predictions_txt2i": {"c%d" % i: i for i in PSEUDO_VALID_IDS}, "predictions_i2txt": {i: "c%d" % i for i in PSEUDO_VALID_IDS},
+           "labels_txt2i": {"c%d" % i: n for n, i in enumerate(PSEUDO_VALID_IDS)}}
+    anchors = Anchors(anchor_scale=4.)(torch.zeros(1, 3, size, size), torch.float32)
+    out = {"anchors": anchors.numpy()}
+    batch_labels = [[] for _ in range(B)]
+    for t in range(n_teachers):
+        c, r = O.synth_teacher_logits(B, anchors, K, seed + 10 * t, size=size)
+        this = ns["logits_to_ground_truth"](logits=(c, r, anchors), anchors=None, valid_classes_dict=vcd, config=cfg["s"],
+                                            include_scores=True)
+        for b in range(B):
+            out["t%d_b%d" % (t, b)] = np.asarray(this[b], dtype=np.float32)
+            if np.asarray(this[b]).size == 0:
+                continue
+            batch_labels[b] = this[b] if len(batch_labels[b]) == 0 else np.concatenate((batch_labels[b], this[b]), axis=0)
+    for b in range(B):
+        if len(batch_labels[b]) == 0:
+            out["merged_b%d" % b] = np.zeros((0, 5), dtype=np.float32)
+            continue
+        idx = nms(boxes=torch.from_numpy(batch_labels[b][:, 0:4]), scores=torch.from_numpy(batch_labels[b][:, 4]),
+                  iou_threshold=0.5).numpy()
+        out["merged_b%d" % b] = np.delete(batch_labels[b], 4, 1)[idx]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "per teacher:", [[out["t%d_b%d" % (t, b)].shape[0] for b in range(B)] for t in range(n_teachers)],
+          "merged:", [out["merged_b%d" % b].shape[0] for b in range(B)])
+
+
 def run_focal_case(name, kind, B, size, K, seed):
     """Reference YetAnotherFocalLoss on the reference's own Anchors for a size x size image: losses and the gradients of
     1.3 * regression_loss + 0.7 * classification_loss w.r.t. the classification scores and box deltas."""
@@ -186,6 +241,9 @@ def main():
     # D2 channel counts (what the CUDA kernels are built for), tiny spatial size; full parameter gradients as well
     run_stack_case("stack2_c112", 112, [48, 120, 352], 2, True, B=2, s3=16, seed=5, save_param_grads=True)
     run_stack_case("cell_c112", 112, [48, 120, 352], 1, False, B=2, s3=16, seed=6, save_param_grads=True)
+    # pseudo-label generation
+    for name, (B, size, K, seed, nt) in PSEUDO_CASES.items():
+        run_pseudo_case(name, B, size, K, seed, nt)
     # detection loss: the reference's own anchors for a 128x128 image (3 069 boxes), 20 classes
     for name, (kind, B, size, K, seed) in FOCAL_CASES.items():
         run_focal_case(name, kind, B, size, K, seed)

@@ -441,6 +441,161 @@ def synth_annotations(kind, B, size, K):
 
 
 # ----------------------------------------------------------------------------------------------
+# pseudo-label generation
+# ----------------------------------------------------------------------------------------------
+def decode_boxes(anchors, regression):
+    """YetAnotherEfficientDetBBoxTransform.forward (src/YetAnotherEfficientDet.py:574-602): anchors [1|B,N,4] (y1,x1,y2,x2),
+    regression [B,N,4] (dy,dx,dh,dw) -> [B,N,4] (xmin, ymin, xmax, ymax)."""
+    yc_a = (anchors[..., 0] + anchors[..., 2]) / 2
+    xc_a = (anchors[..., 1] + anchors[..., 3]) / 2
+    ha = anchors[..., 2] - anchors[..., 0]
+    wa = anchors[..., 3] - anchors[..., 1]
+    w = regression[..., 3].exp() * wa
+    h = regression[..., 2].exp() * ha
+    yc = regression[..., 0] * ha + yc_a
+    xc = regression[..., 1] * wa + xc_a
+    return torch.stack([xc - w / 2., yc - h / 2., xc + w / 2., yc + h / 2.], dim=2)
+
+
+def nms_greedy(boxes, scores, iou_threshold):
+    """torchvision.ops.nms (torchvision 0.26.0, the reference's dependency, not vendored in /root/reference), restated from
+    its published CPU algorithm: candidates in STABLE descending score order; a kept box suppresses every later box whose
+    IoU = inter / (area_i + area_j - inter) is > iou_threshold (areas (x2-x1)*(y2-y1), intersection sides clamped at 0).
+    Returns the kept indices in score order.  boxes [n,4] (x1,y1,x2,y2)."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int64)
+    order = torch.sort(scores, stable=True, descending=True).indices
+    x1, y1, x2, y2 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    areas = (x2 - x1) * (y2 - y1)
+    dead = torch.zeros(n, dtype=torch.bool)
+    keep = []
+    for a in range(n):
+        i = int(order[a])
+        if dead[i]:
+            continue
+        keep.append(i)
+        rest = order[a + 1:]
+        w = (torch.minimum(x2[i], x2[rest]) - torch.maximum(x1[i], x1[rest])).clamp(min=0)
+        h = (torch.minimum(y2[i], y2[rest]) - torch.maximum(y1[i], y1[rest])).clamp(min=0)
+        inter = w * h
+        dead[rest[inter / (areas[i] + areas[rest] - inter) > iou_threshold]] = True
+    return torch.tensor(keep, dtype=torch.int64)
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """torchvision.ops.batched_nms, coordinate-trick branch (what it takes below 4 000 boxes on the CPU / 20 000 on CUDA):
+    every class is moved to its own region by adding class * (max coordinate + 1) to its boxes, then one nms."""
+    if boxes.numel() == 0:
+        return torch.zeros(0, dtype=torch.int64)
+    offsets = idxs.to(boxes) * (boxes.max() + torch.tensor(1).to(boxes))
+    return nms_greedy(boxes + offsets[:, None], scores, iou_threshold)
+
+
+def detections(classification, regression, anchors, valid_prediction_ids, conf_threshold, nms_threshold, image_size,
+               ignore_labels=()):
+    """EfficientDet_post_processing (src/utils/utils.py:144-231) up to the numeric result: per sample an array [n,6]
+    (xmin, ymin, xmax, ymax, score, class) in NMS order.  Decode (:176), clip x/y minima at 0 and maxima at image_size
+    (ClipBoxes :123-141), score = max class probability > conf_threshold (:178-179), arg-max class restricted to
+    `valid_prediction_ids` (:197-204), class-wise NMS (:205), `ignore_labels` dropped (:212-215).
+    Reference quirk kept: the reported score column is taken from the arg-max scores of ALL over-threshold anchors but
+    indexed with positions in the class-FILTERED list (:195 vs :202-209), i.e. row j of the filtered list reports the score
+    of the j-th over-threshold anchor; identical whenever no over-threshold anchor has a non-valid class."""
+    boxes = decode_boxes(anchors[[0]], regression)
+    boxes = torch.stack([boxes[..., 0].clamp(min=0), boxes[..., 1].clamp(min=0), boxes[..., 2].clamp(max=image_size),
+                         boxes[..., 3].clamp(max=image_size)], dim=2)
+    scores = classification.max(dim=2).values
+    out = []
+    valid = torch.tensor(sorted(valid_prediction_ids), dtype=torch.int64)
+    for b in range(classification.shape[0]):
+        over = scores[b] > conf_threshold
+        if int(over.sum()) == 0:
+            out.append(torch.zeros((0, 6), dtype=classification.dtype))
+            continue
+        all_scores, classes = classification[b, over].max(dim=1)
+        bx, sc = boxes[b, over], scores[b, over]
+        m = (classes[:, None] == valid[None, :]).any(-1)
+        bx, cl, sc = bx[m], classes[m], sc[m]
+        keep = batched_nms(bx, sc, cl, nms_threshold)
+        if keep.numel() == 0:
+            out.append(torch.zeros((0, 6), dtype=classification.dtype))
+            continue
+        cl_k, sc_k, bx_k = cl[keep], all_scores[keep], bx[keep]
+        for lab in ignore_labels:
+            sel = cl_k != lab
+            bx_k, sc_k, cl_k = bx_k[sel], sc_k[sel], cl_k[sel]
+        out.append(torch.cat([bx_k, sc_k[:, None], cl_k[:, None].to(bx_k)], dim=1))
+    return out
+
+
+def logits_to_ground_truth(logits, valid_prediction_ids, label_of_prediction, conf_threshold, nms_threshold, image_size,
+                           ignore_labels=(), include_scores=False):
+    """logits_to_ground_truth (src/utils/utils.py:234-324) with text_classes=False: per sample a float32 array of rows
+    [int(max(xmin,0)), int(max(ymin,0)), int(min(xmax,S)), int(min(ymax,S)), (score,) label] where label =
+    labels_txt2i[predictions_i2txt[class]] (here: `label_of_prediction[class]`)."""
+    import numpy as np
+    classification, regression, anchors = logits
+    res = []
+    for det in detections(classification, regression, anchors, valid_prediction_ids, conf_threshold, nms_threshold,
+                          image_size, ignore_labels):
+        rows = []
+        for p in det.tolist():
+            row = [int(max(p[0], 0)), int(max(p[1], 0)), int(min(p[2], image_size)), int(min(p[3], image_size))]
+            if include_scores:
+                row.append(p[4])
+            row.append(label_of_prediction[int(p[5])])
+            rows.append(row)
+        res.append(np.array(rows, dtype=np.float32))
+    return res
+
+
+def merge_teacher_labels(per_teacher, iou_threshold=0.5):
+    """The cross-teacher integration of the step wrappers (src/optimization/train_methods.py:360-411, augment=False):
+    per sample, the teachers' [n,6] label arrays (with scores) are concatenated in teacher order, class-agnostic NMS at
+    IoU 0.5 on the (integer-valued) boxes, the score column dropped, rows taken in NMS order.  A sample no teacher labelled
+    stays an empty list."""
+    import numpy as np
+    B = len(per_teacher[0])
+    out = []
+    for b in range(B):
+        rows = [np.asarray(t[b], dtype=np.float32).reshape(-1, 6) for t in per_teacher if np.asarray(t[b]).size > 0]
+        if not rows:
+            out.append([])
+            continue
+        cat = np.concatenate(rows, axis=0)
+        keep = nms_greedy(torch.from_numpy(cat[:, 0:4]), torch.from_numpy(cat[:, 4]), iou_threshold).numpy()
+        out.append(np.delete(cat, 4, 1)[keep])
+    return out
+
+
+def synth_teacher_logits(B, anchors, K, seed, n_objects=6, size=128):
+    """Detector-like outputs: every anchor gets a low background score; anchors overlapping one of a few pseudo objects get
+    a high score for the object's class and box deltas that pull them towards it, so that thresholding + NMS has real work
+    (clusters of overlapping over-threshold boxes, several classes, some over-threshold boxes of non-valid classes)."""
+    N = anchors.shape[1]
+    a = anchors[0]
+    cls = 0.02 + 0.1 * (0.5 + 0.5 * synth((B, N, K), seed, 1.0, 0.0))
+    reg = 0.05 * synth((B, N, 4), seed + 1, 1.0, 0.0)
+    ha, wa = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+    yc, xc = (a[:, 0] + a[:, 2]) / 2, (a[:, 1] + a[:, 3]) / 2
+    for b in range(B):
+        for j in range(n_objects if b % 3 != 2 else 0):          # every third sample: nothing above the threshold
+            t = 0.77 * (b + 1) + 1.31 * j + 0.013 * seed
+            ox, oy = size * (0.5 + 0.35 * math.sin(t)), size * (0.5 + 0.35 * math.cos(1.3 * t))
+            ow, oh = size * (0.15 + 0.2 * math.sin(2.1 * t) ** 2), size * (0.15 + 0.25 * math.cos(0.7 * t) ** 2)
+            k = (2 * b + 3 * j) % K
+            gt = torch.tensor([[ox - ow / 2, oy - oh / 2, ox + ow / 2, oy + oh / 2]])
+            iou = box_iou_anchor_gt(a, gt)[:, 0]
+            hit = iou > 0.35
+            cls[b, hit, k] = (0.25 + 0.7 * iou[hit]).clamp(max=0.97) + 0.01 * synth((int(hit.sum()),), seed + 7 * j + b, 1.0, 0.0)
+            reg[b, hit, 0] = (oy - yc[hit]) / ha[hit] * 0.9
+            reg[b, hit, 1] = (ox - xc[hit]) / wa[hit] * 0.9
+            reg[b, hit, 2] = torch.log(oh / ha[hit]) * 0.9
+            reg[b, hit, 3] = torch.log(ow / wa[hit]) * 0.9
+    return cls.clamp(0.0, 1.0), reg
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic, RNG-free data so fixtures never depend on a torch/numpy RNG stream
 # ----------------------------------------------------------------------------------------------
 def synth(shape, seed, scale=1.0, offset=0.0, dtype=torch.float32):

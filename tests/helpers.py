@@ -22,6 +22,10 @@ STACK_CASES = {
 HEAD_CASES = {"reg_c112": ("reg", 112, 9, 20, 3, 2, 16, 9), "cls_c112": ("cls", 112, 9, 20, 3, 2, 16, 10)}
 # name -> (annotation kind, B, image size, classes, seed)   (must mirror oracle/make_golden.py FOCAL_CASES)
 FOCAL_CASES = {"focal_mixed": ("mixed", 4, 128, 20, 21), "focal_dense": ("dense", 2, 128, 20, 22), "focal_none": ("none", 2, 128, 20, 23)}
+# pseudo-label generation (must mirror oracle/make_golden.py PSEUDO_*): name -> (B, image size, classes, seed, teachers)
+PSEUDO_VALID_IDS = [2, 4, 6, 7, 9, 11, 14, 16, 19]
+PSEUDO_CASES = {"pseudo_a": (4, 128, 20, 100, 3)}
+PSEUDO_CFG = dict(conf_threshold=0.3, nms_threshold=0.5, ignore_labels=(4,))
 MTA_CASES = {"mta_c112": (2, 112, [12, 6, 3], 7), "mta_c16": (3, 16, [16, 8, 4, 2, 1], 8)}
 
 
@@ -43,6 +47,14 @@ def stack_case_inputs(name, dtype=torch.float32):
     params = O.synth_stack_params(C, cc, n_cells, seed, first_cell_first_time=first, dtype=dtype)
     xs = backbone_inputs(B, cc, s3, seed + 50, dtype) if first else pyramid_inputs(B, C, s3, seed + 50, dtype)
     return params, xs
+
+
+def pseudo_case_inputs(name):
+    """-> anchors [1,N,4] (the reference's), [(classification, regression)] per teacher, label id of every valid prediction id."""
+    B, size, K, seed, nt = PSEUDO_CASES[name]
+    anchors = torch.from_numpy(golden(name)["anchors"])
+    logits = [O.synth_teacher_logits(B, anchors, K, seed + 10 * t, size=size) for t in range(nt)]
+    return anchors, logits, {i: n for n, i in enumerate(PSEUDO_VALID_IDS)}
 
 
 def focal_case_inputs(name, dtype=torch.float32):

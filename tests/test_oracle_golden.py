@@ -56,6 +56,31 @@ def test_stack_matches_reference(name):
             assert abs(v.grad.double().norm().item() - nrm) <= tol * max(nrm, 1e-6), k
 
 
+@pytest.mark.parametrize("name", sorted(H.PSEUDO_CASES))
+def test_pseudo_labels_match_reference(name):
+    """Pseudo-label restatement (decode, clip, threshold, class filter, class-wise NMS, label mapping, the
+    cross-teacher NMS) against the outputs of the reference's own functions: identical rows in identical order."""
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    g = H.golden(name)
+    anchors, logits, label_of = H.pseudo_case_inputs(name)
+    per_teacher = []
+    for t, (c, r) in enumerate(logits):
+        got = O.logits_to_ground_truth((c, r, anchors), H.PSEUDO_VALID_IDS, label_of, image_size=size, include_scores=True,
+                                       **H.PSEUDO_CFG)
+        for b in range(B):
+            ref = g["t%d_b%d" % (t, b)]
+            assert got[b].shape == ref.shape and np.array_equal(got[b], ref), (t, b)
+        per_teacher.append(got)
+    assert sum(g["t0_b%d" % b].shape[0] for b in range(B)) >= 8            # the case has real detections ...
+    assert any(g["t0_b%d" % b].size == 0 for b in range(B))                 # ... and a sample without any
+    merged = O.merge_teacher_labels(per_teacher)
+    for b in range(B):
+        ref = g["merged_b%d" % b]
+        got = np.zeros((0, 5), dtype=np.float32) if len(merged[b]) == 0 else merged[b]
+        assert got.shape == ref.shape and np.array_equal(got, ref), b
+    assert any(g["merged_b%d" % b].shape[0] < sum(g["t%d_b%d" % (t, b)].shape[0] for t in range(nt)) for b in range(B))
+
+
 @pytest.mark.parametrize("name", sorted(H.FOCAL_CASES))
 def test_focal_loss_matches_reference(name):
     """YetAnotherFocalLoss restatement against the reference's losses and gradients on its own anchors."""
