@@ -7,6 +7,9 @@
  *   mmd_mta_fwd / mmd_mta_bwd      replace  MTALoss.forward / .mtaloss / .at and their autograd
  *                                           (src/loss/MTALoss.py:15-34, :36-74, :76-77)
  *   mmd_focal_fwd / mmd_focal_bwd  replace  YetAnotherFocalLoss.forward and its autograd (src/loss/YetAnotherFocalLoss.py:27-190)
+ *   mmd_pseudo_labels              replaces logits_to_ground_truth / EfficientDet_post_processing per teacher
+ *                                           (src/utils/utils.py:144-231, :234-324) and the cross-teacher integration + nms of
+ *                                           the step wrappers (src/optimization/train_methods.py:186-250, :343-411)
  *   mmd_bifpn_run                  replaces nn.Sequential(*[BiFPN(...)]) forward and its autograd
  *                                           (src/YetAnotherEfficientDet.py:639-644, :668; one cell :320-392;
  *                                            SeparableConvBlock.forward :182-192; same-pad conv / pool
@@ -33,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 107
+#define MMD_VERSION 108
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -90,7 +93,9 @@ int mmd_mta_bwd(const MmdMtaArgs* a, const float* grad_loss, void* const* grad_f
  *   summed / max(#positives, 1); smooth-L1 (beta 1/9) of the positives' (dy, dx, dh, dw) against the EfficientDet box
  *   encoding, mean over #positives * 4; loss[0] = mean_b regression, loss[1] = mean_b classification.
  *   A sample whose rows are all padding is the reference's "no annotation" branch (all anchors negative, undivided sum).
- *   The caller handles M == 0 (no box in any sample: the reference returns zeros without touching the predictions).
+ *   No valid box in ANY sample: both losses are zeros that do not depend on the predictions (:61-62, :181-188) and every
+ *   gradient is zero -- decided on the device (acc[b][3] = valid rows of sample b), so `boxes` may come straight from
+ *   mmd_pseudo_labels.  A caller that knows M == 0 on the host simply does not call.
  * ---------------------------------------------------------------------------------------------------------- */
 #define MMD_FOCAL_MAX_BOXES 2048
 typedef struct {
@@ -101,8 +106,8 @@ typedef struct {
   const void* reg;         /* [B][N][4] predicted (dy, dx, dh, dw)                                                       */
   const float* anchors;    /* [N][4] (y1, x1, y2, x2), fp32                                                              */
   const float* boxes;      /* [B][M][5] (x1, y1, x2, y2, class), fp32; class == -1 marks a padding row                   */
-  double* acc;             /* workspace [B][4]: classification sum, regression sum, #positives, unused.  Zero on entry   */
-                           /* of mmd_focal_fwd; read again by mmd_focal_bwd                                              */
+  double* acc;             /* workspace [B][4]: classification sum, regression sum, #positives, #valid boxes.  Zero on   */
+                           /* entry of mmd_focal_fwd; read again by mmd_focal_bwd                                        */
   int32_t* assign;         /* optional out [B][N]: -2 ignored, -1 negative, m >= 0 positive of the sample's m-th valid box */
   float* loss;             /* out [2]: regression_loss, classification_loss                                              */
 } MmdFocalArgs;
@@ -112,6 +117,57 @@ int mmd_focal_fwd(const MmdFocalArgs* a, mmd_stream_t stream);
  * loss[0] / loss[1] (device scalars; NULL = 0).  Needs `acc` as mmd_focal_fwd left it. */
 int mmd_focal_bwd(const MmdFocalArgs* a, const float* grad_reg_loss, const float* grad_cls_loss, void* grad_cls, void* grad_reg,
                   mmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pseudo-label generation: the teachers' detections become the student's annotations without leaving
+ * the device.  Per teacher t and sample b, as EfficientDet_post_processing (src/utils/utils.py:144-231) does:
+ *   score = max_k cls[b][n][k] (first maximum = class), kept when score > conf_threshold (:178-179); the class must be a
+ *   valid prediction id (:197-204, label_of[class] >= 0); box = YetAnotherEfficientDetBBoxTransform (src/
+ *   YetAnotherEfficientDet.py:574-602) of (anchor, regression), clipped by ClipBoxes (:123-141: minima at 0, maxima at
+ *   image_size); class-wise NMS = torchvision batched_nms' coordinate trick (class * (max coordinate + 1) added to the
+ *   boxes) + greedy NMS in stable descending score order, a kept box suppressing IoU > nms_threshold (:205); rows of an
+ *   `ignore` class are dropped AFTER the NMS (:212-215).  Reference quirk kept: the reported score of row j of the
+ *   class-filtered list is the score of the j-th over-threshold anchor (:195 indexes the unfiltered list).
+ *   logits_to_ground_truth (:291-321): row = [trunc(max(x1,0)), trunc(max(y1,0)), trunc(min(x2,S)), trunc(min(y2,S)),
+ *   score, label_of[class]].
+ * Then the step wrappers' integration (train_methods.py:360-411): per sample the teachers' rows are concatenated in
+ * teacher order, ONE class-agnostic greedy NMS at merge_iou (0.5) over the truncated boxes, the score column dropped:
+ *   labels[b][r] = (x1, y1, x2, y2, label) in NMS order, rows >= counts[b] filled with -1 -- exactly the padded
+ *   annotation tensor MmdFocalArgs.boxes takes, so the detection loss follows on the same stream with no host round trip.
+ * All arithmetic that decides an index (threshold compares, IoU, arg-max, ordering) is fp32 with every operation rounded
+ * on its own (no FMA contraction): identical decisions to the fp32 reference.  Launches: 4 for all teachers together.
+ * Capacities (the reference has none): at most `cap` over-threshold anchors per (teacher, sample), `max_rows` rows per
+ * (teacher, sample) after the NMS, `max_labels` merged rows per sample; anything beyond is dropped in score order and
+ * counts[B] (a bit mask: 1 = cap, 2 = max_rows, 4 = max_labels) says so.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define MMD_PL_MAX_TEACHERS 8
+#define MMD_PL_MAX_CAP 8192
+#define MMD_PL_MAX_IGNORE 8
+typedef struct {
+  int32_t B, N, K, T;            /* samples, anchors, classes (<= 255), teachers (<= MMD_PL_MAX_TEACHERS)                     */
+  int32_t dtype;                 /* MMD_F32 / MMD_BF16: element type of cls / reg                                             */
+  int32_t cap;                   /* <= MMD_PL_MAX_CAP over-threshold anchors per (teacher, sample)                            */
+  int32_t max_rows;              /* rows per (teacher, sample) after the class-wise NMS; T * max_rows <= MMD_PL_MAX_CAP       */
+  int32_t max_labels;            /* M: rows per sample of `labels` (<= MMD_FOCAL_MAX_BOXES when the loss consumes them)       */
+  int32_t raw_rows;              /* 1: teacher_rows = EfficientDet_post_processing's rows (unclipped-to-int boxes, score,     */
+                                 /*    class id); 0: logits_to_ground_truth's rows (truncated boxes, score, label)            */
+  int32_t n_ignore;
+  int32_t ignore[MMD_PL_MAX_IGNORE]; /* prediction ids dropped after the NMS (config 'ignore_labels')                         */
+  float conf_threshold, image_size;
+  double nms_threshold, merge_iou;   /* compared as torchvision does: (double)iou > threshold                                 */
+  const void* cls[MMD_PL_MAX_TEACHERS]; /* [B][N][K] class probabilities                                                      */
+  const void* reg[MMD_PL_MAX_TEACHERS]; /* [B][N][4] (dy, dx, dh, dw)                                                         */
+  const float* anchors;          /* [N][4] (y1, x1, y2, x2)                                                                   */
+  const int32_t* label_of;       /* [K]: label id of prediction id k, -1 = not a valid prediction id                          */
+  void* workspace;               /* mmd_pseudo_workspace_bytes(a) bytes, 16-byte aligned; contents need no initialisation     */
+  float* teacher_rows;           /* out [T][B][max_rows][6]                                                                   */
+  int32_t* teacher_counts;       /* out [T][B]                                                                                */
+  float* labels;                 /* out [B][max_labels][5]                                                                    */
+  int32_t* counts;               /* out [B + 1]: merged rows per sample; [B] = overflow bit mask                              */
+} MmdPseudoArgs;
+
+size_t mmd_pseudo_workspace_bytes(const MmdPseudoArgs* a);
+int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BiFPN stack.  The host describes the whole multi-cell forward (or backward) as a flat list of ops over
@@ -271,6 +327,7 @@ int mmd_set_option(const char* name, int32_t value);
 size_t mmd_sizeof_op(void);
 size_t mmd_sizeof_mta_args(void);
 size_t mmd_sizeof_focal_args(void);
+size_t mmd_sizeof_pseudo_args(void);
 
 #ifdef __cplusplus
 }

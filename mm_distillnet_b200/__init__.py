@@ -7,15 +7,23 @@ Public API mirrors the reference (robot-learning-freiburg/MM-DistillNet):
     Regressor, Classifier          src/YetAnotherEfficientDet.py:445-533 (detection heads on the same kernels)
     YetAnotherFocalLoss            src/loss/YetAnotherFocalLoss.py:23-190 (detection loss, one launch per direction)
     MTALoss                        src/loss/MTALoss.py:9-77
+    logits_to_ground_truth,
+    teacher_pseudo_labels          src/utils/utils.py:144-324 + the cross-teacher integration (train_methods.py:360-411):
+                                   pseudo-labels made and consumed on the device
+    ModelWithNMSLoss, ModelWithNMSKDListLoss,
+    ModelWithNMSLossAugmented      the step wrappers src/optimization/train_methods.py:165-262, :265-422, :425-516
     patch_reference()              rebinds the reference's module globals to these classes (drop-in seam)
 """
 from .bifpn import BiFPN, BiFPNStack, SeparableConvBlock  # noqa: F401
 from .heads import Classifier, Regressor  # noqa: F401
 from .focal import YetAnotherFocalLoss  # noqa: F401
 from .mta import MTALoss  # noqa: F401
+from .pseudo import PseudoLabels, logits_to_ground_truth, teacher_pseudo_labels  # noqa: F401
+from .wrappers import ModelWithNMSKDListLoss, ModelWithNMSLoss, ModelWithNMSLossAugmented  # noqa: F401
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
 from .distill import DistillStep  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
-__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
+__all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "PseudoLabels", "logits_to_ground_truth",
+           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
            "launch_count"]

@@ -95,7 +95,9 @@ enum ProfKind {
   // element-wise glue of the detection heads (heads.cu)
   PK_HEAD,
   // detection loss (focal.cu)
-  PK_FOCAL, PK_COUNT
+  PK_FOCAL,
+  // pseudo-label generation (pseudo.cu): the two passes over the anchors
+  PK_PSEUDO, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

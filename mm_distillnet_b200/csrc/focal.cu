@@ -110,7 +110,23 @@ __global__ void __launch_bounds__(kThreads) focal_kernel(const __grid_constant__
   const int b = blockIdx.y, tid = threadIdx.x;
   const int n0 = blockIdx.x * kThreads, n = n0 + tid;
   for (int i = tid; i < 5 * P.M; i += kThreads) s_box[i] = P.boxes[(size_t)b * P.M * 5 + i];
+  __shared__ int s_any;        // backward: does ANY sample of the batch have a valid box (:61-62, :181-188)
+  __shared__ int s_mend;       // rows behind the last valid one are padding: a [B][256][5] tensor of device-made labels
+  if (tid == 0) s_mend = 0;    // with a handful of boxes costs what the boxes cost
+  if (BWD && tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < P.B; ++i) tot += P.acc[4 * i + 3];
+    s_any = tot > 0.0;
+  }
   __syncthreads();
+  for (int m = tid; m < P.M; m += kThreads)
+    if (s_box[5 * m + 4] != -1.f) atomicMax(&s_mend, m + 1);
+  __syncthreads();
+  if (!BWD && blockIdx.x == 0 && tid == 0) {     // acc[b][3] = valid rows of this sample (labels may be device-made)
+    int nv = 0;
+    for (int m = 0; m < P.M; ++m) nv += s_box[5 * m + 4] != -1.f;
+    P.acc[4 * b + 3] = (double)nv;
+  }
 
   // ---- phase A ----
   float reg_part = 0.f, pos_part = 0.f;
@@ -120,11 +136,12 @@ __global__ void __launch_bounds__(kThreads) focal_kernel(const __grid_constant__
     const float g_r = P.g_reg_loss ? *P.g_reg_loss : 0.f, g_c = P.g_cls_loss ? *P.g_cls_loss : 0.f;
     gc_scale = (float)((double)g_c / P.B / (npos > 1.0 ? npos : 1.0));
     gr_scale = npos > 0.0 ? (float)((double)g_r / P.B / (4.0 * npos)) : 0.f;
+    if (!s_any) gc_scale = gr_scale = 0.f;
   }
   int state = kIgnore;
   if (n < P.N) {
     const float4 a = *reinterpret_cast<const float4*>(P.anchors + 4 * (size_t)n);
-    const Assign as = assign_anchor(a, s_box, P.M, P.K);
+    const Assign as = assign_anchor(a, s_box, s_mend, P.K);
     state = as.state >= 0 ? (as.cls >= 0 ? as.cls : 1 << 20) : as.state;   // 1 << 20: positive without a valid class
     if (!BWD && P.assign) P.assign[(size_t)b * P.N + n] = as.state;
     const size_t ro = ((size_t)b * P.N + n) * 4;
@@ -210,8 +227,9 @@ __global__ void __launch_bounds__(kThreads) focal_kernel(const __grid_constant__
 __global__ void focal_finish_kernel(const double* __restrict__ acc, int B, float* __restrict__ loss) {
   // regression_loss = mean_b (npos_b > 0 ? reg_sum_b / (4 npos_b) : 0); classification_loss = mean_b cls_sum_b / max(npos_b, 1)
   if (threadIdx.x == 0) {
-    double r = 0.0, c = 0.0;
-    for (int b = 0; b < B; ++b) {
+    double r = 0.0, c = 0.0, any = 0.0;
+    for (int b = 0; b < B; ++b) any += acc[4 * b + 3];
+    for (int b = 0; b < B && any > 0.0; ++b) {
       const double npos = acc[4 * b + 2];
       c += acc[4 * b + 0] / (npos > 1.0 ? npos : 1.0);
       if (npos > 0.0) r += acc[4 * b + 1] / (4.0 * npos);

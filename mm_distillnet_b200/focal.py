@@ -1,8 +1,8 @@
 """Drop-in for the reference's detection loss (src/loss/YetAnotherFocalLoss.py:23-190) on one sm_100a kernel per direction.
 
 `YetAnotherFocalLoss()(prediction, annotations)` keeps the reference's call: `prediction = (classifications [B,N,K],
-regressions [B,N,4], anchors [1,N,4])`, `annotations` = a list of B numpy arrays `[M_b, 5]` (x1, y1, x2, y2, class), and
-returns `(regression_loss [1], classification_loss [1])`.  The whole batch is ONE launch (`mmd_focal_fwd`): the labels
+regressions [B,N,4], anchors [1,N,4])`, `annotations` = a list of B numpy arrays `[M_b, 5]` (x1, y1, x2, y2, class) — or a
+device-resident `PseudoLabels` (pseudo.py: the teachers' labels, never copied to the host) — and returns `(regression_loss [1], classification_loss [1])`.  The whole batch is ONE launch (`mmd_focal_fwd`): the labels
 are padded on the host and copied once, the IoU matrix, the assignment and the per-sample temporaries never exist in
 HBM.  CUDA only; predictions float32 or bfloat16, loss values float32.  No CPU fallback.
 """
@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .pseudo import PseudoLabels
 
 ALPHA, GAMMA = 0.25, 2.0     # src/loss/YetAnotherFocalLoss.py:44-45
 
@@ -90,15 +91,24 @@ class YetAnotherFocalLoss(nn.Module):
         if anchors.dim() != 3 or anchors.shape[1] != N or anchors.shape[2] != 4:
             raise ValueError("anchors must be [1,N,4] with N=%d, got %s" % (N, tuple(anchors.shape)))
         dev = classifications.device
-        padded = pad_annotations(annotations)
-        if padded.shape[1] == 0:
-            # no box in any sample: the reference skips every sample (:61-62) and returns zeros that do not depend on the
-            # predictions (:181-188)
-            z = torch.zeros(1, dtype=torch.float32, device=dev)
-            return z, z.clone()
-        if padded.shape[1] > _lib.FOCAL_MAX_BOXES:
-            raise ValueError("at most %d boxes per sample, got %d" % (_lib.FOCAL_MAX_BOXES, padded.shape[1]))
-        boxes = torch.from_numpy(padded).to(dev, non_blocking=True)
+        if isinstance(annotations, PseudoLabels):
+            # labels made on this device by mmd_pseudo_labels: already the padded [B, M, 5] tensor; the "no box in any
+            # sample" case (zeros, :61-62 / :181-188) is decided inside the kernels, so nothing synchronises the host
+            boxes = annotations.boxes
+            if boxes.device != dev or boxes.dtype != torch.float32 or not boxes.is_contiguous():
+                raise ValueError("PseudoLabels.boxes must be a contiguous float32 tensor on %s" % dev)
+            if boxes.shape[1] > _lib.FOCAL_MAX_BOXES:
+                raise ValueError("at most %d rows per sample, got %d" % (_lib.FOCAL_MAX_BOXES, boxes.shape[1]))
+        else:
+            padded = pad_annotations(annotations)
+            if padded.shape[1] == 0:
+                # no box in any sample: the reference skips every sample (:61-62) and returns zeros that do not depend on
+                # the predictions (:181-188)
+                z = torch.zeros(1, dtype=torch.float32, device=dev)
+                return z, z.clone()
+            if padded.shape[1] > _lib.FOCAL_MAX_BOXES:
+                raise ValueError("at most %d boxes per sample, got %d" % (_lib.FOCAL_MAX_BOXES, padded.shape[1]))
+            boxes = torch.from_numpy(padded).to(dev, non_blocking=True)
         anc = anchors[0].detach().to(device=dev, dtype=torch.float32).contiguous()
         reg_loss, cls_loss, assign = _FocalFunction.apply(classifications, regressions, anc, boxes, self.record_assignment)
         self.last_assignment = assign if self.record_assignment else None

@@ -9,6 +9,8 @@ Rebinds:
     src.loss.MTALoss.MTALoss, src.utils.utils.MTALoss    -> mm_distillnet_b200.MTALoss (utils.py:50, :1603-1604)
     src.YetAnotherEfficientDet.Regressor / Classifier    -> mm_distillnet_b200.Regressor / Classifier   (heads=True only;
                                                             looked up at :646-652; at most 224 header channels)
+    src.optimization.train_methods.ModelWithNMSLoss / ModelWithNMSKDListLoss / ModelWithNMSLossAugmented,
+    logits_to_ground_truth (train_methods, utils)        -> wrappers.py / pseudo.py   (step_wrappers=True only)
 and wraps YetAnotherEfficientDet.__init__ so `self.bifpn` (an nn.Sequential of cells) becomes a `BiFPNStack` with
 identical children and state_dict keys, which runs all cells as one fused op list.
 """
@@ -31,11 +33,15 @@ def fuse_bifpn_stacks(model):
     return model
 
 
-def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=False, detection_loss=False):
+def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=False, detection_loss=False,
+                    step_wrappers=False, train_methods_module=None):
     """Rebind the reference's globals.  Modules default to the already-imported `src.*` modules.  `heads=True` also
     rebinds the detection heads (their header is limited to 224 output channels, e.g. 9 anchors x 24 classes);
     `detection_loss=True` rebinds YetAnotherFocalLoss in src.loss.YetAnotherFocalLoss and src.utils.utils (bound by
-    `from ... import` at utils.py:53, instantiated at :1581-1582)."""
+    `from ... import` at utils.py:53, instantiated at :1581-1582); `step_wrappers=True` rebinds ModelWithNMSLoss /
+    ModelWithNMSKDListLoss / ModelWithNMSLossAugmented in src.optimization.train_methods (looked up at :899-906 when
+    train() builds the step) and `logits_to_ground_truth` in src.utils.utils and train_methods (bound by `from ... import`
+    at train_methods.py:20-29): pseudo-labels are then made and consumed on the device."""
     import importlib
     det = det_module or importlib.import_module("src.YetAnotherEfficientDet")
     loss = loss_module or importlib.import_module("src.loss.MTALoss")
@@ -54,6 +60,15 @@ def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=
             fl.YetAnotherFocalLoss = YetAnotherFocalLoss
         if utils is not None and hasattr(utils, "YetAnotherFocalLoss"):
             utils.YetAnotherFocalLoss = YetAnotherFocalLoss
+    if step_wrappers:
+        from . import pseudo, wrappers
+        tm = train_methods_module or sys.modules.get("src.optimization.train_methods")
+        if tm is not None:
+            for name in ("ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented"):
+                setattr(tm, name, getattr(wrappers, name))
+            tm.logits_to_ground_truth = pseudo.logits_to_ground_truth
+        if utils is not None and hasattr(utils, "logits_to_ground_truth"):
+            utils.logits_to_ground_truth = pseudo.logits_to_ground_truth
     cls = det.YetAnotherEfficientDet
     if not getattr(cls, "_mmd_patched", False):
         orig_init = cls.__init__

@@ -1,0 +1,107 @@
+"""Drop-ins for the reference's step wrappers: the `nn.Module`s that `train_methods.train()` builds around
+the student, the frozen teachers and the criteria (src/optimization/train_methods.py:894-918), with the constructor,
+`forward(rgb, thermal, depth, audio, label, validate=False, augment=False)` and the 6-entry return value of
+
+    ModelWithNMSLoss            :425-516   per-teacher criterion_kd(features_s, features_t) calls
+    ModelWithNMSLossAugmented   :265-422   the same step for augment = False (the shipped recipe's 70 % branch)
+    ModelWithNMSKDListLoss      :165-262   ONE criterion_kd(features_s, [features_t ...]) call (multi-teacher product)
+
+What changes is where the work between the model outputs and the losses runs.  The reference does, per teacher and per
+sample, a `.cpu()` of the over-threshold boxes, torchvision NMS, numpy concatenation, one more NMS on the host and a
+host→device copy of the labels inside the detection loss: 3·B host synchronisations per step.  Here the teachers'
+predictions go through ONE `mmd_pseudo_labels` call (pseudo.py) whose padded label tensor `YetAnotherFocalLoss` (focal.py)
+reads on the device, and the per-teacher KD calls go through `MTALoss.forward_each` (one set of launches): no host
+synchronisation between the models' outputs and the loss values.
+
+`criterion_main` must be mm_distillnet_b200.YetAnotherFocalLoss (or any callable that accepts `PseudoLabels`; a foreign
+criterion gets the reference's list-of-arrays via `.to_list()`, which synchronises); `criterion_kd` any callable with the
+reference's signature — mm_distillnet_b200.MTALoss takes the fused path.
+"""
+import torch
+import torch.nn as nn
+
+from .focal import YetAnotherFocalLoss
+from .mta import MTALoss
+from .pseudo import DEFAULT_CAP, DEFAULT_MAX_LABELS, DEFAULT_MAX_ROWS, teacher_pseudo_labels
+
+_MODALITIES = ("rgb", "audio", "thermal", "depth")
+
+
+class _NMSStep(nn.Module):
+    """Shared body of the three wrappers (their forward methods differ only in how criterion_kd is called)."""
+
+    kd_list = False          # True: one criterion_kd call on the list of teachers (ModelWithNMSKDListLoss)
+
+    def __init__(self, student_model, teacher_models, criterion_main, criterion_div, criterion_kd, config, valid_classes_dict):
+        super().__init__()
+        self.criterion_main = criterion_main
+        self.criterion_div = criterion_div
+        self.criterion_kd = criterion_kd
+        self.student_model = student_model
+        self.teacher_models = teacher_models
+        self.config = config
+        self.valid_classes_dict = valid_classes_dict
+        # capacities of the device-side label generation (the reference's Python lists have none)
+        self.pseudo_cap, self.pseudo_max_rows, self.pseudo_max_labels = DEFAULT_CAP, DEFAULT_MAX_ROWS, DEFAULT_MAX_LABELS
+        self.last_pseudo_labels = None     # the PseudoLabels of the last call (device-resident; for logging / tests)
+
+    def _teacher_outputs(self, rgb, thermal, depth, audio):
+        inputs = {"rgb": rgb, "audio": audio, "thermal": thermal, "depth": depth}
+        predictions, features = [], []
+        for modality, teacher_model in self.teacher_models.items():
+            if modality not in _MODALITIES:
+                raise ValueError('No valid modality to predict from teacher')          # train_methods.py:453-454
+            with torch.no_grad():
+                prediction, features_t = teacher_model(inputs[modality])
+            if isinstance(features_t, (tuple, list)):
+                features_t = [f.detach() for f in features_t]
+            else:
+                features_t = features_t.detach()
+            predictions.append(prediction)
+            features.append(features_t)
+        return predictions, features
+
+    def forward(self, rgb, thermal, depth, audio, label, validate=False, augment=False):
+        if augment:
+            raise NotImplementedError("augment=True (merge_batch_0_1 / average_batch_0_1, train_methods.py:276-308) is not "
+                                      "built: run the step with augment=False")
+        logits_s, features_s = self.student_model(audio)
+        predictions, features = self._teacher_outputs(rgb, thermal, depth, audio)
+        dev = rgb.device
+        if len(predictions) > 0:
+            with torch.no_grad():
+                labels = teacher_pseudo_labels(predictions, self.valid_classes_dict, self.config, cap=self.pseudo_cap,
+                                               max_rows=self.pseudo_max_rows, max_labels=self.pseudo_max_labels)
+            self.last_pseudo_labels = labels
+            annotations = labels if isinstance(self.criterion_main, YetAnotherFocalLoss) else labels.to_list()
+        else:
+            annotations = [[] for _ in range(rgb.shape[0])]
+        loss_regression, loss_cls = self.criterion_main(logits_s, annotations)
+
+        if self.kd_list:
+            loss_kd = torch.zeros(1)
+            if self.criterion_kd is not None:
+                loss_kd = self.criterion_kd(features_s, features)
+            kd_losses = [loss_kd]
+        elif self.criterion_kd is None:
+            kd_losses = [torch.zeros(1) for _ in features]
+        elif isinstance(self.criterion_kd, MTALoss) and 1 < len(features) <= 4 and \
+                all(isinstance(f, (list, tuple)) for f in features):
+            kd_losses = list(self.criterion_kd.forward_each(features_s, features).unbind(0))
+        else:
+            kd_losses = [self.criterion_kd(features_s, f) for f in features]
+        z = torch.zeros(1, device=dev)
+        return [[loss_regression], [loss_cls], kd_losses, z, z.clone(), z.clone()]
+
+
+class ModelWithNMSLoss(_NMSStep):
+    """src/optimization/train_methods.py:425-516."""
+
+
+class ModelWithNMSLossAugmented(_NMSStep):
+    """src/optimization/train_methods.py:265-422 (augment=False)."""
+
+
+class ModelWithNMSKDListLoss(_NMSStep):
+    """src/optimization/train_methods.py:165-262."""
+    kd_list = True

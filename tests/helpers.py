@@ -105,3 +105,36 @@ def max_rel(a, b):
     m = b.abs().max().item()
     d = (a - b).abs().max().item()
     return d / m if m > 0 else d
+
+
+def efficientdet_anchors(size):
+    """The anchor table of the reference's `Anchors(anchor_scale=4.)` (src/YetAnotherEfficientDet.py:71-152) for a size x
+    size image, [1, N, 4] (y1, x1, y2, x2): strides 8..128, 3 scales x 3 ratios per position.  tests/test_gpu_focal.py
+    checks the same construction against the stored reference anchors."""
+    ys = []
+    for lvl in range(3, 8):
+        stride = 2 ** lvl
+        for sc in (2 ** 0, 2 ** (1.0 / 3.0), 2 ** (2.0 / 3.0)):
+            for ra in ((1.0, 1.0), (1.4, 0.7), (0.7, 1.4)):
+                half_x, half_y = 4.0 * stride * sc * ra[0] / 2.0, 4.0 * stride * sc * ra[1] / 2.0
+                x = np.arange(stride / 2, size, stride)
+                xv, yv = np.meshgrid(x, x)
+                ys.append((lvl, np.stack((yv.reshape(-1) - half_y, xv.reshape(-1) - half_x, yv.reshape(-1) + half_y,
+                                          xv.reshape(-1) + half_x), axis=1)))
+    per_level = [np.stack([b for l, b in ys if l == lvl], axis=1).reshape(-1, 4) for lvl in range(3, 8)]
+    return torch.from_numpy(np.concatenate(per_level, axis=0).astype(np.float32)).unsqueeze(0)
+
+
+def pseudo_config(size, **over):
+    """The reference's config section for the pseudo-label path (a dict works like the configparser section)."""
+    cfg = {"conf_threshold": str(PSEUDO_CFG["conf_threshold"]), "nms_threshold": str(PSEUDO_CFG["nms_threshold"]),
+           "image_size": str(size), "student": "YetAnotherEfficientDet",
+           "ignore_labels": ",".join(str(i) for i in PSEUDO_CFG["ignore_labels"])}
+    cfg.update(over)
+    return cfg
+
+
+def pseudo_valid_classes_dict():
+    """valid_classes_dict as oracle/make_golden.py::run_pseudo_case builds it."""
+    return {"predictions_txt2i": {"c%d" % i: i for i in PSEUDO_VALID_IDS}, "predictions_i2txt": {i: "c%d" % i for i in PSEUDO_VALID_IDS},
+            "labels_txt2i": {"c%d" % i: n for n, i in enumerate(PSEUDO_VALID_IDS)}}

@@ -476,3 +476,61 @@ def test_focal_loss_host_side():
     utils.MTALoss, utils.YetAnotherFocalLoss = object, object
     mmd.patch_reference(det, loss, utils, detection_loss=True)
     assert utils.YetAnotherFocalLoss is mmd.YetAnotherFocalLoss and utils.MTALoss is mmd.MTALoss
+
+
+def test_pseudo_label_host_side():
+    """Pseudo-label generation and the step wrappers (8 f5), host logic only: the mirrored argument struct and
+    constants, the class-id -> label table of logits_to_ground_truth (utils.py:197-201, :299-300), config access through a
+    configparser section or a dict, no CPU fallback, wrapper construction, and the opt-in rebinding of the reference's names."""
+    import configparser
+    import types
+    import numpy as np
+    from mm_distillnet_b200 import pseudo, wrappers
+    from tests import helpers as H
+    assert _lib.lib().mmd_sizeof_pseudo_args() == ctypes.sizeof(_lib.PseudoArgs)
+    hdr = open(os.path.join(ROOT, "include", "mmd.h")).read()
+    defs = dict(re.findall(r"#define\s+(MMD_[A-Z_]+)\s+(\d+)", hdr))
+    assert (int(defs["MMD_PL_MAX_TEACHERS"]), int(defs["MMD_PL_MAX_CAP"]), int(defs["MMD_PL_MAX_IGNORE"])) == \
+        (_lib.PL_MAX_TEACHERS, _lib.PL_MAX_CAP, _lib.PL_MAX_IGNORE)
+    assert pseudo.DEFAULT_CAP <= _lib.PL_MAX_CAP and pseudo.DEFAULT_MAX_LABELS <= _lib.FOCAL_MAX_BOXES
+    vcd = H.pseudo_valid_classes_dict()
+    tab = pseudo.label_table(vcd, 20)
+    assert tab.dtype == np.int32 and [int(tab[i]) for i in H.PSEUDO_VALID_IDS] == list(range(len(H.PSEUDO_VALID_IDS)))
+    assert (tab[[i for i in range(20) if i not in H.PSEUDO_VALID_IDS]] == -1).all()
+    cp = configparser.ConfigParser()
+    cp.read_dict({"s": H.pseudo_config(128)})
+    for cfg in (cp["s"], H.pseudo_config(128)):
+        assert pseudo._cfg_get(cfg, "conf_threshold", "float") == 0.3 and pseudo._cfg_get(cfg, "image_size", "int") == 128
+        assert pseudo._cfg_get(cfg, "ignore_labels", "str", default="") == "4"
+        assert pseudo._cfg_get(cfg, "missing", "str", default="") == ""
+        with pytest.raises(KeyError):
+            pseudo._cfg_get(cfg, "missing", "float")
+    # workspace size: a pure function of the sizes (no device needed)
+    a = _lib.PseudoArgs()
+    a.B, a.N, a.K, a.T, a.cap = 4, 110484, 20, 3, 4096
+    need = _lib.lib().mmd_pseudo_workspace_bytes(ctypes.byref(a))
+    assert 12 * 110484 * 5 <= need <= 12 * 110484 * 5 + 12 * 4096 * 28 + (1 << 20)
+    c, r, anchors = torch.rand(1, 8, 20), torch.rand(1, 8, 4), torch.rand(1, 8, 4)
+    with pytest.raises(RuntimeError):
+        pseudo.teacher_pseudo_labels([(c, r, anchors)], vcd, H.pseudo_config(128))
+    with pytest.raises(NotImplementedError):
+        pseudo.logits_to_ground_truth((c, r, anchors), None, vcd, H.pseudo_config(128, student="EfficientDet"))
+    # the wrappers keep the reference's constructor and attribute names (train_methods.py:166-175)
+    student, teachers = torch.nn.Identity(), torch.nn.ModuleDict({"rgb": torch.nn.Identity()})
+    for cls in (wrappers.ModelWithNMSLoss, wrappers.ModelWithNMSKDListLoss, wrappers.ModelWithNMSLossAugmented):
+        m = cls(student, teachers, mmd.YetAnotherFocalLoss(), None, mmd.MTALoss("9", "2"), cp["s"], vcd)
+        assert m.student_model is student and m.teacher_models is teachers and m.criterion_div is None
+        assert {"student_model", "teacher_models", "criterion_main", "criterion_kd"} <= {n for n, _ in m.named_children()}
+    assert wrappers.ModelWithNMSKDListLoss.kd_list and not wrappers.ModelWithNMSLoss.kd_list
+    det, loss, utils, tm = (types.ModuleType(n) for n in ("det", "loss", "utils", "tm"))
+
+    class _Det:
+        def __init__(self):
+            pass
+    det.YetAnotherEfficientDet, det.BiFPN = _Det, object
+    loss.MTALoss = object
+    utils.MTALoss, utils.logits_to_ground_truth = object, object
+    tm.ModelWithNMSLoss = tm.ModelWithNMSKDListLoss = tm.ModelWithNMSLossAugmented = tm.logits_to_ground_truth = object
+    mmd.patch_reference(det, loss, utils, step_wrappers=True, train_methods_module=tm)
+    assert tm.ModelWithNMSLoss is mmd.ModelWithNMSLoss and tm.ModelWithNMSKDListLoss is mmd.ModelWithNMSKDListLoss
+    assert tm.logits_to_ground_truth is mmd.logits_to_ground_truth and utils.logits_to_ground_truth is mmd.logits_to_ground_truth

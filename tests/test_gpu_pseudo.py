@@ -1,0 +1,231 @@
+"""GPU parity of the device-side pseudo-label generation (src/utils/utils.py:144-324 and the cross-teacher
+integration of src/optimization/train_methods.py:360-411) and of the step wrappers built on it (8 f5, :165-262, :425-516),
+through the public Python API -> C ABI (mmd_pseudo_labels, mmd_focal_*, mmd_mta_*).
+
+Index work: the bar is bit-exact.  Every row (box, score, label), the row ORDER (NMS order) and the row counts must equal
+the stored outputs of the unmodified reference functions (tests/golden/pseudo_a.npz) and, at the D2 problem size
+(768 x 768 -> 110 484 anchors, 20 classes), the oracle restatement on the same inputs.  bf16 storage: the kernels compute in
+fp32 on the bf16 values, so the oracle is run on the same rounded values and the bar stays bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import mm_distillnet_b200 as mmd
+from mm_distillnet_b200 import pseudo as PS
+from mm_distillnet_b200 import wrappers as W
+from oracle import mmd_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _device_predictions(logits, anchors, dtype=torch.float32):
+    return [(c.to(DEV).to(dtype), r.to(DEV).to(dtype), anchors.to(DEV)) for c, r in logits]
+
+
+def _oracle_labels(logits, anchors, size, label_of, dtype=torch.float32):
+    per_teacher = [O.logits_to_ground_truth((c.to(dtype).float(), r.to(dtype).float(), anchors), H.PSEUDO_VALID_IDS, label_of,
+                                            image_size=size, include_scores=True, **H.PSEUDO_CFG) for c, r in logits]
+    return per_teacher, O.merge_teacher_labels(per_teacher)
+
+
+def _assert_rows(got, ref, what):
+    got = np.asarray(got, dtype=np.float32)
+    ref = np.asarray(ref, dtype=np.float32)
+    if ref.size == 0:
+        assert got.size == 0, what
+        return
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert np.array_equal(got, ref), (what, got, ref)
+
+
+@pytest.mark.parametrize("name", sorted(H.PSEUDO_CASES))
+def test_pseudo_golden(name):
+    """Per-teacher rows and merged labels == the reference's own outputs, row for row, bit for bit."""
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    g = H.golden(name)
+    anchors, logits, label_of = H.pseudo_case_inputs(name)
+    out = PS.teacher_pseudo_labels(_device_predictions(logits, anchors), H.pseudo_valid_classes_dict(), H.pseudo_config(size))
+    per_teacher, merged = out.teacher_lists(), out.to_list()
+    for t in range(nt):
+        for b in range(B):
+            _assert_rows(per_teacher[t][b], g["t%d_b%d" % (t, b)], (t, b))
+    for b in range(B):
+        _assert_rows(merged[b], g["merged_b%d" % b], ("merged", b))
+    # the padded tensor is what the detection loss reads: -1 behind the valid rows
+    boxes, counts = out.boxes.cpu().numpy(), out.counts.cpu().numpy()
+    for b in range(B):
+        assert counts[b] == g["merged_b%d" % b].shape[0]
+        assert (boxes[b, counts[b]:] == -1).all()
+    assert counts[B] == 0
+    # the reference's own entry point, one teacher, with and without scores
+    c, r = logits[0]
+    lst = mmd.logits_to_ground_truth((c.to(DEV), r.to(DEV), anchors.to(DEV)), None, H.pseudo_valid_classes_dict(),
+                                     H.pseudo_config(size), include_scores=True)
+    noscore = mmd.logits_to_ground_truth((c.to(DEV), r.to(DEV), anchors.to(DEV)), None, H.pseudo_valid_classes_dict(),
+                                         H.pseudo_config(size))
+    for b in range(B):
+        _assert_rows(lst[b], g["t0_b%d" % b], ("l2gt", b))
+        if g["t0_b%d" % b].size:
+            _assert_rows(noscore[b], np.delete(g["t0_b%d" % b], 4, 1), ("l2gt-noscore", b))
+        assert isinstance(lst[b], np.ndarray) and lst[b].dtype == np.float32
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pseudo_full_size_vs_oracle(dtype):
+    """D2 size: 110 484 anchors, 20 classes, B = 4, 3 teachers; hundreds of over-threshold anchors per sample."""
+    size, K, B, nt = 768, 20, 4, 3
+    anchors = H.efficientdet_anchors(size)
+    assert anchors.shape[1] == 110484
+    label_of = {i: n for n, i in enumerate(H.PSEUDO_VALID_IDS)}
+    logits = [O.synth_teacher_logits(B, anchors, K, 300 + 10 * t, n_objects=7, size=size) for t in range(nt)]
+    ref_t, ref_m = _oracle_labels(logits, anchors, size, label_of, dtype)
+    out = PS.teacher_pseudo_labels(_device_predictions(logits, anchors, dtype), H.pseudo_valid_classes_dict(), H.pseudo_config(size))
+    got_t, got_m = out.teacher_lists(), out.to_list()
+    n_over = 0
+    for t in range(nt):
+        for b in range(B):
+            _assert_rows(got_t[t][b], ref_t[t][b], (t, b))
+            n_over += np.asarray(ref_t[t][b]).shape[0] if np.asarray(ref_t[t][b]).size else 0
+    for b in range(B):
+        _assert_rows(got_m[b], ref_m[b] if len(ref_m[b]) else np.zeros((0, 5)), ("merged", b))
+    assert n_over >= 20 and any(len(m) == 0 for m in ref_m)          # real work, and a sample nobody labelled
+
+
+def test_pseudo_raw_rows_and_text_classes():
+    """EfficientDet_post_processing's own rows (float boxes, class ids) and the text_classes=True form."""
+    name = "pseudo_a"
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    anchors, logits, label_of = H.pseudo_case_inputs(name)
+    c, r = logits[1]
+    ref = O.detections(c, r, anchors, H.PSEUDO_VALID_IDS, image_size=size, **H.PSEUDO_CFG)
+    out = PS.teacher_pseudo_labels(_device_predictions([logits[1]], anchors), H.pseudo_valid_classes_dict(), H.pseudo_config(size),
+                                   raw_rows=True)
+    got = out.teacher_lists()[0]
+    for b in range(B):
+        _assert_rows(got[b], ref[b].numpy(), b)
+    txt = mmd.logits_to_ground_truth((c.to(DEV), r.to(DEV), anchors.to(DEV)), None, H.pseudo_valid_classes_dict(),
+                                     H.pseudo_config(size), text_classes=True)
+    for b in range(B):
+        assert len(txt[b]) == ref[b].shape[0]
+        for row, rr in zip(txt[b], ref[b].tolist()):
+            assert row[4] == "c%d" % int(rr[5]) and row[0] == int(max(rr[0], 0)) and row[3] == int(min(rr[3], size))
+
+
+def test_pseudo_edge_cases():
+    """Nothing above the threshold anywhere; capacities; ties in the scores (stable order); argument checks."""
+    size, K, B = 128, 20, 3
+    anchors = H.efficientdet_anchors(size)
+    N = anchors.shape[1]
+    vcd, cfg = H.pseudo_valid_classes_dict(), H.pseudo_config(size)
+    c = torch.full((B, N, K), 0.05)
+    r = torch.zeros(B, N, 4)
+    out = PS.teacher_pseudo_labels(_device_predictions([(c, r)], anchors), vcd, cfg)
+    assert out.to_list() == [[], [], []] and float(out.boxes.max()) == -1.0 and int(out.counts.sum()) == 0
+    # the detection loss on such labels: zeros, zero gradients, no host decision involved
+    crit = mmd.YetAnotherFocalLoss()
+    cd = torch.rand(B, N, K, device=DEV).requires_grad_(True)
+    rd = torch.randn(B, N, 4, device=DEV).requires_grad_(True)
+    rl, cl = crit((cd, rd, anchors.to(DEV)), out)
+    (rl + cl).sum().backward()
+    assert float(rl.detach()) == 0.0 and float(cl.detach()) == 0.0 and float(cd.grad.abs().max()) == 0.0 and float(rd.grad.abs().max()) == 0.0
+    # equal scores: identical boxes of one class collapse to the FIRST anchor index; disjoint ones keep anchor order
+    c2 = torch.full((1, N, K), 0.05)
+    idx = [5, 700, 1500, 2500, 3000]
+    c2[0, idx, 6] = 0.75
+    label_of = {i: n for n, i in enumerate(H.PSEUDO_VALID_IDS)}
+    ref = O.logits_to_ground_truth((c2, r[:1], anchors), H.PSEUDO_VALID_IDS, label_of, image_size=size, include_scores=True,
+                                   **H.PSEUDO_CFG)
+    out2 = PS.teacher_pseudo_labels(_device_predictions([(c2, r[:1])], anchors), vcd, cfg)
+    _assert_rows(out2.teacher_lists()[0][0], ref[0], "ties")
+    # capacities: a sample with more over-threshold anchors than `cap` raises at the first host read
+    c3 = torch.full((1, N, K), 0.05)
+    c3[0, :600, 6] = 0.9
+    out3 = PS.teacher_pseudo_labels(_device_predictions([(c3, r[:1])], anchors), vcd, cfg, cap=256)
+    with pytest.raises(RuntimeError, match="cap"):
+        out3.to_list()
+    out4 = PS.teacher_pseudo_labels(_device_predictions([(c3, r[:1])], anchors), vcd, cfg, cap=1024)
+    ref4 = O.logits_to_ground_truth((c3, r[:1], anchors), H.PSEUDO_VALID_IDS, label_of, image_size=size, include_scores=True,
+                                    **H.PSEUDO_CFG)
+    _assert_rows(out4.teacher_lists()[0][0], ref4[0], "600 over-threshold anchors")
+    with pytest.raises(RuntimeError):
+        PS.teacher_pseudo_labels([(c, r, anchors)], vcd, cfg)                       # CPU tensors
+    with pytest.raises(ValueError):
+        PS.teacher_pseudo_labels(_device_predictions([(c, r[:, :-1])], anchors), vcd, cfg)
+
+
+def test_focal_on_device_labels_equals_host_labels():
+    """YetAnotherFocalLoss(PseudoLabels) == YetAnotherFocalLoss(list of arrays) bit for bit (same kernel, same rows)."""
+    name = "pseudo_a"
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    anchors, logits, _ = H.pseudo_case_inputs(name)
+    out = PS.teacher_pseudo_labels(_device_predictions(logits, anchors), H.pseudo_valid_classes_dict(), H.pseudo_config(size))
+    host = out.to_list()
+    cs, rs = O.synth_detections(B, anchors.shape[1], K, 77)
+    res = []
+    for ann in (out, host):
+        crit = mmd.YetAnotherFocalLoss()
+        cd, rd = cs.to(DEV).requires_grad_(True), rs.to(DEV).requires_grad_(True)
+        rl, cl = crit((cd, rd, anchors.to(DEV)), ann)
+        (rl + cl).sum().backward()
+        res.append((rl.detach().cpu(), cl.detach().cpu(), cd.grad.cpu(), rd.grad.cpu()))
+    assert float(res[0][0]) > 0 and float(res[0][1]) > 0
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+class _FakeDet(nn.Module):
+    """Stands in for YetAnotherEfficientDet: returns ((classification, regression, anchors), features) like :667-675."""
+
+    def __init__(self, c, r, anchors, feats, trainable):
+        super().__init__()
+        self.c, self.r, self.anchors = c, r, anchors
+        self.feats = nn.ParameterList([nn.Parameter(f.clone(), requires_grad=trainable) for f in feats])
+        self.head = nn.Parameter(torch.zeros(1), requires_grad=trainable)
+
+    def forward(self, x):
+        return (self.c + self.head, self.r + self.head, self.anchors), tuple(f for f in self.feats)
+
+
+@pytest.mark.parametrize("wrapper", ["ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented"])
+def test_step_wrappers(wrapper):
+    """The wrappers' 6-entry return value against the restated step: detection loss of the student on the oracle's merged
+    labels (fp64 oracle loss), KD losses against the oracle's MTA loss (per teacher / product of the teachers)."""
+    name = "pseudo_a"
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    anchors, logits, label_of = H.pseudo_case_inputs(name)
+    sizes = [16, 8, 4]
+    fs = H.structured_features(B, 112, sizes, 5)
+    fts = [H.structured_features(B, 112, sizes, 11 + t) for t in range(nt)]
+    cs, rs = O.synth_detections(B, anchors.shape[1], K, 78)
+    student = _FakeDet(cs.to(DEV), rs.to(DEV), anchors.to(DEV), [f.to(DEV) for f in fs], True).to(DEV)
+    teachers = nn.ModuleDict({m: _FakeDet(c.to(DEV), r.to(DEV), anchors.to(DEV), [f.to(DEV) for f in ft], False)
+                              for m, (c, r), ft in zip(("rgb", "thermal", "depth"), logits, fts)}).to(DEV)
+    model = getattr(W, wrapper)(student, teachers, mmd.YetAnotherFocalLoss(), None, mmd.MTALoss("9", "2"), H.pseudo_config(size),
+                                H.pseudo_valid_classes_dict())
+    x = torch.zeros(B, 1, 4, 4, device=DEV)
+    out = model(x, x, x, x, None)
+    assert len(out) == 6 and len(out[0]) == 1 and len(out[1]) == 1
+    _, merged = _oracle_labels(logits, anchors, size, label_of)
+    rl, cl = O.focal_loss(cs.double(), rs.double(), anchors.double(), merged)
+    assert abs(float(out[0][0]) - float(rl)) <= 1e-5 * abs(float(rl)) and abs(float(out[1][0]) - float(cl)) <= 1e-5 * abs(float(cl))
+    if wrapper == "ModelWithNMSKDListLoss":
+        assert len(out[2]) == 1
+        ref = O.mta_loss([f.double() for f in fs], [[f.double() for f in ft] for ft in fts])
+        assert torch.allclose(out[2][0].cpu().double(), ref, atol=2e-6, rtol=0)
+    else:
+        assert len(out[2]) == nt
+        for t in range(nt):
+            ref = O.mta_loss([f.double() for f in fs], [f.double() for f in fts[t]])
+            assert torch.allclose(out[2][t].cpu().double(), ref, atol=2e-6, rtol=0)
+    # traditional.py:171-182: the losses combine and differentiate through the student only
+    loss = out[0][0].mean() + out[1][0].mean() + 0.005 * torch.stack([k.sum() for k in out[2]]).sum()
+    loss.backward()
+    assert all(p.grad is not None and float(p.grad.abs().max()) > 0 for p in student.feats) and student.head.grad is not None
+    assert all(p.grad is None for p in teachers.parameters())
+    for z in out[3:]:
+        assert z.shape == (1,) and float(z) == 0.0
+    with pytest.raises(NotImplementedError):
+        model(x, x, x, x, None, augment=True)
