@@ -37,7 +37,6 @@ struct Ws {                          // carved from MmdPseudoArgs.workspace
   float4* cand_box;                  // [T][B][cap] (x1, y1, x2, y2) decoded + clipped
   float* cand_score;                 // [T][B][cap]
   int* cand_cls;                     // [T][B][cap]
-  int* n_cand;                       // [T][B]
   size_t bytes;
 };
 
@@ -56,7 +55,6 @@ static Ws carve(const MmdPseudoArgs* a) {
   w.cand_box = reinterpret_cast<float4*>(take(TB * a->cap * sizeof(float4)));
   w.cand_score = reinterpret_cast<float*>(take(TB * a->cap * sizeof(float)));
   w.cand_cls = reinterpret_cast<int*>(take(TB * a->cap * sizeof(int)));
-  w.n_cand = reinterpret_cast<int*>(take(TB * sizeof(int)));
   w.bytes = off;
   return w;
 }
@@ -85,30 +83,30 @@ template <>
 __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ---- pass 1: score, class, flags, per-CTA counts -----------------------------------------------------------------------
-// Row maximum + first arg-max of K values that sit in 8-byte (bf16) / 16-byte (fp32) groups of 4.
+// Row maximum of K values that sit in 8-byte (bf16) / 16-byte (fp32) groups of 4: one max instruction per value (fp32) or
+// per pair (bf16 HMNMX2); the arg-max is only looked up for the few anchors above the threshold.
 template <typename T>
-__device__ __forceinline__ void row_max4(const T* row, int K, float& best, int& arg);
+__device__ __forceinline__ float row_max4(const T* row, int K);
 template <>
-__device__ __forceinline__ void row_max4<float>(const float* row, int K, float& best, int& arg) {
-  for (int k = 0; k < K; k += 4) {
+__device__ __forceinline__ float row_max4<float>(const float* row, int K) {
+  float4 m = *reinterpret_cast<const float4*>(row);
+  for (int k = 4; k < K; k += 4) {
     const float4 v = *reinterpret_cast<const float4*>(row + k);
-    if (v.x > best) { best = v.x; arg = k; }
-    if (v.y > best) { best = v.y; arg = k + 1; }
-    if (v.z > best) { best = v.z; arg = k + 2; }
-    if (v.w > best) { best = v.w; arg = k + 3; }
+    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
   }
+  return fmaxf(fmaxf(m.x, m.y), fmaxf(m.z, m.w));
 }
 template <>
-__device__ __forceinline__ void row_max4<__nv_bfloat16>(const __nv_bfloat16* row, int K, float& best, int& arg) {
-  for (int k = 0; k < K; k += 4) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(row + k);
-    const float v0 = __uint_as_float(raw.x << 16), v1 = __uint_as_float(raw.x & 0xffff0000u);
-    const float v2 = __uint_as_float(raw.y << 16), v3 = __uint_as_float(raw.y & 0xffff0000u);
-    if (v0 > best) { best = v0; arg = k; }
-    if (v1 > best) { best = v1; arg = k + 1; }
-    if (v2 > best) { best = v2; arg = k + 2; }
-    if (v3 > best) { best = v3; arg = k + 3; }
+__device__ __forceinline__ float row_max4<__nv_bfloat16>(const __nv_bfloat16* row, int K) {
+  uint2 raw = *reinterpret_cast<const uint2*>(row);
+  __nv_bfloat162 m0 = *reinterpret_cast<__nv_bfloat162*>(&raw.x), m1 = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  for (int k = 4; k < K; k += 4) {
+    raw = *reinterpret_cast<const uint2*>(row + k);
+    m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&raw.x));
+    m1 = __hmax2(m1, *reinterpret_cast<__nv_bfloat162*>(&raw.y));
   }
+  m0 = __hmax2(m0, m1);
+  return fmaxf(__low2float(m0), __high2float(m0));
 }
 
 // The CTA's 256 x K scores are copied to shared memory AS THEY LIE in HBM (16-byte vectors, consecutive threads on
@@ -135,39 +133,52 @@ __global__ void __launch_bounds__(kThreads) pl_score_kernel(const __grid_constan
   }
   __syncthreads();
   bool over = false, valid = false;
+  float best = -1.f;
+  int arg = 0;
   if (tid < rows) {
     const T* row = s_sc + tid * p.K;
-    float best = -INFINITY;                          // torch.max(dim): the FIRST maximum
-    int arg = 0;
     if ((p.K & 3) == 0) {
-      row_max4<T>(row, p.K, best, arg);
+      best = row_max4<T>(row, p.K);
     } else {
-      for (int k = 0; k < p.K; ++k) {
-        const float v = to_f<T>(row[k]);
-        if (v > best) { best = v; arg = k; }
-      }
+      best = to_f<T>(row[0]);
+      for (int k = 1; k < p.K; ++k) best = fmaxf(best, to_f<T>(row[k]));
     }
     over = best > p.conf;                           // utils.py:178-179
-    valid = over && p.label_of[arg] >= 0;           // :197-204
-    const size_t o = ((size_t)t * p.B + b) * p.N + n0 + tid;
-    p.w.sc[o] = over ? best : -1.f;
-    p.w.cl[o] = (uint8_t)arg;
+    if (over) {
+      while (to_f<T>(row[arg]) != best) ++arg;      // torch.max(dim): the FIRST maximum
+      valid = p.label_of[arg] >= 0;                 // :197-204
+    }
   }
   const int c_over = __syncthreads_count(over);
   const int c_valid = __syncthreads_count(valid);
   if (tid == 0) p.w.blk[((size_t)t * p.B + b) * p.nblk + blockIdx.x] = make_int2(c_over, c_valid);
+  if (c_over > 0 && tid < rows) {                   // pass 2 only looks at the CTAs that counted something
+    const size_t o = ((size_t)t * p.B + b) * p.N + n0 + tid;
+    p.w.sc[o] = over ? best : -1.f;
+    p.w.cl[o] = (uint8_t)arg;
+  }
 }
 
 // ---- pass 2: order-preserving compaction + box decode ------------------------------------------------------------------
+// One CTA owns kSpan consecutive 256-anchor blocks of one (teacher, sample) and visits only those whose pass-1 count is
+// non-zero (a trained detector fires on a few hundred of 110 484 anchors: almost every block is skipped unread).
+constexpr int kSpan = 16;
 template <typename T>
 __global__ void __launch_bounds__(kThreads) pl_compact_kernel(const __grid_constant__ P p) {
   __shared__ int s_red[2][kThreads / 32];
   __shared__ int s_off[2];
+  __shared__ int2 s_cnt[kSpan];
   const int t = blockIdx.z, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t tb = (size_t)t * p.B + b;
-  // offsets of this CTA = counts of the CTAs before it
+  const int blk0 = blockIdx.x * kSpan, nspan = min(kSpan, p.nblk - blk0);
+  if (tid < nspan) s_cnt[tid] = p.w.blk[tb * p.nblk + blk0 + tid];
+  __syncthreads();
+  int any = 0;
+  for (int i = 0; i < nspan; ++i) any |= s_cnt[i].x;
+  if (any == 0) return;
+  // offsets of this CTA = counts of the blocks before its span
   int so = 0, sv = 0;
-  for (int i = tid; i < (int)blockIdx.x; i += kThreads) {
+  for (int i = tid; i < blk0; i += kThreads) {
     const int2 c = p.w.blk[tb * p.nblk + i];
     so += c.x;
     sv += c.y;
@@ -186,50 +197,49 @@ __global__ void __launch_bounds__(kThreads) pl_compact_kernel(const __grid_const
     s_off[1] = a1;
   }
   __syncthreads();
-  const int off_o = s_off[0], off_v = s_off[1];
-  const int n = blockIdx.x * kThreads + tid;
-  float score = -1.f;
-  int cls = 0;
-  if (n < p.N) {
-    score = p.w.sc[tb * p.N + n];
-    cls = p.w.cl[tb * p.N + n];
-  }
-  const bool over = score >= 0.f;
-  const bool valid = over && p.label_of[cls] >= 0;
-  const unsigned m_o = __ballot_sync(0xffffffffu, over), m_v = __ballot_sync(0xffffffffu, valid);
-  __syncthreads();
-  if (lane == 0) { s_red[0][warp] = __popc(m_o); s_red[1][warp] = __popc(m_v); }
-  __syncthreads();
-  int base_o = off_o, base_v = off_v;
-  for (int w = 0; w < warp; ++w) { base_o += s_red[0][w]; base_v += s_red[1][w]; }
-  const unsigned below = (1u << lane) - 1u;
-  const int pos_o = base_o + __popc(m_o & below), pos_v = base_v + __popc(m_v & below);
-  if (over && pos_o < p.cap) p.w.over_score[tb * p.cap + pos_o] = score;
-  if (valid && pos_v < p.cap) {
-    // YetAnotherEfficientDetBBoxTransform.forward (YetAnotherEfficientDet.py:586-602), one rounding per operation
-    const float4 a = *reinterpret_cast<const float4*>(p.anchors + 4 * (size_t)n);      // y1, x1, y2, x2
-    const T* rp = reinterpret_cast<const T*>(p.reg[t]) + ((size_t)b * p.N + n) * 4;
-    const float r0 = to_f<T>(rp[0]), r1 = to_f<T>(rp[1]), r2 = to_f<T>(rp[2]), r3 = to_f<T>(rp[3]);
-    const float yca = __fdiv_rn(__fadd_rn(a.x, a.z), 2.f), xca = __fdiv_rn(__fadd_rn(a.y, a.w), 2.f);
-    const float ha = __fsub_rn(a.z, a.x), wa = __fsub_rn(a.w, a.y);
-    const float w = __fmul_rn((float)exp((double)r3), wa), h = __fmul_rn((float)exp((double)r2), ha);
-    const float yc = __fadd_rn(__fmul_rn(r0, ha), yca), xc = __fadd_rn(__fmul_rn(r1, wa), xca);
-    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-    float4 bx;
-    bx.x = fmaxf(__fsub_rn(xc, hw), 0.f);            // ClipBoxes (utils.py:134-138)
-    bx.y = fmaxf(__fsub_rn(yc, hh), 0.f);
-    bx.z = fminf(__fadd_rn(xc, hw), p.size);
-    bx.w = fminf(__fadd_rn(yc, hh), p.size);
-    p.w.cand_box[tb * p.cap + pos_v] = bx;
-    p.w.cand_score[tb * p.cap + pos_v] = score;
-    p.w.cand_cls[tb * p.cap + pos_v] = cls;
-  }
-  if (blockIdx.x == gridDim.x - 1) {                 // the last CTA knows the totals
-    const int tot_o = off_o + __syncthreads_count(over), tot_v = off_v + __syncthreads_count(valid);
-    if (tid == 0) {
-      p.w.n_cand[tb] = min(tot_v, p.cap);
-      if (tot_o > p.cap) atomicOr(p.counts + p.B, 1);
+  int off_o = s_off[0], off_v = s_off[1];
+  for (int i = 0; i < nspan; ++i) {
+    const int2 cnt = s_cnt[i];
+    if (cnt.x == 0) continue;
+    const int n = (blk0 + i) * kThreads + tid;
+    float score = -1.f;
+    int cls = 0;
+    if (n < p.N) {
+      score = p.w.sc[tb * p.N + n];
+      cls = p.w.cl[tb * p.N + n];
     }
+    const bool over = score >= 0.f;
+    const bool valid = over && p.label_of[cls] >= 0;
+    const unsigned m_o = __ballot_sync(0xffffffffu, over), m_v = __ballot_sync(0xffffffffu, valid);
+    __syncthreads();
+    if (lane == 0) { s_red[0][warp] = __popc(m_o); s_red[1][warp] = __popc(m_v); }
+    __syncthreads();
+    int base_o = off_o, base_v = off_v;
+    for (int w = 0; w < warp; ++w) { base_o += s_red[0][w]; base_v += s_red[1][w]; }
+    const unsigned below = (1u << lane) - 1u;
+    const int pos_o = base_o + __popc(m_o & below), pos_v = base_v + __popc(m_v & below);
+    if (over && pos_o < p.cap) p.w.over_score[tb * p.cap + pos_o] = score;
+    if (valid && pos_v < p.cap) {
+      // YetAnotherEfficientDetBBoxTransform.forward (YetAnotherEfficientDet.py:586-602), one rounding per operation
+      const float4 a = *reinterpret_cast<const float4*>(p.anchors + 4 * (size_t)n);      // y1, x1, y2, x2
+      const T* rp = reinterpret_cast<const T*>(p.reg[t]) + ((size_t)b * p.N + n) * 4;
+      const float r0 = to_f<T>(rp[0]), r1 = to_f<T>(rp[1]), r2 = to_f<T>(rp[2]), r3 = to_f<T>(rp[3]);
+      const float yca = __fdiv_rn(__fadd_rn(a.x, a.z), 2.f), xca = __fdiv_rn(__fadd_rn(a.y, a.w), 2.f);
+      const float ha = __fsub_rn(a.z, a.x), wa = __fsub_rn(a.w, a.y);
+      const float w = __fmul_rn((float)exp((double)r3), wa), h = __fmul_rn((float)exp((double)r2), ha);
+      const float yc = __fadd_rn(__fmul_rn(r0, ha), yca), xc = __fadd_rn(__fmul_rn(r1, wa), xca);
+      const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+      float4 bx;
+      bx.x = fmaxf(__fsub_rn(xc, hw), 0.f);            // ClipBoxes (utils.py:134-138)
+      bx.y = fmaxf(__fsub_rn(yc, hh), 0.f);
+      bx.z = fminf(__fadd_rn(xc, hw), p.size);
+      bx.w = fminf(__fadd_rn(yc, hh), p.size);
+      p.w.cand_box[tb * p.cap + pos_v] = bx;
+      p.w.cand_score[tb * p.cap + pos_v] = score;
+      p.w.cand_cls[tb * p.cap + pos_v] = cls;
+    }
+    off_o += cnt.x;
+    off_v += cnt.y;
   }
 }
 
@@ -332,7 +342,30 @@ __global__ void __launch_bounds__(kNmsThreads) pl_nms_kernel(const __grid_consta
   nms_smem(s_raw, p.cap, s_key, s_box, s_dead);
   const int b = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
   const size_t tb = (size_t)t * p.B + b;
-  const int n = p.w.n_cand[tb];
+  // totals of the two pass-1 counts over the sample's blocks
+  __shared__ int s_tot[2];
+  if (tid < 2) s_tot[tid] = 0;
+  __syncthreads();
+  {
+    int so = 0, sv = 0;
+    for (int i = tid; i < p.nblk; i += kNmsThreads) {
+      const int2 c = p.w.blk[tb * p.nblk + i];
+      so += c.x;
+      sv += c.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      so += __shfl_xor_sync(0xffffffffu, so, o);
+      sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if ((tid & 31) == 0 && (so | sv) != 0) {
+      atomicAdd(&s_tot[0], so);
+      atomicAdd(&s_tot[1], sv);
+    }
+  }
+  __syncthreads();
+  if (tid == 0 && s_tot[0] > p.cap) atomicOr(p.counts + p.B, 1);
+  const int n = min(s_tot[1], p.cap);
   if (n == 0) {
     if (tid == 0) p.teacher_counts[tb] = 0;
     return;
@@ -515,7 +548,7 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
   const size_t es = a->dtype == MMD_F32 ? 4 : 2;
   const size_t smem1 = (((size_t)pl::kThreads * a->K * es) + 15) & ~(size_t)15;
   {
-    ProfScope prof(PK_PSEUDO, (double)a->T * a->B * a->N * (a->K * es + 5), s);
+    ProfScope prof(PK_PSEUDO, (double)a->T * a->B * a->N * (a->K * es), s);
     if (a->dtype == MMD_F32) {
       MMD_SMEM(pl::pl_score_kernel<float>, smem1);
       pl::pl_score_kernel<float><<<grid, pl::kThreads, smem1, s>>>(p);
@@ -526,9 +559,10 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
     MMD_LAUNCH_CHECK();
   }
   {
-    ProfScope prof(PK_PSEUDO, (double)a->T * a->B * a->N * 5, s);
-    if (a->dtype == MMD_F32) pl::pl_compact_kernel<float><<<grid, pl::kThreads, 0, s>>>(p);
-    else pl::pl_compact_kernel<__nv_bfloat16><<<grid, pl::kThreads, 0, s>>>(p);
+    ProfScope prof(PK_PSEUDO, 0.0, s);
+    const dim3 grid2((p.nblk + pl::kSpan - 1) / pl::kSpan, a->B, a->T);
+    if (a->dtype == MMD_F32) pl::pl_compact_kernel<float><<<grid2, pl::kThreads, 0, s>>>(p);
+    else pl::pl_compact_kernel<__nv_bfloat16><<<grid2, pl::kThreads, 0, s>>>(p);
     MMD_LAUNCH_CHECK();
   }
   const size_t smem3 = pl::nms_smem_bytes(a->cap);

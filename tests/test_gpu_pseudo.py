@@ -229,3 +229,49 @@ def test_step_wrappers(wrapper):
         assert z.shape == (1,) and float(z) == 0.0
     with pytest.raises(NotImplementedError):
         model(x, x, x, x, None, augment=True)
+
+
+def test_pseudo_labels_and_loss_replay_inside_a_cuda_graph():
+    """No host decision anywhere between the teachers' outputs and the loss gradients: label generation + detection loss
+    (forward and backward) are captured once into a CUDA graph and replayed on other predictions — including a batch
+    nobody labels (the zero-loss branch is decided on the device) — and equal the eager results bit for bit."""
+    name = "pseudo_a"
+    B, size, K, seed, nt = H.PSEUDO_CASES[name]
+    anchors, logits, _ = H.pseudo_case_inputs(name)
+    vcd, cfg = H.pseudo_valid_classes_dict(), H.pseudo_config(size)
+    anc = anchors.to(DEV)
+    static = [(c.to(DEV).clone(), r.to(DEV).clone(), anc) for c, r in logits]
+    cs, rs = O.synth_detections(B, anchors.shape[1], K, 79)
+    cd, rd = cs.to(DEV).requires_grad_(True), rs.to(DEV).requires_grad_(True)
+    crit = mmd.YetAnotherFocalLoss()
+
+    def step():
+        labels = PS.teacher_pseudo_labels(static, vcd, cfg)
+        rl, cl = crit((cd, rd, anc), labels)
+        gc, gr = torch.autograd.grad((rl + cl).sum(), (cd, rd))
+        return labels.boxes, labels.counts, rl, cl, gc, gr
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        outs = step()
+    variants = [[(c, r) for c, r in logits],
+                [(c.flip(0), r.flip(0)) for c, r in logits],
+                [(torch.full_like(c, 0.05), r) for c, r in logits]]
+    for var in variants:
+        for (sc, sr, _), (c, r) in zip(static, var):
+            sc.copy_(c)
+            sr.copy_(r)
+        graph.replay()
+        torch.cuda.synchronize()
+        got = [o.detach().clone() for o in outs]
+        ref = [o.detach() for o in step()]
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    assert int(got[1][:B].sum()) == 0 and float(got[2]) == 0.0 and float(got[4].abs().max()) == 0.0      # last variant: no labels

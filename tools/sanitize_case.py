@@ -46,3 +46,30 @@ for dtype in (torch.bfloat16, torch.float32):
         reg([f.detach() for f in feats])
     torch.cuda.synchronize()
     print(dtype, "heads + focal ok", float(lr), float(lc))
+
+# pseudo-label generation (score / compact / NMS / merge kernels) feeding the detection loss on device-made labels
+from mm_distillnet_b200 import pseudo as PS  # noqa: E402
+for dtype in (torch.bfloat16, torch.float32):
+    B, K, T = 2, 20, 2
+    ys, xs_ = torch.meshgrid(torch.arange(4, 128, 8.0), torch.arange(4, 128, 8.0), indexing="ij")
+    ctr = torch.stack([ys.reshape(-1), xs_.reshape(-1)], dim=1).repeat_interleave(3, dim=0)
+    half = torch.tensor([16.0, 20.0, 26.0]).repeat(ctr.shape[0] // 3).unsqueeze(1)
+    anchors = torch.cat([ctr - half, ctr + half], dim=1).unsqueeze(0).to(dev)          # [1, 768, 4] (y1, x1, y2, x2)
+    N = anchors.shape[1]
+    preds = []
+    for t in range(T):
+        c = 0.02 + 0.1 * torch.rand(B, N, K, device=dev)
+        hot = torch.randint(0, N, (B, 40), device=dev)
+        for b in range(B):
+            c[b, hot[b], torch.randint(0, K, (40,), device=dev)] = 0.4 + 0.5 * torch.rand(40, device=dev)
+        preds.append((c.to(dtype), (0.1 * torch.randn(B, N, 4, device=dev)).to(dtype), anchors))
+    vcd = {"predictions_txt2i": {"c%d" % i: i for i in range(0, K, 2)}, "predictions_i2txt": {i: "c%d" % i for i in range(0, K, 2)},
+           "labels_txt2i": {"c%d" % i: i // 2 for i in range(0, K, 2)}}
+    cfg = {"conf_threshold": "0.3", "nms_threshold": "0.5", "image_size": "128", "ignore_labels": "4"}
+    labels = PS.teacher_pseudo_labels(preds, vcd, cfg, cap=512, max_rows=64, max_labels=64)
+    cs = torch.rand(B, N, K, device=dev).to(dtype).requires_grad_(True)
+    rs = torch.randn(B, N, 4, device=dev).to(dtype).requires_grad_(True)
+    lr, lc = mmd.YetAnotherFocalLoss()((cs, rs, anchors), labels)
+    (lr + lc).sum().backward()
+    torch.cuda.synchronize()
+    print(dtype, "pseudo-labels + focal ok", labels.counts.tolist(), float(lr), float(lc))
