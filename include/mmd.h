@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 108
+#define MMD_VERSION 109
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -153,6 +153,10 @@ typedef struct {
                                  /*    class id); 0: logits_to_ground_truth's rows (truncated boxes, score, label)            */
   int32_t n_ignore;
   int32_t ignore[MMD_PL_MAX_IGNORE]; /* prediction ids dropped after the NMS (config 'ignore_labels')                         */
+  int32_t merge01;               /* 1: the augmented step (train_methods.py:384-386): when samples 0 and 1 both have rows,    */
+                                 /*    sample 1's list = sample 0's rows (all teachers) followed by its own, before the NMS  */
+                                 /*    (needs B >= 2 and 2 * T * max_rows <= MMD_PL_MAX_CAP)                                  */
+  int32_t pad_;
   float conf_threshold, image_size;
   double nms_threshold, merge_iou;   /* compared as torchvision does: (double)iou > threshold                                 */
   const void* cls[MMD_PL_MAX_TEACHERS]; /* [B][N][K] class probabilities                                                      */

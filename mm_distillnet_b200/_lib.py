@@ -49,7 +49,7 @@ PL_MAX_TEACHERS, PL_MAX_CAP, PL_MAX_IGNORE = 8, 8192, 8
 class PseudoArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("T", C.c_int32), ("dtype", C.c_int32), ("cap", C.c_int32),
                 ("max_rows", C.c_int32), ("max_labels", C.c_int32), ("raw_rows", C.c_int32), ("n_ignore", C.c_int32),
-                ("ignore", C.c_int32 * PL_MAX_IGNORE), ("conf_threshold", C.c_float), ("image_size", C.c_float),
+                ("ignore", C.c_int32 * PL_MAX_IGNORE), ("merge01", C.c_int32), ("pad_", C.c_int32), ("conf_threshold", C.c_float), ("image_size", C.c_float),
                 ("nms_threshold", C.c_double), ("merge_iou", C.c_double),
                 ("cls", C.c_void_p * PL_MAX_TEACHERS), ("reg", C.c_void_p * PL_MAX_TEACHERS), ("anchors", C.c_void_p),
                 ("label_of", C.c_void_p), ("workspace", C.c_void_p), ("teacher_rows", C.c_void_p),

@@ -60,7 +60,7 @@ static Ws carve(const MmdPseudoArgs* a) {
 }
 
 struct P {
-  int B, N, K, T, cap, max_rows, max_labels, raw_rows, n_ignore, nblk;
+  int B, N, K, T, cap, max_rows, max_labels, raw_rows, n_ignore, nblk, merge01;
   int ignore[MMD_PL_MAX_IGNORE];
   float conf, size;
   double nms_thr, merge_thr;
@@ -425,49 +425,56 @@ __global__ void __launch_bounds__(kNmsThreads) pl_nms_kernel(const __grid_consta
 }
 
 // ---- pass 4: cross-teacher integration (train_methods.py:360-411) -------------------------------------------------------
+// The list of sample b = the teachers' rows in teacher order; with merge01 (the augmented step, :384-386) sample 1's list
+// is sample 0's list followed by its own when both are non-empty.
 __global__ void __launch_bounds__(kNmsThreads) pl_merge_kernel(const __grid_constant__ P p) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ int s_next, s_rows, s_start[MMD_PL_MAX_TEACHERS + 1];
+  constexpr int kSeg = 2 * MMD_PL_MAX_TEACHERS;
+  __shared__ int s_next, s_rows, s_nseg, s_start[kSeg + 1], s_src[kSeg];     // s_src: (sample, teacher) segment -> tb index
   unsigned long long* s_key;
   float4* s_box;
   uint8_t* s_dead;
-  const int capm = p.T * p.max_rows;
+  const int capm = (p.merge01 ? 2 : 1) * p.T * p.max_rows;
   nms_smem(s_raw, capm, s_key, s_box, s_dead);
-  float* s_label = reinterpret_cast<float*>(s_dead + ((capm + 15) & ~15));      // [capm] label of concatenated row i
+  float* s_label = reinterpret_cast<float*>(s_dead + ((capm + 15) & ~15));      // [capm] label of sorted row r
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
-    int acc = 0;
+    int acc = 0, nseg = 0, own = 0, first = 0;
+    for (int t = 0; t < p.T; ++t) own += p.teacher_counts[(size_t)t * p.B + b];
+    if (p.merge01 && b == 1 && own > 0) {
+      for (int t = 0; t < p.T; ++t) first += p.teacher_counts[(size_t)t * p.B + 0];
+      if (first > 0)
+        for (int t = 0; t < p.T; ++t) {
+          s_start[nseg] = acc;
+          s_src[nseg++] = t * p.B + 0;
+          acc += p.teacher_counts[(size_t)t * p.B + 0];
+        }
+    }
     for (int t = 0; t < p.T; ++t) {
-      s_start[t] = acc;
+      s_start[nseg] = acc;
+      s_src[nseg++] = t * p.B + b;
       acc += p.teacher_counts[(size_t)t * p.B + b];
     }
-    s_start[p.T] = acc;
+    s_start[nseg] = acc;
+    s_nseg = nseg;
     s_rows = 0;
   }
   __syncthreads();
-  const int n = s_start[p.T];
+  const int nseg = s_nseg, n = s_start[nseg];
   float* out = p.labels + (size_t)b * p.max_labels * 5;
+  auto row_of = [&](int i) -> const float* {
+    int g = 0;
+    while (i >= s_start[g + 1]) ++g;
+    return p.teacher_rows + ((size_t)s_src[g] * p.max_rows + (i - s_start[g])) * 6;
+  };
   if (n > 0) {
     const int n2 = next_pow2(n);
-    // concatenated row i -> (teacher, row): scores as keys, boxes staged in concatenation order behind the sorted ones is
-    // not needed: the sorted copy is built from global memory
-    for (int i = tid; i < n2; i += kNmsThreads) {
-      unsigned long long k = ~0ull;
-      if (i < n) {
-        int t = 0;
-        while (i >= s_start[t + 1]) ++t;
-        const float* r = p.teacher_rows + (((size_t)t * p.B + b) * p.max_rows + (i - s_start[t])) * 6;
-        k = ((unsigned long long)(~__float_as_uint(r[4])) << 32) | (unsigned)i;
-      }
-      s_key[i] = k;
-    }
+    for (int i = tid; i < n2; i += kNmsThreads)
+      s_key[i] = i < n ? ((unsigned long long)(~__float_as_uint(row_of(i)[4])) << 32) | (unsigned)i : ~0ull;
     __syncthreads();
     bitonic_sort(s_key, n2);
     for (int r = tid; r < n; r += kNmsThreads) {
-      const int i = (int)(s_key[r] & 0xffffffffu);
-      int t = 0;
-      while (i >= s_start[t + 1]) ++t;
-      const float* row = p.teacher_rows + (((size_t)t * p.B + b) * p.max_rows + (i - s_start[t])) * 6;
+      const float* row = row_of((int)(s_key[r] & 0xffffffffu));
       s_box[r] = make_float4(row[0], row[1], row[2], row[3]);
       s_label[r] = row[5];
       s_dead[r] = 0;
@@ -501,6 +508,8 @@ static int check_args(const MmdPseudoArgs* a) {
   MMD_CHECK_ARG(a->cap >= 1 && a->cap <= MMD_PL_MAX_CAP && a->max_rows >= 1 && (long long)a->T * a->max_rows <= MMD_PL_MAX_CAP &&
                     a->max_labels >= 1,
                 "pseudo: cap=%d max_rows=%d max_labels=%d (cap, T * max_rows <= %d)", a->cap, a->max_rows, a->max_labels, MMD_PL_MAX_CAP);
+  MMD_CHECK_ARG(a->merge01 == 0 || (a->B >= 2 && 2LL * a->T * a->max_rows <= MMD_PL_MAX_CAP),
+                "pseudo: merge01 needs B >= 2 and 2 * T * max_rows <= %d (B=%d T=%d max_rows=%d)", MMD_PL_MAX_CAP, a->B, a->T, a->max_rows);
   MMD_CHECK_ARG(a->n_ignore >= 0 && a->n_ignore <= MMD_PL_MAX_IGNORE, "pseudo: n_ignore=%d", a->n_ignore);
   MMD_CHECK_ARG(a->conf_threshold >= 0.f, "pseudo: conf_threshold %g must be >= 0 (scores are probabilities)", (double)a->conf_threshold);
   MMD_CHECK_ARG(a->anchors && a->label_of && a->workspace && a->teacher_rows && a->teacher_counts && a->labels && a->counts,
@@ -532,7 +541,7 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
   if (rc) return rc;
   pl::P p;
   p.B = a->B; p.N = a->N; p.K = a->K; p.T = a->T; p.cap = a->cap; p.max_rows = a->max_rows; p.max_labels = a->max_labels;
-  p.raw_rows = a->raw_rows; p.n_ignore = a->n_ignore;
+  p.raw_rows = a->raw_rows; p.n_ignore = a->n_ignore; p.merge01 = a->merge01 ? 1 : 0;
   p.nblk = (a->N + pl::kThreads - 1) / pl::kThreads;
   for (int i = 0; i < MMD_PL_MAX_IGNORE; ++i) p.ignore[i] = a->ignore[i];
   p.conf = a->conf_threshold; p.size = a->image_size;
@@ -569,7 +578,7 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
   MMD_SMEM(pl::pl_nms_kernel, smem3);
   pl::pl_nms_kernel<<<dim3(a->B, a->T), pl::kNmsThreads, smem3, s>>>(p);
   MMD_LAUNCH_CHECK();
-  const int capm = a->T * a->max_rows;
+  const int capm = (a->merge01 ? 2 : 1) * a->T * a->max_rows;
   const size_t smem4 = pl::nms_smem_bytes(capm) + 16 + (size_t)capm * sizeof(float);
   MMD_SMEM(pl::pl_merge_kernel, smem4);
   pl::pl_merge_kernel<<<a->B, pl::kNmsThreads, smem4, s>>>(p);

@@ -101,10 +101,12 @@ def _device_table(tab, dev):
 
 
 def teacher_pseudo_labels(predictions, valid_classes_dict, config, cap=DEFAULT_CAP, max_rows=DEFAULT_MAX_ROWS,
-                          max_labels=DEFAULT_MAX_LABELS, raw_rows=False, merge_iou=0.5):
+                          max_labels=DEFAULT_MAX_LABELS, raw_rows=False, merge_iou=0.5, merge_batch_0_1=False):
     """predictions: list (one per teacher, in teacher order) of `(classification [B,N,K], regression [B,N,4], anchors
     [1|B,N,4])` — the first element of what the reference's models return.  Runs, for every teacher,
-    logits_to_ground_truth(include_scores=True) and then the wrappers' integration; returns PseudoLabels (device)."""
+    logits_to_ground_truth(include_scores=True) and then the wrappers' integration; returns PseudoLabels (device).
+    `merge_batch_0_1=True` is the augmented step's label merge (train_methods.py:384-386): when samples 0 and 1 both have
+    labels, sample 1 gets sample 0's rows in front of its own before the cross-teacher NMS."""
     if len(predictions) < 1 or len(predictions) > _lib.PL_MAX_TEACHERS:
         raise ValueError("1..%d teachers, got %d" % (_lib.PL_MAX_TEACHERS, len(predictions)))
     cls0, reg0, anchors = predictions[0][0], predictions[0][1], predictions[0][2]
@@ -122,6 +124,7 @@ def teacher_pseudo_labels(predictions, valid_classes_dict, config, cap=DEFAULT_C
     a.nms_threshold = _cfg_get(config, "nms_threshold", "float")
     a.image_size = float(_cfg_get(config, "image_size", "int"))
     a.merge_iou = float(merge_iou)
+    a.merge01 = 1 if merge_batch_0_1 else 0
     ignore = _cfg_get(config, "ignore_labels", "str", default="")
     ignore = [int(x) for x in ignore.split(",") if x.strip()] if isinstance(ignore, str) else [int(x) for x in ignore]
     if len(ignore) > _lib.PL_MAX_IGNORE:

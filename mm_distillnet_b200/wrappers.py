@@ -3,7 +3,7 @@ the student, the frozen teachers and the criteria (src/optimization/train_method
 `forward(rgb, thermal, depth, audio, label, validate=False, augment=False)` and the 6-entry return value of
 
     ModelWithNMSLoss            :425-516   per-teacher criterion_kd(features_s, features_t) calls
-    ModelWithNMSLossAugmented   :265-422   the same step for augment = False (the shipped recipe's 70 % branch)
+    ModelWithNMSLossAugmented   :265-422   the same step + the augment = True branch (samples 0 and 1 merged)
     ModelWithNMSKDListLoss      :165-262   ONE criterion_kd(features_s, [features_t ...]) call (multi-teacher product)
 
 What changes is where the work between the model outputs and the losses runs.  The reference does, per teacher and per
@@ -61,17 +61,43 @@ class _NMSStep(nn.Module):
             features.append(features_t)
         return predictions, features
 
+    augmented = False        # True: `augment=True` merges samples 0 and 1 (ModelWithNMSLossAugmented); the other wrappers
+                             # accept the argument and ignore it, as the reference's do (:176, :436)
+
+    @staticmethod
+    def merge_batch_0_1(audio):
+        """train_methods.py:290-308, as written (in place, no grad): audio[1] <- log10(max(audio[0]^10 + audio[1]^10, 1e-7))."""
+        with torch.no_grad():
+            audio[1] = torch.pow(audio[0], 10) + torch.pow(audio[1], 10)
+            eps = 1e-7
+            audio[1][audio[1] < eps] = eps
+            audio[1] = torch.log10(audio[1])
+        return audio
+
+    @staticmethod
+    def average_batch_0_1(features_t):
+        """train_methods.py:276-288: sample 1 of every teacher feature map <- mean of samples 0 and 1 (in place)."""
+        with torch.no_grad():
+            for i in range(len(features_t)):
+                features_t[i][1] = (features_t[i][0] + features_t[i][1]) / 2
+        return features_t
+
     def forward(self, rgb, thermal, depth, audio, label, validate=False, augment=False):
+        augment = bool(augment) and self.augmented
         if augment:
-            raise NotImplementedError("augment=True (merge_batch_0_1 / average_batch_0_1, train_methods.py:276-308) is not "
-                                      "built: run the step with augment=False")
+            if rgb.shape[0] < 2:
+                raise ValueError("augment=True merges samples 0 and 1: the batch needs at least 2 samples")
+            audio = self.merge_batch_0_1(audio)                                         # :315-316
         logits_s, features_s = self.student_model(audio)
         predictions, features = self._teacher_outputs(rgb, thermal, depth, audio)
+        if augment:
+            features = [self.average_batch_0_1(list(f)) if isinstance(f, (list, tuple)) else f for f in features]   # :340-341
         dev = rgb.device
         if len(predictions) > 0:
             with torch.no_grad():
                 labels = teacher_pseudo_labels(predictions, self.valid_classes_dict, self.config, cap=self.pseudo_cap,
-                                               max_rows=self.pseudo_max_rows, max_labels=self.pseudo_max_labels)
+                                               max_rows=self.pseudo_max_rows, max_labels=self.pseudo_max_labels,
+                                               merge_batch_0_1=augment)                # :384-386
             self.last_pseudo_labels = labels
             annotations = labels if isinstance(self.criterion_main, YetAnotherFocalLoss) else labels.to_list()
         else:
@@ -99,7 +125,9 @@ class ModelWithNMSLoss(_NMSStep):
 
 
 class ModelWithNMSLossAugmented(_NMSStep):
-    """src/optimization/train_methods.py:265-422 (augment=False)."""
+    """src/optimization/train_methods.py:265-422, including the augment=True branch (spectrogram merge of samples 0 and 1,
+    averaged teacher features, merged labels)."""
+    augmented = True
 
 
 class ModelWithNMSKDListLoss(_NMSStep):

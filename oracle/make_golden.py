@@ -199,13 +199,17 @@ def run_pseudo_case(name, B, size, K, seed, n_teachers):
             if np.asarray(this[b]).size == 0:
                 continue
             batch_labels[b] = this[b] if len(batch_labels[b]) == 0 else np.concatenate((batch_labels[b], this[b]), axis=0)
-    for b in range(B):
-        if len(batch_labels[b]) == 0:
-            out["merged_b%d" % b] = np.zeros((0, 5), dtype=np.float32)
-            continue
-        idx = nms(boxes=torch.from_numpy(batch_labels[b][:, 0:4]), scores=torch.from_numpy(batch_labels[b][:, 4]),
-                  iou_threshold=0.5).numpy()
-        out["merged_b%d" % b] = np.delete(batch_labels[b], 4, 1)[idx]
+    for tag, augment in (("merged", False), ("merged_aug", True)):
+        labels = [x if len(x) == 0 else x.copy() for x in batch_labels]
+        if augment and len(labels[1]) != 0 and len(labels[0]) != 0:          # train_methods.py:384-386
+            labels[1] = np.concatenate((labels[0], labels[1]), axis=0)
+        for b in range(B):
+            if len(labels[b]) == 0:
+                out["%s_b%d" % (tag, b)] = np.zeros((0, 5), dtype=np.float32)
+                continue
+            idx = nms(boxes=torch.from_numpy(labels[b][:, 0:4]), scores=torch.from_numpy(labels[b][:, 4]),
+                      iou_threshold=0.5).numpy()
+            out["%s_b%d" % (tag, b)] = np.delete(labels[b], 4, 1)[idx]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, "per teacher:", [[out["t%d_b%d" % (t, b)].shape[0] for b in range(B)] for t in range(n_teachers)],
           "merged:", [out["merged_b%d" % b].shape[0] for b in range(B)])

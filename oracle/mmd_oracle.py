@@ -549,20 +549,26 @@ def logits_to_ground_truth(logits, valid_prediction_ids, label_of_prediction, co
     return res
 
 
-def merge_teacher_labels(per_teacher, iou_threshold=0.5):
-    """The cross-teacher integration of the step wrappers (src/optimization/train_methods.py:360-411, augment=False):
+def merge_teacher_labels(per_teacher, iou_threshold=0.5, augment=False):
+    """The cross-teacher integration of the step wrappers (src/optimization/train_methods.py:360-411):
     per sample, the teachers' [n,6] label arrays (with scores) are concatenated in teacher order, class-agnostic NMS at
     IoU 0.5 on the (integer-valued) boxes, the score column dropped, rows taken in NMS order.  A sample no teacher labelled
-    stays an empty list."""
+    stays an empty list.  `augment` (:384-386): when samples 0 and 1 both have rows, sample 1's list becomes sample 0's
+    rows followed by its own before the NMS (sample 0 keeps its list)."""
     import numpy as np
     B = len(per_teacher[0])
-    out = []
+    cats = []
     for b in range(B):
         rows = [np.asarray(t[b], dtype=np.float32).reshape(-1, 6) for t in per_teacher if np.asarray(t[b]).size > 0]
-        if not rows:
+        cats.append(np.concatenate(rows, axis=0) if rows else None)
+    if augment and B >= 2 and cats[0] is not None and cats[1] is not None:
+        cats[1] = np.concatenate((cats[0], cats[1]), axis=0)
+    out = []
+    for b in range(B):
+        cat = cats[b]
+        if cat is None:
             out.append([])
             continue
-        cat = np.concatenate(rows, axis=0)
         keep = nms_greedy(torch.from_numpy(cat[:, 0:4]), torch.from_numpy(cat[:, 4]), iou_threshold).numpy()
         out.append(np.delete(cat, 4, 1)[keep])
     return out

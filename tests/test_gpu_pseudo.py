@@ -54,6 +54,11 @@ def test_pseudo_golden(name):
             _assert_rows(per_teacher[t][b], g["t%d_b%d" % (t, b)], (t, b))
     for b in range(B):
         _assert_rows(merged[b], g["merged_b%d" % b], ("merged", b))
+    # the augmented step's merge (train_methods.py:384-386)
+    aug = PS.teacher_pseudo_labels(_device_predictions(logits, anchors), H.pseudo_valid_classes_dict(), H.pseudo_config(size),
+                                   merge_batch_0_1=True).to_list()
+    for b in range(B):
+        _assert_rows(aug[b], g["merged_aug_b%d" % b], ("merged_aug", b))
     # the padded tensor is what the detection loss reads: -1 behind the valid rows
     boxes, counts = out.boxes.cpu().numpy(), out.counts.cpu().numpy()
     for b in range(B):
@@ -227,8 +232,27 @@ def test_step_wrappers(wrapper):
     assert all(p.grad is None for p in teachers.parameters())
     for z in out[3:]:
         assert z.shape == (1,) and float(z) == 0.0
-    with pytest.raises(NotImplementedError):
-        model(x, x, x, x, None, augment=True)
+    # augment=True: only ModelWithNMSLossAugmented acts on it (:315-316, :340-341, :384-386); the others ignore it (:176, :436)
+    audio = torch.rand(B, 8, 4, 4, device=DEV) + 0.5
+    a0 = audio.clone()
+    out_a = model(x, x, x, audio, None, augment=True)
+    if wrapper == "ModelWithNMSLossAugmented":
+        want = torch.log10((a0[0] ** 10 + a0[1] ** 10).clamp_min(1e-7))
+        assert torch.allclose(audio[1], want, rtol=1e-6, atol=1e-6) and torch.equal(audio[0], a0[0]) and torch.equal(audio[2:], a0[2:])
+        per_teacher, _ = _oracle_labels(logits, anchors, size, label_of)
+        merged_aug = O.merge_teacher_labels(per_teacher, augment=True)
+        rl, cl = O.focal_loss(cs.double(), rs.double(), anchors.double(), merged_aug)
+        assert abs(float(out_a[0][0]) - float(rl)) <= 1e-5 * abs(float(rl)) and abs(float(out_a[1][0]) - float(cl)) <= 1e-5 * abs(float(cl))
+        assert abs(float(out_a[1][0]) - float(out[1][0])) > 1e-6 * abs(float(cl))          # the merged labels differ
+        for t in range(nt):
+            ft = [f.double().clone() for f in fts[t]]
+            for f in ft:
+                f[1] = (f[0] + f[1]) / 2
+            ref = O.mta_loss([f.double() for f in fs], ft)
+            assert torch.allclose(out_a[2][t].detach().cpu().double(), ref, atol=2e-6, rtol=0)
+    else:
+        assert torch.equal(audio, a0)
+        assert float(out_a[0][0]) == float(out[0][0]) and float(out_a[1][0]) == float(out[1][0])
 
 
 def test_pseudo_labels_and_loss_replay_inside_a_cuda_graph():

@@ -79,6 +79,13 @@ def test_pseudo_labels_match_reference(name):
         got = np.zeros((0, 5), dtype=np.float32) if len(merged[b]) == 0 else merged[b]
         assert got.shape == ref.shape and np.array_equal(got, ref), b
     assert any(g["merged_b%d" % b].shape[0] < sum(g["t%d_b%d" % (t, b)].shape[0] for t in range(nt)) for b in range(B))
+    # the augmented step's label merge (train_methods.py:384-386): sample 1 <- sample 0's rows + its own, before the NMS
+    merged = O.merge_teacher_labels(per_teacher, augment=True)
+    for b in range(B):
+        ref = g["merged_aug_b%d" % b]
+        got = np.zeros((0, 5), dtype=np.float32) if len(merged[b]) == 0 else merged[b]
+        assert got.shape == ref.shape and np.array_equal(got, ref), ("augment", b)
+    assert g["merged_aug_b1"].shape[0] > g["merged_b1"].shape[0] and np.array_equal(g["merged_aug_b0"], g["merged_b0"])
 
 
 @pytest.mark.parametrize("name", sorted(H.FOCAL_CASES))
