@@ -19,11 +19,12 @@ from .heads import Classifier, Regressor  # noqa: F401
 from .focal import YetAnotherFocalLoss  # noqa: F401
 from .mta import MTALoss  # noqa: F401
 from .pseudo import PseudoLabels, logits_to_ground_truth, teacher_pseudo_labels  # noqa: F401
-from .wrappers import ModelWithNMSKDListLoss, ModelWithNMSLoss, ModelWithNMSLossAugmented  # noqa: F401
+from .wrappers import (ModelWithNMSKDListLoss, ModelWithNMSKDListLossAugmented, ModelWithNMSLoss,  # noqa: F401
+                       ModelWithNMSLossAugmented)
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
 from .distill import DistillStep  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
 __all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "PseudoLabels", "logits_to_ground_truth",
-           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
+           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSKDListLossAugmented", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
            "launch_count"]

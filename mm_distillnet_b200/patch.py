@@ -64,7 +64,7 @@ def patch_reference(det_module=None, loss_module=None, utils_module=None, heads=
         from . import pseudo, wrappers
         tm = train_methods_module or sys.modules.get("src.optimization.train_methods")
         if tm is not None:
-            for name in ("ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented"):
+            for name in ("ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented", "ModelWithNMSKDListLossAugmented"):
                 setattr(tm, name, getattr(wrappers, name))
             tm.logits_to_ground_truth = pseudo.logits_to_ground_truth
         if utils is not None and hasattr(utils, "logits_to_ground_truth"):

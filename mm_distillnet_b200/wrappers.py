@@ -5,6 +5,7 @@ the student, the frozen teachers and the criteria (src/optimization/train_method
     ModelWithNMSLoss            :425-516   per-teacher criterion_kd(features_s, features_t) calls
     ModelWithNMSLossAugmented   :265-422   the same step + the augment = True branch (samples 0 and 1 merged)
     ModelWithNMSKDListLoss      :165-262   ONE criterion_kd(features_s, [features_t ...]) call (multi-teacher product)
+    ModelWithNMSKDListLossAugmented :50-162  the same + (augment = True) the rgb teacher on the images in `label` as one more teacher
 
 What changes is where the work between the model outputs and the losses runs.  The reference does, per teacher and per
 sample, a `.cpu()` of the over-threshold boxes, torchvision NMS, numpy concatenation, one more NMS on the host and a
@@ -30,7 +31,8 @@ _MODALITIES = ("rgb", "audio", "thermal", "depth")
 class _NMSStep(nn.Module):
     """Shared body of the three wrappers (their forward methods differ only in how criterion_kd is called)."""
 
-    kd_list = False          # True: one criterion_kd call on the list of teachers (ModelWithNMSKDListLoss)
+    kd_list = False          # True: one criterion_kd call on the list of teachers (ModelWithNMSKDListLoss[Augmented])
+    kd_list_augmented = False   # True: `augment=True` adds the rgb teacher's view of `label` as one more teacher
 
     def __init__(self, student_model, teacher_models, criterion_main, criterion_div, criterion_kd, config, valid_classes_dict):
         super().__init__()
@@ -45,11 +47,16 @@ class _NMSStep(nn.Module):
         self.pseudo_cap, self.pseudo_max_rows, self.pseudo_max_labels = DEFAULT_CAP, DEFAULT_MAX_ROWS, DEFAULT_MAX_LABELS
         self.last_pseudo_labels = None     # the PseudoLabels of the last call (device-resident; for logging / tests)
 
-    def _teacher_outputs(self, rgb, thermal, depth, audio):
+    def _teacher_outputs(self, rgb, thermal, depth, audio, extra=None):
         inputs = {"rgb": rgb, "audio": audio, "thermal": thermal, "depth": depth}
         predictions, features = [], []
-        for modality, teacher_model in self.teacher_models.items():
-            if modality not in _MODALITIES:
+        runs = [(m, self.teacher_models[m]) for m in self.teacher_models.keys()]
+        if extra is not None:
+            # ModelWithNMSKDListLossAugmented (:72-75, :90-95): one more "teacher" = the rgb teacher on the images in `label`
+            runs.append(("augmentation", self.teacher_models["rgb"]))
+            inputs["augmentation"] = extra
+        for modality, teacher_model in runs:
+            if modality not in inputs:
                 raise ValueError('No valid modality to predict from teacher')          # train_methods.py:453-454
             with torch.no_grad():
                 prediction, features_t = teacher_model(inputs[modality])
@@ -83,13 +90,14 @@ class _NMSStep(nn.Module):
         return features_t
 
     def forward(self, rgb, thermal, depth, audio, label, validate=False, augment=False):
+        extra = label if (augment and self.kd_list_augmented) else None
         augment = bool(augment) and self.augmented
         if augment:
             if rgb.shape[0] < 2:
                 raise ValueError("augment=True merges samples 0 and 1: the batch needs at least 2 samples")
             audio = self.merge_batch_0_1(audio)                                         # :315-316
         logits_s, features_s = self.student_model(audio)
-        predictions, features = self._teacher_outputs(rgb, thermal, depth, audio)
+        predictions, features = self._teacher_outputs(rgb, thermal, depth, audio, extra)
         if augment:
             features = [self.average_batch_0_1(list(f)) if isinstance(f, (list, tuple)) else f for f in features]   # :340-341
         dev = rgb.device
@@ -133,3 +141,10 @@ class ModelWithNMSLossAugmented(_NMSStep):
 class ModelWithNMSKDListLoss(_NMSStep):
     """src/optimization/train_methods.py:165-262."""
     kd_list = True
+
+
+class ModelWithNMSKDListLossAugmented(_NMSStep):
+    """src/optimization/train_methods.py:50-162: the list-loss step; with augment=True the rgb teacher also sees the images
+    passed as `label`, and its predictions / features join the label integration and the KD list as one more teacher."""
+    kd_list = True
+    kd_list_augmented = True

@@ -517,7 +517,8 @@ def test_pseudo_label_host_side():
         pseudo.logits_to_ground_truth((c, r, anchors), None, vcd, H.pseudo_config(128, student="EfficientDet"))
     # the wrappers keep the reference's constructor and attribute names (train_methods.py:166-175)
     student, teachers = torch.nn.Identity(), torch.nn.ModuleDict({"rgb": torch.nn.Identity()})
-    for cls in (wrappers.ModelWithNMSLoss, wrappers.ModelWithNMSKDListLoss, wrappers.ModelWithNMSLossAugmented):
+    for cls in (wrappers.ModelWithNMSLoss, wrappers.ModelWithNMSKDListLoss, wrappers.ModelWithNMSLossAugmented,
+                wrappers.ModelWithNMSKDListLossAugmented):
         m = cls(student, teachers, mmd.YetAnotherFocalLoss(), None, mmd.MTALoss("9", "2"), cp["s"], vcd)
         assert m.student_model is student and m.teacher_models is teachers and m.criterion_div is None
         assert {"student_model", "teacher_models", "criterion_main", "criterion_kd"} <= {n for n, _ in m.named_children()}
@@ -531,6 +532,8 @@ def test_pseudo_label_host_side():
     loss.MTALoss = object
     utils.MTALoss, utils.logits_to_ground_truth = object, object
     tm.ModelWithNMSLoss = tm.ModelWithNMSKDListLoss = tm.ModelWithNMSLossAugmented = tm.logits_to_ground_truth = object
+    tm.ModelWithNMSKDListLossAugmented = object
     mmd.patch_reference(det, loss, utils, step_wrappers=True, train_methods_module=tm)
     assert tm.ModelWithNMSLoss is mmd.ModelWithNMSLoss and tm.ModelWithNMSKDListLoss is mmd.ModelWithNMSKDListLoss
+    assert tm.ModelWithNMSKDListLossAugmented is mmd.ModelWithNMSKDListLossAugmented
     assert tm.logits_to_ground_truth is mmd.logits_to_ground_truth and utils.logits_to_ground_truth is mmd.logits_to_ground_truth

@@ -194,7 +194,8 @@ class _FakeDet(nn.Module):
         return (self.c + self.head, self.r + self.head, self.anchors), tuple(f for f in self.feats)
 
 
-@pytest.mark.parametrize("wrapper", ["ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented"])
+@pytest.mark.parametrize("wrapper", ["ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSLossAugmented",
+                                     "ModelWithNMSKDListLossAugmented"])
 def test_step_wrappers(wrapper):
     """The wrappers' 6-entry return value against the restated step: detection loss of the student on the oracle's merged
     labels (fp64 oracle loss), KD losses against the oracle's MTA loss (per teacher / product of the teachers)."""
@@ -216,7 +217,7 @@ def test_step_wrappers(wrapper):
     _, merged = _oracle_labels(logits, anchors, size, label_of)
     rl, cl = O.focal_loss(cs.double(), rs.double(), anchors.double(), merged)
     assert abs(float(out[0][0]) - float(rl)) <= 1e-5 * abs(float(rl)) and abs(float(out[1][0]) - float(cl)) <= 1e-5 * abs(float(cl))
-    if wrapper == "ModelWithNMSKDListLoss":
+    if wrapper.startswith("ModelWithNMSKDListLoss"):
         assert len(out[2]) == 1
         ref = O.mta_loss([f.double() for f in fs], [[f.double() for f in ft] for ft in fts])
         assert torch.allclose(out[2][0].cpu().double(), ref, atol=2e-6, rtol=0)
@@ -250,6 +251,16 @@ def test_step_wrappers(wrapper):
                 f[1] = (f[0] + f[1]) / 2
             ref = O.mta_loss([f.double() for f in fs], ft)
             assert torch.allclose(out_a[2][t].detach().cpu().double(), ref, atol=2e-6, rtol=0)
+    elif wrapper == "ModelWithNMSKDListLossAugmented":
+        # :72-95: the rgb teacher also runs on `label`; the fake teacher ignores its input, so this is the rgb teacher twice
+        assert torch.equal(audio, a0)
+        out_a = model(x, x, x, audio, x, augment=True)
+        lg4 = list(logits) + [logits[0]]
+        per_teacher, merged4 = _oracle_labels(lg4, anchors, size, label_of)
+        rl, cl = O.focal_loss(cs.double(), rs.double(), anchors.double(), merged4)
+        assert abs(float(out_a[0][0]) - float(rl)) <= 1e-5 * abs(float(rl)) and abs(float(out_a[1][0]) - float(cl)) <= 1e-5 * abs(float(cl))
+        ref = O.mta_loss([f.double() for f in fs], [[f.double() for f in ft] for ft in fts + [fts[0]]])
+        assert torch.allclose(out_a[2][0].detach().cpu().double(), ref, atol=2e-6, rtol=0)
     else:
         assert torch.equal(audio, a0)
         assert float(out_a[0][0]) == float(out[0][0]) and float(out_a[1][0]) == float(out[1][0])
