@@ -331,7 +331,9 @@ def measure(B, args, rank, world, dev, dtype, min_timed_s):
     # microseconds each are host-bound otherwise.  --no-graph times the eager path instead.
     use_graph = not args.no_graph
     if use_graph:
-        step.capture(dev_s, dev_t, warmup=max(args.warmup, 3))
+        # two graphs over two static input sets: the pipelined feed of the e2e leg copies the next step's inputs straight
+        # into the set that is not running (no staging-to-static copy); the resident leg replays one of them
+        step.capture(dev_s, dev_t, warmup=max(args.warmup, 3), double_buffer=not args.no_prefetch)
 
     def resident_step():
         if use_graph:
@@ -501,9 +503,10 @@ def run_ours(args, rank, world, local_rank):
                    "precision": "activations stored as %s, all arithmetic fp32 (TMEM accumulators, BatchNorm statistics "
                                 "in double, fp32 master weights and gradients)" % args.dtype,
                    "launch": "CUDA graph replay of the whole step" if r["use_graph"] else "eager",
-                   "e2e_feed": ("pinned host inputs copied on a side stream into a staging set while the previous step "
-                                "replays (DistillStep.prefetch / replay_prefetched); K copies, K replays, K loss "
-                                "read-backs inside the timed region") if (r["use_graph"] and not args.no_prefetch)
+                   "e2e_feed": ("pinned host inputs copied on a side stream into the static input set of the graph that is "
+                                "NOT running while the previous step replays (DistillStep.capture(double_buffer=True) / "
+                                "prefetch / replay_prefetched: two graphs over two input sets, no staging copy); K copies, "
+                                "K replays, K (blocking) loss read-backs inside the timed region") if (r["use_graph"] and not args.no_prefetch)
                                else "inputs copied in front of every step"},
         "roofline": r["roof"], "cpu_baseline": cpu,
         "e2e": {"value": B * world * steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d"],

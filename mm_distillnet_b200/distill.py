@@ -125,46 +125,78 @@ class DistillStep:
         return kd.detach()
 
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------------------------
-    def capture(self, student_inputs, teacher_inputs, warmup=3):
-        """Capture one full step (teacher forwards on their side streams, student forward, MTA, backward, gradient
-        all-reduce) into a CUDA graph over static device copies of the inputs.  The step is ~400 kernel launches of a
-        few microseconds each: replaying it as one graph takes the host (and any driver contention, e.g. a clock
-        monitor) out of the critical path.  Returns self; use replay()."""
+    def _capture_set(self, student_inputs, teacher_inputs, warmup):
+        """One static input set (channels_last views of ONE flat buffer) + the step captured over it."""
         dev = self.device
-        # all static inputs are channels_last views into ONE flat buffer: replay_prefetched() moves a whole staging set
-        # into them with a single device-to-device copy
         srcs = list(student_inputs) + [x for xs in teacher_inputs for x in xs]
-        self._flat_static, views = _flat_channels_last(srcs, dev)
+        flat, views = _flat_channels_last(srcs, dev)
         with torch.no_grad():
             for v, x in zip(views, srcs):
                 v.copy_(x.detach())
         ns = len(student_inputs)
-        self._g_xs = [v.requires_grad_(bool(x.requires_grad)) for v, x in zip(views[:ns], student_inputs)]
-        self._g_xt, k = [], ns
+        g_xs = [v.requires_grad_(bool(x.requires_grad)) for v, x in zip(views[:ns], student_inputs)]
+        g_xt, k = [], ns
         for xs in teacher_inputs:
-            self._g_xt.append(views[k:k + len(xs)])
+            g_xt.append(views[k:k + len(xs)])
             k += len(xs)
-        self._stage_xs = None
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(int(warmup), 1)):      # plans, arenas and packed blocks exist before the capture starts
-                for x in self._g_xs:
+                for x in g_xs:
                     x.grad = None
-                self(self._g_xs, self._g_xt)
+                self(g_xs, g_xt)
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
-        for x in self._g_xs:
+        for x in g_xs:
             x.grad = None
+        if self._want_master and self._flat_master is None:
+            self._flat_master = torch.zeros_like(self.flat_grad)
         try:   # the static inputs' AccumulateGrad nodes were created on another stream than the capture stream
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=side):   # the stream the warm-up ran on (autograd leaf streams match)
-            self._g_out = self(self._g_xs, self._g_xt)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):   # the stream the warm-up ran on (autograd leaf streams match)
+            out = self(g_xs, g_xt)
+            if self._flat_master is not None:
+                # double-buffered capture: every graph leaves the averaged gradient in the SAME buffer (2.8 MB copy),
+                # which is what the parameters' .grad view, whichever graph ran last
+                self._flat_master.copy_(self.flat_grad)
+        return {"flat": flat, "xs": g_xs, "xt": g_xt, "graph": graph, "out": out}
+
+    def capture(self, student_inputs, teacher_inputs, warmup=3, double_buffer=False):
+        """Capture one full step (teacher forwards on their side streams, student forward, MTA, backward, gradient
+        all-reduce) into a CUDA graph over static device copies of the inputs.  The step is ~400 kernel launches of a
+        few microseconds each: replaying it as one graph takes the host (and any driver contention, e.g. a clock
+        monitor) out of the critical path.  Returns self; use replay().
+
+        `double_buffer=True` captures the step TWICE over two static input sets: prefetch() fills the set the running
+        graph does not read and replay_prefetched() replays that set's graph, so the pipelined feed needs no
+        staging-to-static copy (2 x 236 MB of HBM traffic per step at B = 32).  Both graphs leave the averaged gradient
+        in one buffer (`flat_grad`, viewed by every parameter's .grad)."""
+        self._flat_master, self._want_master = None, bool(double_buffer)
+        self._sets = [self._capture_set(student_inputs, teacher_inputs, warmup)]
+        if double_buffer:
+            self._sets.append(self._capture_set(student_inputs, teacher_inputs, warmup))
+            flat = self.flat_grad
+            for p in self.student.parameters():
+                if p.requires_grad and p.grad is not None:
+                    off = p.grad.storage_offset() - flat.storage_offset()
+                    p.grad = self._flat_master[off:off + p.grad.numel()].view(p.grad.shape)
+            self.flat_grad = self._flat_master
+        self._cur = 0
+        self._bind(0)
+        self._stage_xs = None
+        self._fill = 0
         return self
+
+    def _bind(self, k):
+        """The legacy single-set attribute names follow the set whose graph ran last."""
+        st = self._sets[k]
+        self._cur = k
+        self._flat_static, self._g_xs, self._g_xt, self._graph, self._g_out = st["flat"], st["xs"], st["xt"], st["graph"], st["out"]
 
     def replay(self, student_inputs=None, teacher_inputs=None):
         """Copy new inputs (host or device tensors; pinned host memory makes the copies asynchronous) into the static
@@ -184,45 +216,67 @@ class DistillStep:
 
     # ---- pipelined input feed for replay(): the host->device copy of step i+1 overlaps the replay of step i -----------
     def prefetch(self, student_inputs, teacher_inputs):
-        """Start copying the NEXT step's inputs (host tensors, ideally pinned) into a device staging set on a side
-        stream.  The copy waits until the previous replay_prefetched() has consumed the staging set, so one call per
-        step is safe; it never blocks the host for pinned inputs."""
+        """Start copying the NEXT step's inputs (host tensors, ideally pinned) into a device input set on a side stream:
+        a staging set (single-buffered capture) or the static set of the graph that is not running (double_buffer).
+        The copy waits until the set's previous consumer is done, so one call per step is safe; it never blocks the host
+        for pinned inputs."""
         if getattr(self, "_graph", None) is None:
             raise RuntimeError("DistillStep.prefetch() needs capture() first")
         dev = self.device
+        double = len(self._sets) == 2
         if getattr(self, "_stage_xs", None) is None:
-            self._flat_stage, views = _flat_channels_last([x.detach() for x in self._g_xs] + [x for xs in self._g_xt for x in xs], dev)
-            ns = len(self._g_xs)
-            self._stage_xs, self._stage_xt, k = views[:ns], [], ns
-            for xs in self._g_xt:
-                self._stage_xt.append(views[k:k + len(xs)])
-                k += len(xs)
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._ev_ready = torch.cuda.Event()
-            self._ev_consumed = torch.cuda.Event()
-            self._ev_consumed.record(torch.cuda.current_stream(dev))
+            self._ev_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._ev_consumed:
+                e.record(torch.cuda.current_stream(dev))
+            if double:
+                self._stage_xs = True
+            else:
+                self._flat_stage, views = _flat_channels_last([x.detach() for x in self._g_xs] + [x for xs in self._g_xt for x in xs], dev)
+                ns = len(self._g_xs)
+                self._stage_xs, self._stage_xt, k = views[:ns], [], ns
+                for xs in self._g_xt:
+                    self._stage_xt.append(views[k:k + len(xs)])
+                    k += len(xs)
+        if double:
+            k = self._fill
+            dst_xs, dst_xt = [x.detach() for x in self._sets[k]["xs"]], self._sets[k]["xt"]
+        else:
+            k = 0
+            dst_xs, dst_xt = self._stage_xs, self._stage_xt
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._ev_consumed)
-            for d, x in zip(self._stage_xs, student_inputs):
+            self._copy_stream.wait_event(self._ev_consumed[k])
+            for d, x in zip(dst_xs, student_inputs):
                 d.copy_(x, non_blocking=True)
-            for ds, xs in zip(self._stage_xt, teacher_inputs):
+            for ds, xs in zip(dst_xt, teacher_inputs):
                 for d, x in zip(ds, xs):
                     d.copy_(x, non_blocking=True)
-            self._ev_ready.record(self._copy_stream)
+            self._ev_ready[k].record(self._copy_stream)
+        self._pending = k
+        if double:
+            self._fill ^= 1
         self._prefetched = True
 
     def replay_prefetched(self):
-        """Replay the captured step on the inputs of the last prefetch(): waits for that copy, moves the staging set into
-        the graph's static inputs (device-to-device, ~0.1 ms for the D2 pyramid at B=16) and replays."""
+        """Replay the captured step on the inputs of the last prefetch(): waits for that copy, then either moves the staging
+        set into the graph's static inputs (device-to-device) and replays, or — double_buffer — replays the graph that was
+        captured over the set the copy went into."""
         if not getattr(self, "_prefetched", False):
             raise RuntimeError("DistillStep.replay_prefetched() needs prefetch() first")
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(self._ev_ready)
-        with torch.no_grad():
-            self._flat_static.copy_(self._flat_stage)       # one copy: both sets share the flat layout
-        self._ev_consumed.record(cur)
+        k = self._pending
+        cur.wait_event(self._ev_ready[k])
+        if len(self._sets) == 2:
+            self._bind(k)
+            self._graph.replay()
+            self._ev_consumed[k].record(cur)     # the first-cell projections' backward reads the inputs at the very end
+        else:
+            with torch.no_grad():
+                self._flat_static.copy_(self._flat_stage)       # one copy: both sets share the flat layout
+            self._ev_consumed[k].record(cur)
+            self._graph.replay()
         self._prefetched = False
-        self._graph.replay()
         return self._g_out
 
     def graph_inputs(self):
