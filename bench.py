@@ -70,6 +70,8 @@ def cpu_step(student_p, teacher_ps, xs_s, xs_ts):
         kd.append(O.mta_loss(fs, [f.detach() for f in ft]))
     kd = torch.stack(kd)
     (W_KD * kd.sum()).backward()
+    # optimizer.step() (src/optimization/traditional.py:190) with the shipped recipe's Adam (train_methods.py:825-833)
+    torch.optim.Adam([v for v in leaf.values() if v.requires_grad], lr=1e-4, betas=(0.9, 0.999)).step()
     return kd.detach()
 
 
@@ -127,7 +129,7 @@ def run_reference(args, rank):
 WORKLOAD = ("hot path of cfg3/cfg4 (3-teacher -> student distillation step, batch 32 per GPU, bf16) on the cfg2 microbench "
             "inputs: MTA loss + 5-cell EfficientDet-D2 BiFPN on synthetic pyramid features (C3 48@96^2, C4 120@48^2, "
             "C5 352@24^2 -> 112 ch P3-P7): student fwd+bwd (train BN) + 3 teacher fwd (eval) + 3 MTA calls "
-            "[+ flat-gradient NCCL all-reduce for N > 1]; the cfg2 batch (16) is measured in the same run (cfg2_b16)")
+            "[+ flat-gradient NCCL all-reduce for N > 1] + Adam update of the student's parameters; the cfg2 batch (16) is measured in the same run (cfg2_b16)")
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -269,7 +271,10 @@ def measure(B, args, rank, world, dev, dtype, min_timed_s):
     for k in range(N_TEACHERS):
         torch.manual_seed(1 + k)
         teachers.append(mmd.BiFPNStack(*[mmd.BiFPN(C, CC, first_time=(i == 0)) for i in range(N_CELLS)]).to(dev).eval())
-    step = mmd.DistillStep(student, teachers, mmd.MTALoss(T=9.0, p=2.0), w_kd=W_KD)
+    # the shipped recipe's optimizer (configs/mm-distillnet.cfg: Adam, lr 1e-4, b1 0.9, b2 0.999; train_methods.py:825-833) as
+    # ONE launch over the flat gradient, inside the step (and inside its captured graph)
+    opt = None if args.no_optimizer else mmd.FlatAdam(student.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    step = mmd.DistillStep(student, teachers, mmd.MTALoss(T=9.0, p=2.0), w_kd=W_KD, optimizer=opt)
 
     gen = torch.Generator().manual_seed(1000 + rank)
 
@@ -499,7 +504,9 @@ def run_ours(args, rank, world, local_rank):
                                    "min / max block %.3f / %.3f ms per step"
                                    % (len(r["blocks"]), steps, sum(r["blocks"]) * 1e-3, min(r["blocks"]) / steps,
                                       max(r["blocks"]) / steps),
-                   "optimizer": "none (the microbench ends at the averaged gradients)",
+                   "optimizer": ("none (--no-optimizer: the step ends at the averaged gradients)" if args.no_optimizer else
+                                 "Adam, lr 1e-4, betas (0.9, 0.999) — the shipped recipe's (configs/mm-distillnet.cfg) — as one "
+                                 "launch over the flat gradient inside the timed step (mmd_adam_step)"),
                    "precision": "activations stored as %s, all arithmetic fp32 (TMEM accumulators, BatchNorm statistics "
                                 "in double, fp32 master weights and gradients)" % args.dtype,
                    "launch": "CUDA graph replay of the whole step" if r["use_graph"] else "eager",
@@ -542,6 +549,7 @@ def main():
                     "seconds have been timed; the median block is reported")
     ap.add_argument("--no-cfg2", action="store_true", help="skip the extra cfg2 (batch 16) measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-optimizer", action="store_true", help="end the step at the averaged gradients (no Adam update)")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the CUDA-graph replay")
     ap.add_argument("--no-prefetch", action="store_true",
                     help="e2e leg: copy each step's inputs synchronously in front of its replay instead of overlapping the "

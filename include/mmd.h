@@ -10,6 +10,9 @@
  *   mmd_pseudo_labels              replaces logits_to_ground_truth / EfficientDet_post_processing per teacher
  *                                           (src/utils/utils.py:144-231, :234-324) and the cross-teacher integration + nms of
  *                                           the step wrappers (src/optimization/train_methods.py:186-250, :343-411)
+ *   mmd_adam_step                  replaces torch.optim.Adam / AdamW .step() over the student's parameters
+ *                                           (constructed at src/optimization/train_methods.py:825-842, stepped at
+ *                                            src/optimization/traditional.py:190)
  *   mmd_bifpn_run                  replaces nn.Sequential(*[BiFPN(...)]) forward and its autograd
  *                                           (src/YetAnotherEfficientDet.py:639-644, :668; one cell :320-392;
  *                                            SeparableConvBlock.forward :182-192; same-pad conv / pool
@@ -36,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MMD_VERSION 109
+#define MMD_VERSION 110
 
 typedef void* mmd_stream_t; /* cudaStream_t */
 
@@ -172,6 +175,32 @@ typedef struct {
 
 size_t mmd_pseudo_workspace_bytes(const MmdPseudoArgs* a);
 int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step (cfg 3): torch.optim.Adam as the reference builds it (train_methods.py:825-833; AdamW :834-842)
+ * for every parameter tensor in ONE launch over the flat fp32 gradient buffer of the backward.
+ *   t = *step + 1;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
+ *   p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps);  then *step = t (a second, 1-thread launch).
+ *   weight_decay: g += wd * p (Adam) or p *= 1 - lr * wd first (decoupled_weight_decay = 1, AdamW).
+ * Parameter tensors stay the caller's own fp32 tensors (params[i]); grad / exp_avg / exp_avg_sq are flat buffers in which
+ * tensor i starts at element offsets[i].  chunks[c] = (tensor, first element inside the tensor, length <= 1024): one CTA each.
+ * Everything (tables included) lives on the device; the call is CUDA-graph capture safe.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_chunks, decoupled_weight_decay;
+  int64_t n_elements;            /* sum of the tensors' sizes (profiling only)                                                */
+  double lr, beta1, beta2, eps, weight_decay; /* doubles, as the reference's Python scalars: 1 - beta2 is formed in double    */
+                                              /* and rounded once (0.001f), not as 1.f - 0.999f                             */
+  const int64_t* chunks;         /* device [n_chunks][3]                                                                      */
+  const int64_t* offsets;        /* device [n_tensors]                                                                        */
+  float* const* params;          /* device [n_tensors] pointers to the fp32 parameter tensors                                 */
+  const float* grad;             /* flat gradient                                                                             */
+  float* exp_avg;                /* flat first moment (zero before the first step)                                            */
+  float* exp_avg_sq;             /* flat second moment (zero before the first step)                                           */
+  int64_t* step;                 /* device scalar: number of steps taken so far                                               */
+} MmdAdamArgs;
+
+int mmd_adam_step(const MmdAdamArgs* a, mmd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BiFPN stack.  The host describes the whole multi-cell forward (or backward) as a flat list of ops over
@@ -332,6 +361,7 @@ size_t mmd_sizeof_op(void);
 size_t mmd_sizeof_mta_args(void);
 size_t mmd_sizeof_focal_args(void);
 size_t mmd_sizeof_pseudo_args(void);
+size_t mmd_sizeof_adam_args(void);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,8 @@ Public API mirrors the reference (robot-learning-freiburg/MM-DistillNet):
                                    pseudo-labels made and consumed on the device
     ModelWithNMSLoss, ModelWithNMSKDListLoss,
     ModelWithNMSLossAugmented      the step wrappers src/optimization/train_methods.py:165-262, :265-422, :425-516
+    FlatAdam                       torch.optim.Adam / AdamW as built at src/optimization/train_methods.py:825-842, one launch
+                                   over DistillStep's flat gradient buffer
     patch_reference()              rebinds the reference's module globals to these classes (drop-in seam)
 """
 from .bifpn import BiFPN, BiFPNStack, SeparableConvBlock  # noqa: F401
@@ -23,8 +25,9 @@ from .wrappers import (ModelWithNMSKDListLoss, ModelWithNMSKDListLossAugmented, 
                        ModelWithNMSLossAugmented)
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
 from .distill import DistillStep  # noqa: F401
+from .optim import FlatAdam  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
 __all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "PseudoLabels", "logits_to_ground_truth",
-           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSKDListLossAugmented", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "build",
+           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSKDListLossAugmented", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "FlatAdam", "build",
            "launch_count"]

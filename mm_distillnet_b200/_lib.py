@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmmd_b200.so")
 SOURCES = ("api.cu", "mta.cu", "prep.cu", "bifpn_fwd.cu", "bifpn_fwd_tc.cu", "bifpn_fwd_v4.cu", "bifpn_proj_tma.cu", "bifpn_bwd.cu",
-           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "heads.cu", "focal.cu", "pseudo.cu", "bifpn_run.cu")
+           "bifpn_bwd_tc.cu", "bifpn_bwd_v4.cu", "heads.cu", "focal.cu", "pseudo.cu", "adam.cu", "bifpn_run.cu")
 
 MMD_F32, MMD_BF16 = 0, 1
 MMD_NHWC, MMD_NCHW = 0, 1
@@ -54,6 +54,13 @@ class PseudoArgs(C.Structure):
                 ("cls", C.c_void_p * PL_MAX_TEACHERS), ("reg", C.c_void_p * PL_MAX_TEACHERS), ("anchors", C.c_void_p),
                 ("label_of", C.c_void_p), ("workspace", C.c_void_p), ("teacher_rows", C.c_void_p),
                 ("teacher_counts", C.c_void_p), ("labels", C.c_void_p), ("counts", C.c_void_p)]
+
+
+class AdamArgs(C.Structure):
+    _fields_ = [("n_chunks", C.c_int32), ("decoupled_weight_decay", C.c_int32), ("n_elements", C.c_int64),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+                ("chunks", C.c_void_p), ("offsets", C.c_void_p), ("params", C.c_void_p), ("grad", C.c_void_p),
+                ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("step", C.c_void_p)]
 
 
 class Ref(C.Structure):
@@ -203,6 +210,9 @@ def lib():
     L.mmd_pseudo_workspace_bytes.restype = C.c_size_t
     L.mmd_pseudo_workspace_bytes.argtypes = [C.POINTER(PseudoArgs)]
     L.mmd_sizeof_pseudo_args.restype = C.c_size_t
+    L.mmd_adam_step.restype = C.c_int
+    L.mmd_adam_step.argtypes = [C.POINTER(AdamArgs), C.c_void_p]
+    L.mmd_sizeof_adam_args.restype = C.c_size_t
     L.mmd_bifpn_run.restype = C.c_int
     L.mmd_bifpn_run.argtypes = [C.POINTER(Op), C.c_int32, C.POINTER(C.c_void_p), C.c_int32,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -224,6 +234,8 @@ def lib():
     L.mmd_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     if L.mmd_sizeof_focal_args() != C.sizeof(FocalArgs):
         raise RuntimeError("libmmd_b200.so / _lib.py struct mismatch: MmdFocalArgs %d vs %d" % (L.mmd_sizeof_focal_args(), C.sizeof(FocalArgs)))
+    if L.mmd_sizeof_adam_args() != C.sizeof(AdamArgs):
+        raise RuntimeError("libmmd_b200.so / _lib.py struct mismatch: MmdAdamArgs %d vs %d" % (L.mmd_sizeof_adam_args(), C.sizeof(AdamArgs)))
     if L.mmd_sizeof_pseudo_args() != C.sizeof(PseudoArgs):
         raise RuntimeError("libmmd_b200.so / _lib.py struct mismatch: MmdPseudoArgs %d vs %d" % (L.mmd_sizeof_pseudo_args(), C.sizeof(PseudoArgs)))
     if L.mmd_sizeof_op() != C.sizeof(Op) or L.mmd_sizeof_mta_args() != C.sizeof(MtaArgs):
@@ -263,7 +275,7 @@ def prof_collect():
 
 
 EXPORTS = ("mmd_version", "mmd_last_error", "mmd_launch_count", "mmd_set_option", "mmd_mta_fwd", "mmd_mta_bwd", "mmd_focal_fwd",
-           "mmd_focal_bwd", "mmd_sizeof_focal_args", "mmd_pseudo_labels", "mmd_pseudo_workspace_bytes", "mmd_sizeof_pseudo_args", "mmd_bifpn_run", "mmd_bifpn_run_multi",
+           "mmd_focal_bwd", "mmd_sizeof_focal_args", "mmd_pseudo_labels", "mmd_pseudo_workspace_bytes", "mmd_sizeof_pseudo_args", "mmd_adam_step", "mmd_sizeof_adam_args", "mmd_bifpn_run", "mmd_bifpn_run_multi",
            "mmd_bifpn_prep", "mmd_packed_bytes",
            "mmd_sizeof_op", "mmd_sizeof_mta_args", "mmd_prof_enable", "mmd_prof_num_kinds", "mmd_prof_kind_name",
            "mmd_prof_collect")

@@ -823,6 +823,14 @@ def debug_pool_argmax(output):
     return [res.get(i, {}) for i in range(max(res) + 1 if res else 0)]
 
 
+def mark_state_changed(modules):
+    """Tell the plan caches that parameters / running statistics of these BiFPN cells (or head modules) were changed behind
+    PyTorch's back — by a CUDA-graph replay of a training step, whose host-side bookkeeping does not run, or by an
+    optimizer kernel writing through raw pointers: eval-mode plans re-fold their packed parameter blocks on next use."""
+    for m in modules:
+        object.__setattr__(m, _EPOCH_ATTR, getattr(m, _EPOCH_ATTR, 0) + 1)
+
+
 def forward_multi(items):
     """items = [(BiFPNStack, inputs), ...] (<= 4 fusable stacks sharing batch size and dtype, e.g. the student and its
     three frozen teachers): all forwards are enqueued by ONE mmd_bifpn_run_multi call on the current stream, so that

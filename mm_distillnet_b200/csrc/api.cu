@@ -73,7 +73,7 @@ int ensure_dynamic_smem(const void* kernel, size_t bytes) {
 // ---- profiler: event pairs around individual launches, summed per kernel kind on collect --------------------
 static const char* kProfNames[PK_COUNT] = {"mta_pool", "mta_level", "mta_finish", "mta_bwd", "node_fwd", "proj_fwd",
                                            "bnapply", "node_bwd_a", "node_bwd_b", "proj_bwd", "pull", "slot",
-                                           "poolfuse", "node_fwd<16,8>", "node_bwd_a<16,8>", "node_bwd_b<16,8>", "chain_fwd", "chain_bwd", "head_glue", "focal", "pseudo"};
+                                           "poolfuse", "node_fwd<16,8>", "node_bwd_a<16,8>", "node_bwd_b<16,8>", "chain_fwd", "chain_bwd", "head_glue", "focal", "pseudo", "adam"};
 struct ProfRec { cudaEvent_t a, b; int kind; double bytes; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;

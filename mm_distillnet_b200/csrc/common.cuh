@@ -97,7 +97,9 @@ enum ProfKind {
   // detection loss (focal.cu)
   PK_FOCAL,
   // pseudo-label generation (pseudo.cu): the two passes over the anchors
-  PK_PSEUDO, PK_COUNT
+  PK_PSEUDO,
+  // optimizer step (adam.cu)
+  PK_ADAM, PK_COUNT
 };
 bool prof_enabled();
 void prof_begin(int kind, double algo_bytes, cudaStream_t s);

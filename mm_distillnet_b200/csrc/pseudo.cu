@@ -539,6 +539,10 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   int rc = pl::check_args(a);
   if (rc) return rc;
+  const int capm = (a->merge01 ? 2 : 1) * a->T * a->max_rows;
+  const size_t smem4 = pl::nms_smem_bytes(capm) + 16 + (size_t)capm * sizeof(float);
+  MMD_CHECK_ARG(smem4 <= 232448, "pseudo: %d concatenated rows per sample need %zu bytes of shared memory in the merge kernel "
+                "(limit 232448): lower max_rows", capm, smem4);
   pl::P p;
   p.B = a->B; p.N = a->N; p.K = a->K; p.T = a->T; p.cap = a->cap; p.max_rows = a->max_rows; p.max_labels = a->max_labels;
   p.raw_rows = a->raw_rows; p.n_ignore = a->n_ignore; p.merge01 = a->merge01 ? 1 : 0;
@@ -578,8 +582,6 @@ extern "C" int mmd_pseudo_labels(const MmdPseudoArgs* a, mmd_stream_t stream_) {
   MMD_SMEM(pl::pl_nms_kernel, smem3);
   pl::pl_nms_kernel<<<dim3(a->B, a->T), pl::kNmsThreads, smem3, s>>>(p);
   MMD_LAUNCH_CHECK();
-  const int capm = (a->merge01 ? 2 : 1) * a->T * a->max_rows;
-  const size_t smem4 = pl::nms_smem_bytes(capm) + 16 + (size_t)capm * sizeof(float);
   MMD_SMEM(pl::pl_merge_kernel, smem4);
   pl::pl_merge_kernel<<<a->B, pl::kNmsThreads, smem4, s>>>(p);
   MMD_LAUNCH_CHECK();

@@ -11,7 +11,7 @@ student's flat fp32 gradient buffer (mean over ranks = DDP semantics; BatchNorm 
 import torch
 import torch.distributed as dist
 
-from .bifpn import BiFPN, BiFPNStack, forward_multi
+from .bifpn import BiFPN, BiFPNStack, forward_multi, mark_state_changed
 from .mta import MTALoss
 
 
@@ -40,7 +40,7 @@ class DistillStep:
     """
 
     def __init__(self, student, teachers, criterion=None, w_kd=0.005, process_group=None, device=None,
-                 batch_networks=True, kd_mode="each"):
+                 batch_networks=True, kd_mode="each", optimizer=None):
         if not isinstance(student, (BiFPN, BiFPNStack)):
             raise TypeError("DistillStep drives mm_distillnet_b200 BiFPN / BiFPNStack modules")
         self.student, self.teachers = student, list(teachers)
@@ -50,6 +50,10 @@ class DistillStep:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.device = device if device is not None else next(student.parameters()).device
         self.flat_grad = None
+        # optional mm_distillnet_b200.FlatAdam over the student's parameters: its one-launch step runs right behind the
+        # gradient all-reduce, inside the call (and therefore inside a captured graph) — optimizer.step() of
+        # src/optimization/traditional.py:190
+        self.optimizer = optimizer
         self.batch_networks = bool(batch_networks)
         # "each": criterion_kd(features_s, features_t) per teacher, the shipped ModelWithNMSLossAugmented wrapper
         #         (train_methods.py:351-358) -> losses [n_teachers, n_levels];
@@ -122,6 +126,8 @@ class DistillStep:
         if g is None or g.shape != kd.shape or g.device != kd.device:
             g = self._kd_grad = torch.full_like(kd.detach(), self.w_kd)
         torch.autograd.backward([kd], [g])
+        if self.optimizer is not None:
+            self.optimizer.step(self.flat_grad)
         return kd.detach()
 
     # ---- CUDA-graph replay of the whole step -----------------------------------------------------------------------
@@ -212,7 +218,13 @@ class DistillStep:
                 for d, x in zip(ds, xs):
                     d.copy_(x, non_blocking=True)
         self._graph.replay()
+        self._after_replay()
         return self._g_out
+
+    def _after_replay(self):
+        """A replay updates running statistics (and, with an optimizer, the parameters) on the device only: bump the cells'
+        state epoch so that eval-mode plans of the student re-fold their packed blocks on next use."""
+        mark_state_changed(list(self.student) if isinstance(self.student, BiFPNStack) else [self.student])
 
     # ---- pipelined input feed for replay(): the host->device copy of step i+1 overlaps the replay of step i -----------
     def prefetch(self, student_inputs, teacher_inputs):
@@ -277,6 +289,7 @@ class DistillStep:
             self._ev_consumed[k].record(cur)
             self._graph.replay()
         self._prefetched = False
+        self._after_replay()
         return self._g_out
 
     def graph_inputs(self):

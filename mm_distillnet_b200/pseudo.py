@@ -105,6 +105,8 @@ def teacher_pseudo_labels(predictions, valid_classes_dict, config, cap=DEFAULT_C
     """predictions: list (one per teacher, in teacher order) of `(classification [B,N,K], regression [B,N,4], anchors
     [1|B,N,4])` — the first element of what the reference's models return.  Runs, for every teacher,
     logits_to_ground_truth(include_scores=True) and then the wrappers' integration; returns PseudoLabels (device).
+    CUDA-graph capture: call once eagerly first (the class-id table and the workspace are created on the first call; the
+    captured call then only allocates its outputs from the graph's pool).
     `merge_batch_0_1=True` is the augmented step's label merge (train_methods.py:384-386): when samples 0 and 1 both have
     labels, sample 1 gets sample 0's rows in front of its own before the cross-teacher NMS."""
     if len(predictions) < 1 or len(predictions) > _lib.PL_MAX_TEACHERS:

@@ -537,3 +537,16 @@ def test_pseudo_label_host_side():
     assert tm.ModelWithNMSLoss is mmd.ModelWithNMSLoss and tm.ModelWithNMSKDListLoss is mmd.ModelWithNMSKDListLoss
     assert tm.ModelWithNMSKDListLossAugmented is mmd.ModelWithNMSKDListLossAugmented
     assert tm.logits_to_ground_truth is mmd.logits_to_ground_truth and utils.logits_to_ground_truth is mmd.logits_to_ground_truth
+
+
+def test_flat_adam_host_side():
+    """Optimizer step (SURVEY 8d cfg 3): mirrored argument struct, export, no CPU fallback, DistillStep accepts it."""
+    from mm_distillnet_b200 import optim
+    assert _lib.lib().mmd_sizeof_adam_args() == ctypes.sizeof(_lib.AdamArgs)
+    assert "mmd_adam_step" in _lib.EXPORTS
+    with pytest.raises(RuntimeError):
+        optim.FlatAdam([torch.nn.Parameter(torch.zeros(4))])
+    with pytest.raises(ValueError):
+        optim.FlatAdam([])
+    import inspect
+    assert "optimizer" in inspect.signature(mmd.DistillStep.__init__).parameters
