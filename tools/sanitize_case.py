@@ -73,3 +73,16 @@ for dtype in (torch.bfloat16, torch.float32):
     (lr + lc).sum().backward()
     torch.cuda.synchronize()
     print(dtype, "pseudo-labels + focal ok", labels.counts.tolist(), float(lr), float(lc))
+
+# the one-launch optimizer step over a flat gradient buffer (adam.cu)
+ps = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s in ((112,), (112, 112, 1, 1), (3,), (1025,))]
+flat = torch.randn(sum(p.numel() for p in ps) + 8, device=dev)
+o = 0
+for p in ps:
+    p.grad = flat[o:o + p.numel()].view(p.shape)
+    o += p.numel() + 2
+opt = mmd.FlatAdam(ps, lr=1e-3, weight_decay=1e-2, decoupled_weight_decay=True)
+for _ in range(3):
+    opt.step(flat)
+torch.cuda.synchronize()
+print("adam ok", int(opt.step_count), float(ps[1].abs().mean()))
