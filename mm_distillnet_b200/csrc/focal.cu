@@ -27,11 +27,14 @@ struct Assign {
 
 // calc_iou (:6-20) for one anchor (y1, x1, y2, x2) and one box (x1, y1, x2, y2), every operation rounded on its own
 __device__ __forceinline__ float iou_anchor_box(const float4 a, const float* b) {
-  const float area = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
   float iw = __fsub_rn(fminf(a.w, b[2]), fmaxf(a.y, b[0]));
   float ih = __fsub_rn(fminf(a.z, b[3]), fmaxf(a.x, b[1]));
   iw = fmaxf(iw, 0.f);
   ih = fmaxf(ih, 0.f);
+  // no overlap: the reference's quotient is 0 / ua = +0 exactly (ua >= 1e-8); most (anchor, box) pairs end here, without
+  // the areas and the IEEE division — with the labels of three teachers a sample carries up to a few hundred boxes
+  if (iw == 0.f || ih == 0.f) return 0.f;
+  const float area = __fmul_rn(__fsub_rn(b[2], b[0]), __fsub_rn(b[3], b[1]));
   const float inter = __fmul_rn(iw, ih);
   float ua = __fsub_rn(__fadd_rn(__fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)), area), inter);
   ua = fmaxf(ua, 1e-8f);
