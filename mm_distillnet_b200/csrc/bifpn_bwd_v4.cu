@@ -14,6 +14,7 @@
 //                 BN backward) and, by the last CTA, the fusion-weight gradient.
 // Thread = one channel pair x two columns; every shared-memory offset is a compile-time constant and both kernels are
 // fully unrolled over the tile rows (see bifpn_fwd_v4.cu for the measurements that motivated this).
+#include <stdlib.h>
 #include "bifpn_bwd_common.cuh"
 #include "tc.cuh"
 
@@ -1030,6 +1031,10 @@ static int launch_proj_geom(const NodeBwdP& p, cudaStream_t s) {
 
 static int pick_geom(int H, int W) {
   if (W % 16 == 0 && H % 8 == 0) return 0;
+  // A/B switch (MMD_BWD_GEOM_8x8=1): 24x24 (P5 of the D2 pyramid) as nine 8x8 tiles per sample instead of six 12x8 ones —
+  // at B = 32 the student's 192 12x8 tiles are 1.3 waves of the one-CTA-per-SM small-level kernels, 288 8x8 tiles 1.95
+  static const bool prefer8 = getenv("MMD_BWD_GEOM_8x8") != nullptr && atoi(getenv("MMD_BWD_GEOM_8x8")) != 0;
+  if (prefer8 && W % 8 == 0 && H % 8 == 0) return 2;
   if (W % 12 == 0 && H % 8 == 0) return 1;
   if (W % 8 == 0 && H % 8 == 0) return 2;
   if (W % 12 == 0 && H % 6 == 0) return 3;
