@@ -24,10 +24,10 @@ from .pseudo import PseudoLabels, logits_to_ground_truth, teacher_pseudo_labels 
 from .wrappers import (ModelWithNMSKDListLoss, ModelWithNMSKDListLossAugmented, ModelWithNMSLoss,  # noqa: F401
                        ModelWithNMSLossAugmented)
 from .patch import patch_reference, fuse_bifpn_stacks  # noqa: F401
-from .distill import DistillStep  # noqa: F401
+from .distill import DistillStep, lockstep_detection_forward  # noqa: F401
 from .optim import FlatAdam  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 
 __all__ = ["BiFPN", "BiFPNStack", "SeparableConvBlock", "Regressor", "Classifier", "YetAnotherFocalLoss", "MTALoss", "PseudoLabels", "logits_to_ground_truth",
-           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSKDListLossAugmented", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "FlatAdam", "build",
+           "teacher_pseudo_labels", "ModelWithNMSLoss", "ModelWithNMSKDListLoss", "ModelWithNMSKDListLossAugmented", "ModelWithNMSLossAugmented", "patch_reference", "fuse_bifpn_stacks", "DistillStep", "lockstep_detection_forward", "FlatAdam", "build",
            "launch_count"]

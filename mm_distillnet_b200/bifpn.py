@@ -836,15 +836,25 @@ def forward_multi(items):
     three frozen teachers): all forwards are enqueued by ONE mmd_bifpn_run_multi call on the current stream, so that
     nodes of the same pyramid level share a launch.  Returns the per-stack output tuples; a train-mode stack under grad
     mode gets its usual autograd node (the backward is unchanged)."""
+    return _forward_multi([(stack, list(stack), tuple(inputs), "cells") for stack, inputs in items])
+
+
+def forward_multi_heads(items):
+    """items = [(Regressor | Classifier, the 5 pyramid tensors), ...] — <= 4 heads of ONE type on the same pyramid geometry,
+    e.g. the student's regressor (train) and its three frozen teachers' (eval): like forward_multi(), ONE
+    mmd_bifpn_run_multi call, the tower / header nodes of the same level share a launch (blockIdx.y = network), which fills
+    the small levels (a P7 tower layer of one network is 32 tiles at B = 32).  Returns [(predictions, alignment), ...]."""
+    return _forward_multi([(head, [head], tuple(inputs), "head") for head, inputs in items])
+
+
+def _forward_multi(specs):
     L = _lib.lib()
     prepared = []
-    for stack, inputs in items:
-        cells = list(stack)
-        inputs = tuple(inputs)
-        plan, params, need_grad = stack._runner._plan_for(cells, inputs, cells[0].training, "cells")
+    for owner, mods, inputs, kind in specs:
+        plan, params, need_grad = owner._runner._plan_for(mods, inputs, mods[0].training, kind)
         with torch.no_grad():
-            bases, outs, saved = stack._runner._forward_prepare(plan, inputs)
-        prepared.append((stack, inputs, plan, bases, outs, saved))
+            bases, outs, saved = owner._runner._forward_prepare(plan, inputs)
+        prepared.append((owner, inputs, plan, bases, outs, saved, mods, kind))
     p0 = prepared[0][2]
     if any(p[2].B != p0.B or p[2].dtype != p0.dtype or p[2].device != p0.device for p in prepared):
         raise ValueError("forward_multi: stacks must share batch size, dtype and device")
@@ -860,9 +870,8 @@ def forward_multi(items):
                                    _lib.MMD_F32 if p0.dtype == torch.float32 else _lib.MMD_BF16, stream)
     _lib.check(rc, "mmd_bifpn_run_multi")
     results = []
-    for stack, inputs, plan, _, outs, saved in prepared:
-        cells = list(stack)
-        results.append(stack._runner.run(cells, inputs, cells[0].training, "cells", pre=(outs, saved)))
+    for owner, inputs, plan, _, outs, saved, mods, kind in prepared:
+        results.append(owner._runner.run(mods, inputs, mods[0].training, kind, pre=(outs, saved)))
     return results
 
 

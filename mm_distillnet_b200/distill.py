@@ -11,7 +11,7 @@ student's flat fp32 gradient buffer (mean over ranks = DDP semantics; BatchNorm 
 import torch
 import torch.distributed as dist
 
-from .bifpn import BiFPN, BiFPNStack, forward_multi, mark_state_changed
+from .bifpn import BiFPN, BiFPNStack, forward_multi, forward_multi_heads, mark_state_changed
 from .mta import MTALoss
 
 
@@ -294,3 +294,23 @@ class DistillStep:
 
     def graph_inputs(self):
         return self._g_xs
+
+
+def lockstep_detection_forward(student, teachers, student_feats, teacher_feats):
+    """YetAnotherEfficientDet.forward behind the backbone (src/YetAnotherEfficientDet.py:667-675: features = bifpn(p3, p4, p5);
+    regression = regressor(features); classification = classifier(features)) for the student AND its frozen teachers in
+    lockstep: three mmd_bifpn_run_multi calls (stacks, regressors, classifiers) instead of 3 x (1 + n_teachers) op lists, the
+    same node of every network sharing a launch.  `student` / every teacher: a module with `.bifpn` (BiFPNStack),
+    `.regressor`, `.classifier` (mm_distillnet_b200 modules, e.g. a patched YetAnotherEfficientDet); `student_feats` /
+    `teacher_feats[i]`: that network's backbone features (C3, C4, C5).  At most 3 teachers, bf16, equal batch sizes.
+    Returns [(classification, regression, features)] — student first; the teachers' entries are computed under no_grad in
+    whatever mode the modules are in (eval), the student's carry their autograd nodes."""
+    nets = [student] + list(teachers)
+    feats = [tuple(student_feats)] + [tuple(f) for f in teacher_feats]
+    if len(nets) > 4 or len(nets) != len(feats):
+        raise ValueError("lockstep_detection_forward: one student + at most 3 teachers, one feature tuple each")
+    stacks = forward_multi([(n.bifpn, f) for n, f in zip(nets, feats)])
+    pyramids = [stacks[0]] + [tuple(t.detach() for t in o) for o in stacks[1:]]
+    regs = forward_multi_heads([(n.regressor, p) for n, p in zip(nets, pyramids)])
+    clss = forward_multi_heads([(n.classifier, p) for n, p in zip(nets, pyramids)])
+    return [(c[0], r[0], f) for c, r, f in zip(clss, regs, pyramids)]

@@ -300,3 +300,52 @@ def test_neck_and_heads_end_to_end(dtype):
     fwd_tol, grad_tol = (2e-5, 1e-4) if dtype == torch.float32 else BF16_E2E_TOL
     bad = {k: v for k, v in m.items() if not v < (fwd_tol if k in ("reg", "cls", "align") else grad_tol)}
     assert not bad, (bad, m)
+
+
+def test_lockstep_detection_forward_matches_separate_calls():
+    """lockstep_detection_forward (stacks, regressors, classifiers of the student and its frozen teachers as three
+    run_multi calls): the frozen networks' outputs are bit-identical to calling the modules one after the other, the
+    student's (train-mode BatchNorm statistics are accumulated atomically) agree to bf16 rounding, and the student's
+    gradients flow."""
+    import torch.nn as nn
+    C, cc, A, K, L, B, s3 = 112, [48, 120, 352], 9, 20, 3, 2, 48
+
+    class Det(nn.Module):
+        def __init__(self, seed):
+            super().__init__()
+            torch.manual_seed(seed)
+            self.bifpn = mmd.BiFPNStack(*[mmd.BiFPN(C, cc, first_time=(i == 0)) for i in range(2)])
+            self.regressor, self.classifier = mmd.Regressor(C, A, L), mmd.Classifier(C, A, K, L)
+
+        def forward(self, xs):
+            f = self.bifpn(tuple(xs))
+            return self.classifier(f)[0], self.regressor(f)[0], f
+
+    student = Det(1).to(DEV).train()
+    teachers = [Det(10 + i).to(DEV).eval() for i in range(3)]
+    for t in teachers:
+        for p in t.parameters():
+            p.requires_grad_(False)                     # train_methods.py:891-893 (an eval-mode forward that needs grad is refused)
+    gen = torch.Generator().manual_seed(4)
+
+    def feats(grad):
+        return [torch.randn(B, c, s3 >> i, s3 >> i, generator=gen).to(torch.bfloat16).to(DEV)
+                .contiguous(memory_format=torch.channels_last).requires_grad_(grad) for i, c in enumerate(cc)]
+    xs, xts = feats(True), [feats(False) for _ in teachers]
+    with torch.no_grad():
+        ref_t = [t(x) for t, x in zip(teachers, xts)]
+    sd = {k: v.clone() for k, v in student.state_dict().items()}
+    ref_s = student(xs)
+    student.load_state_dict(sd)
+    outs = mmd.lockstep_detection_forward(student, teachers, xs, xts)
+    assert len(outs) == 4
+    for (c, r, f), (rc, rr, rf) in zip(outs[1:], ref_t):
+        assert torch.equal(c, rc) and torch.equal(r, rr) and all(torch.equal(a, b) for a, b in zip(f, rf))
+        assert not c.requires_grad
+    c, r, f = outs[0]
+    assert H.rel_l2(c.detach().float().cpu(), ref_s[0].detach().float().cpu()) < 1e-2
+    assert H.rel_l2(r.detach().float().cpu(), ref_s[1].detach().float().cpu()) < 1e-2
+    (c.float().mean() + r.float().mean() + sum(t.float().mean() for t in f)).backward()
+    assert xs[0].grad is not None and float(xs[0].grad.float().abs().max()) > 0
+    assert student.regressor.header.pointwise_conv.conv.weight.grad is not None
+    assert student.bifpn[0].conv6_up.pointwise_conv.conv.weight.grad is not None

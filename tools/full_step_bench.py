@@ -63,6 +63,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--lockstep", action="store_true", help="student + teachers through lockstep_detection_forward (3 run_multi "
+                    "calls) instead of one module call per network")
     ap.add_argument("--fire", type=float, default=0.0003, help="fraction of anchors above the confidence threshold")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -99,9 +101,23 @@ def main():
     model.pseudo_max_rows, model.pseudo_max_labels = 1024, 2048     # random detections do not cluster like a trained detector's
     opt = torch.optim.Adam(student.parameters(), lr=1e-4, betas=(0.9, 0.999), fused=True, capturable=True)
 
+    from mm_distillnet_b200 import pseudo as PS
+    crit_main, crit_kd = model.criterion_main, model.criterion_kd
+
+    def lockstep_model():
+        # ModelWithNMSLoss.forward (train_methods.py:436-516) with the networks' forwards batched across networks
+        outs = mmd.lockstep_detection_forward(student, [teachers[m] for m in ("rgb", "thermal", "depth")], xs, [xr, xt, xd])
+        (cs, rs, fs), touts = outs[0], outs[1:]
+        with torch.no_grad():
+            labels = PS.teacher_pseudo_labels([(c, r, anchors) for c, r, _ in touts], vcd, cfg, max_rows=1024, max_labels=2048)
+        model.last_pseudo_labels = labels
+        rl, cl = crit_main((cs, rs, anchors), labels)
+        kd = crit_kd.forward_each(fs, [f for _, _, f in touts])
+        return [[rl], [cl], list(kd.unbind(0))]
+
     def step():
         opt.zero_grad(set_to_none=True)
-        out = model(xr, xt, xd, xs, None)
+        out = lockstep_model() if a.lockstep else model(xr, xt, xd, xs, None)
         loss = 1.0 * (out[0][0].mean() + out[1][0].mean()) + 0.005 * torch.stack(out[2]).sum()      # traditional.py:171-182
         loss.backward()
         opt.step()
@@ -133,7 +149,7 @@ def main():
     with torch.cuda.stream(side):
         ms_eager = timed(step, a.steps)
     line = {"what": "full distillation step behind the backbone (student stack + heads fwd/bwd, 3 teachers' stacks + heads fwd, "
-                    "device pseudo-labels, detection loss, 3 MTA calls, backward, Adam)", "batch": B, "dtype": "bf16",
+                    "device pseudo-labels, detection loss, 3 MTA calls, backward, Adam)", "batch": B, "dtype": "bf16", "lockstep": bool(a.lockstep),
             "ms_eager": round(ms_eager, 3), "samples_per_s_eager": round(B / ms_eager * 1e3, 1), "library_launches_per_step": launches,
             "labels_per_sample": counts[:8], "conf_threshold": round(thr, 5)}
     try:
