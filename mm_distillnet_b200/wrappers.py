@@ -12,12 +12,16 @@ sample, a `.cpu()` of the over-threshold boxes, torchvision NMS, numpy concatena
 host→device copy of the labels inside the detection loss: 3·B host synchronisations per step.  Here the teachers'
 predictions go through ONE `mmd_pseudo_labels` call (pseudo.py) whose padded label tensor `YetAnotherFocalLoss` (focal.py)
 reads on the device, and the per-teacher KD calls go through `MTALoss.forward_each` (one set of launches): no host
-synchronisation between the models' outputs and the loss values.
+synchronisation between the models' outputs and the loss values.  When the student and its (<= 3, frozen) teachers are
+YetAnotherEfficientDet models built from this package's stack and heads (patch_reference(heads=True)), their forwards behind
+the backbones also run in lockstep (`lockstep_detection_forward`: same nodes of all networks share launches).
 
 `criterion_main` must be mm_distillnet_b200.YetAnotherFocalLoss (or any callable that accepts `PseudoLabels`; a foreign
 criterion gets the reference's list-of-arrays via `.to_list()`, which synchronises); `criterion_kd` any callable with the
 reference's signature — mm_distillnet_b200.MTALoss takes the fused path.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -46,6 +50,62 @@ class _NMSStep(nn.Module):
         # capacities of the device-side label generation (the reference's Python lists have none)
         self.pseudo_cap, self.pseudo_max_rows, self.pseudo_max_labels = DEFAULT_CAP, DEFAULT_MAX_ROWS, DEFAULT_MAX_LABELS
         self.last_pseudo_labels = None     # the PseudoLabels of the last call (device-resident; for logging / tests)
+
+    # ---- lockstep across networks ---------------------------------------------------------------------------------------
+    lockstep = True          # use lockstep_detection_forward when every model allows it (see _lockstep_models)
+
+    def _lockstep_models(self, extra):
+        """The student and its teachers as YetAnotherEfficientDet-shaped modules (`backbone_net`, `bifpn`, `regressor`,
+        `classifier`, `anchors`; features_from == 'efficientnet', src/YetAnotherEfficientDet.py:656-680) built from this
+        package's BiFPNStack / Regressor / Classifier — or None when anything differs (another model class, the reference's
+        own PyTorch heads, more than 3 teachers, a teacher that is not frozen, the `augmentation` teacher), in which case the
+        wrappers call one model after the other exactly like the reference."""
+        from .bifpn import BiFPNStack
+        from .heads import _Head
+        if not self.lockstep or extra is not None:
+            return None
+        models = [self.student_model] + [self.teacher_models[m] for m in self.teacher_models.keys()]
+        if not 2 <= len(models) <= 4:
+            return None
+        for i, m in enumerate(models):
+            if not all(hasattr(m, a) for a in ("backbone_net", "bifpn", "regressor", "classifier", "anchors")):
+                return None
+            if getattr(m, "features_from", "efficientnet") != "efficientnet":
+                return None
+            if not isinstance(m.bifpn, BiFPNStack) or not m.bifpn.fusable() or not isinstance(m.regressor, _Head) or \
+                    not isinstance(m.classifier, _Head):
+                return None
+            if i > 0 and (m.training or any(p.requires_grad for p in m.parameters())):
+                return None
+        return models
+
+    def _lockstep_outputs(self, models, inputs):
+        """YetAnotherEfficientDet.forward (:660-680) for all networks: every backbone on its own input (PyTorch), then the
+        stacks, regressors and classifiers in lockstep.  -> logits_s, features_s, predictions, features."""
+        from .distill import lockstep_detection_forward
+        feats = []
+        for i, (m, x) in enumerate(zip(models, inputs)):
+            if i == 0:
+                _, p3, p4, p5 = m.backbone_net(x)
+            else:
+                with torch.no_grad():
+                    _, p3, p4, p5 = m.backbone_net(x)
+            feats.append((p3, p4, p5))
+        if len({(f[0].dtype, f[0].shape[0]) for f in feats}) == 1 and feats[0][0].dtype == torch.bfloat16:
+            outs = lockstep_detection_forward(models[0], models[1:], feats[0], [tuple(t.detach() for t in f) for f in feats[1:]])
+        else:       # fp32 features (the parity mode) or unequal batches: network by network, from the features computed above
+            outs = []
+            for i, (m, f) in enumerate(zip(models, feats)):
+                with contextlib.nullcontext() if i == 0 else torch.no_grad():
+                    fe = m.bifpn(f)
+                    r, _ = m.regressor(fe)
+                    c, _ = m.classifier(fe)
+                outs.append((c, r, fe))
+        res = []
+        for m, x, (c, r, f) in zip(models, inputs, outs):
+            res.append(([c, r, m.anchors(x, x.dtype)], f))
+        (logits_s, features_s), rest = res[0], res[1:]
+        return logits_s, features_s, [p for p, _ in rest], [[t.detach() for t in f] for _, f in rest]
 
     def _teacher_outputs(self, rgb, thermal, depth, audio, extra=None):
         inputs = {"rgb": rgb, "audio": audio, "thermal": thermal, "depth": depth}
@@ -96,8 +156,18 @@ class _NMSStep(nn.Module):
             if rgb.shape[0] < 2:
                 raise ValueError("augment=True merges samples 0 and 1: the batch needs at least 2 samples")
             audio = self.merge_batch_0_1(audio)                                         # :315-316
-        logits_s, features_s = self.student_model(audio)
-        predictions, features = self._teacher_outputs(rgb, thermal, depth, audio, extra)
+        done = None
+        models = self._lockstep_models(extra)
+        if models is not None:
+            by_name = {"rgb": rgb, "audio": audio, "thermal": thermal, "depth": depth}
+            names = list(self.teacher_models.keys())
+            if all(n in by_name for n in names):
+                done = self._lockstep_outputs(models, [audio] + [by_name[n] for n in names])
+        if done is not None:
+            logits_s, features_s, predictions, features = done
+        else:
+            logits_s, features_s = self.student_model(audio)
+            predictions, features = self._teacher_outputs(rgb, thermal, depth, audio, extra)
         if augment:
             features = [self.average_batch_0_1(list(f)) if isinstance(f, (list, tuple)) else f for f in features]   # :340-341
         dev = rgb.device

@@ -357,3 +357,77 @@ def test_pseudo_labels_and_loss_replay_inside_a_cuda_graph():
         for a, b in zip(got, ref):
             assert torch.equal(a, b)
     assert int(got[1][:B].sum()) == 0 and float(got[2]) == 0.0 and float(got[4].abs().max()) == 0.0      # last variant: no labels
+
+
+def test_step_wrapper_lockstep_path_equals_model_by_model():
+    """With YetAnotherEfficientDet-shaped models built from this package's stack and heads, the wrapper runs the networks'
+    forwards behind the backbones in lockstep (wrappers._lockstep_models); the result equals the model-by-model path
+    (`lockstep = False`): the teachers' labels bit for bit, the losses to the student's bf16 / atomic-statistics noise."""
+    C, cc, A, K, L, B, s3, size = 112, [48, 120, 352], 9, 20, 3, 2, 32, 256
+    anchors = H.efficientdet_anchors(size).to(DEV)
+
+    class Backbone(nn.Module):
+        def __init__(self, seed):
+            super().__init__()
+            g = torch.Generator().manual_seed(seed)
+            self.w = nn.ParameterList([nn.Parameter(torch.randn(c, 3, generator=g) * 0.5) for c in cc])
+
+        def forward(self, x):        # image [B,3,size,size] -> (c2, p3, p4, p5) like EfficientNet.forward
+            outs = []
+            for i, w in enumerate(self.w):
+                pooled = torch.nn.functional.avg_pool2d(x, 8 << i)
+                outs.append(torch.einsum("bchw,oc->bohw", pooled, w).to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            return (None, *outs)
+
+    class Det(nn.Module):
+        features_from = "efficientnet"
+
+        def __init__(self, seed):
+            super().__init__()
+            torch.manual_seed(seed)
+            self.backbone_net = Backbone(seed)
+            self.bifpn = mmd.BiFPNStack(*[mmd.BiFPN(C, cc, first_time=(i == 0)) for i in range(2)])
+            self.regressor, self.classifier = mmd.Regressor(C, A, L), mmd.Classifier(C, A, K, L)
+            with torch.no_grad():
+                self.classifier.header.pointwise_conv.conv.weight.normal_(0.0, 0.3)
+            self.anchors = lambda x, dt: anchors
+
+        def forward(self, x):
+            _, p3, p4, p5 = self.backbone_net(x)
+            f = self.bifpn((p3, p4, p5))
+            r, _ = self.regressor(f)
+            c, _ = self.classifier(f)
+            return [c, r, self.anchors(x, x.dtype)], f
+
+    student = Det(1).to(DEV).train()
+    teachers = nn.ModuleDict({m: Det(10 + i).to(DEV).eval() for i, m in enumerate(("rgb", "thermal", "depth"))})
+    for p in teachers.parameters():
+        p.requires_grad_(False)
+    gen = torch.Generator().manual_seed(2)
+    imgs = [torch.randn(B, 3, size, size, generator=gen).to(DEV) for _ in range(4)]
+    with torch.no_grad():
+        smax = torch.cat([teachers[m](x)[0][0].float().max(dim=2).values.flatten() for m, x in zip(("rgb", "thermal", "depth"), imgs[:3])])
+    cfg = H.pseudo_config(size, conf_threshold=repr(float(torch.quantile(smax.cpu(), 0.995))))
+    model = mmd.ModelWithNMSLoss(student, teachers, mmd.YetAnotherFocalLoss(), None, mmd.MTALoss("9", "2"), cfg, H.pseudo_valid_classes_dict())
+    model.pseudo_max_rows, model.pseudo_max_labels = 1024, 2048
+    assert model._lockstep_models(None) is not None
+    sd = {k: v.clone() for k, v in student.state_dict().items()}
+    res = {}
+    for mode in (True, False):
+        student.load_state_dict(sd)
+        model.lockstep = mode
+        out = model(imgs[0], imgs[1], imgs[2], imgs[3], None)
+        loss = out[0][0].mean() + out[1][0].mean() + 0.005 * torch.stack(out[2]).sum()
+        student.zero_grad(set_to_none=True)
+        loss.backward()
+        res[mode] = (model.last_pseudo_labels.boxes.clone(), model.last_pseudo_labels.counts.clone(),
+                     float(out[0][0]), float(out[1][0]), torch.stack(out[2]).detach().clone(),
+                     student.backbone_net.w[0].grad.clone())
+    a, b = res[True], res[False]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and int(a[1][:B].sum()) > 0     # same labels (frozen teachers)
+    assert abs(a[2] - b[2]) <= 2e-2 * abs(b[2]) + 1e-6 and abs(a[3] - b[3]) <= 2e-2 * abs(b[3])
+    assert torch.allclose(a[4], b[4], rtol=0, atol=1e-3)
+    assert H.rel_l2(a[5].float().cpu(), b[5].float().cpu()) <= 0.1 and float(a[5].abs().max()) > 0
+    # anything that does not fit falls back to the reference's order of calls
+    teachers["rgb"].classifier.weight_holder = nn.Parameter(torch.zeros(1, device=DEV))           # a teacher that is not frozen
+    assert model._lockstep_models(None) is None
