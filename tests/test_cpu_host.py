@@ -550,3 +550,45 @@ def test_flat_adam_host_side():
         optim.FlatAdam([])
     import inspect
     assert "optimizer" in inspect.signature(mmd.DistillStep.__init__).parameters
+
+
+def test_step_wrapper_lockstep_eligibility():
+    """wrappers._lockstep_models (host logic): YetAnotherEfficientDet-shaped models made of this package's stack and heads,
+    <= 3 frozen eval-mode teachers -> the lockstep path; anything else -> None (the reference's model-by-model order)."""
+    import torch.nn as nn
+    from mm_distillnet_b200 import wrappers
+
+    class Det(nn.Module):
+        features_from = "efficientnet"
+
+        def __init__(self, ours=True):
+            super().__init__()
+            self.backbone_net = nn.Identity()
+            self.bifpn = mmd.BiFPNStack(*[mmd.BiFPN(112, [48, 120, 352], first_time=(i == 0)) for i in range(2)])
+            self.regressor = mmd.Regressor(112, 9, 3) if ours else nn.Identity()
+            self.classifier = mmd.Classifier(112, 9, 20, 3)
+            self.anchors = nn.Identity()
+
+    def frozen(m):
+        m.eval()
+        for p in m.parameters():
+            p.requires_grad_(False)
+        return m
+
+    def build(teachers, student=None):
+        return wrappers.ModelWithNMSLoss(student or Det(), nn.ModuleDict(teachers), mmd.YetAnotherFocalLoss(), None, mmd.MTALoss(),
+                                         {"conf_threshold": "0.3"}, {})
+    ok = build({"rgb": frozen(Det()), "depth": frozen(Det())})
+    models = ok._lockstep_models(None)
+    assert models is not None and len(models) == 3 and models[0] is ok.student_model
+    assert ok._lockstep_models(torch.zeros(1)) is None                               # the kdlist `augmentation` teacher
+    ok.lockstep = False
+    assert ok._lockstep_models(None) is None
+    assert build({"rgb": Det().eval()})._lockstep_models(None) is None                # a teacher that still requires grad
+    assert build({"rgb": frozen(Det()).train()})._lockstep_models(None) is None       # a teacher in train mode
+    assert build({"rgb": frozen(Det(ours=False))})._lockstep_models(None) is None     # the reference's own PyTorch head
+    assert build({m: frozen(Det()) for m in ("rgb", "depth", "thermal", "audio")})._lockstep_models(None) is None   # 4 teachers
+    other = frozen(Det())
+    other.features_from = "header"
+    assert build({"rgb": other})._lockstep_models(None) is None
+    assert build({"rgb": frozen(Det())}, student=nn.Identity())._lockstep_models(None) is None
